@@ -1,0 +1,62 @@
+"""ctypes loader for libcm3p_b200.so (the C ABI declared in include/cm3p_b200.h).
+
+There is no fallback: if the shared library is missing `load()` raises, and every compute entry
+point itself returns CM3P_ERR_ARCH on a non-sm_100 device, which `check()` turns into a
+RuntimeError carrying `cm3p_last_error()`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcm3p_b200.so")
+
+_P = c_void_p
+_I = c_int
+_L = c_int64
+_F = c_float
+
+# name -> (restype, argtypes); must list every symbol declared in include/cm3p_b200.h
+SIGNATURES = {
+    "cm3p_last_error": (c_char_p, []),
+    "cm3p_version": (_I, []),
+    "cm3p_num_sms": (_I, []),
+    "cm3p_gemm_bf16": (_I, [_P, _L, _I, _P, _L, _I, _P, _L, _L, _L, _L, _I, _P, _L, _P, _L, _F, _I, _P, _P, _L, _P]),
+    "cm3p_attn_varlen_fwd": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
+    "cm3p_layernorm_fwd": (_I, [_P, _P, _P, _P, _L, _I, _F, _P]),
+    "cm3p_embed_gather_ln": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _F, _P]),
+    "cm3p_conv1d_k3_gelu_fwd": (_I, [_P, _I, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P]),
+    "cm3p_pool_project_normalize": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "cm3p_clip_loss_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m cm3p_b200.build` (nvcc, sm_100a). "
+            "cm3p_b200 has no CPU or PyTorch fallback for its kernels.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here == header/library mismatch
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    msg = load().cm3p_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        raise RuntimeError(f"{what} failed with status {status}: {last_error()}")

@@ -1,0 +1,123 @@
+// extern "C" boundary of libcm3p_b200.so (declared in include/cm3p_b200.h).  Nothing here throws;
+// every entry returns a status code and records a message for cm3p_last_error().
+#include "../../include/cm3p_b200.h"
+
+#include "attn.h"
+#include "common.h"
+#include "gemm.h"
+#include "rowwise.h"
+
+using namespace cm3p;
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+const char* cm3p_last_error(void) { return last_error(); }
+int cm3p_version(void) { return CM3P_B200_VERSION; }
+int cm3p_num_sms(void) { return num_sms(); }
+
+int cm3p_gemm_bf16(const void* a, int64_t lda, int trans_a, const void* b, int64_t ldb, int trans_b, void* c,
+                   int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue, const void* aux, int64_t ld_aux,
+                   void* c2, int64_t ldc2, float scale, int accumulate, const int32_t* positions,
+                   const float* rope_table, int64_t rope_cols, void* stream) {
+  GemmArgs g;
+  g.a = a; g.lda = lda; g.trans_a = trans_a;
+  g.b = b; g.ldb = ldb; g.trans_b = trans_b;
+  g.c = c; g.ldc = ldc;
+  g.M = M; g.N = N; g.K = K;
+  g.epilogue = epilogue;
+  g.aux = aux; g.ld_aux = ld_aux;
+  g.c2 = c2; g.ldc2 = ldc2;
+  g.scale = scale; g.accumulate = accumulate;
+  g.positions = positions; g.rope_table = rope_table; g.rope_cols = rope_cols;
+  return gemm_bf16(g, as_stream(stream));
+}
+
+int cm3p_attn_varlen_fwd(const void* qkv, void* out, float* lse, const int32_t* cu_seqlens, int64_t total_tokens,
+                         int batch, int heads, int head_dim, int max_seqlen, int window, void* stream) {
+  AttnFwdArgs a;
+  a.qkv = qkv; a.out = out; a.lse = lse; a.cu_seqlens = cu_seqlens;
+  a.total_tokens = total_tokens; a.batch = batch; a.heads = heads; a.head_dim = head_dim;
+  a.max_seqlen = max_seqlen; a.window = window;
+  return attn_varlen_fwd(a, as_stream(stream));
+}
+
+int cm3p_layernorm_fwd(const void* x, const float* gamma, void* y, float* stats, int64_t rows, int hidden, float eps,
+                       void* stream) {
+  int rc = check_arch();
+  if (rc != kOk) return rc;
+  return layernorm_fwd(x, gamma, y, stats, rows, hidden, eps, as_stream(stream));
+}
+
+int cm3p_embed_gather_ln(const int64_t* ids, const int32_t* src_index, const int32_t* audio_slot, const void* tok_emb,
+                         const void* audio_embeds, const float* gamma, void* y, float* stats, int64_t rows, int hidden,
+                         int vocab, float eps, void* stream) {
+  int rc = check_arch();
+  if (rc != kOk) return rc;
+  return embed_gather_ln(ids, src_index, audio_slot, tok_emb, audio_embeds, gamma, y, stats, rows, hidden, vocab, eps,
+                         as_stream(stream));
+}
+
+int cm3p_conv1d_k3_gelu_fwd(const void* x, int x_layout, const void* weight, const float* bias, void* ws,
+                            int64_t ld_ws, void* out, int batch, int c_in, int frames, int c_out, int stride,
+                            void* stream) {
+  int rc = check_arch();
+  if (rc != kOk) return rc;
+  CM3P_REQUIRE((x_layout == 0 && stride == 1) || (x_layout == 1 && stride == 2), kBadShape,
+               "conv1d_k3_gelu: supported forms are (fp32 channels-first, stride 1) and (bf16 channels-last, stride 2)");
+  CM3P_REQUIRE(ld_ws >= 3 * c_in && ld_ws % 8 == 0, kBadShape, "conv1d_k3_gelu: ld_ws=%lld must be >= 3*c_in and %% 8",
+               (long long)ld_ws);
+  cudaStream_t s = as_stream(stream);
+  if (x_layout == 0) {
+    rc = im2col_conv1(reinterpret_cast<const float*>(x), ws, batch, c_in, frames, static_cast<int>(ld_ws), s);
+  } else {
+    CM3P_REQUIRE(ld_ws == 3 * c_in, kBadShape, "conv1d_k3_gelu: channels-last form needs ld_ws == 3*c_in");
+    rc = im2col_conv2(x, ws, batch, frames, c_in, s);
+  }
+  if (rc != kOk) return rc;
+  GemmArgs g;
+  g.a = ws; g.lda = ld_ws;
+  g.b = weight; g.ldb = 3 * c_in;
+  g.c = out; g.ldc = c_out;
+  g.M = static_cast<int64_t>(batch) * (frames / stride);
+  g.N = c_out;
+  g.K = 3 * c_in;
+  g.epilogue = EPI_BIAS_GELU;
+  g.aux = bias;
+  return gemm_bf16(g, s);
+}
+
+int cm3p_pool_project_normalize(const void* hidden_states, const int32_t* cu_seqlens, int mode, const void* proj_w,
+                                void* pooled, float* proj_f32, float* inv_norm, float* embeds_f32, void* embeds_bf16,
+                                int batch, int hidden, int proj_dim, void* stream) {
+  int rc = check_arch();
+  if (rc != kOk) return rc;
+  cudaStream_t s = as_stream(stream);
+  if (mode == 0)
+    rc = gather_rows(hidden_states, cu_seqlens, pooled, batch, hidden, s);
+  else
+    rc = mean_pool(hidden_states, cu_seqlens, pooled, batch, hidden, s);
+  if (rc != kOk) return rc;
+  if (!proj_w) return kOk;  // pooling only
+  GemmArgs g;
+  g.a = pooled; g.lda = hidden;
+  g.b = proj_w; g.ldb = hidden;
+  g.c = proj_f32; g.ldc = proj_dim;
+  g.M = batch; g.N = proj_dim; g.K = hidden;
+  g.epilogue = EPI_SCALE_F32;
+  g.scale = 1.f;
+  rc = gemm_bf16(g, s);
+  if (rc != kOk) return rc;
+  if (!embeds_f32 && !embeds_bf16) return kOk;
+  return l2norm_rows(proj_f32, embeds_f32, embeds_bf16, inv_norm, batch, proj_dim, s);
+}
+
+int cm3p_clip_loss_fwd(const float* S, const int32_t* true_idx, float* row_lse, float* col_lse, float* loss, int Bm,
+                       int V, int Bb, void* stream) {
+  int rc = check_arch();
+  if (rc != kOk) return rc;
+  return clip_loss_fwd(S, true_idx, row_lse, col_lse, loss, Bm, V, Bb, as_stream(stream));
+}
+
+}  // extern "C"

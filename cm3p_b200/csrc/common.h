@@ -1,0 +1,48 @@
+// Host-side helpers shared by the kernels' launchers: error reporting across the C ABI and
+// CUtensorMap encoding through the driver entry point (no link-time dependency on libcuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cm3p {
+
+enum Status : int {
+  kOk = 0,
+  kBadShape = -1,
+  kBadAlignment = -2,
+  kUnsupportedArch = -3,
+  kCudaError = -4,
+  kDriverError = -5,
+};
+
+int set_error(int code, const char* fmt, ...);
+const char* last_error();
+
+// device properties cached per process
+int num_sms();
+int check_arch();  // kOk on sm_100, error otherwise (no fallback)
+
+// 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows, row pitch in BYTES,
+// 128-byte swizzle, zero fill out of bounds.  box_inner * 2 bytes must be <= 128.
+int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                        uint32_t box_inner, uint32_t box_outer);
+// 3-D variant (inner, mid, outer) with byte pitches for mid and outer.
+int encode_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t mid, uint64_t outer,
+                        uint64_t pitch_mid_bytes, uint64_t pitch_outer_bytes, uint32_t box_inner, uint32_t box_mid,
+                        uint32_t box_outer);
+
+#define CM3P_CUDA_TRY(expr)                                                                        \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return ::cm3p::set_error(::cm3p::kCudaError, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                               __FILE__, __LINE__);                                                \
+  } while (0)
+
+#define CM3P_REQUIRE(cond, code, ...)                        \
+  do {                                                       \
+    if (!(cond)) return ::cm3p::set_error(code, __VA_ARGS__); \
+  } while (0)
+
+}  // namespace cm3p

@@ -1,0 +1,45 @@
+// Internal C++ interface of the tcgen05 GEMM (the C ABI wrapper is in api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cm3p {
+
+// Fused epilogues.  Values are part of the C ABI (include/cm3p_b200.h: CM3P_EPI_*).
+enum Epilogue : int {
+  EPI_STORE = 0,       // C = acc                                  (bf16)
+  EPI_RESIDUAL = 1,    // C = acc + aux[M,N]                       (bf16 residual stream update)
+  EPI_GELU = 2,        // C = gelu_erf(acc)                        (audio projector linear_1)
+  EPI_BIAS_GELU = 3,   // C = gelu_erf(acc + bias[N])              (conv1d as GEMM over im2col rows)
+  EPI_BIAS = 4,        // C = acc + bias[N]                        (MLM decoder)
+  EPI_GEGLU = 5,       // C[M,N/2] = gelu_erf(u) * g, B rows interleaved (16 u, 16 g)
+  EPI_GEGLU_SAVE = 6,  // same, and C2[M,N] = raw acc (kept for the backward pass)
+  EPI_ROPE = 7,        // rotate-half RoPE on columns [0, rope_cols) per 64-wide head, rest copied
+  EPI_SCALE_F32 = 8,   // C(fp32) = scale * acc (+ C when accumulate)   (logits, weight gradients)
+  EPI_COUNT = 9,
+};
+
+struct GemmArgs {
+  const void* a = nullptr;  // trans_a == 0: [M, K] K contiguous;  trans_a == 1: [K, M] M contiguous
+  int64_t lda = 0;          // row pitch in elements
+  const void* b = nullptr;  // trans_b == 0: [N, K] K contiguous (nn.Linear weight);  1: [K, N] N contiguous
+  int64_t ldb = 0;
+  void* c = nullptr;
+  int64_t ldc = 0;
+  int64_t M = 0, N = 0, K = 0;
+  int epilogue = EPI_STORE;
+  const void* aux = nullptr;
+  int64_t ld_aux = 0;
+  void* c2 = nullptr;
+  int64_t ldc2 = 0;
+  float scale = 1.f;
+  const int32_t* positions = nullptr;
+  const float* rope_table = nullptr;
+  int64_t rope_cols = 0;
+  int trans_a = 0, trans_b = 0;
+  int accumulate = 0;
+};
+
+int gemm_bf16(const GemmArgs& args, cudaStream_t stream);
+
+}  // namespace cm3p

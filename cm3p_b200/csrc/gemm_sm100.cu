@@ -1,0 +1,417 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma
+// (cta_group::1, M=128, N=256, K=16) -> fp32 accumulators in TMEM (2 stages x 256 columns, so the
+// epilogue of tile i overlaps the MMAs of tile i+1) -> fused epilogue straight from tcgen05.ld
+// registers to global memory.
+//
+//   C[M,N] = epilogue( A[M,K] . B[N,K]^T )
+//
+// Replaces every nn.Linear on the hot path (reference: ModernBERT Wqkv/Wo/Wi/Wo, the audio projector
+// modeling_cm3p.py:470-481, the projections :959/:971, the logits matmul :976-977, the MLM head
+// :1229-1238) and, through im2col rows, the two Conv1d of the audio front-end (:488-489).
+//
+// Warp roles (256 threads, 1 CTA / SM):
+//   warp 0 lane 0 : TMA producer            warp 1 lane 0 : MMA issuer
+//   warp 2        : TMEM alloc / dealloc    warps 4..7    : epilogue (TMEM lane quadrant = warp - 4)
+#include <cuda_bf16.h>
+
+#include "common.h"
+#include "gemm.h"
+#include "ptx.cuh"
+
+namespace cm3p {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int THREADS = 256;
+
+struct Params {
+  int64_t M, N, K;
+  void* c;
+  int64_t ldc;
+  const void* aux;  // residual [M, N] bf16 (ld_aux) or bias [N] fp32
+  int64_t ld_aux;
+  void* c2;  // second output (raw pre-activation for GEGLU_SAVE)
+  int64_t ldc2;
+  float scale;
+  const int32_t* positions;  // [M] token position inside its sequence (ROPE)
+  const float2* rope_table;  // [max_pos][32] (cos, sin)
+  int64_t rope_cols;         // columns [0, rope_cols) are rotated per 64-wide head
+  int trans_a, trans_b;
+  int accumulate;  // F32 epilogue: C += acc
+};
+
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32], int64_t col, int64_t ncols) {
+  // dst points at (row, col); 16-byte stores, guarded per 8 columns
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (col + i * 8 + 8 <= ncols) {
+      uint4 u;
+      u.x = ptx::pack_bf16x2(v[i * 8 + 0], v[i * 8 + 1]);
+      u.y = ptx::pack_bf16x2(v[i * 8 + 2], v[i * 8 + 3]);
+      u.z = ptx::pack_bf16x2(v[i * 8 + 4], v[i * 8 + 5]);
+      u.w = ptx::pack_bf16x2(v[i * 8 + 6], v[i * 8 + 7]);
+      *reinterpret_cast<uint4*>(dst + i * 8) = u;
+    } else {
+      for (int j = 0; j < 8; ++j)
+        if (col + i * 8 + j < ncols) dst[i * 8 + j] = __float2bfloat16(v[i * 8 + j]);
+    }
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc, int quad, int64_t m0, int64_t n0) {
+  const int lane = ptx::lane_id();
+  const int64_t row = m0 + quad * 32 + lane;
+  const bool row_ok = row < p.M;
+  const uint32_t taddr_row = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16);
+
+  if constexpr (EPI == EPI_ROPE) {
+    // one 64-wide head per iteration: x1 = cols [0,32), x2 = cols [32,64)
+    // (cos, sin) of this row's position: loaded once per tile, reused by the tile's 4 heads
+    float2 cs[32];
+    if (n0 < p.rope_cols) {
+      const int pos = row_ok ? p.positions[row] : 0;
+      const float4* tab = reinterpret_cast<const float4*>(p.rope_table + static_cast<int64_t>(pos) * 32);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float4 f = __ldg(tab + k);
+        cs[2 * k] = make_float2(f.x, f.y);
+        cs[2 * k + 1] = make_float2(f.z, f.w);
+      }
+    }
+#pragma unroll 1
+    for (int hcol = 0; hcol < BN; hcol += 64) {
+      const int64_t col = n0 + hcol;
+      if (col >= p.N) break;
+      uint32_t r1[32], r2[32];
+      ptx::tmem_ld_32x32b_x32(taddr_row + hcol, r1);
+      ptx::tmem_ld_32x32b_x32(taddr_row + hcol + 32, r2);
+      ptx::tmem_ld_wait();
+      float o1[32], o2[32];
+      if (col < p.rope_cols) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float x1 = __uint_as_float(r1[k]), x2 = __uint_as_float(r2[k]);
+          o1[k] = x1 * cs[k].x - x2 * cs[k].y;
+          o2[k] = x2 * cs[k].x + x1 * cs[k].y;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          o1[k] = __uint_as_float(r1[k]);
+          o2[k] = __uint_as_float(r2[k]);
+        }
+      }
+      if (row_ok) {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + col;
+        store_bf16x32(dst, o1, col, p.N);
+        store_bf16x32(dst + 32, o2, col + 32, p.N);
+      }
+    }
+    return;
+  }
+
+#pragma unroll 1
+  for (int c = 0; c < BN; c += 32) {
+    const int64_t col = n0 + c;
+    if (col >= p.N) break;  // warp-uniform
+    uint32_t r[32];
+    ptx::tmem_ld_32x32b_x32(taddr_row + c, r);
+    ptx::tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+
+    if constexpr (EPI == EPI_STORE) {
+      if (row_ok) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + col, v, col, p.N);
+    } else if constexpr (EPI == EPI_RESIDUAL) {
+      if (row_ok) {
+        const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(p.aux) + row * p.ld_aux + col;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (col + i * 8 + 8 <= p.N) {
+            const uint4 u = *reinterpret_cast<const uint4*>(res + i * 8);
+            float2 f;
+            f = ptx::unpack_bf16x2(u.x); v[i * 8 + 0] += f.x; v[i * 8 + 1] += f.y;
+            f = ptx::unpack_bf16x2(u.y); v[i * 8 + 2] += f.x; v[i * 8 + 3] += f.y;
+            f = ptx::unpack_bf16x2(u.z); v[i * 8 + 4] += f.x; v[i * 8 + 5] += f.y;
+            f = ptx::unpack_bf16x2(u.w); v[i * 8 + 6] += f.x; v[i * 8 + 7] += f.y;
+          } else {
+            for (int j = 0; j < 8; ++j)
+              if (col + i * 8 + j < p.N) v[i * 8 + j] += __bfloat162float(res[i * 8 + j]);
+          }
+        }
+        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + col, v, col, p.N);
+      }
+    } else if constexpr (EPI == EPI_GELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = ptx::gelu_erf(v[i]);
+      if (row_ok) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + col, v, col, p.N);
+    } else if constexpr (EPI == EPI_BIAS_GELU || EPI == EPI_BIAS) {
+      const float* bias = reinterpret_cast<const float*>(p.aux);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float b = (col + i < p.N) ? __ldg(bias + col + i) : 0.f;
+        v[i] = (EPI == EPI_BIAS_GELU) ? ptx::gelu_erf(v[i] + b) : v[i] + b;
+      }
+      if (row_ok) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + col, v, col, p.N);
+    } else if constexpr (EPI == EPI_GEGLU || EPI == EPI_GEGLU_SAVE) {
+      // Wi rows are interleaved in groups of 16 (u0..u15, g0..g15, u16.., g16..): see host prep.
+      if constexpr (EPI == EPI_GEGLU_SAVE) {
+        if (row_ok) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.c2) + row * p.ldc2 + col, v, col, p.N);
+      }
+      float o[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = ptx::gelu_erf(v[i]) * v[16 + i];
+      if (row_ok) {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + (col >> 1);
+        uint4 u0, u1;
+        u0.x = ptx::pack_bf16x2(o[0], o[1]);   u0.y = ptx::pack_bf16x2(o[2], o[3]);
+        u0.z = ptx::pack_bf16x2(o[4], o[5]);   u0.w = ptx::pack_bf16x2(o[6], o[7]);
+        u1.x = ptx::pack_bf16x2(o[8], o[9]);   u1.y = ptx::pack_bf16x2(o[10], o[11]);
+        u1.z = ptx::pack_bf16x2(o[12], o[13]); u1.w = ptx::pack_bf16x2(o[14], o[15]);
+        *reinterpret_cast<uint4*>(dst) = u0;
+        *reinterpret_cast<uint4*>(dst + 8) = u1;
+      }
+    } else if constexpr (EPI == EPI_SCALE_F32) {
+      if (row_ok) {
+        float* dst = reinterpret_cast<float*>(p.c) + row * p.ldc + col;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (col + i * 4 + 4 <= p.N) {
+            float4 f = make_float4(v[i * 4] * p.scale, v[i * 4 + 1] * p.scale, v[i * 4 + 2] * p.scale,
+                                   v[i * 4 + 3] * p.scale);
+            if (p.accumulate) {
+              const float4 old = *reinterpret_cast<const float4*>(dst + i * 4);
+              f.x += old.x; f.y += old.y; f.z += old.z; f.w += old.w;
+            }
+            *reinterpret_cast<float4*>(dst + i * 4) = f;
+          } else {
+            for (int j = 0; j < 4; ++j)
+              if (col + i * 4 + j < p.N)
+                dst[i * 4 + j] = v[i * 4 + j] * p.scale + (p.accumulate ? dst[i * 4 + j] : 0.f);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                       const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = bars + 2 * STAGES + ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tma_a);
+    ptx::prefetch_tmap(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < ACC_STAGES; ++s) {
+      ptx::mbar_init(&tmem_full[s], 1);
+      ptx::mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t tiles_m = (p.M + BM - 1) / BM;
+  const int64_t tiles_n = (p.N + BN - 1) / BN;
+  const int64_t num_tiles = tiles_m * tiles_n;
+  const int num_kb = static_cast<int>((p.K + BK - 1) / BK);
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int s = 0;
+    uint32_t ph = 0;
+    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int32_t m0 = static_cast<int32_t>((t / tiles_n) * BM);
+      const int32_t n0 = static_cast<int32_t>((t % tiles_n) * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&empty[s], ph ^ 1);
+        ptx::mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+        uint8_t* sa = smem_a + s * A_STAGE_BYTES;
+        uint8_t* sb = smem_b + s * B_STAGE_BYTES;
+        if (!p.trans_a) {
+          ptx::tma_load_2d(sa, &tma_a, &full[s], kb * BK, m0);  // box {64 k, 128 m}
+        } else {
+#pragma unroll
+          for (int i = 0; i < BM / 64; ++i)  // box {64 m, 64 k} per 64-wide M chunk
+            ptx::tma_load_2d(sa + i * (BK * 128), &tma_a, &full[s], m0 + i * 64, kb * BK);
+        }
+        if (!p.trans_b) {
+          ptx::tma_load_2d(sb, &tma_b, &full[s], kb * BK, n0);  // box {64 k, 256 n}
+        } else {
+#pragma unroll
+          for (int i = 0; i < BN / 64; ++i)  // box {64 n, 64 k}
+            ptx::tma_load_2d(sb + i * (BK * 128), &tma_b, &full[s], n0 + i * 64, kb * BK);
+        }
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, p.trans_a ? 1u : 0u, p.trans_b ? 1u : 0u);
+    // K-major: 8-row groups 1024 B apart; one UMMA_K (16 elem) step = +32 B inside the swizzle row.
+    // MN-major: 8-k groups 1024 B apart (SBO), 64-wide MN chunks BK*128 B apart (LBO); UMMA_K step = +2048 B.
+    const uint32_t a_lbo = p.trans_a ? BK * 128 : 16, b_lbo = p.trans_b ? BK * 128 : 16;
+    const uint32_t a_kstep = p.trans_a ? 2048 : 32, b_kstep = p.trans_b ? 2048 : 32;
+    int s = 0;
+    uint32_t ph = 0;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      ptx::mbar_wait(&tmem_empty[as], aph ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&full[s], ph);
+        ptx::tc_fence_after();
+        const uint32_t a_addr = ptx::smem_u32(smem_a + s * A_STAGE_BYTES);
+        const uint32_t b_addr = ptx::smem_u32(smem_b + s * B_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t da = ptx::umma_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
+          const uint64_t db = ptx::umma_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
+          ptx::umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+        if (kb == num_kb - 1) ptx::umma_commit(&tmem_full[as]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int quad = warp - 4;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int64_t m0 = (t / tiles_n) * BM;
+      const int64_t n0 = (t % tiles_n) * BN;
+      ptx::mbar_wait(&tmem_full[as], aph);
+      ptx::tc_fence_after();
+      epilogue_tile<EPI>(p, tmem_base + as * BN, quad, m0, n0);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
+      if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int EPI>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    CM3P_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_sm100_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SMEM_BYTES));
+    configured = true;
+  }
+  const int64_t tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+  gemm_bf16_sm100_kernel<EPI><<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+  CM3P_CUDA_TRY(cudaGetLastError());
+  return kOk;
+}
+
+}  // namespace
+
+int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
+  int rc = check_arch();
+  if (rc != kOk) return rc;
+  CM3P_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, kBadShape, "gemm: empty problem M=%lld N=%lld K=%lld", (long long)g.M,
+               (long long)g.N, (long long)g.K);
+  CM3P_REQUIRE(g.epilogue >= 0 && g.epilogue < EPI_COUNT, kBadShape, "gemm: unknown epilogue %d", g.epilogue);
+  CM3P_REQUIRE(g.a && g.b && g.c, kBadShape, "gemm: null operand");
+  if (g.epilogue == EPI_GEGLU || g.epilogue == EPI_GEGLU_SAVE)
+    CM3P_REQUIRE(g.N % 32 == 0 && g.ldc % 8 == 0, kBadShape, "gemm(geglu): N=%lld must be a multiple of 32",
+                 (long long)g.N);
+  if (g.epilogue == EPI_ROPE)
+    CM3P_REQUIRE(g.N % 64 == 0 && g.rope_cols % 64 == 0 && g.positions && g.rope_table, kBadShape,
+                 "gemm(rope): N and rope_cols must be multiples of 64 and positions/table given");
+  if (g.epilogue == EPI_RESIDUAL || g.epilogue == EPI_BIAS || g.epilogue == EPI_BIAS_GELU)
+    CM3P_REQUIRE(g.aux != nullptr, kBadShape, "gemm: epilogue %d needs aux", g.epilogue);
+  const int out_elt = (g.epilogue == EPI_SCALE_F32) ? 4 : 2;
+  CM3P_REQUIRE((reinterpret_cast<uintptr_t>(g.c) % 16) == 0 && (g.ldc * out_elt) % 16 == 0, kBadAlignment,
+               "gemm: C pointer / pitch must be 16-byte aligned (ldc=%lld)", (long long)g.ldc);
+
+  CUtensorMap ta, tb;
+  if (!g.trans_a)
+    rc = encode_tmap_2d_bf16(&ta, g.a, g.K, g.M, g.lda * 2, BK, BM);
+  else
+    rc = encode_tmap_2d_bf16(&ta, g.a, g.M, g.K, g.lda * 2, 64, BK);
+  if (rc != kOk) return rc;
+  if (!g.trans_b)
+    rc = encode_tmap_2d_bf16(&tb, g.b, g.K, g.N, g.ldb * 2, BK, BN);
+  else
+    rc = encode_tmap_2d_bf16(&tb, g.b, g.N, g.K, g.ldb * 2, 64, BK);
+  if (rc != kOk) return rc;
+
+  Params p;
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.c = g.c; p.ldc = g.ldc;
+  p.aux = g.aux; p.ld_aux = g.ld_aux;
+  p.c2 = g.c2; p.ldc2 = g.ldc2;
+  p.scale = g.scale;
+  p.positions = g.positions;
+  p.rope_table = reinterpret_cast<const float2*>(g.rope_table);
+  p.rope_cols = g.rope_cols;
+  p.trans_a = g.trans_a; p.trans_b = g.trans_b;
+  p.accumulate = g.accumulate;
+
+  switch (g.epilogue) {
+    case EPI_STORE: return launch<EPI_STORE>(ta, tb, p, stream);
+    case EPI_RESIDUAL: return launch<EPI_RESIDUAL>(ta, tb, p, stream);
+    case EPI_GELU: return launch<EPI_GELU>(ta, tb, p, stream);
+    case EPI_BIAS_GELU: return launch<EPI_BIAS_GELU>(ta, tb, p, stream);
+    case EPI_BIAS: return launch<EPI_BIAS>(ta, tb, p, stream);
+    case EPI_GEGLU: return launch<EPI_GEGLU>(ta, tb, p, stream);
+    case EPI_GEGLU_SAVE: return launch<EPI_GEGLU_SAVE>(ta, tb, p, stream);
+    case EPI_ROPE: return launch<EPI_ROPE>(ta, tb, p, stream);
+    case EPI_SCALE_F32: return launch<EPI_SCALE_F32>(ta, tb, p, stream);
+  }
+  return set_error(kBadShape, "gemm: unreachable epilogue %d", g.epilogue);
+}
+
+}  // namespace cm3p

@@ -1,0 +1,223 @@
+"""Thin torch-tensor wrappers over the C ABI (include/cm3p_b200.h).
+
+PyTorch is used here only for device memory and the current CUDA stream; every function forwards
+raw pointers to libcm3p_b200.so and raises on a non-zero status.  No function in this module has a
+PyTorch implementation to fall back to.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+EPI_STORE, EPI_RESIDUAL, EPI_GELU, EPI_BIAS_GELU, EPI_BIAS = 0, 1, 2, 3, 4
+EPI_GEGLU, EPI_GEGLU_SAVE, EPI_ROPE, EPI_SCALE_F32 = 5, 6, 7, 8
+
+# kernel launches issued through this module (bench.py reports it as `gpu_launches`)
+LAUNCH_COUNT = 0
+_LAUNCHES_PER_CALL = {
+    "gemm": 1, "attn": 1, "layernorm": 1, "embed": 1, "conv": 2, "pool_project": 3, "pool": 1, "clip_loss": 2,
+}
+
+
+def _count(kind: str) -> None:
+    global LAUNCH_COUNT
+    LAUNCH_COUNT += _LAUNCHES_PER_CALL[kind]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (cm3p_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, epilogue: int = EPI_STORE, out: torch.Tensor | None = None,
+         aux: torch.Tensor | None = None, c2: torch.Tensor | None = None, scale: float = 1.0,
+         accumulate: bool = False, positions: torch.Tensor | None = None, rope_table: torch.Tensor | None = None,
+         rope_cols: int = 0, trans_a: bool = False, trans_b: bool = False) -> torch.Tensor:
+    """out[M,N] = epilogue(A @ B^T).  A: [M,K] (or [K,M] if trans_a); B: [N,K] (or [K,N] if trans_b)."""
+    _req(a, torch.bfloat16, "a")
+    _req(b, torch.bfloat16, "b")
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    M, K = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    N, Kb = (b.shape[1], b.shape[0]) if trans_b else b.shape
+    if K != Kb:
+        raise ValueError(f"gemm: inner dimensions differ ({K} vs {Kb})")
+    n_out = N // 2 if epilogue in (EPI_GEGLU, EPI_GEGLU_SAVE) else N
+    out_dtype = torch.float32 if epilogue == EPI_SCALE_F32 else torch.bfloat16
+    if out is None:
+        out = torch.empty((M, n_out), device=a.device, dtype=out_dtype)
+    else:
+        _req(out, out_dtype, "out")
+        assert out.shape == (M, n_out) and out.stride(1) == 1
+    if epilogue == EPI_GEGLU_SAVE and c2 is None:
+        c2 = torch.empty((M, N), device=a.device, dtype=torch.bfloat16)
+    lib = _lib.load()
+    rc = lib.cm3p_gemm_bf16(
+        a.data_ptr(), a.stride(0), int(trans_a), b.data_ptr(), b.stride(0), int(trans_b), out.data_ptr(),
+        out.stride(0), M, N, K, epilogue, _ptr(aux), (aux.stride(0) if aux is not None and aux.dim() == 2 else 0),
+        _ptr(c2), (c2.stride(0) if c2 is not None else 0), float(scale), int(accumulate), _ptr(positions),
+        _ptr(rope_table), rope_cols, _stream())
+    _lib.check(rc, "cm3p_gemm_bf16")
+    _count("gemm")
+    return out
+
+
+def attn_varlen_fwd(qkv: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int, heads: int, window: int = -1,
+                    out: torch.Tensor | None = None, lse: torch.Tensor | None = None) -> torch.Tensor:
+    """qkv [T, 3*heads*64] bf16 (rotated) -> out [T, heads*64] bf16.  window < 0 = global."""
+    _req(qkv, torch.bfloat16, "qkv")
+    _req(cu_seqlens, torch.int32, "cu_seqlens")
+    T = qkv.shape[0]
+    H = heads * 64
+    assert qkv.shape[1] == 3 * H and qkv.is_contiguous()
+    if out is None:
+        out = torch.empty((T, H), device=qkv.device, dtype=torch.bfloat16)
+    rc = _lib.load().cm3p_attn_varlen_fwd(qkv.data_ptr(), out.data_ptr(), _ptr(lse), cu_seqlens.data_ptr(), T,
+                                          cu_seqlens.numel() - 1, heads, 64, int(max_seqlen), int(window), _stream())
+    _lib.check(rc, "cm3p_attn_varlen_fwd")
+    _count("attn")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, eps: float, out: torch.Tensor | None = None,
+              stats: torch.Tensor | None = None) -> torch.Tensor:
+    _req(x, torch.bfloat16, "x")
+    _req(gamma, torch.float32, "gamma")
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    rows = x.numel() // x.shape[-1]
+    rc = _lib.load().cm3p_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), out.data_ptr(), _ptr(stats), rows,
+                                        x.shape[-1], float(eps), _stream())
+    _lib.check(rc, "cm3p_layernorm_fwd")
+    _count("layernorm")
+    return out
+
+
+def embed_gather_ln(ids: torch.Tensor, src_index: torch.Tensor | None, audio_slot: torch.Tensor | None,
+                    tok_emb: torch.Tensor, audio_embeds: torch.Tensor | None, gamma: torch.Tensor, eps: float,
+                    rows: int, out: torch.Tensor | None = None, stats: torch.Tensor | None = None) -> torch.Tensor:
+    _req(ids, torch.int64, "ids")
+    _req(tok_emb, torch.bfloat16, "tok_emb")
+    _req(gamma, torch.float32, "gamma")
+    H = tok_emb.shape[1]
+    if out is None:
+        out = torch.empty((rows, H), device=tok_emb.device, dtype=torch.bfloat16)
+    rc = _lib.load().cm3p_embed_gather_ln(ids.data_ptr(), _ptr(src_index), _ptr(audio_slot), tok_emb.data_ptr(),
+                                          _ptr(audio_embeds), gamma.data_ptr(), out.data_ptr(), _ptr(stats), rows, H,
+                                          tok_emb.shape[0], float(eps), _stream())
+    _lib.check(rc, "cm3p_embed_gather_ln")
+    _count("embed")
+    return out
+
+
+def conv1d_k3_gelu(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride: int,
+                   out: torch.Tensor | None = None, ws: torch.Tensor | None = None) -> torch.Tensor:
+    """x fp32 [B,C,F] (stride 1) or bf16 [B,F,C] channels-last (stride 2) -> bf16 [B, F/stride, C_out]."""
+    _req(weight, torch.bfloat16, "weight")
+    _req(bias, torch.float32, "bias")
+    if x.dtype == torch.float32:
+        layout, (B, C, F) = 0, x.shape
+    else:
+        _req(x, torch.bfloat16, "x")
+        layout, (B, F, C) = 1, x.shape
+    assert x.is_contiguous() and weight.is_contiguous() and weight.shape[1] == 3 * C
+    c_out = weight.shape[0]
+    ld_ws = 3 * C
+    if ws is None:
+        ws = torch.empty((B * (F // stride), ld_ws), device=x.device, dtype=torch.bfloat16)
+    if out is None:
+        out = torch.empty((B, F // stride, c_out), device=x.device, dtype=torch.bfloat16)
+    rc = _lib.load().cm3p_conv1d_k3_gelu_fwd(x.data_ptr(), layout, weight.data_ptr(), bias.data_ptr(), ws.data_ptr(),
+                                             ld_ws, out.data_ptr(), B, C, F, c_out, stride, _stream())
+    _lib.check(rc, "cm3p_conv1d_k3_gelu_fwd")
+    _count("conv")
+    return out
+
+
+def pool_project_normalize(hidden: torch.Tensor, cu_seqlens: torch.Tensor, mean_pool: bool,
+                           proj_w: torch.Tensor | None, want_bf16: bool = True):
+    """-> (pooled bf16 [B,H], proj fp32 [B,P] | None, inv_norm [B] | None, embeds fp32 | None, embeds bf16 | None)."""
+    _req(hidden, torch.bfloat16, "hidden")
+    _req(cu_seqlens, torch.int32, "cu_seqlens")
+    B = cu_seqlens.numel() - 1
+    H = hidden.shape[1]
+    dev = hidden.device
+    pooled = torch.empty((B, H), device=dev, dtype=torch.bfloat16)
+    proj = inv = emb = emb16 = None
+    P = 0
+    if proj_w is not None:
+        _req(proj_w, torch.bfloat16, "proj_w")
+        P = proj_w.shape[0]
+        proj = torch.empty((B, P), device=dev, dtype=torch.float32)
+        inv = torch.empty((B,), device=dev, dtype=torch.float32)
+        emb = torch.empty((B, P), device=dev, dtype=torch.float32)
+        emb16 = torch.empty((B, P), device=dev, dtype=torch.bfloat16) if want_bf16 else None
+    rc = _lib.load().cm3p_pool_project_normalize(hidden.data_ptr(), cu_seqlens.data_ptr(), int(mean_pool),
+                                                 _ptr(proj_w), pooled.data_ptr(), _ptr(proj), _ptr(inv), _ptr(emb),
+                                                 _ptr(emb16), B, H, P, _stream())
+    _lib.check(rc, "cm3p_pool_project_normalize")
+    _count("pool_project" if proj_w is not None else "pool")
+    return pooled, proj, inv, emb, emb16
+
+
+def clip_loss_fwd(S: torch.Tensor, true_idx: torch.Tensor, V: int):
+    """S fp32 [Bm*V, Bb] -> (loss [1] fp32, row_lse [Bm], col_lse [Bb])."""
+    _req(S, torch.float32, "S")
+    _req(true_idx, torch.int32, "true_idx")
+    assert S.is_contiguous()
+    Bb = S.shape[1]
+    Bm = S.shape[0] // V
+    row_lse = torch.empty((Bm,), device=S.device, dtype=torch.float32)
+    col_lse = torch.empty((Bb,), device=S.device, dtype=torch.float32)
+    loss = torch.empty((1,), device=S.device, dtype=torch.float32)
+    rc = _lib.load().cm3p_clip_loss_fwd(S.data_ptr(), true_idx.data_ptr(), row_lse.data_ptr(), col_lse.data_ptr(),
+                                        loss.data_ptr(), Bm, V, Bb, _stream())
+    _lib.check(rc, "cm3p_clip_loss_fwd")
+    _count("clip_loss")
+    return loss, row_lse, col_lse
+
+
+# ------------------------------------------------------------------------------------------------
+# host-side preparation helpers (layout only, no arithmetic on the hot path)
+
+_ROPE_CACHE: dict = {}
+
+
+def rope_table(theta: float, max_pos: int, device) -> torch.Tensor:
+    """[max_pos, 32, 2] fp32 (cos, sin) with the reference's fp32 recipe (MB:94-172): inv_freq =
+    theta^(-2k/64), angle = float(pos) * inv_freq."""
+    key = (float(theta), int(max_pos), str(device))
+    tab = _ROPE_CACHE.get(key)
+    if tab is None:
+        inv_freq = 1.0 / (theta ** (torch.arange(0, 64, 2, dtype=torch.int64).float() / 64))
+        ang = torch.arange(max_pos, dtype=torch.float32)[:, None] * inv_freq[None, :]
+        tab = torch.stack((ang.cos(), ang.sin()), dim=-1).contiguous().to(device)
+        _ROPE_CACHE[key] = tab
+    return tab
+
+
+def interleave_wi(w: torch.Tensor) -> torch.Tensor:
+    """Wi [2I, H] (rows: I 'input' then I 'gate', MB:90) -> rows interleaved in groups of 16 so one
+    32-column accumulator chunk of the GEMM epilogue holds 16 inputs and their 16 gates."""
+    two_i, H = w.shape
+    I = two_i // 2
+    assert I % 16 == 0, "intermediate_size must be a multiple of 16"
+    return torch.stack((w[:I].reshape(I // 16, 16, H), w[I:].reshape(I // 16, 16, H)), dim=1).reshape(two_i, H)
+
+
+def deinterleave_wi(w: torch.Tensor) -> torch.Tensor:
+    two_i, H = w.shape
+    I = two_i // 2
+    v = w.reshape(I // 16, 2, 16, H)
+    return torch.cat((v[:, 0].reshape(I, H), v[:, 1].reshape(I, H)), dim=0)

@@ -1,0 +1,113 @@
+/* cm3p_b200 — C ABI of the B200-native CM3P hot path (libcm3p_b200.so).
+ *
+ * The reference (OliBomby/CM3P) is pure Python/PyTorch and has no FFI of its own; every device op on
+ * its hot path is a torch library call.  Each entry point below therefore cites the reference *call
+ * site(s)* it replaces (paths relative to the reference checkout; "MB:" is the third-party
+ * transformers/models/modernbert/modeling_modernbert.py that holds the encoder arithmetic).
+ * INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise
+ *   - the caller owns all memory (inputs, outputs, workspaces); the library never allocates or frees
+ *     device memory and keeps no state besides cached device properties
+ *   - every function enqueues work on `stream` (a cudaStream_t passed as void*) and returns without
+ *     synchronising; 0 = success, negative = error (see CM3P_ERR_*), message via cm3p_last_error()
+ *   - bf16 activations / weights, fp32 statistics, LayerNorm weights, biases, logits and losses
+ *   - sm_100a only: on any other device every compute entry returns CM3P_ERR_ARCH (no fallback)
+ */
+#ifndef CM3P_B200_H_
+#define CM3P_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CM3P_B200_VERSION 100 /* 0.1.0 */
+
+#define CM3P_OK 0
+#define CM3P_ERR_SHAPE (-1)
+#define CM3P_ERR_ALIGN (-2)
+#define CM3P_ERR_ARCH (-3)
+#define CM3P_ERR_CUDA (-4)
+#define CM3P_ERR_DRIVER (-5)
+
+/* GEMM epilogues (cm3p_gemm_bf16.epilogue) */
+#define CM3P_EPI_STORE 0      /* C = acc                                   bf16 */
+#define CM3P_EPI_RESIDUAL 1   /* C = acc + aux[M,N]                        bf16, aux may alias C */
+#define CM3P_EPI_GELU 2       /* C = gelu_erf(acc) */
+#define CM3P_EPI_BIAS_GELU 3  /* C = gelu_erf(acc + bias[N]), bias fp32 in aux */
+#define CM3P_EPI_BIAS 4       /* C = acc + bias[N] */
+#define CM3P_EPI_GEGLU 5      /* C[M,N/2] = gelu_erf(u)*g; B rows interleaved in groups of 16 (u,g) */
+#define CM3P_EPI_GEGLU_SAVE 6 /* as GEGLU, and C2[M,N] = acc (pre-activation kept for backward) */
+#define CM3P_EPI_ROPE 7       /* rotate-half RoPE on columns [0, rope_cols) per 64-wide head */
+#define CM3P_EPI_SCALE_F32 8  /* C(fp32) = scale*acc (+ C if accumulate) */
+
+const char* cm3p_last_error(void);
+int cm3p_version(void);
+int cm3p_num_sms(void); /* host query; 0 if no CUDA device */
+
+/* C[M,N] = epilogue(A . B^T) on tcgen05 tensor cores, fp32 accumulation in TMEM.
+ * Replaces nn.Linear everywhere on the path: MB:74-91 (Wi/Wo), MB:232-310 (Wqkv/Wo),
+ * cm3p/modeling_cm3p.py:470-481 (projector), :959/:971 (projections), :976-977 (logits matmul and
+ * logit-scale multiply), :1229-1238 (MLM head); with CM3P_EPI_ROPE also MB:197-228.
+ *   a: trans_a == 0 -> [M,K] K-contiguous, else [K,M] M-contiguous; lda = row pitch in elements
+ *   b: trans_b == 0 -> [N,K] K-contiguous (nn.Linear.weight layout), else [K,N]
+ *   positions [M] int32 + rope_table [max_pos][32][2] fp32 (cos,sin) only for CM3P_EPI_ROPE */
+int cm3p_gemm_bf16(const void* a, int64_t lda, int trans_a, const void* b, int64_t ldb, int trans_b, void* c,
+                   int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue, const void* aux, int64_t ld_aux,
+                   void* c2, int64_t ldc2, float scale, int accumulate, const int32_t* positions,
+                   const float* rope_table, int64_t rope_cols, void* stream);
+
+/* Unpadded bidirectional attention, head_dim 64: out = softmax(q k^T / 8 | mask) v per sequence/head.
+ * Replaces ALL_ATTENTION_FUNCTIONS[...] in MB:286-300 (sdpa / flash_attention_2 / eager) together
+ * with the padding + sliding-window masks (transformers/masking_utils.py:121-131) and the
+ * unpad/repad helpers cm3p/modeling_cm3p.py:65-134.
+ *   qkv [T,3,heads,64] bf16 (q,k already rotated), out [T,heads*64] bf16, lse [heads,T] fp32 or NULL
+ *   window < 0: global layer; window = w: attend iff |i-j| <= w (ModernBERT: local_attention/2) */
+int cm3p_attn_varlen_fwd(const void* qkv, void* out, float* lse, const int32_t* cu_seqlens, int64_t total_tokens,
+                         int batch, int heads, int head_dim, int max_seqlen, int window, void* stream);
+
+/* y = LayerNorm(x) * gamma (no bias), rows of H bf16; stats [rows][2] = (mean, rstd) or NULL.
+ * Replaces nn.LayerNorm at MB:63 (embeddings.norm), MB:318-323 (attn_norm / mlp_norm), final_norm. */
+int cm3p_layernorm_fwd(const void* x, const float* gamma, void* y, float* stats, int64_t rows, int hidden, float eps,
+                       void* stream);
+
+/* x0[t] = LayerNorm(audio_slot[t] >= 0 ? audio_embeds[audio_slot[t]] : tok_emb[ids[src_index[t]]]).
+ * Replaces cm3p/modeling_cm3p.py:591-592 (embedding gather), :603-605 (audio scatter) and MB:63.
+ *   ids: padded int64 [B*L]; src_index [T] int32 flat index of every real token (NULL = identity);
+ *   audio_slot [T] int32 running count of [AUDIO] tokens, -1 elsewhere (NULL = no audio) */
+int cm3p_embed_gather_ln(const int64_t* ids, const int32_t* src_index, const int32_t* audio_slot, const void* tok_emb,
+                         const void* audio_embeds, const float* gamma, void* y, float* stats, int64_t rows, int hidden,
+                         int vocab, float eps, void* stream);
+
+/* gelu(conv1d(x, k=3, pad=1, stride)) written channels-last [B, F/stride, C_out] bf16.
+ * Replaces cm3p/modeling_cm3p.py:501-504 (conv1 + gelu, conv2 + gelu, permute).
+ *   x_layout 0: x fp32 [B,C_in,F] (log-mel), weight [C_out, C_in*3] bf16 = conv.weight.view(C_out,-1)
+ *   x_layout 1: x bf16 [B,F,C_in] channels-last, weight [C_out, 3*C_in] bf16 = weight.permute(0,2,1)
+ *   ws: workspace of B*(F/stride)*ld_ws bf16 for the GEMM rows; ld_ws >= 3*C_in, multiple of 8 */
+int cm3p_conv1d_k3_gelu_fwd(const void* x, int x_layout, const void* weight, const float* bias, void* ws,
+                            int64_t ld_ws, void* out, int batch, int c_in, int frames, int c_out, int stride,
+                            void* stream);
+
+/* pooled = first token (mode 0) or masked mean (mode 1) of every sequence; e = pooled . W^T;
+ * embeds = e / sqrt(sum e^2) (no epsilon).  Replaces cm3p/modeling_cm3p.py:624-642 / :382-396
+ * (pooling), :959-960 / :971-972 (projection + _get_vector_norm :54-62).
+ *   pooled [B,H] bf16 (output), proj_f32 [B,P] fp32 (output, un-normalised), inv_norm [B] or NULL,
+ *   embeds_f32 [B,P] / embeds_bf16 [B,P] outputs (either may be NULL) */
+int cm3p_pool_project_normalize(const void* hidden_states, const int32_t* cu_seqlens, int mode, const void* proj_w,
+                                void* pooled, float* proj_f32, float* inv_norm, float* embeds_f32, void* embeds_bf16,
+                                int batch, int hidden, int proj_dim, void* stream);
+
+/* CLIP-style symmetric cross-entropy on S = logits_per_metadata [Bm*V, Bb] fp32 (already scaled).
+ * Replaces cm3p_loss / contrastive_loss, cm3p/modeling_cm3p.py:27-51.
+ *   true_idx [Bm] int32 = argmax(classes == 0) (all zeros for the 2-D case)
+ *   row_lse [Bm], col_lse [Bb] fp32 outputs (kept for backward); loss: 1 fp32 */
+int cm3p_clip_loss_fwd(const float* S, const int32_t* true_idx, float* row_lse, float* col_lse, float* loss, int Bm,
+                       int V, int Bb, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CM3P_B200_H_ */

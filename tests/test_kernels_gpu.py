@@ -1,0 +1,258 @@
+"""Per-kernel numerics on a real B200: every CUDA kernel (called through the C ABI) against a plain
+PyTorch fp32 reference of the same op on the same bf16-rounded inputs."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from cm3p_b200 import ops
+    return ops
+
+
+def _rand(shape, scale=1.0, seed=0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+def _report(name, got, want, atol, rtol):
+    got, want = got.float(), want.float()
+    err = (got - want).abs()
+    tol = atol + rtol * want.abs()
+    bad = err > tol
+    if bad.any():
+        idx = bad.nonzero()[:8].tolist()
+        msg = [f"{name}: {int(bad.sum())}/{bad.numel()} mismatches, max abs err {float(err.max()):.4g}"]
+        for i in idx:
+            msg.append(f"  at {i}: got {float(got[tuple(i)]):.5g} want {float(want[tuple(i)]):.5g}")
+        if got.dim() == 2:
+            # localise: error per 128-row block and per 32-column chunk
+            R, C = got.shape
+            rb = [float(err[r:r + 128].max()) for r in range(0, R, 128)][:16]
+            cb = [float(err[:, c:c + 32].max()) for c in range(0, C, 32)][:24]
+            msg.append(f"  max err per 128-row block: {['%.3g' % v for v in rb]}")
+            msg.append(f"  max err per 32-col chunk : {['%.3g' % v for v in cb]}")
+        pytest.fail("\n".join(msg))
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 384, 128), (1000, 768, 768), (4096, 2304, 768),
+                                   (77, 64, 240), (515, 1536, 512)])
+def test_gemm_store(M, N, K):
+    ops = _ops()
+    a, b = _rand((M, K), seed=1), _rand((N, K), 0.05, seed=2)
+    out = ops.gemm(a, b)
+    torch.cuda.synchronize()
+    _report(f"gemm_store {M}x{N}x{K}", out, a.float() @ b.float().t(), 2e-2, 1e-2)
+
+
+def test_gemm_residual_inplace():
+    ops = _ops()
+    M, N, K = 1000, 768, 1152
+    a, b, r = _rand((M, K), seed=1), _rand((N, K), 0.03, seed=2), _rand((M, N), seed=3)
+    want = a.float() @ b.float().t() + r.float()
+    x = r.clone()
+    ops.gemm(a, b, epilogue=ops.EPI_RESIDUAL, out=x, aux=x)
+    _report("gemm_residual", x, want, 3e-2, 1e-2)
+
+
+def test_gemm_gelu_and_bias():
+    ops = _ops()
+    M, N, K = 600, 512, 240
+    a, b = _rand((M, K), seed=1), _rand((N, K), 0.1, seed=2)
+    bias = _rand((N,), 0.5, seed=3, dtype=torch.float32)
+    acc = a.float() @ b.float().t()
+    _report("gemm_gelu", ops.gemm(a, b, epilogue=ops.EPI_GELU), F.gelu(acc), 2e-2, 1e-2)
+    _report("gemm_bias_gelu", ops.gemm(a, b, epilogue=ops.EPI_BIAS_GELU, aux=bias), F.gelu(acc + bias), 2e-2, 1e-2)
+    _report("gemm_bias", ops.gemm(a, b, epilogue=ops.EPI_BIAS, aux=bias), acc + bias, 2e-2, 1e-2)
+
+
+@pytest.mark.parametrize("I,H", [(1152, 768), (96, 128)])
+def test_gemm_geglu(I, H):
+    ops = _ops()
+    M = 700
+    a, wi = _rand((M, H), seed=1), _rand((2 * I, H), 0.05, seed=2)
+    acc = a.float() @ wi.float().t()
+    want = F.gelu(acc[:, :I]) * acc[:, I:]
+    wi_il = ops.interleave_wi(wi).contiguous()
+    assert torch.equal(ops.deinterleave_wi(wi_il), wi)
+    got = ops.gemm(a, wi_il, epilogue=ops.EPI_GEGLU)
+    _report("gemm_geglu", got, want, 2e-2, 2e-2)
+    raw = torch.empty((M, 2 * I), device=DEV, dtype=torch.bfloat16)
+    got2 = ops.gemm(a, wi_il, epilogue=ops.EPI_GEGLU_SAVE, c2=raw)
+    _report("gemm_geglu_save.out", got2, want, 2e-2, 2e-2)
+    _report("gemm_geglu_save.raw", ops.deinterleave_wi(raw.t().contiguous()).t(), acc, 2e-2, 1e-2)
+
+
+def test_gemm_rope():
+    ops = _ops()
+    heads, T = 3, 500
+    H = heads * 64
+    a, w = _rand((T, H), seed=1), _rand((3 * H, H), 0.08, seed=2)
+    pos = (torch.arange(T, dtype=torch.int32) % 211).to(DEV)
+    tab = ops.rope_table(160000.0, 256, DEV)
+    got = ops.gemm(a, w, epilogue=ops.EPI_ROPE, positions=pos, rope_table=tab, rope_cols=2 * H)
+    acc = (a.float() @ w.float().t()).view(T, 3, heads, 64)
+    cos, sin = tab[pos.long(), :, 0], tab[pos.long(), :, 1]  # [T, 32]
+    cos, sin = torch.cat((cos, cos), -1)[:, None, None], torch.cat((sin, sin), -1)[:, None, None]
+    rot = torch.cat((-acc[..., 32:], acc[..., :32]), dim=-1)
+    want = acc.clone()
+    want[:, :2] = (acc * cos + rot * sin)[:, :2]
+    _report("gemm_rope", got, want.view(T, 3 * H), 3e-2, 1e-2)
+
+
+def test_gemm_scale_f32_accumulate():
+    ops = _ops()
+    M, N, K = 260, 200, 512
+    a, b = _rand((M, K), 0.1, seed=1), _rand((N, K), 0.1, seed=2)
+    acc = a.float() @ b.float().t()
+    out = ops.gemm(a, b, epilogue=ops.EPI_SCALE_F32, scale=14.25)
+    _report("gemm_scale_f32", out, acc * 14.25, 1e-3, 1e-3)
+    ops.gemm(a, b, epilogue=ops.EPI_SCALE_F32, scale=0.5, accumulate=True, out=out)
+    _report("gemm_scale_f32_acc", out, acc * 14.75, 1e-3, 1e-3)
+
+
+def test_gemm_transposed_operands():
+    """dgrad form (B stored [K,N]) and wgrad form (A stored [K,M], B stored [K,N])."""
+    ops = _ops()
+    T, Nout, Kin = 900, 768, 320
+    dy, w, x = _rand((T, Nout), seed=1), _rand((Nout, Kin), 0.05, seed=2), _rand((T, Kin), seed=3)
+    dx = ops.gemm(dy, w, trans_b=True)  # dX = dY @ W
+    _report("gemm_dgrad", dx, dy.float() @ w.float(), 5e-2, 1e-2)
+    dw = ops.gemm(dy, x, trans_a=True, trans_b=True, epilogue=ops.EPI_SCALE_F32)  # dW = dY^T @ X
+    _report("gemm_wgrad", dw, dy.float().t() @ x.float(), 5e-2, 1e-2)
+
+
+# ------------------------------------------------------------------------------------- attention
+def _attn_ref(qkv, cu, heads, window):
+    T = qkv.shape[0]
+    out = torch.empty((T, heads * 64), device=qkv.device, dtype=torch.float32)
+    q3 = qkv.float().view(T, 3, heads, 64)
+    for b in range(len(cu) - 1):
+        s, e = cu[b], cu[b + 1]
+        q, k, v = (q3[s:e, i].transpose(0, 1) for i in range(3))  # [h, L, 64]
+        sc = q @ k.transpose(1, 2) / 8.0
+        if window >= 0:
+            idx = torch.arange(e - s, device=qkv.device)
+            sc = sc.masked_fill((idx[:, None] - idx[None, :]).abs() > window, float("-inf"))
+        out[s:e] = (sc.softmax(-1) @ v).transpose(0, 1).reshape(e - s, heads * 64)
+    return out
+
+
+@pytest.mark.parametrize("lens,heads,window", [
+    ([128], 1, -1), ([300, 77, 129, 512, 1], 2, -1), ([300, 77, 129, 512, 1], 2, 64),
+    ([2000, 613, 1500], 12, -1), ([2000, 613, 1500], 12, 64), ([800] * 4, 8, 64), ([25, 17, 21, 19], 4, -1)])
+def test_attention_fwd(lens, heads, window):
+    ops = _ops()
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    T = cu[-1]
+    qkv = _rand((T, 3 * heads * 64), 1.0, seed=5)
+    cu_t = torch.tensor(cu, dtype=torch.int32, device=DEV)
+    lse = torch.empty((heads, T), device=DEV, dtype=torch.float32)
+    out = ops.attn_varlen_fwd(qkv, cu_t, max(lens), heads, window, lse=lse)
+    torch.cuda.synchronize()
+    want = _attn_ref(qkv, cu, heads, window)
+    _report(f"attn lens={lens} h={heads} w={window}", out, want, 2e-2, 2e-2)
+    # lse (log2 domain) against the reference for the first head of the first sequence
+    L = lens[0]
+    q3 = qkv.float().view(T, 3, heads, 64)
+    sc = (q3[:L, 0, 0] @ q3[:L, 1, 0].t()) / 8.0
+    if window >= 0:
+        idx = torch.arange(L, device=DEV)
+        sc = sc.masked_fill((idx[:, None] - idx[None, :]).abs() > window, float("-inf"))
+    _report("attn lse", lse[0, :L], torch.logsumexp(sc, -1) / math.log(2.0), 2e-2, 1e-3)
+
+
+# --------------------------------------------------------------------------------- row-wise kernels
+@pytest.mark.parametrize("H", [768, 512, 256, 128, 64])
+def test_layernorm(H):
+    ops = _ops()
+    x = _rand((1001, H), 2.0, seed=1) + 0.5
+    g = _rand((H,), 0.2, seed=2, dtype=torch.float32) + 1.0
+    stats = torch.empty((1001, 2), device=DEV, dtype=torch.float32)
+    y = ops.layernorm(x, g, 1e-5, stats=stats)
+    want = F.layer_norm(x.float(), (H,), g, None, 1e-5)
+    _report("layernorm", y, want, 2e-2, 1e-2)
+    _report("layernorm mean", stats[:, 0], x.float().mean(-1), 1e-4, 1e-4)
+    _report("layernorm rstd", stats[:, 1], (x.float().var(-1, unbiased=False) + 1e-5).rsqrt(), 1e-4, 1e-4)
+
+
+def test_embed_gather_ln():
+    ops = _ops()
+    B, L, H, vocab, A = 3, 50, 128, 300, 5
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(0, vocab - 1, (B, L), generator=g)
+    ids[:, 1:1 + A] = vocab - 1  # audio token
+    lens = torch.tensor([50, 20, 33])
+    mask = torch.arange(L)[None] < lens[:, None]
+    src = mask.flatten().nonzero().flatten().to(torch.int32)
+    is_audio = (ids == vocab - 1).flatten()
+    slot_all = torch.where(is_audio, torch.cumsum(is_audio.int(), 0) - 1, torch.full_like(is_audio, -1, dtype=torch.int32))
+    slot = slot_all[src.long()].to(torch.int32)
+    tok = _rand((vocab, H), seed=1)
+    aud = _rand((B * A, H), seed=2)
+    gam = _rand((H,), 0.1, seed=3, dtype=torch.float32) + 1.0
+    y = ops.embed_gather_ln(ids.to(DEV), src.to(DEV), slot.to(DEV), tok, aud, gam, 1e-5, rows=src.numel())
+    emb = tok.float()[ids.flatten().to(DEV)]
+    emb[is_audio.to(DEV)] = aud.float()
+    want = F.layer_norm(emb[src.long().to(DEV)], (H,), gam, None, 1e-5)
+    _report("embed_gather_ln", y, want, 2e-2, 1e-2)
+
+
+def test_conv1d_gelu_both_layers():
+    ops = _ops()
+    B, C, Fr, Co = 3, 80, 320, 64
+    x = _rand((B, C, Fr), seed=1, dtype=torch.float32)
+    w1, b1 = _rand((Co, C, 3), 0.1, seed=2), _rand((Co,), 0.1, seed=3, dtype=torch.float32)
+    w2, b2 = _rand((Co, Co, 3), 0.1, seed=4), _rand((Co,), 0.1, seed=5, dtype=torch.float32)
+    y1 = ops.conv1d_k3_gelu(x, w1.reshape(Co, C * 3).contiguous(), b1, stride=1)
+    want1 = F.gelu(F.conv1d(x.bfloat16().float(), w1.float(), b1, padding=1)).permute(0, 2, 1)
+    _report("conv1", y1.reshape(B * Fr, Co), want1.reshape(B * Fr, Co), 2e-2, 1e-2)
+    y2 = ops.conv1d_k3_gelu(y1, w2.permute(0, 2, 1).reshape(Co, 3 * Co).contiguous(), b2, stride=2)
+    want2 = F.gelu(F.conv1d(y1.float().permute(0, 2, 1), w2.float(), b2, stride=2, padding=1)).permute(0, 2, 1)
+    _report("conv2", y2.reshape(B * Fr // 2, Co), want2.reshape(B * Fr // 2, Co), 2e-2, 1e-2)
+
+
+@pytest.mark.parametrize("mean_pool", [False, True])
+def test_pool_project_normalize(mean_pool):
+    ops = _ops()
+    lens = [300, 1, 77, 129]
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    H, P = 128, 64
+    x = _rand((cu[-1], H), seed=1)
+    w = _rand((P, H), 0.1, seed=2)
+    cu_t = torch.tensor(cu, dtype=torch.int32, device=DEV)
+    pooled, proj, inv, emb, emb16 = ops.pool_project_normalize(x, cu_t, mean_pool, w)
+    if mean_pool:
+        want_pool = torch.stack([x.float()[cu[i]:cu[i + 1]].mean(0) for i in range(len(lens))])
+    else:
+        want_pool = x.float()[cu_t[:-1].long()]
+    _report("pooled", pooled, want_pool, 1e-2, 1e-2)
+    e = pooled.float() @ w.float().t()
+    _report("proj", proj, e, 1e-3, 1e-3)
+    _report("embeds", emb, e / e.norm(dim=-1, keepdim=True), 1e-4, 1e-3)
+    _report("embeds16", emb16, e / e.norm(dim=-1, keepdim=True), 1e-2, 1e-2)
+
+
+@pytest.mark.parametrize("B,V", [(8, 1), (5, 3), (64, 8), (33, 17)])
+def test_clip_loss(B, V):
+    ops = _ops()
+    S = _rand((B, V, B), 3.0, seed=1, dtype=torch.float32)
+    g = torch.Generator().manual_seed(2)
+    t = torch.randint(0, V, (B,), generator=g).to(DEV)
+    loss, row_lse, col_lse = ops.clip_loss_fwd(S.view(B * V, B), t.to(torch.int32), V)
+    rows = S[torch.arange(B, device=DEV), t]
+    ml = F.cross_entropy(rows, torch.arange(B, device=DEV))
+    bl = F.cross_entropy(S.permute(2, 0, 1).reshape(B, B * V), torch.arange(B, device=DEV) * V + t)
+    _report("clip_loss", loss, ((ml + bl) / 2).reshape(1), 1e-4, 1e-4)
+    _report("col_lse", col_lse, torch.logsumexp(S.view(B * V, B), 0), 1e-4, 1e-4)

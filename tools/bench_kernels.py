@@ -1,0 +1,99 @@
+"""Micro-benchmarks of the individual kernels at base-config shapes (CUDA events, L2-cold inputs by
+rotating through buffers larger than L2).  Prints one line per kernel; used to decide what to tune."""
+import json
+import sys
+import os
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cm3p_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+
+
+def timeit(fn, iters=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters * 1e-3
+
+
+def bench_gemm(M, N, K, epi=0, name=""):
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    b = (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
+    kw = {}
+    n_out = N
+    if epi == ops.EPI_RESIDUAL:
+        kw["aux"] = torch.randn(M, N, device=DEV).bfloat16()
+    if epi == ops.EPI_GEGLU:
+        n_out = N // 2
+    if epi == ops.EPI_ROPE:
+        kw["positions"] = (torch.arange(M, device=DEV, dtype=torch.int32) % 2000)
+        kw["rope_table"] = ops.rope_table(160000.0, 2048, DEV)
+        kw["rope_cols"] = 2 * N // 3
+    out = torch.empty(M, n_out, device=DEV, dtype=torch.bfloat16)
+    t = timeit(lambda: ops.gemm(a, b, epilogue=epi, out=out, **kw))
+    t_ref = timeit(lambda: torch.matmul(a, b.t()))
+    flops = 2.0 * M * N * K
+    print(json.dumps(dict(kernel=f"gemm{name}", M=M, N=N, K=K, epi=epi, ms=round(t * 1e3, 4),
+                          tflops=round(flops / t / 1e12, 1), cublas_ms=round(t_ref * 1e3, 4),
+                          cublas_tflops=round(flops / t_ref / 1e12, 1))), flush=True)
+
+
+def bench_attn(B, L, heads, window):
+    g = torch.Generator().manual_seed(0)
+    lens = torch.randint(600, L + 1, (B,), generator=g).tolist()
+    lens[0] = L
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    T = cu[-1]
+    qkv = torch.randn(T, 3 * heads * 64, device=DEV).bfloat16()
+    cu_t = torch.tensor(cu, dtype=torch.int32, device=DEV)
+    out = torch.empty(T, heads * 64, device=DEV, dtype=torch.bfloat16)
+    t = timeit(lambda: ops.attn_varlen_fwd(qkv, cu_t, L, heads, window, out=out))
+    if window < 0:
+        flops = sum(4.0 * n * n * 64 * heads for n in lens)
+    else:
+        flops = sum(4.0 * n * min(n, 2 * window + 1) * 64 * heads for n in lens)
+    print(json.dumps(dict(kernel="attn_fwd", B=B, L=L, T=T, heads=heads, window=window, ms=round(t * 1e3, 4),
+                          tflops=round(flops / t / 1e12, 1))), flush=True)
+    try:
+        from flash_attn import flash_attn_varlen_qkvpacked_func
+        q4 = qkv.view(T, 3, heads, 64)
+        ws = (window, window) if window >= 0 else (-1, -1)
+        t2 = timeit(lambda: flash_attn_varlen_qkvpacked_func(q4, cu_t, L, window_size=ws))
+        print(json.dumps(dict(kernel="flash_attn2_ref", window=window, ms=round(t2 * 1e3, 4),
+                              tflops=round(flops / t2 / 1e12, 1))), flush=True)
+    except Exception as ex:  # library comparison only
+        print(json.dumps(dict(kernel="flash_attn2_ref", error=str(ex)[:200])), flush=True)
+
+
+def bench_ln(T, H):
+    x = torch.randn(T, H, device=DEV).bfloat16()
+    g = torch.ones(H, device=DEV)
+    y = torch.empty_like(x)
+    t = timeit(lambda: ops.layernorm(x, g, 1e-5, out=y))
+    print(json.dumps(dict(kernel="layernorm", T=T, H=H, ms=round(t * 1e3, 4),
+                          gbs=round(2.0 * T * H * 2 / t / 1e9, 1))), flush=True)
+
+
+if __name__ == "__main__":
+    T = 64 * 1300
+    for (N, K, epi, name) in [(2304, 768, ops.EPI_ROPE, "_wqkv_rope"), (2304, 768, 0, "_wqkv_plain"),
+                              (768, 768, ops.EPI_RESIDUAL, "_wo_res"), (2304, 768, ops.EPI_GEGLU, "_wi_geglu"),
+                              (768, 1152, ops.EPI_RESIDUAL, "_wo2_res")]:
+        bench_gemm(T, N, K, epi, name)
+    bench_gemm(8192, 8192, 8192, 0, "_square")
+    bench_gemm(64 * 800, 1536, 512, ops.EPI_ROPE, "_audio_wqkv")
+    bench_attn(64, 2000, 12, -1)
+    bench_attn(64, 2000, 12, 64)
+    bench_attn(64, 800, 8, -1)
+    bench_ln(T, 768)
