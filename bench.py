@@ -1,0 +1,354 @@
+"""bench.py — headline benchmark of the CM3P hot path on B200 (contract: see the build brief).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload infer|train]
+
+One "step" = one pass of the hot path over one batch of synthetic input per GPU.
+
+  workload infer (default; BASELINE.json configs[1]): base CM3P, bf16, batch 64 windows/GPU of 16 s
+      (L = 2000 padded, real lengths U{600..2000}, 200 audio tokens + 80x1600 log-mel per window),
+      beatmap tower + audio encoder + metadata tower (V = 1) + projections + logits,
+      `return_loss=False`  ->  beatmap embeds/s.
+  workload train (BASELINE.json configs[2]): the contrastive train step -> pairs/s.
+
+Prints ONE JSON line on rank 0.  `value` is measured with inputs resident in HBM; `e2e` goes through
+the public `CM3PModel.__call__` with pinned host inputs (H2D inside the timed region) and a D2H
+read of the result.  `--impl reference` times the CPU oracle (the reference's algorithm on the host
+cores) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import copy
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from cm3p_b200.configuration_cm3p import CM3PConfig, base_config_dict  # noqa: E402
+from cm3p_b200.synthetic import synthetic_batch, synthetic_state_dict  # noqa: E402
+
+BATCH_PER_GPU = {"infer": 64, "train": 256}
+SEQ_LEN = 2000
+MIN_LEN = 600
+TRAIN_VARIATIONS = 8
+METRIC = {"infer": ("beatmap_embeds_per_sec", "embeds/s"), "train": ("train_pairs_per_sec", "pairs/s")}
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], tflops=p["bf16_tflops_sustained"], source="MEASURED_PEAKS.json (sustained)")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def _algorithmic_flops_infer(cfg: CM3PConfig, batch: dict) -> float:
+    """Forward FLOPs of one step, real tokens only."""
+    bc, mc, ac = cfg.beatmap_config, cfg.metadata_config, cfg.beatmap_config.audio_config
+
+    def tower_linear(c):
+        H, I = c.hidden_size, int(c.intermediate_size)
+        return c.num_hidden_layers * 2 * (H * 3 * H + H * H + H * 2 * I + I * H)
+
+    def attn(c, ln):
+        n_glob = sum(1 for i in range(c.num_hidden_layers) if c.layer_is_global(i))
+        n_loc = c.num_hidden_layers - n_glob
+        return n_glob * 4 * ln * ln * c.hidden_size + n_loc * 4 * ln * min(ln, 2 * c.window_half + 1) * c.hidden_size
+
+    lens = batch["attention_mask"].sum(-1).tolist()
+    B = len(lens)
+    total = sum(lens) * tower_linear(bc) + sum(attn(bc, n) for n in lens)
+    frames = batch["input_features"].shape[-1]
+    t2 = frames // 2
+    total += B * (2 * frames * ac.hidden_size * 3 * ac.n_mels + 2 * t2 * ac.hidden_size * 3 * ac.hidden_size)
+    total += B * (t2 * tower_linear(ac) + attn(ac, t2))
+    total += B * (t2 // 4) * 2 * (ac.projector_intermediate_size * ac.projector_dim + ac.projector_dim ** 2)
+    mlens = batch["metadata_attention_mask"].reshape(-1, batch["metadata_attention_mask"].shape[-1]).sum(-1).tolist()
+    total += sum(mlens) * tower_linear(mc) + sum(attn(mc, n) for n in mlens)
+    total += B * 2 * bc.hidden_size * cfg.projection_dim + len(mlens) * 2 * mc.hidden_size * cfg.projection_dim
+    total += 2 * len(mlens) * B * cfg.projection_dim
+    return float(total)
+
+
+def _make_batch(cfg, workload, rank):
+    B = BATCH_PER_GPU[workload]
+    V = 1 if workload == "infer" else TRAIN_VARIATIONS
+    return synthetic_batch(cfg, batch=B, seq_len=SEQ_LEN, variations=V, seed=1 + rank, min_len=MIN_LEN)
+
+
+def run_ours(args) -> dict:
+    import torch.distributed as dist
+
+    from cm3p_b200 import ops
+    from cm3p_b200.modeling_cm3p import CM3PModel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA sm_100a device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    workload = args.workload
+    if workload == "train":
+        raise SystemExit("bench.py: the train workload is enabled once the backward kernels land")
+    cfg = CM3PConfig(attn_implementation="flash_attention_2", **copy.deepcopy(base_config_dict()))
+    model = CM3PModel(cfg)
+    model.load_state_dict(synthetic_state_dict(cfg, seed=0), strict=True)
+    model = model.to(dev).to(torch.bfloat16).eval()
+
+    host = _make_batch(cfg, workload, rank)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    B = BATCH_PER_GPU[workload]
+
+    def step(feed):
+        with torch.no_grad():
+            return model(**feed, return_loss=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps
+
+    # ---- device-resident timing (value)
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.LAUNCH_COUNT
+    ms_step = timed(lambda: step(resident), args.steps)
+    launches = (ops.LAUNCH_COUNT - launches0) // args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end through the public API with pinned host inputs
+    def e2e_step():
+        feed = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        out = step(feed)
+        return out.beatmap_embeds.float().cpu()  # D2H read of the result (synchronises)
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+    d2h = B * cfg.projection_dim * 4
+
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM), timed live with CUDA events around
+    #      every GEMM launch of one extra step on the launching stream
+    gemm_events = []
+    orig_gemm = ops.gemm
+
+    def timed_gemm(a, b, **kw):
+        M, K = (a.shape[1], a.shape[0]) if kw.get("trans_a") else a.shape
+        N = b.shape[1] if kw.get("trans_b") else b.shape[0]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig_gemm(a, b, **kw)
+        e1.record()
+        gemm_events.append((e0, e1, 2.0 * M * N * K))
+        return out
+
+    import cm3p_b200.modeling_cm3p as mod
+    ops.gemm = timed_gemm
+    try:
+        step(resident)
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm = orig_gemm
+    assert mod.ops.gemm is orig_gemm
+    gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in gemm_events)
+    gemm_flops = sum(f for _, _, f in gemm_events)
+    peaks = _peaks()
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+
+    total_flops = _algorithmic_flops_infer(cfg, host)
+    metric, unit = METRIC[workload]
+    result = {
+        "metric": metric, "value": round(world * B / (ms_step * 1e-3), 2), "unit": unit, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "impl": "ours",
+        "config": {
+            "workload": "BASELINE.json configs[1]: CM3P base inference, beatmap tower + audio encoder + metadata "
+                        "tower (V=1) bf16, batch 64 synthetic 16 s windows per GPU (L=2000 padded, real lengths "
+                        "U{600..2000}), return_loss=False",
+            "batch_per_gpu": B, "seq_len": SEQ_LEN, "real_tokens_per_step": int(host["attention_mask"].sum()),
+            "weights": "random init (seeded), 136.9 M params",
+            "l2": "per-step working set (~1.5 GB of activations) exceeds the 126 MB L2; no explicit flush",
+        },
+        "e2e": {"value": round(world * B / (ms_e2e * 1e-3), 2), "unit": unit, "ms_per_step": round(ms_e2e, 3),
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "model_tflops": round(total_flops / (ms_step * 1e-3) / 1e12, 1),
+        "roofline": {"kernel": "gemm_bf16_sm100_kernel (all epilogues)", "bound": "tensor",
+                     "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
+                     "frac": round(achieved / peaks["tflops"], 4), "traffic": None,
+                     "launches_per_step": len(gemm_events), "share_of_step": round(gemm_ms / ms_step, 3),
+                     "peak_source": peaks["source"]},
+        "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        result["cpu_baseline"] = cpu_baseline(cfg, workload, sample_batch=2, reps=1)
+    if world > 1:
+        dist.destroy_process_group()
+    return result if rank == 0 else None
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(cfg, workload, sample_batch, reps):
+    """The reference's algorithm (CPU oracle, fp32, torch SDPA like the reference's `sdpa` path) on
+    the host cores, on a bounded sample of the same workload."""
+    from oracle import cm3p_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synthetic_state_dict(cfg, seed=0)
+    V = 1 if workload == "infer" else TRAIN_VARIATIONS
+    batch = synthetic_batch(cfg, batch=sample_batch, seq_len=SEQ_LEN, variations=V, seed=1, min_len=MIN_LEN)
+    best = float("inf")
+    with torch.no_grad():
+        warm = synthetic_batch(cfg, batch=1, seq_len=256, variations=1, seed=5, min_len=220)
+        O.model_forward(sd, cfg, **warm, return_loss=False)
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            O.model_forward(sd, cfg, **batch, return_loss=False)
+            best = min(best, time.perf_counter() - t0)
+    metric, unit = METRIC[workload]
+    return {"value": round(sample_batch / best, 4), "unit": unit, "cores": cores, "kind": "port",
+            "sample": f"{sample_batch} windows of the same workload (L={SEQ_LEN}), fp32, torch CPU SDPA, "
+                      f"{cores} threads, best of {reps}; {best:.2f} s"}
+
+
+def run_reference(args) -> dict | None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    from oracle import cm3p_oracle as O
+
+    workload = args.workload
+    cfg = CM3PConfig(**copy.deepcopy(base_config_dict()))
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synthetic_state_dict(cfg, seed=0)
+    sample = 2
+    V = 1 if workload == "infer" else TRAIN_VARIATIONS
+    batch = synthetic_batch(cfg, batch=sample, seq_len=SEQ_LEN, variations=V, seed=1, min_len=MIN_LEN)
+    times = []
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            O.model_forward(sd, cfg, **batch, return_loss=False)
+            if i >= args.warmup:
+                times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    metric, unit = METRIC[workload]
+    value = round(sample / (ms * 1e-3), 4)
+    return {
+        "impl": "reference", "metric": metric, "value": value, "unit": unit,
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[1] (same as impl=ours), CPU: each step = a bounded sample of "
+                               f"{sample} windows", "seq_len": SEQ_LEN},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port",
+                         "sample": f"{sample} windows/step (L={SEQ_LEN}), fp32, torch CPU SDPA, {cores} threads"},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=["infer", "train"], default="infer")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    res = run_reference(args) if args.impl == "reference" else run_ours(args)
+    if res is not None:
+        print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()

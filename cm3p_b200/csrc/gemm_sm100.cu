@@ -47,13 +47,15 @@ struct Params {
   int64_t rope_cols;         // columns [0, rope_cols) are rotated per 64-wide head
   int trans_a, trans_b;
   int accumulate;  // F32 epilogue: C += acc
+  int vec_c;       // C (and C2 / aux) rows allow 16-byte accesses
 };
 
-__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32], int64_t col, int64_t ncols) {
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32], int64_t col, int64_t ncols,
+                                              bool vec = true) {
   // dst points at (row, col); 16-byte stores, guarded per 8 columns
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    if (col + i * 8 + 8 <= ncols) {
+    if (vec && col + i * 8 + 8 <= ncols) {
       uint4 u;
       u.x = ptx::pack_bf16x2(v[i * 8 + 0], v[i * 8 + 1]);
       u.y = ptx::pack_bf16x2(v[i * 8 + 2], v[i * 8 + 3]);
@@ -113,8 +115,8 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc
       }
       if (row_ok) {
         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + col;
-        store_bf16x32(dst, o1, col, p.N);
-        store_bf16x32(dst + 32, o2, col + 32, p.N);
+        store_bf16x32(dst, o1, col, p.N, p.vec_c);
+        store_bf16x32(dst + 32, o2, col + 32, p.N, p.vec_c);
       }
     }
     return;
@@ -132,13 +134,13 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 
     if constexpr (EPI == EPI_STORE) {
-      if (row_ok) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + col, v, col, p.N);
+      if (row_ok) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + col, v, col, p.N, p.vec_c);
     } else if constexpr (EPI == EPI_RESIDUAL) {
       if (row_ok) {
         const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(p.aux) + row * p.ld_aux + col;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (col + i * 8 + 8 <= p.N) {
+          if (p.vec_c && col + i * 8 + 8 <= p.N) {
             const uint4 u = *reinterpret_cast<const uint4*>(res + i * 8);
             float2 f;
             f = ptx::unpack_bf16x2(u.x); v[i * 8 + 0] += f.x; v[i * 8 + 1] += f.y;
@@ -150,12 +152,12 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc
               if (col + i * 8 + j < p.N) v[i * 8 + j] += __bfloat162float(res[i * 8 + j]);
           }
         }
-        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + col, v, col, p.N);
+        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + col, v, col, p.N, p.vec_c);
       }
     } else if constexpr (EPI == EPI_GELU) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = ptx::gelu_erf(v[i]);
-      if (row_ok) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + col, v, col, p.N);
+      if (row_ok) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + col, v, col, p.N, p.vec_c);
     } else if constexpr (EPI == EPI_BIAS_GELU || EPI == EPI_BIAS) {
       const float* bias = reinterpret_cast<const float*>(p.aux);
 #pragma unroll
@@ -163,11 +165,11 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc
         const float b = (col + i < p.N) ? __ldg(bias + col + i) : 0.f;
         v[i] = (EPI == EPI_BIAS_GELU) ? ptx::gelu_erf(v[i] + b) : v[i] + b;
       }
-      if (row_ok) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + col, v, col, p.N);
+      if (row_ok) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + col, v, col, p.N, p.vec_c);
     } else if constexpr (EPI == EPI_GEGLU || EPI == EPI_GEGLU_SAVE) {
       // Wi rows are interleaved in groups of 16 (u0..u15, g0..g15, u16.., g16..): see host prep.
       if constexpr (EPI == EPI_GEGLU_SAVE) {
-        if (row_ok) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.c2) + row * p.ldc2 + col, v, col, p.N);
+        if (row_ok) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.c2) + row * p.ldc2 + col, v, col, p.N, p.vec_c);
       }
       float o[16];
 #pragma unroll
@@ -187,7 +189,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc
         float* dst = reinterpret_cast<float*>(p.c) + row * p.ldc + col;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          if (col + i * 4 + 4 <= p.N) {
+          if (p.vec_c && col + i * 4 + 4 <= p.N) {
             float4 f = make_float4(v[i * 4] * p.scale, v[i * 4 + 1] * p.scale, v[i * 4 + 2] * p.scale,
                                    v[i * 4 + 3] * p.scale);
             if (p.accumulate) {
@@ -373,8 +375,14 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   if (g.epilogue == EPI_RESIDUAL || g.epilogue == EPI_BIAS || g.epilogue == EPI_BIAS_GELU)
     CM3P_REQUIRE(g.aux != nullptr, kBadShape, "gemm: epilogue %d needs aux", g.epilogue);
   const int out_elt = (g.epilogue == EPI_SCALE_F32) ? 4 : 2;
-  CM3P_REQUIRE((reinterpret_cast<uintptr_t>(g.c) % 16) == 0 && (g.ldc * out_elt) % 16 == 0, kBadAlignment,
-               "gemm: C pointer / pitch must be 16-byte aligned (ldc=%lld)", (long long)g.ldc);
+  auto aligned16 = [](const void* ptr, int64_t ld, int elt) {
+    return (reinterpret_cast<uintptr_t>(ptr) % 16) == 0 && (ld * elt) % 16 == 0;
+  };
+  bool vec = aligned16(g.c, g.ldc, out_elt);
+  if (g.epilogue == EPI_RESIDUAL) vec = vec && aligned16(g.aux, g.ld_aux, 2);
+  if (g.epilogue == EPI_GEGLU_SAVE) vec = vec && aligned16(g.c2, g.ldc2, 2);
+  if (g.epilogue == EPI_GEGLU || g.epilogue == EPI_GEGLU_SAVE)
+    CM3P_REQUIRE(vec, kBadAlignment, "gemm(geglu): outputs must be 16-byte aligned with ld %% 8 == 0");
 
   CUtensorMap ta, tb;
   if (!g.trans_a)
@@ -399,6 +407,7 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   p.rope_cols = g.rope_cols;
   p.trans_a = g.trans_a; p.trans_b = g.trans_b;
   p.accumulate = g.accumulate;
+  p.vec_c = vec ? 1 : 0;
 
   switch (g.epilogue) {
     case EPI_STORE: return launch<EPI_STORE>(ta, tb, p, stream);

@@ -43,7 +43,7 @@ def _report(name, got, want, atol, rtol):
 
 # ------------------------------------------------------------------------------------------ GEMM
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 384, 128), (1000, 768, 768), (4096, 2304, 768),
-                                   (77, 64, 240), (515, 1536, 512)])
+                                   (77, 64, 240), (515, 1536, 512), (100, 7, 64), (9, 3, 512)])
 def test_gemm_store(M, N, K):
     ops = _ops()
     a, b = _rand((M, K), seed=1), _rand((N, K), 0.05, seed=2)
@@ -116,6 +116,9 @@ def test_gemm_scale_f32_accumulate():
     _report("gemm_scale_f32", out, acc * 14.25, 1e-3, 1e-3)
     ops.gemm(a, b, epilogue=ops.EPI_SCALE_F32, scale=0.5, accumulate=True, out=out)
     _report("gemm_scale_f32_acc", out, acc * 14.75, 1e-3, 1e-3)
+    # row pitch that is not 16-byte aligned (logits of an odd batch): scalar store path
+    out3 = ops.gemm(a, b[:3].contiguous(), epilogue=ops.EPI_SCALE_F32, scale=2.0)
+    _report("gemm_scale_f32_n3", out3, acc[:, :3] * 2.0, 1e-3, 1e-3)
 
 
 def test_gemm_transposed_operands():
