@@ -191,7 +191,8 @@ def run_ours(args) -> dict:
         return float(ms.item()) / steps
 
     # ---- device-resident timing (value)
-    for _ in range(max(args.warmup, 3)):
+    n_warm = args.warmup if args.quick else max(args.warmup, 3)
+    for _ in range(n_warm):
         step(resident)
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -200,6 +201,10 @@ def run_ours(args) -> dict:
     ms_step = timed(lambda: step(resident), args.steps)
     launches = (ops.LAUNCH_COUNT - launches0) // args.steps
     clocks = sampler.stop() if rank == 0 else None
+    if args.quick:
+        if world > 1:
+            dist.destroy_process_group()
+        return {"quick": True, "ms_per_step": round(ms_step, 3), "gpu_launches": int(launches)} if rank == 0 else None
 
     # ---- end-to-end through the public API with pinned host inputs
     def e2e_step():
@@ -245,7 +250,7 @@ def run_ours(args) -> dict:
     metric, unit = METRIC[workload]
     result = {
         "metric": metric, "value": round(world * B / (ms_step * 1e-3), 2), "unit": unit, "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 3),
+        "steps": args.steps, "warmup": n_warm, "ms_per_step": round(ms_step, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "impl": "ours",
         "config": {
@@ -344,6 +349,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=["infer", "train"], default="infer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true",
+                    help="profiling aid: only the device-resident timed loop (no e2e / roofline / CPU legs)")
     args = ap.parse_args()
     res = run_reference(args) if args.impl == "reference" else run_ours(args)
     if res is not None:
