@@ -1,7 +1,9 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma
 // (cta_group::1, M=128, N=256, K=16) -> fp32 accumulators in TMEM (2 stages x 256 columns, so the
-// epilogue of tile i overlaps the MMAs of tile i+1) -> fused epilogue straight from tcgen05.ld
-// registers to global memory.
+// epilogue of tile i overlaps the MMAs of tile i+1) -> fused epilogue.  bf16 outputs are staged per
+// 128x64 slab in 128B-swizzled shared memory and written with TMA stores (the residual slab is
+// TMA-loaded into the same buffer one slab ahead), so the LSU never sees row-strided global
+// accesses; fp32 / unaligned outputs use the direct register->global path.
 //
 //   C[M,N] = epilogue( A[M,K] . B[N,K]^T )
 //
@@ -30,8 +32,10 @@ constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SLAB_BYTES = BM * 128;  // 128 rows x 64 bf16
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int THREADS = 256;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
 struct Params {
   int64_t M, N, K;
@@ -208,20 +212,192 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Staged epilogue (bf16 outputs with 16-byte aligned rows): per 128x64 output slab
+//   TMEM -> registers -> (op) -> 128B-swizzled smem slab -> TMA store.
+// For EPI_RESIDUAL the residual slab is TMA-loaded into the same smem buffer one slab ahead and the
+// sum is written back in place.  Two slab buffers alternate; `leader` = first epilogue thread.
+struct EpiState {
+  int g = 0;                  // processed-slab counter (selects the buffer)
+  uint32_t res_parity[2] = {0, 0};
+};
+
 template <int EPI>
+__device__ __forceinline__ constexpr int slab_acc_cols() {
+  return (EPI == EPI_GEGLU) ? 128 : 64;  // accumulator columns consumed per 64-column output slab
+}
+
+__device__ __forceinline__ void slab_write_row(uint8_t* slab, int r, int chunk, const uint4& v) {
+  *reinterpret_cast<uint4*>(slab + r * 128 + ((chunk ^ (r & 7)) << 4)) = v;
+}
+__device__ __forceinline__ uint4 slab_read_row(const uint8_t* slab, int r, int chunk) {
+  return *reinterpret_cast<const uint4*>(slab + r * 128 + ((chunk ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ uint4 pack8f(const float* v) {
+  return make_uint4(ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]), ptx::pack_bf16x2(v[4], v[5]),
+                    ptx::pack_bf16x2(v[6], v[7]));
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile_staged(const Params& p, const CUtensorMap* tma_c,
+                                                     const CUtensorMap* tma_c2, const CUtensorMap* tma_aux,
+                                                     uint8_t* slabs, uint64_t* res_full, EpiState& st,
+                                                     uint32_t tmem_acc, int quad, int64_t m0, int64_t n0,
+                                                     int64_t next_m0, int64_t next_n0, bool has_next_tile) {
+  constexpr int ACC = slab_acc_cols<EPI>();
+  constexpr int NSLAB = BN / ACC;
+  const int lane = ptx::lane_id();
+  const int r = quad * 32 + lane;  // row inside the tile == TMEM lane
+  const int64_t row = m0 + r;
+  const bool leader = (quad == 0 && lane == 0);
+  const uint32_t taddr_row = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16);
+
+  float2 cs[32];
+  if constexpr (EPI == EPI_ROPE) {
+    if (n0 < p.rope_cols) {
+      const int pos = (row < p.M) ? p.positions[row] : 0;
+      const float4* tab = reinterpret_cast<const float4*>(p.rope_table + static_cast<int64_t>(pos) * 32);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float4 f = __ldg(tab + k);
+        cs[2 * k] = make_float2(f.x, f.y);
+        cs[2 * k + 1] = make_float2(f.z, f.w);
+      }
+    }
+  }
+
+#pragma unroll 1
+  for (int sl = 0; sl < NSLAB; ++sl) {
+    const int64_t col = n0 + sl * ACC;  // first accumulator column of the slab
+    if (col >= p.N) break;              // CTA-uniform
+    const int buf = st.g & 1;
+    uint8_t* slab = slabs + buf * SLAB_BYTES;
+    const int64_t out_col = (EPI == EPI_GEGLU) ? (col >> 1) : col;
+
+    // ---- free the buffer(s); prefetch the next residual slab
+    if (leader) {
+      if constexpr (EPI == EPI_RESIDUAL) {
+        ptx::tma_store_wait_read<0>();
+        int64_t ncol = col + ACC, nm0 = m0;
+        bool have = (sl + 1 < NSLAB) && (ncol < p.N);
+        if (!have && has_next_tile) { have = true; ncol = next_n0; nm0 = next_m0; }
+        if (have) {
+          ptx::mbar_arrive_expect_tx(&res_full[buf ^ 1], SLAB_BYTES);
+          ptx::tma_load_2d(slabs + (buf ^ 1) * SLAB_BYTES, tma_aux, &res_full[buf ^ 1], static_cast<int32_t>(ncol),
+                           static_cast<int32_t>(nm0));
+        }
+      } else {
+        ptx::tma_store_wait_read<1>();
+      }
+    }
+    ptx::named_bar_sync(1, 128);
+
+    if constexpr (EPI == EPI_GEGLU) {
+      // 128 accumulator columns (interleaved 16 u / 16 g) -> 64 output columns
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t ra[32], rb[32];
+        ptx::tmem_ld_32x32b_x32(taddr_row + sl * ACC + h * 64, ra);
+        ptx::tmem_ld_32x32b_x32(taddr_row + sl * ACC + h * 64 + 32, rb);
+        ptx::tmem_ld_wait();
+        float o[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          o[i] = ptx::gelu_erf(__uint_as_float(ra[i])) * __uint_as_float(ra[16 + i]);
+          o[16 + i] = ptx::gelu_erf(__uint_as_float(rb[i])) * __uint_as_float(rb[16 + i]);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) slab_write_row(slab, r, h * 4 + c, pack8f(o + c * 8));
+      }
+    } else {
+      uint32_t r1[32], r2[32];
+      ptx::tmem_ld_32x32b_x32(taddr_row + sl * ACC, r1);
+      ptx::tmem_ld_32x32b_x32(taddr_row + sl * ACC + 32, r2);
+      ptx::tmem_ld_wait();
+      float v[64];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        v[i] = __uint_as_float(r1[i]);
+        v[32 + i] = __uint_as_float(r2[i]);
+      }
+      if constexpr (EPI == EPI_RESIDUAL) {
+        ptx::mbar_wait(&res_full[buf], st.res_parity[buf]);
+        st.res_parity[buf] ^= 1;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 u = slab_read_row(slab, r, c);
+          float2 f;
+          f = ptx::unpack_bf16x2(u.x); v[c * 8 + 0] += f.x; v[c * 8 + 1] += f.y;
+          f = ptx::unpack_bf16x2(u.y); v[c * 8 + 2] += f.x; v[c * 8 + 3] += f.y;
+          f = ptx::unpack_bf16x2(u.z); v[c * 8 + 4] += f.x; v[c * 8 + 5] += f.y;
+          f = ptx::unpack_bf16x2(u.w); v[c * 8 + 6] += f.x; v[c * 8 + 7] += f.y;
+        }
+      } else if constexpr (EPI == EPI_GELU) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = ptx::gelu_erf(v[i]);
+      } else if constexpr (EPI == EPI_BIAS_GELU || EPI == EPI_BIAS) {
+        const float* bias = reinterpret_cast<const float*>(p.aux);
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          const float b = (col + i < p.N) ? __ldg(bias + col + i) : 0.f;
+          v[i] = (EPI == EPI_BIAS_GELU) ? ptx::gelu_erf(v[i] + b) : v[i] + b;
+        }
+      } else if constexpr (EPI == EPI_ROPE) {
+        if (col < p.rope_cols) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float x1 = v[k], x2 = v[32 + k];
+            v[k] = x1 * cs[k].x - x2 * cs[k].y;
+            v[32 + k] = x2 * cs[k].x + x1 * cs[k].y;
+          }
+        }
+      } else if constexpr (EPI == EPI_GEGLU_SAVE) {
+        // product written directly (1/3 of the bytes); the raw slab goes through the staged path
+        if (row < p.M) {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + (col >> 1);
+          float o[32];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            o[i] = ptx::gelu_erf(v[i]) * v[16 + i];
+            o[16 + i] = ptx::gelu_erf(v[32 + i]) * v[48 + i];
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(dst + c * 8) = pack8f(o + c * 8);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) slab_write_row(slab, r, c, pack8f(v + c * 8));
+    }
+
+    ptx::fence_proxy_async_smem();
+    ptx::named_bar_sync(2, 128);
+    if (leader) {
+      ptx::tma_store_2d((EPI == EPI_GEGLU_SAVE) ? tma_c2 : tma_c, slab, static_cast<int32_t>(out_col),
+                        static_cast<int32_t>(m0));
+      ptx::tma_store_commit();
+    }
+    ++st.g;
+  }
+}
+
+template <int EPI, bool STAGED>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                       const Params p) {
+                       const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_c2,
+                       const __grid_constant__ CUtensorMap tma_aux, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* slabs = smem + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slabs + 2 * SLAB_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + ACC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
+  uint64_t* res_full = bars + 2 * STAGES + 2 * ACC_STAGES;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -238,6 +414,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     for (int s = 0; s < ACC_STAGES; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
       ptx::mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&res_full[s], 1);
     }
     ptx::fence_barrier_init();
   }
@@ -321,16 +498,35 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     const int quad = warp - 4;
     int as = 0;
     uint32_t aph = 0;
+    EpiState st;
+    if constexpr (STAGED && EPI == EPI_RESIDUAL) {
+      // residual slab of the very first output slab
+      if (quad == 0 && lane == 0 && static_cast<int64_t>(blockIdx.x) < num_tiles) {
+        const int64_t t0 = blockIdx.x;
+        ptx::mbar_arrive_expect_tx(&res_full[0], SLAB_BYTES);
+        ptx::tma_load_2d(slabs, &tma_aux, &res_full[0], static_cast<int32_t>((t0 % tiles_n) * BN),
+                         static_cast<int32_t>((t0 / tiles_n) * BM));
+      }
+    }
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int64_t m0 = (t / tiles_n) * BM;
       const int64_t n0 = (t % tiles_n) * BN;
       ptx::mbar_wait(&tmem_full[as], aph);
       ptx::tc_fence_after();
-      epilogue_tile<EPI>(p, tmem_base + as * BN, quad, m0, n0);
+      if constexpr (STAGED) {
+        const int64_t tn = t + gridDim.x;
+        epilogue_tile_staged<EPI>(p, &tma_c, &tma_c2, &tma_aux, slabs, res_full, st, tmem_base + as * BN, quad, m0,
+                                  n0, (tn / tiles_n) * BM, (tn % tiles_n) * BN, tn < num_tiles);
+      } else {
+        epilogue_tile<EPI>(p, tmem_base + as * BN, quad, m0, n0);
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
       if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
+    }
+    if constexpr (STAGED) {
+      if (quad == 0 && lane == 0) ptx::tma_store_wait_all<0>();
     }
   }
 
@@ -342,19 +538,31 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
   }
 }
 
-template <int EPI>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t stream) {
+template <int EPI, bool STAGED>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2,
+           const CUtensorMap& taux, const Params& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    CM3P_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_sm100_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       SMEM_BYTES));
+    CM3P_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_sm100_kernel<EPI, STAGED>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
   const int64_t tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-  gemm_bf16_sm100_kernel<EPI><<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+  gemm_bf16_sm100_kernel<EPI, STAGED><<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, tc, tc2, taux, p);
   CM3P_CUDA_TRY(cudaGetLastError());
   return kOk;
+}
+
+template <int EPI>
+int launch_any(bool staged, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+               const CUtensorMap& tc2, const CUtensorMap& taux, const Params& p, cudaStream_t stream) {
+  if constexpr (EPI == EPI_SCALE_F32) {
+    return launch<EPI, false>(ta, tb, tc, tc2, taux, p, stream);
+  } else {
+    return staged ? launch<EPI, true>(ta, tb, tc, tc2, taux, p, stream)
+                  : launch<EPI, false>(ta, tb, tc, tc2, taux, p, stream);
+  }
 }
 
 }  // namespace
@@ -396,6 +604,23 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
     rc = encode_tmap_2d_bf16(&tb, g.b, g.N, g.K, g.ldb * 2, 64, BK);
   if (rc != kOk) return rc;
 
+  // staged epilogue: output (and residual / raw) rows must allow TMA (16-byte aligned base and pitch)
+  const bool staged = vec && g.epilogue != EPI_SCALE_F32;
+  CUtensorMap tc = ta, tc2 = ta, taux = ta;  // placeholders when unused
+  if (staged) {
+    const int64_t n_out = (g.epilogue == EPI_GEGLU) ? g.N / 2 : g.N;
+    if (g.epilogue == EPI_GEGLU_SAVE) {
+      rc = encode_tmap_2d_bf16(&tc2, g.c2, g.N, g.M, g.ldc2 * 2, 64, BM);
+    } else {
+      rc = encode_tmap_2d_bf16(&tc, g.c, n_out, g.M, g.ldc * 2, 64, BM);
+    }
+    if (rc != kOk) return rc;
+    if (g.epilogue == EPI_RESIDUAL) {
+      rc = encode_tmap_2d_bf16(&taux, g.aux, g.N, g.M, g.ld_aux * 2, 64, BM);
+      if (rc != kOk) return rc;
+    }
+  }
+
   Params p;
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.c = g.c; p.ldc = g.ldc;
@@ -410,15 +635,15 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   p.vec_c = vec ? 1 : 0;
 
   switch (g.epilogue) {
-    case EPI_STORE: return launch<EPI_STORE>(ta, tb, p, stream);
-    case EPI_RESIDUAL: return launch<EPI_RESIDUAL>(ta, tb, p, stream);
-    case EPI_GELU: return launch<EPI_GELU>(ta, tb, p, stream);
-    case EPI_BIAS_GELU: return launch<EPI_BIAS_GELU>(ta, tb, p, stream);
-    case EPI_BIAS: return launch<EPI_BIAS>(ta, tb, p, stream);
-    case EPI_GEGLU: return launch<EPI_GEGLU>(ta, tb, p, stream);
-    case EPI_GEGLU_SAVE: return launch<EPI_GEGLU_SAVE>(ta, tb, p, stream);
-    case EPI_ROPE: return launch<EPI_ROPE>(ta, tb, p, stream);
-    case EPI_SCALE_F32: return launch<EPI_SCALE_F32>(ta, tb, p, stream);
+    case EPI_STORE: return launch_any<EPI_STORE>(staged, ta, tb, tc, tc2, taux, p, stream);
+    case EPI_RESIDUAL: return launch_any<EPI_RESIDUAL>(staged, ta, tb, tc, tc2, taux, p, stream);
+    case EPI_GELU: return launch_any<EPI_GELU>(staged, ta, tb, tc, tc2, taux, p, stream);
+    case EPI_BIAS_GELU: return launch_any<EPI_BIAS_GELU>(staged, ta, tb, tc, tc2, taux, p, stream);
+    case EPI_BIAS: return launch_any<EPI_BIAS>(staged, ta, tb, tc, tc2, taux, p, stream);
+    case EPI_GEGLU: return launch_any<EPI_GEGLU>(staged, ta, tb, tc, tc2, taux, p, stream);
+    case EPI_GEGLU_SAVE: return launch_any<EPI_GEGLU_SAVE>(staged, ta, tb, tc, tc2, taux, p, stream);
+    case EPI_ROPE: return launch_any<EPI_ROPE>(staged, ta, tb, tc, tc2, taux, p, stream);
+    case EPI_SCALE_F32: return launch_any<EPI_SCALE_F32>(staged, ta, tb, tc, tc2, taux, p, stream);
   }
   return set_error(kBadShape, "gemm: unreachable epilogue %d", g.epilogue);
 }
