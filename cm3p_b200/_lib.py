@@ -30,6 +30,18 @@ SIGNATURES = {
     "cm3p_conv1d_k3_gelu_fwd": (_I, [_P, _I, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P]),
     "cm3p_pool_project_normalize": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "cm3p_clip_loss_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "cm3p_im2col_k3": (_I, [_P, _I, _P, _L, _I, _I, _I, _I, _P]),
+    "cm3p_attn_varlen_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
+    "cm3p_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _F, _P]),
+    "cm3p_embed_gather_ln_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _F, _P]),
+    "cm3p_geglu_bwd": (_I, [_P, _P, _P, _P, _L, _I, _P]),
+    "cm3p_gelu_fwd": (_I, [_P, _P, _L, _P]),
+    "cm3p_gelu_bwd": (_I, [_P, _P, _P, _L, _P]),
+    "cm3p_colsum_f32": (_I, [_P, _P, _L, _I, _P]),
+    "cm3p_pool_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "cm3p_l2norm_bwd": (_I, [_P, _P, _P, _P, _I, _I, _P]),
+    "cm3p_clip_loss_bwd": (_I, [_P, _P, _P, _P, _P, _P, _L, _P, _I, _I, _I, _P]),
+    "cm3p_conv2_col2im_gelu_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P]),
 }
 
 _lib = None

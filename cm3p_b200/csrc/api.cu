@@ -88,6 +88,21 @@ int cm3p_conv1d_k3_gelu_fwd(const void* x, int x_layout, const void* weight, con
   return gemm_bf16(g, s);
 }
 
+int cm3p_im2col_k3(const void* x, int x_layout, void* ws, int64_t ld_ws, int batch, int c_in, int frames, int stride,
+                   void* stream) {
+  int rc = check_arch();
+  if (rc != kOk) return rc;
+  CM3P_REQUIRE((x_layout == 0 && stride == 1) || (x_layout == 1 && stride == 2), kBadShape,
+               "im2col_k3: supported forms are (fp32 channels-first, stride 1) and (bf16 channels-last, stride 2)");
+  CM3P_REQUIRE(ld_ws >= 3 * c_in && ld_ws % 8 == 0, kBadShape, "im2col_k3: ld_ws=%lld must be >= 3*c_in and %% 8",
+               (long long)ld_ws);
+  if (x_layout == 0)
+    return im2col_conv1(reinterpret_cast<const float*>(x), ws, batch, c_in, frames, static_cast<int>(ld_ws),
+                        as_stream(stream));
+  CM3P_REQUIRE(ld_ws == 3 * c_in, kBadShape, "im2col_k3: channels-last form needs ld_ws == 3*c_in");
+  return im2col_conv2(x, ws, batch, frames, c_in, as_stream(stream));
+}
+
 int cm3p_pool_project_normalize(const void* hidden_states, const int32_t* cu_seqlens, int mode, const void* proj_w,
                                 void* pooled, float* proj_f32, float* inv_norm, float* embeds_f32, void* embeds_bf16,
                                 int batch, int hidden, int proj_dim, void* stream) {
@@ -118,6 +133,85 @@ int cm3p_clip_loss_fwd(const float* S, const int32_t* true_idx, float* row_lse, 
   int rc = check_arch();
   if (rc != kOk) return rc;
   return clip_loss_fwd(S, true_idx, row_lse, col_lse, loss, Bm, V, Bb, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------------ backward
+int cm3p_attn_varlen_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
+                         const int32_t* cu_seqlens, const int32_t* positions, const float* rope_table,
+                         int64_t total_tokens, int batch, int heads, int head_dim, int max_seqlen, int window,
+                         void* stream) {
+  AttnBwdArgs a;
+  a.qkv = qkv; a.out = out; a.dout = dout; a.lse = lse; a.delta = delta; a.dqkv = dqkv;
+  a.cu_seqlens = cu_seqlens; a.positions = positions; a.rope_table = rope_table;
+  a.total_tokens = total_tokens; a.batch = batch; a.heads = heads; a.head_dim = head_dim;
+  a.max_seqlen = max_seqlen; a.window = window;
+  return attn_varlen_bwd(a, as_stream(stream));
+}
+
+#define CM3P_ARCH_GUARD()      \
+  do {                         \
+    int _rc = check_arch();    \
+    if (_rc != kOk) return _rc; \
+  } while (0)
+
+int cm3p_layernorm_bwd(const void* x, const void* dy, const float* gamma, const void* dres, void* dx, float* dgamma,
+                       int64_t rows, int hidden, float eps, void* stream) {
+  CM3P_ARCH_GUARD();
+  return layernorm_bwd(x, dy, gamma, dres, dx, dgamma, rows, hidden, eps, as_stream(stream));
+}
+
+int cm3p_embed_gather_ln_bwd(const int64_t* ids, const int32_t* src_index, const int32_t* audio_slot,
+                             const void* tok_emb, const void* audio_embeds, const float* gamma, const void* dy,
+                             float* d_tok_emb, void* d_audio_embeds, float* dgamma, int64_t rows, int hidden, int vocab,
+                             float eps, void* stream) {
+  CM3P_ARCH_GUARD();
+  return embed_gather_ln_bwd(ids, src_index, audio_slot, tok_emb, audio_embeds, gamma, dy, d_tok_emb, d_audio_embeds,
+                             dgamma, rows, hidden, vocab, eps, as_stream(stream));
+}
+
+int cm3p_geglu_bwd(const void* ug, const void* dh, void* dug, void* h, int64_t rows, int intermediate, void* stream) {
+  CM3P_ARCH_GUARD();
+  return geglu_bwd(ug, dh, dug, h, rows, intermediate, as_stream(stream));
+}
+
+int cm3p_gelu_fwd(const void* z, void* y, int64_t n, void* stream) {
+  CM3P_ARCH_GUARD();
+  return gelu_fwd(z, y, n, as_stream(stream));
+}
+
+int cm3p_gelu_bwd(const void* z, const void* dy, void* dz, int64_t n, void* stream) {
+  CM3P_ARCH_GUARD();
+  return gelu_bwd(z, dy, dz, n, as_stream(stream));
+}
+
+int cm3p_colsum_f32(const void* dy, float* out, int64_t rows, int n, void* stream) {
+  CM3P_ARCH_GUARD();
+  return colsum_f32(dy, out, rows, n, as_stream(stream));
+}
+
+int cm3p_pool_bwd(const void* dpooled, const int32_t* cu_seqlens, void* dhidden, int mode, int accumulate, int batch,
+                  int hidden, void* stream) {
+  CM3P_ARCH_GUARD();
+  return pool_bwd(dpooled, cu_seqlens, dhidden, mode, accumulate, batch, hidden, as_stream(stream));
+}
+
+int cm3p_l2norm_bwd(const float* proj_f32, const float* inv_norm, const float* dembeds, void* dproj_bf16, int rows,
+                    int proj_dim, void* stream) {
+  CM3P_ARCH_GUARD();
+  return l2norm_bwd(proj_f32, inv_norm, dembeds, dproj_bf16, rows, proj_dim, as_stream(stream));
+}
+
+int cm3p_clip_loss_bwd(const float* S, const int32_t* true_idx, const float* row_lse, const float* col_lse,
+                       const float* grad_out, void* dS, int64_t ld_ds, float* dlogit_scale, int Bm, int V, int Bb,
+                       void* stream) {
+  CM3P_ARCH_GUARD();
+  return clip_loss_bwd(S, true_idx, row_lse, col_lse, grad_out, dS, ld_ds, dlogit_scale, Bm, V, Bb, as_stream(stream));
+}
+
+int cm3p_conv2_col2im_gelu_bwd(const void* da2, const void* z1, void* dz1, int batch, int frames, int channels,
+                               void* stream) {
+  CM3P_ARCH_GUARD();
+  return conv2_col2im_gelu_bwd(da2, z1, dz1, batch, frames, channels, as_stream(stream));
 }
 
 }  // extern "C"

@@ -20,4 +20,24 @@ struct AttnFwdArgs {
 
 int attn_varlen_fwd(const AttnFwdArgs& args, cudaStream_t stream);
 
+struct AttnBwdArgs {
+  const void* qkv = nullptr;    // [T, 3, heads, 64] bf16 as given to the forward (q/k rotated)
+  const void* out = nullptr;    // [T, heads*64] bf16 forward output
+  const void* dout = nullptr;   // [T, heads*64] bf16
+  const float* lse = nullptr;   // [heads, T] fp32 from the forward (log2 domain)
+  float* delta = nullptr;       // [heads, T] fp32 workspace
+  void* dqkv = nullptr;         // [T, 3, heads, 64] bf16 gradient w.r.t. the un-rotated Wqkv output
+  const int32_t* cu_seqlens = nullptr;
+  const int32_t* positions = nullptr;  // [T] + rope_table: undo the forward's RoPE on dq/dk (both or neither)
+  const float* rope_table = nullptr;
+  int64_t total_tokens = 0;
+  int batch = 0;
+  int heads = 0;
+  int head_dim = 64;
+  int max_seqlen = 0;
+  int window = -1;
+};
+
+int attn_varlen_bwd(const AttnBwdArgs& args, cudaStream_t stream);
+
 }  // namespace cm3p

@@ -1,0 +1,572 @@
+// Unpadded (varlen) attention backward for sm_100a, head_dim 64, global and +-window layers.
+//
+// Gradient of what attn_fwd_sm100.cu computes (reference: autograd through the third-party
+// ModernBertAttention called from /root/reference/cm3p/modeling_cm3p.py:359-369,509-514,607-619):
+//   P = softmax(Q K^T / 8 | mask),  O = P V
+//   dV = P^T dO,  dP = dO V^T,  dZ = P o (dP - delta),  delta_i = <dO_i, O_i>,
+//   dQ = dZ K / 8,  dK = dZ^T Q / 8
+// followed by the inverse RoPE rotation on dQ / dK (the forward rotates q, k in the Wqkv GEMM
+// epilogue), so the result is the gradient w.r.t. the *un-rotated* Wqkv output.
+//
+// Two kernels, no atomics, deterministic:
+//   attn_bwd_dq_kernel   one CTA = (sequence, head, 128 queries), streams 64-row K/V tiles:
+//                        S = Q K^T, dP = dO V^T (tcgen05, TMEM), dZ -> bf16 smem, dQ += dZ K (TMEM).
+//                        Also produces delta[head][token] for the second kernel.
+//   attn_bwd_dkv_kernel  one CTA = (sequence, head, 128 keys), streams 64-row Q/dO tiles, working on
+//                        the transposed problem so that TMEM lanes are key rows:
+//                        S^T = K Q^T, dP^T = V dO^T, P^T and dZ^T -> bf16 smem, dV += P^T dO, dK += dZ^T Q.
+// P is recomputed from the forward's log2-domain logsumexp.  Each CTA uses 256 TMEM columns and
+// < 100 KB of shared memory, so two CTAs share an SM and overlap each other's MMA and exp phases.
+//
+// Warps: 0..3 = element-wise stage / epilogue (thread t <-> TMEM lane t), 4 = TMA producer (+ TMEM
+// alloc, + lse/delta staging), 5 = MMA issuer.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "attn.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace cm3p {
+namespace {
+
+constexpr int BT = 128;  // outer tile (rows owned by the CTA == TMEM lanes)
+constexpr int BI = 64;   // inner (streamed) tile
+constexpr int D = 64;
+constexpr int OUTER_BYTES = BT * D * 2;  // 16 KB
+constexpr int INNER_BYTES = BI * D * 2;  // 8 KB
+constexpr int STAGES = 2;
+constexpr int THREADS = 192;
+constexpr int TMEM_COLS = 256;
+
+struct BwdParams {
+  const int32_t* cu_seqlens;
+  const __nv_bfloat16* out;   // [T, H]   forward output
+  const __nv_bfloat16* dout;  // [T, H]
+  const float* lse;           // [heads, T] log2-domain logsumexp from the forward
+  float* delta;               // [heads, T] workspace: written by the dQ kernel, read by the dKV kernel
+  __nv_bfloat16* dqkv;        // [T, 3, heads, 64]
+  const int32_t* positions;   // [T] or nullptr (no inverse RoPE)
+  const float2* rope_table;   // [max_pos][32] (cos, sin) or nullptr
+  int64_t total_tokens;
+  int heads;
+  int hidden;
+  int window;
+  float scale_log2;  // (1/8) * log2(e)
+  float scale;       // 1/8
+};
+
+__device__ __forceinline__ uint4 pack8f(const float* v) {
+  return make_uint4(ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]), ptx::pack_bf16x2(v[4], v[5]),
+                    ptx::pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ void unpack8f(const uint4& u, float* f) {
+  float2 t;
+  t = ptx::unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = ptx::unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = ptx::unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = ptx::unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+
+// Row `t` of a [rows][64] bf16 K-major tile with the 128-byte swizzle the MMA descriptors expect:
+// 16-byte unit u of row t lives at unit (u ^ (t & 7)).
+__device__ __forceinline__ void store_row_units(uint8_t* tile, int t, int first_unit, const uint32_t (&packed)[16]) {
+  uint8_t* row = tile + t * 128;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int unit = (first_unit + u) ^ (t & 7);
+    *reinterpret_cast<uint4*>(row + unit * 16) =
+        make_uint4(packed[u * 4], packed[u * 4 + 1], packed[u * 4 + 2], packed[u * 4 + 3]);
+  }
+}
+
+// TMEM accumulator row (64 fp32 columns) -> optional inverse RoPE -> bf16 -> global.
+//   forward: y1 = x1 c - x2 s, y2 = x2 c + x1 s   =>   dx1 = dy1 c + dy2 s, dx2 = dy2 c - dy1 s
+__device__ __forceinline__ void store_grad_row(uint32_t taddr, __nv_bfloat16* dst, const float2* cs, bool valid) {
+  uint32_t r1[32], r2[32];
+  ptx::tmem_ld_32x32b_x32(taddr, r1);
+  ptx::tmem_ld_32x32b_x32(taddr + 32, r2);
+  ptx::tmem_ld_wait();
+  if (!valid) return;
+  float o1[32], o2[32];
+  if (cs) {
+    const float4* tab = reinterpret_cast<const float4*>(cs);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 f = __ldg(tab + k);  // (cos, sin) of frequencies 2k, 2k+1
+      const float a0 = __uint_as_float(r1[2 * k]), b0 = __uint_as_float(r2[2 * k]);
+      const float a1 = __uint_as_float(r1[2 * k + 1]), b1 = __uint_as_float(r2[2 * k + 1]);
+      o1[2 * k] = a0 * f.x + b0 * f.y;
+      o2[2 * k] = b0 * f.x - a0 * f.y;
+      o1[2 * k + 1] = a1 * f.z + b1 * f.w;
+      o2[2 * k + 1] = b1 * f.z - a1 * f.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      o1[k] = __uint_as_float(r1[k]);
+      o2[k] = __uint_as_float(r2[k]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    *reinterpret_cast<uint4*>(dst + i * 8) = pack8f(o1 + i * 8);
+    *reinterpret_cast<uint4*>(dst + 32 + i * 8) = pack8f(o2 + i * 8);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dQ kernel.  smem: Q 16K | dO 16K | K 2x8K | V 2x8K | dZ 16K | barriers.   TMEM: S [0,64) dP [64,128) dQ [128,192)
+constexpr int DQ_SMEM_TILES = 2 * OUTER_BYTES + STAGES * 2 * INNER_BYTES + OUTER_BYTES;  // 80 KB
+constexpr int DQ_SMEM_BYTES = DQ_SMEM_TILES + 256;
+
+__global__ void __launch_bounds__(THREADS, 2)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __grid_constant__ CUtensorMap tma_qkv64,
+                   const __grid_constant__ CUtensorMap tma_do128, const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int seq = blockIdx.z, head = blockIdx.y;
+  const int seq_start = p.cu_seqlens[seq];
+  const int len = p.cu_seqlens[seq + 1] - seq_start;
+  const int q0 = blockIdx.x * BT;
+  if (q0 >= len) return;
+
+  uint8_t* smem_q = smem;
+  uint8_t* smem_do = smem + OUTER_BYTES;
+  uint8_t* smem_k = smem + 2 * OUTER_BYTES;
+  uint8_t* smem_v = smem_k + STAGES * INNER_BYTES;
+  uint8_t* smem_dz = smem_v + STAGES * INNER_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_SMEM_TILES);
+  uint64_t* q_full = bars;        // Q + dO landed
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;    // S and dP of the current tile are in TMEM
+  uint64_t* dz_full = bars + 6;   // dZ in smem, S/dP consumed (128 arrivals)
+  uint64_t* acc_full = bars + 7;  // all MMAs done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
+
+  int kv_lo = 0, kv_hi = len - 1;
+  if (p.window >= 0) {
+    kv_lo = max(0, q0 - p.window);
+    kv_hi = min(len - 1, q0 + BT - 1 + p.window);
+  }
+  const int tile_lo = kv_lo / BI;
+  const int n_tiles = kv_hi / BI - tile_lo + 1;
+
+  if (warp == 5 && lane == 0) {
+    ptx::mbar_init(q_full, 1);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&kv_full[s], 1);
+      ptx::mbar_init(&kv_empty[s], 1);
+    }
+    ptx::mbar_init(s_full, 1);
+    ptx::mbar_init(dz_full, 128);
+    ptx::mbar_init(acc_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 4) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tma_qkv128);
+      ptx::prefetch_tmap(&tma_qkv64);
+      ptx::prefetch_tmap(&tma_do128);
+    }
+    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t TM_S = 0, TM_DP = 64, TM_DQ = 128;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const int col_q = head * D, col_k = p.hidden + head * D, col_v = 2 * p.hidden + head * D;
+      ptx::mbar_arrive_expect_tx(q_full, 2 * OUTER_BYTES);
+      ptx::tma_load_2d(smem_q, &tma_qkv128, q_full, col_q, seq_start + q0);
+      ptx::tma_load_2d(smem_do, &tma_do128, q_full, head * D, seq_start + q0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        ptx::mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&kv_full[s], 2 * INNER_BYTES);
+        const int row = seq_start + (tile_lo + j) * BI;
+        ptx::tma_load_2d(smem_k + s * INNER_BYTES, &tma_qkv64, &kv_full[s], col_k, row);
+        ptx::tma_load_2d(smem_v + s * INNER_BYTES, &tma_qkv64, &kv_full[s], col_v, row);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc_s = ptx::umma_idesc_bf16(BT, BI, 0, 0);   // [128 q] x [64 kv], both K-major (d)
+      const uint32_t idesc_dq = ptx::umma_idesc_bf16(BT, D, 0, 1);   // A = dZ K-major (kv), B = K MN-major (d)
+      const uint32_t q_addr = ptx::smem_u32(smem_q), do_addr = ptx::smem_u32(smem_do);
+      const uint32_t dz_addr = ptx::smem_u32(smem_dz);
+      auto issue_s_dp = [&](int j) {
+        const int s = j & 1;
+        ptx::mbar_wait(&kv_full[s], (j >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t k_addr = ptx::smem_u32(smem_k + s * INNER_BYTES);
+        const uint32_t v_addr = ptx::smem_u32(smem_v + s * INNER_BYTES);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          ptx::umma_bf16(tmem_base + TM_S, ptx::umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                         ptx::umma_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          ptx::umma_bf16(tmem_base + TM_DP, ptx::umma_smem_desc_sw128(do_addr + k * 32, 16, 1024),
+                         ptx::umma_smem_desc_sw128(v_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+        ptx::umma_commit(s_full);
+      };
+      ptx::mbar_wait(q_full, 0);
+      issue_s_dp(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        ptx::mbar_wait(dz_full, j & 1);
+        ptx::tc_fence_after();
+        const int s = j & 1;
+        const uint32_t k_addr = ptx::smem_u32(smem_k + s * INNER_BYTES);
+#pragma unroll
+        for (int k = 0; k < BI / 16; ++k)
+          ptx::umma_bf16(tmem_base + TM_DQ, ptx::umma_smem_desc_sw128(dz_addr + k * 32, 16, 1024),
+                         ptx::umma_smem_desc_sw128(k_addr + k * 2048, 8192, 1024), idesc_dq, (j | k) != 0 ? 1u : 0u);
+        ptx::umma_commit(&kv_empty[s]);
+        // S/dP of tile j+1 are issued behind dQ_j: their commit (s_full) therefore also tells the
+        // element-wise warps that the MMAs reading the dZ buffer have retired.
+        if (j + 1 < n_tiles) issue_s_dp(j + 1);
+      }
+      ptx::umma_commit(acc_full);
+    }
+  } else {
+    const int t = threadIdx.x;  // query row inside the tile == TMEM lane
+    const int qi = q0 + t;
+    const bool valid = qi < len;
+    const int64_t row = static_cast<int64_t>(seq_start) + qi;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    // delta_i = <dO_i, O_i>
+    float delta = 0.f, lse = 0.f;
+    if (valid) {
+      const uint4* po = reinterpret_cast<const uint4*>(p.out + row * p.hidden + head * D);
+      const uint4* pd = reinterpret_cast<const uint4*>(p.dout + row * p.hidden + head * D);
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i) {
+        float a[8], b[8];
+        unpack8f(__ldg(po + i), a);
+        unpack8f(__ldg(pd + i), b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) delta += a[k] * b[k];
+      }
+      lse = p.lse[static_cast<int64_t>(head) * p.total_tokens + row];
+      p.delta[static_cast<int64_t>(head) * p.total_tokens + row] = delta;
+    }
+    const float c = p.scale_log2;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int kv0 = (tile_lo + j) * BI;
+      ptx::mbar_wait(s_full, j & 1);
+      ptx::tc_fence_after();
+      int a = 0, b = valid ? min(BI, len - kv0) : 0;
+      if (p.window >= 0) {
+        a = max(a, qi - p.window - kv0);
+        b = min(b, qi + p.window + 1 - kv0);
+      }
+#pragma unroll
+      for (int cidx = 0; cidx < BI; cidx += 32) {
+        uint32_t rs[32], rp[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + TM_S + lane_off + cidx, rs);
+        ptx::tmem_ld_32x32b_x32(tmem_base + TM_DP + lane_off + cidx, rp);
+        ptx::tmem_ld_wait();
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const int kj = cidx + i;
+          const float p0 = (kj >= a && kj < b) ? ptx::ex2_approx(__uint_as_float(rs[i]) * c - lse) : 0.f;
+          const float p1 = (kj + 1 >= a && kj + 1 < b) ? ptx::ex2_approx(__uint_as_float(rs[i + 1]) * c - lse) : 0.f;
+          const float z0 = p0 * (__uint_as_float(rp[i]) - delta) * p.scale;
+          const float z1 = p1 * (__uint_as_float(rp[i + 1]) - delta) * p.scale;
+          packed[i >> 1] = ptx::pack_bf16x2(z0, z1);
+        }
+        store_row_units(smem_dz, t, cidx >> 3, packed);
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(dz_full);
+    }
+    ptx::mbar_wait(acc_full, 0);
+    ptx::tc_fence_after();
+    const float2* cs = nullptr;
+    if (p.rope_table && p.positions && valid) cs = p.rope_table + static_cast<int64_t>(p.positions[row]) * 32;
+    store_grad_row(tmem_base + TM_DQ + lane_off, p.dqkv + row * 3 * p.hidden + head * D, cs, valid);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dKV kernel.  smem: K 16K | V 16K | Q 2x8K | dO 2x8K | P^T 16K | dZ^T 16K | lse/delta 2x512 B | barriers
+// TMEM: S^T [0,64)  dP^T [64,128)  dK [128,192)  dV [192,256)
+constexpr int DKV_SMEM_TILES = 2 * OUTER_BYTES + STAGES * 2 * INNER_BYTES + 2 * OUTER_BYTES;  // 96 KB
+constexpr int DKV_VEC_BYTES = STAGES * 2 * BI * 4;                                            // 1 KB
+constexpr int DKV_SMEM_BYTES = DKV_SMEM_TILES + DKV_VEC_BYTES + 256;
+
+__global__ void __launch_bounds__(THREADS, 2)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __grid_constant__ CUtensorMap tma_qkv64,
+                    const __grid_constant__ CUtensorMap tma_do64, const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int seq = blockIdx.z, head = blockIdx.y;
+  const int seq_start = p.cu_seqlens[seq];
+  const int len = p.cu_seqlens[seq + 1] - seq_start;
+  const int k0 = blockIdx.x * BT;
+  if (k0 >= len) return;
+
+  uint8_t* smem_k = smem;
+  uint8_t* smem_v = smem + OUTER_BYTES;
+  uint8_t* smem_q = smem + 2 * OUTER_BYTES;
+  uint8_t* smem_do = smem_q + STAGES * INNER_BYTES;
+  uint8_t* smem_pt = smem_do + STAGES * INNER_BYTES;
+  uint8_t* smem_dzt = smem_pt + OUTER_BYTES;
+  float* smem_vec = reinterpret_cast<float*>(smem + DKV_SMEM_TILES);  // [stage][lse 64 | delta 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DKV_SMEM_TILES + DKV_VEC_BYTES);
+  uint64_t* kv_full = bars;
+  uint64_t* qdo_full = bars + 1;   // [2]  TMA bytes + 32 staging-lane arrivals
+  uint64_t* qdo_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* pz_full = bars + 6;    // P^T and dZ^T in smem (128 arrivals)
+  uint64_t* acc_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
+
+  int q_lo = 0, q_hi = len - 1;
+  if (p.window >= 0) {
+    q_lo = max(0, k0 - p.window);
+    q_hi = min(len - 1, k0 + BT - 1 + p.window);
+  }
+  const int tile_lo = q_lo / BI;
+  const int n_tiles = q_hi / BI - tile_lo + 1;
+
+  if (warp == 5 && lane == 0) {
+    ptx::mbar_init(kv_full, 1);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&qdo_full[s], 33);
+      ptx::mbar_init(&qdo_empty[s], 1);
+    }
+    ptx::mbar_init(s_full, 1);
+    ptx::mbar_init(pz_full, 128);
+    ptx::mbar_init(acc_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 4) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tma_qkv128);
+      ptx::prefetch_tmap(&tma_qkv64);
+      ptx::prefetch_tmap(&tma_do64);
+    }
+    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t TM_ST = 0, TM_DPT = 64, TM_DK = 128, TM_DV = 192;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ producer (whole warp)
+    const int col_q = head * D, col_k = p.hidden + head * D, col_v = 2 * p.hidden + head * D;
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(kv_full, 2 * OUTER_BYTES);
+      ptx::tma_load_2d(smem_k, &tma_qkv128, kv_full, col_k, seq_start + k0);
+      ptx::tma_load_2d(smem_v, &tma_qkv128, kv_full, col_v, seq_start + k0);
+    }
+    const float* lse_h = p.lse + static_cast<int64_t>(head) * p.total_tokens;
+    const float* delta_h = p.delta + static_cast<int64_t>(head) * p.total_tokens;
+    for (int i = 0; i < n_tiles; ++i) {
+      const int s = i & 1;
+      ptx::mbar_wait(&qdo_empty[s], ((i >> 1) & 1) ^ 1);
+      const int64_t row = static_cast<int64_t>(seq_start) + (tile_lo + i) * BI;
+      if (lane == 0) {
+        ptx::mbar_arrive_expect_tx(&qdo_full[s], 2 * INNER_BYTES);
+        ptx::tma_load_2d(smem_q + s * INNER_BYTES, &tma_qkv64, &qdo_full[s], col_q, static_cast<int32_t>(row));
+        ptx::tma_load_2d(smem_do + s * INNER_BYTES, &tma_do64, &qdo_full[s], col_q, static_cast<int32_t>(row));
+      }
+      float* vec = smem_vec + s * 2 * BI;
+#pragma unroll
+      for (int h = 0; h < BI; h += 32) {
+        const int64_t r = row + h + lane;
+        const bool ok = r < p.total_tokens;
+        vec[h + lane] = ok ? lse_h[r] : 0.f;
+        vec[BI + h + lane] = ok ? delta_h[r] : 0.f;
+      }
+      ptx::mbar_arrive(&qdo_full[s]);
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc_s = ptx::umma_idesc_bf16(BT, BI, 0, 0);   // [128 kv] x [64 q], both K-major (d)
+      const uint32_t idesc_acc = ptx::umma_idesc_bf16(BT, D, 0, 1);  // A = P^T / dZ^T K-major (q), B MN-major (d)
+      const uint32_t k_addr = ptx::smem_u32(smem_k), v_addr = ptx::smem_u32(smem_v);
+      const uint32_t pt_addr = ptx::smem_u32(smem_pt), dzt_addr = ptx::smem_u32(smem_dzt);
+      auto issue_s_dp = [&](int i) {
+        const int s = i & 1;
+        ptx::mbar_wait(&qdo_full[s], (i >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t q_addr = ptx::smem_u32(smem_q + s * INNER_BYTES);
+        const uint32_t do_addr = ptx::smem_u32(smem_do + s * INNER_BYTES);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          ptx::umma_bf16(tmem_base + TM_ST, ptx::umma_smem_desc_sw128(k_addr + k * 32, 16, 1024),
+                         ptx::umma_smem_desc_sw128(q_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          ptx::umma_bf16(tmem_base + TM_DPT, ptx::umma_smem_desc_sw128(v_addr + k * 32, 16, 1024),
+                         ptx::umma_smem_desc_sw128(do_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+        ptx::umma_commit(s_full);
+      };
+      ptx::mbar_wait(kv_full, 0);
+      issue_s_dp(0);
+      for (int i = 0; i < n_tiles; ++i) {
+        ptx::mbar_wait(pz_full, i & 1);
+        ptx::tc_fence_after();
+        const int s = i & 1;
+        const uint32_t q_addr = ptx::smem_u32(smem_q + s * INNER_BYTES);
+        const uint32_t do_addr = ptx::smem_u32(smem_do + s * INNER_BYTES);
+#pragma unroll
+        for (int k = 0; k < BI / 16; ++k)
+          ptx::umma_bf16(tmem_base + TM_DV, ptx::umma_smem_desc_sw128(pt_addr + k * 32, 16, 1024),
+                         ptx::umma_smem_desc_sw128(do_addr + k * 2048, 8192, 1024), idesc_acc, (i | k) != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < BI / 16; ++k)
+          ptx::umma_bf16(tmem_base + TM_DK, ptx::umma_smem_desc_sw128(dzt_addr + k * 32, 16, 1024),
+                         ptx::umma_smem_desc_sw128(q_addr + k * 2048, 8192, 1024), idesc_acc, (i | k) != 0 ? 1u : 0u);
+        ptx::umma_commit(&qdo_empty[s]);
+        if (i + 1 < n_tiles) issue_s_dp(i + 1);
+      }
+      ptx::umma_commit(acc_full);
+    }
+  } else {
+    const int t = threadIdx.x;  // key row inside the tile == TMEM lane
+    const int kj = k0 + t;
+    const bool valid = kj < len;
+    const int64_t row = static_cast<int64_t>(seq_start) + kj;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const float c = p.scale_log2;
+    for (int i = 0; i < n_tiles; ++i) {
+      const int s = i & 1;
+      const int q0i = (tile_lo + i) * BI;
+      ptx::mbar_wait(s_full, i & 1);
+      ptx::mbar_wait(&qdo_full[s], (i >> 1) & 1);  // already complete: orders the lse/delta staging writes
+      ptx::tc_fence_after();
+      int a = 0, b = valid ? min(BI, len - q0i) : 0;
+      if (p.window >= 0) {
+        a = max(a, kj - p.window - q0i);
+        b = min(b, kj + p.window + 1 - q0i);
+      }
+      const float4* lse4 = reinterpret_cast<const float4*>(smem_vec + s * 2 * BI);
+      const float4* del4 = lse4 + BI / 4;
+#pragma unroll
+      for (int cidx = 0; cidx < BI; cidx += 32) {
+        uint32_t rs[32], rp[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + TM_ST + lane_off + cidx, rs);
+        ptx::tmem_ld_32x32b_x32(tmem_base + TM_DPT + lane_off + cidx, rp);
+        ptx::tmem_ld_wait();
+        uint32_t pp[16], pz[16];
+#pragma unroll
+        for (int i4 = 0; i4 < 32; i4 += 4) {
+          const float4 l4 = lse4[(cidx + i4) >> 2];
+          const float4 d4 = del4[(cidx + i4) >> 2];
+          const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
+          const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
+          float pv[4], zv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int qj = cidx + i4 + e;
+            pv[e] = (qj >= a && qj < b) ? ptx::ex2_approx(__uint_as_float(rs[i4 + e]) * c - ls[e]) : 0.f;
+            zv[e] = pv[e] * (__uint_as_float(rp[i4 + e]) - dl[e]) * p.scale;
+          }
+          pp[i4 >> 1] = ptx::pack_bf16x2(pv[0], pv[1]);
+          pp[(i4 >> 1) + 1] = ptx::pack_bf16x2(pv[2], pv[3]);
+          pz[i4 >> 1] = ptx::pack_bf16x2(zv[0], zv[1]);
+          pz[(i4 >> 1) + 1] = ptx::pack_bf16x2(zv[2], zv[3]);
+        }
+        store_row_units(smem_pt, t, cidx >> 3, pp);
+        store_row_units(smem_dzt, t, cidx >> 3, pz);
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(pz_full);
+    }
+    ptx::mbar_wait(acc_full, 0);
+    ptx::tc_fence_after();
+    const float2* cs = nullptr;
+    if (p.rope_table && p.positions && valid) cs = p.rope_table + static_cast<int64_t>(p.positions[row]) * 32;
+    __nv_bfloat16* base = p.dqkv + row * 3 * p.hidden + head * D;
+    store_grad_row(tmem_base + TM_DK + lane_off, base + p.hidden, cs, valid);
+    store_grad_row(tmem_base + TM_DV + lane_off, base + 2 * p.hidden, nullptr, valid);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace
+
+int attn_varlen_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
+  int rc = check_arch();
+  if (rc != kOk) return rc;
+  CM3P_REQUIRE(a.head_dim == 64, kBadShape, "attn_bwd: head_dim %d unsupported (kernel is specialised for 64)",
+               a.head_dim);
+  CM3P_REQUIRE(a.batch > 0 && a.heads > 0 && a.total_tokens > 0 && a.max_seqlen > 0, kBadShape,
+               "attn_bwd: empty problem (batch=%d heads=%d tokens=%lld max_seqlen=%d)", a.batch, a.heads,
+               (long long)a.total_tokens, a.max_seqlen);
+  CM3P_REQUIRE(a.qkv && a.out && a.dout && a.lse && a.delta && a.dqkv && a.cu_seqlens, kBadShape,
+               "attn_bwd: null pointer");
+  CM3P_REQUIRE((a.positions == nullptr) == (a.rope_table == nullptr), kBadShape,
+               "attn_bwd: positions and rope_table must be given together");
+  const uint64_t H = static_cast<uint64_t>(a.heads) * 64;
+  const uint64_t T = static_cast<uint64_t>(a.total_tokens);
+  CUtensorMap qkv128, qkv64, do128, do64;
+  if ((rc = encode_tmap_2d_bf16(&qkv128, a.qkv, 3 * H, T, 3 * H * 2, 64, BT)) != kOk) return rc;
+  if ((rc = encode_tmap_2d_bf16(&qkv64, a.qkv, 3 * H, T, 3 * H * 2, 64, BI)) != kOk) return rc;
+  if ((rc = encode_tmap_2d_bf16(&do128, a.dout, H, T, H * 2, 64, BT)) != kOk) return rc;
+  if ((rc = encode_tmap_2d_bf16(&do64, a.dout, H, T, H * 2, 64, BI)) != kOk) return rc;
+  static bool configured = false;
+  if (!configured) {
+    CM3P_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM_BYTES));
+    CM3P_CUDA_TRY(
+        cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM_BYTES));
+    configured = true;
+  }
+  BwdParams p;
+  p.cu_seqlens = a.cu_seqlens;
+  p.out = reinterpret_cast<const __nv_bfloat16*>(a.out);
+  p.dout = reinterpret_cast<const __nv_bfloat16*>(a.dout);
+  p.lse = a.lse;
+  p.delta = a.delta;
+  p.dqkv = reinterpret_cast<__nv_bfloat16*>(a.dqkv);
+  p.positions = a.positions;
+  p.rope_table = reinterpret_cast<const float2*>(a.rope_table);
+  p.total_tokens = a.total_tokens;
+  p.heads = a.heads;
+  p.hidden = static_cast<int>(H);
+  p.window = a.window;
+  p.scale = 0.125f;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  dim3 grid((a.max_seqlen + BT - 1) / BT, a.heads, a.batch);
+  attn_bwd_dq_kernel<<<grid, THREADS, DQ_SMEM_BYTES, stream>>>(qkv128, qkv64, do128, p);
+  CM3P_CUDA_TRY(cudaGetLastError());
+  attn_bwd_dkv_kernel<<<grid, THREADS, DKV_SMEM_BYTES, stream>>>(qkv128, qkv64, do64, p);
+  CM3P_CUDA_TRY(cudaGetLastError());
+  return kOk;
+}
+
+}  // namespace cm3p

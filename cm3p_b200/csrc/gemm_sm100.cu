@@ -50,9 +50,16 @@ struct Params {
   const float2* rope_table;  // [max_pos][32] (cos, sin)
   int64_t rope_cols;         // columns [0, rope_cols) are rotated per 64-wide head
   int trans_a, trans_b;
-  int accumulate;  // F32 epilogue: C += acc
+  int accumulate;  // F32 epilogue: C += acc (atomic, so K may be split across CTAs)
   int vec_c;       // C (and C2 / aux) rows allow 16-byte accesses
+  int splits;        // split-K factor (>1 only with the atomic F32 epilogue: weight gradients, K = tokens)
+  int kb_per_split;  // k-blocks per split
 };
+
+__device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
 
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32], int64_t col, int64_t ncols,
                                               bool vec = true) {
@@ -194,17 +201,21 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           if (p.vec_c && col + i * 4 + 4 <= p.N) {
-            float4 f = make_float4(v[i * 4] * p.scale, v[i * 4 + 1] * p.scale, v[i * 4 + 2] * p.scale,
-                                   v[i * 4 + 3] * p.scale);
             if (p.accumulate) {
-              const float4 old = *reinterpret_cast<const float4*>(dst + i * 4);
-              f.x += old.x; f.y += old.y; f.z += old.z; f.w += old.w;
+              red_add_f32x4(dst + i * 4, v[i * 4] * p.scale, v[i * 4 + 1] * p.scale, v[i * 4 + 2] * p.scale,
+                            v[i * 4 + 3] * p.scale);
+            } else {
+              *reinterpret_cast<float4*>(dst + i * 4) = make_float4(v[i * 4] * p.scale, v[i * 4 + 1] * p.scale,
+                                                                    v[i * 4 + 2] * p.scale, v[i * 4 + 3] * p.scale);
             }
-            *reinterpret_cast<float4*>(dst + i * 4) = f;
           } else {
             for (int j = 0; j < 4; ++j)
-              if (col + i * 4 + j < p.N)
-                dst[i * 4 + j] = v[i * 4 + j] * p.scale + (p.accumulate ? dst[i * 4 + j] : 0.f);
+              if (col + i * 4 + j < p.N) {
+                if (p.accumulate)
+                  atomicAdd(dst + i * 4 + j, v[i * 4 + j] * p.scale);
+                else
+                  dst[i * 4 + j] = v[i * 4 + j] * p.scale;
+              }
           }
         }
       }
@@ -429,17 +440,21 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
 
   const int64_t tiles_m = (p.M + BM - 1) / BM;
   const int64_t tiles_n = (p.N + BN - 1) / BN;
-  const int64_t num_tiles = tiles_m * tiles_n;
-  const int num_kb = static_cast<int>((p.K + BK - 1) / BK);
+  const int64_t mn_tiles = tiles_m * tiles_n;
+  const int64_t num_tiles = mn_tiles * p.splits;  // work units: (output tile, K split)
+  const int num_kb_total = static_cast<int>((p.K + BK - 1) / BK);
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
     int s = 0;
     uint32_t ph = 0;
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int32_t m0 = static_cast<int32_t>((t / tiles_n) * BM);
-      const int32_t n0 = static_cast<int32_t>((t % tiles_n) * BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int64_t mn = t % mn_tiles;
+      const int32_t m0 = static_cast<int32_t>((mn / tiles_n) * BM);
+      const int32_t n0 = static_cast<int32_t>((mn % tiles_n) * BN);
+      const int kb0 = static_cast<int>(t / mn_tiles) * p.kb_per_split;
+      const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&empty[s], ph ^ 1);
         ptx::mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
         uint8_t* sa = smem_a + s * A_STAGE_BYTES;
@@ -476,7 +491,9 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       ptx::mbar_wait(&tmem_empty[as], aph ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int kb0 = static_cast<int>(t / mn_tiles) * p.kb_per_split;
+      const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&full[s], ph);
         ptx::tc_fence_after();
         const uint32_t a_addr = ptx::smem_u32(smem_a + s * A_STAGE_BYTES);
@@ -485,10 +502,10 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         for (int k = 0; k < BK / 16; ++k) {
           const uint64_t da = ptx::umma_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
           const uint64_t db = ptx::umma_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
-          ptx::umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          ptx::umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
         }
         ptx::umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
-        if (kb == num_kb - 1) ptx::umma_commit(&tmem_full[as]);
+        if (kb == kb1 - 1) ptx::umma_commit(&tmem_full[as]);
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
       if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
@@ -502,19 +519,20 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     if constexpr (STAGED && EPI == EPI_RESIDUAL) {
       // residual slab of the very first output slab
       if (quad == 0 && lane == 0 && static_cast<int64_t>(blockIdx.x) < num_tiles) {
-        const int64_t t0 = blockIdx.x;
+        const int64_t t0 = blockIdx.x % mn_tiles;
         ptx::mbar_arrive_expect_tx(&res_full[0], SLAB_BYTES);
         ptx::tma_load_2d(slabs, &tma_aux, &res_full[0], static_cast<int32_t>((t0 % tiles_n) * BN),
                          static_cast<int32_t>((t0 / tiles_n) * BM));
       }
     }
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int64_t m0 = (t / tiles_n) * BM;
-      const int64_t n0 = (t % tiles_n) * BN;
+      const int64_t mn = t % mn_tiles;
+      const int64_t m0 = (mn / tiles_n) * BM;
+      const int64_t n0 = (mn % tiles_n) * BN;
       ptx::mbar_wait(&tmem_full[as], aph);
       ptx::tc_fence_after();
       if constexpr (STAGED) {
-        const int64_t tn = t + gridDim.x;
+        const int64_t tn = t + gridDim.x;  // staged epilogues never split K: unit index == tile index
         epilogue_tile_staged<EPI>(p, &tma_c, &tma_c2, &tma_aux, slabs, res_full, st, tmem_base + as * BN, quad, m0,
                                   n0, (tn / tiles_n) * BM, (tn % tiles_n) * BN, tn < num_tiles);
       } else {
@@ -547,7 +565,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
-  const int64_t tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  const int64_t tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.splits;
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
   gemm_bf16_sm100_kernel<EPI, STAGED><<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, tc, tc2, taux, p);
   CM3P_CUDA_TRY(cudaGetLastError());
@@ -633,6 +651,19 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   p.trans_a = g.trans_a; p.trans_b = g.trans_b;
   p.accumulate = g.accumulate;
   p.vec_c = vec ? 1 : 0;
+  p.splits = 1;
+  const int num_kb = static_cast<int>((g.K + BK - 1) / BK);
+  p.kb_per_split = num_kb;
+  if (g.epilogue == EPI_SCALE_F32 && g.accumulate) {
+    // weight gradients: few output tiles, K = number of tokens.  Split K so that ~4 work units per SM
+    // exist; partial sums meet in C through fp32 atomics.
+    const int64_t tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+    int64_t want = (4LL * num_sms()) / tiles;
+    if (want > num_kb / 8) want = num_kb / 8;
+    if (want < 1) want = 1;
+    p.kb_per_split = static_cast<int>((num_kb + want - 1) / want);
+    p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  }
 
   switch (g.epilogue) {
     case EPI_STORE: return launch_any<EPI_STORE>(staged, ta, tb, tc, tc2, taux, p, stream);

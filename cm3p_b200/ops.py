@@ -17,6 +17,7 @@ EPI_GEGLU, EPI_GEGLU_SAVE, EPI_ROPE, EPI_SCALE_F32 = 5, 6, 7, 8
 LAUNCH_COUNT = 0
 _LAUNCHES_PER_CALL = {
     "gemm": 1, "attn": 1, "layernorm": 1, "embed": 1, "conv": 2, "pool_project": 3, "pool": 1, "clip_loss": 2,
+    "attn_bwd": 2, "rowwise": 1,
 }
 
 
@@ -186,6 +187,186 @@ def clip_loss_fwd(S: torch.Tensor, true_idx: torch.Tensor, V: int):
     _lib.check(rc, "cm3p_clip_loss_fwd")
     _count("clip_loss")
     return loss, row_lse, col_lse
+
+
+# ------------------------------------------------------------------------------------------------
+# backward entry points (include/cm3p_b200.h, "Backward entry points")
+
+def attn_varlen_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, lse: torch.Tensor,
+                    cu_seqlens: torch.Tensor, max_seqlen: int, heads: int, window: int = -1,
+                    positions: torch.Tensor | None = None, rope_table: torch.Tensor | None = None,
+                    dqkv: torch.Tensor | None = None, delta: torch.Tensor | None = None) -> torch.Tensor:
+    """-> dqkv [T, 3*heads*64] bf16, gradient w.r.t. the un-rotated Wqkv output when positions/rope_table
+    are given (otherwise w.r.t. the qkv passed in)."""
+    for t, n in ((qkv, "qkv"), (out, "out"), (dout, "dout")):
+        _req(t, torch.bfloat16, n)
+    _req(lse, torch.float32, "lse")
+    _req(cu_seqlens, torch.int32, "cu_seqlens")
+    T, H = out.shape
+    assert qkv.shape == (T, 3 * H) and dout.shape == (T, H) and lse.shape == (heads, T)
+    assert qkv.is_contiguous() and out.is_contiguous() and dout.is_contiguous() and lse.is_contiguous()
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    if delta is None:
+        delta = torch.empty_like(lse)
+    rc = _lib.load().cm3p_attn_varlen_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+                                          delta.data_ptr(), dqkv.data_ptr(), cu_seqlens.data_ptr(), _ptr(positions),
+                                          _ptr(rope_table), T, cu_seqlens.numel() - 1, heads, 64, int(max_seqlen),
+                                          int(window), _stream())
+    _lib.check(rc, "cm3p_attn_varlen_bwd")
+    _count("attn_bwd")
+    return dqkv
+
+
+def layernorm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: float,
+                  dres: torch.Tensor | None = None, dx: torch.Tensor | None = None,
+                  dgamma: torch.Tensor | None = None) -> torch.Tensor:
+    """dx = LN'(x).dy (+ dres); dgamma (fp32 [H]) is accumulated into."""
+    _req(x, torch.bfloat16, "x")
+    _req(dy, torch.bfloat16, "dy")
+    _req(gamma, torch.float32, "gamma")
+    assert x.is_contiguous() and dy.is_contiguous() and x.shape == dy.shape
+    if dx is None:
+        dx = torch.empty_like(x)
+    rows = x.numel() // x.shape[-1]
+    rc = _lib.load().cm3p_layernorm_bwd(x.data_ptr(), dy.data_ptr(), gamma.data_ptr(), _ptr(dres), dx.data_ptr(),
+                                        _ptr(dgamma), rows, x.shape[-1], float(eps), _stream())
+    _lib.check(rc, "cm3p_layernorm_bwd")
+    _count("rowwise")
+    return dx
+
+
+def embed_gather_ln_bwd(ids, src_index, audio_slot, tok_emb, audio_embeds, gamma, dy, eps, d_tok_emb=None,
+                        d_audio_embeds=None, dgamma=None) -> None:
+    _req(dy, torch.bfloat16, "dy")
+    rows, H = dy.shape
+    rc = _lib.load().cm3p_embed_gather_ln_bwd(ids.data_ptr(), _ptr(src_index), _ptr(audio_slot), tok_emb.data_ptr(),
+                                              _ptr(audio_embeds), gamma.data_ptr(), dy.data_ptr(), _ptr(d_tok_emb),
+                                              _ptr(d_audio_embeds), _ptr(dgamma), rows, H, tok_emb.shape[0], float(eps),
+                                              _stream())
+    _lib.check(rc, "cm3p_embed_gather_ln_bwd")
+    _count("rowwise")
+
+
+def geglu_bwd(ug: torch.Tensor, dh: torch.Tensor, dug: torch.Tensor | None = None, h: torch.Tensor | None = None,
+              want_h: bool = True):
+    """ug [T,2I] interleaved pre-activation, dh [T,I] -> (dug [T,2I], h [T,I] = gelu(u)*g recomputed)."""
+    _req(ug, torch.bfloat16, "ug")
+    _req(dh, torch.bfloat16, "dh")
+    rows, I = dh.shape
+    assert ug.shape == (rows, 2 * I) and ug.is_contiguous() and dh.is_contiguous()
+    if dug is None:
+        dug = torch.empty_like(ug)
+    if h is None and want_h:
+        h = torch.empty_like(dh)
+    rc = _lib.load().cm3p_geglu_bwd(ug.data_ptr(), dh.data_ptr(), dug.data_ptr(), _ptr(h), rows, I, _stream())
+    _lib.check(rc, "cm3p_geglu_bwd")
+    _count("rowwise")
+    return dug, h
+
+
+def gelu_fwd(z: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    _req(z, torch.bfloat16, "z")
+    assert z.is_contiguous()
+    if out is None:
+        out = torch.empty_like(z)
+    _lib.check(_lib.load().cm3p_gelu_fwd(z.data_ptr(), out.data_ptr(), z.numel(), _stream()), "cm3p_gelu_fwd")
+    _count("rowwise")
+    return out
+
+
+def gelu_bwd(z: torch.Tensor, dy: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    _req(z, torch.bfloat16, "z")
+    _req(dy, torch.bfloat16, "dy")
+    assert z.is_contiguous() and dy.is_contiguous() and z.numel() == dy.numel()
+    if out is None:
+        out = torch.empty_like(z)
+    _lib.check(_lib.load().cm3p_gelu_bwd(z.data_ptr(), dy.data_ptr(), out.data_ptr(), z.numel(), _stream()),
+               "cm3p_gelu_bwd")
+    _count("rowwise")
+    return out
+
+
+def colsum_f32(dy: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out [N] fp32 += column sums of dy [rows, N] bf16."""
+    _req(dy, torch.bfloat16, "dy")
+    _req(out, torch.float32, "out")
+    assert dy.dim() == 2 and dy.is_contiguous() and out.numel() == dy.shape[1]
+    _lib.check(_lib.load().cm3p_colsum_f32(dy.data_ptr(), out.data_ptr(), dy.shape[0], dy.shape[1], _stream()),
+               "cm3p_colsum_f32")
+    _count("rowwise")
+    return out
+
+
+def pool_bwd(dpooled: torch.Tensor, cu_seqlens: torch.Tensor, mean_pool: bool, dhidden: torch.Tensor,
+             accumulate: bool) -> torch.Tensor:
+    _req(dpooled, torch.bfloat16, "dpooled")
+    _req(dhidden, torch.bfloat16, "dhidden")
+    B, H = dpooled.shape
+    assert dpooled.is_contiguous() and dhidden.is_contiguous() and dhidden.shape[1] == H
+    rc = _lib.load().cm3p_pool_bwd(dpooled.data_ptr(), cu_seqlens.data_ptr(), dhidden.data_ptr(), int(mean_pool),
+                                   int(accumulate), B, H, _stream())
+    _lib.check(rc, "cm3p_pool_bwd")
+    _count("rowwise")
+    return dhidden
+
+
+def l2norm_bwd(proj: torch.Tensor, inv_norm: torch.Tensor, dembeds: torch.Tensor) -> torch.Tensor:
+    """-> dproj bf16 [B,P]."""
+    _req(proj, torch.float32, "proj")
+    _req(dembeds, torch.float32, "dembeds")
+    B, P = proj.shape
+    assert proj.is_contiguous() and dembeds.is_contiguous() and dembeds.shape == proj.shape
+    out = torch.empty((B, P), device=proj.device, dtype=torch.bfloat16)
+    rc = _lib.load().cm3p_l2norm_bwd(proj.data_ptr(), inv_norm.data_ptr(), dembeds.data_ptr(), out.data_ptr(), B, P,
+                                     _stream())
+    _lib.check(rc, "cm3p_l2norm_bwd")
+    _count("rowwise")
+    return out
+
+
+def clip_loss_bwd(S: torch.Tensor, true_idx: torch.Tensor, row_lse: torch.Tensor, col_lse: torch.Tensor, V: int,
+                  grad_out: torch.Tensor | None, dlogit_scale: torch.Tensor):
+    """-> dS bf16 [Bm*V, ld] (ld = Bb rounded up to 8; columns >= Bb are padding), dlogit_scale += sum dS*S."""
+    _req(S, torch.float32, "S")
+    R, Bb = S.shape
+    ld = (Bb + 7) // 8 * 8
+    dS = torch.empty((R, ld), device=S.device, dtype=torch.bfloat16)
+    rc = _lib.load().cm3p_clip_loss_bwd(S.data_ptr(), true_idx.data_ptr(), row_lse.data_ptr(), col_lse.data_ptr(),
+                                        _ptr(grad_out), dS.data_ptr(), ld, dlogit_scale.data_ptr(), R // V, V, Bb,
+                                        _stream())
+    _lib.check(rc, "cm3p_clip_loss_bwd")
+    _count("rowwise")
+    return dS[:, :Bb]
+
+
+def im2col_k3(x: torch.Tensor, stride: int, ws: torch.Tensor | None = None) -> torch.Tensor:
+    """GEMM rows of a k=3/pad=1 conv1d: x fp32 [B,C,F] (stride 1) or bf16 [B,F,C] (stride 2) -> [B*F/stride, 3C]."""
+    if x.dtype == torch.float32:
+        layout, (B, C, F) = 0, x.shape
+    else:
+        _req(x, torch.bfloat16, "x")
+        layout, (B, F, C) = 1, x.shape
+    assert x.is_contiguous()
+    if ws is None:
+        ws = torch.empty((B * (F // stride), 3 * C), device=x.device, dtype=torch.bfloat16)
+    rc = _lib.load().cm3p_im2col_k3(x.data_ptr(), layout, ws.data_ptr(), 3 * C, B, C, F, stride, _stream())
+    _lib.check(rc, "cm3p_im2col_k3")
+    _count("rowwise")
+    return ws
+
+
+def conv2_col2im_gelu_bwd(da2: torch.Tensor, z1: torch.Tensor) -> torch.Tensor:
+    """da2 [B*F/2, 3C] bf16, z1 [B,F,C] bf16 (conv1 pre-activation) -> dz1 [B,F,C]."""
+    _req(da2, torch.bfloat16, "da2")
+    _req(z1, torch.bfloat16, "z1")
+    B, F, C = z1.shape
+    assert da2.is_contiguous() and z1.is_contiguous() and da2.shape == (B * (F // 2), 3 * C)
+    out = torch.empty_like(z1)
+    rc = _lib.load().cm3p_conv2_col2im_gelu_bwd(da2.data_ptr(), z1.data_ptr(), out.data_ptr(), B, F, C, _stream())
+    _lib.check(rc, "cm3p_conv2_col2im_gelu_bwd")
+    _count("rowwise")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

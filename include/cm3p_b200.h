@@ -42,7 +42,8 @@ extern "C" {
 #define CM3P_EPI_GEGLU 5      /* C[M,N/2] = gelu_erf(u)*g; B rows interleaved in groups of 16 (u,g) */
 #define CM3P_EPI_GEGLU_SAVE 6 /* as GEGLU, and C2[M,N] = acc (pre-activation kept for backward) */
 #define CM3P_EPI_ROPE 7       /* rotate-half RoPE on columns [0, rope_cols) per 64-wide head */
-#define CM3P_EPI_SCALE_F32 8  /* C(fp32) = scale*acc (+ C if accumulate) */
+#define CM3P_EPI_SCALE_F32 8  /* C(fp32) = scale*acc; accumulate != 0: C += scale*acc with fp32 atomics, K split
+                                 across CTAs (weight gradients: K = number of tokens) */
 
 const char* cm3p_last_error(void);
 int cm3p_version(void);
@@ -106,6 +107,69 @@ int cm3p_pool_project_normalize(const void* hidden_states, const int32_t* cu_seq
  *   row_lse [Bm], col_lse [Bb] fp32 outputs (kept for backward); loss: 1 fp32 */
 int cm3p_clip_loss_fwd(const float* S, const int32_t* true_idx, float* row_lse, float* col_lse, float* loss, int Bm,
                        int V, int Bb, void* stream);
+
+/* im2col rows of a k=3, pad=1 conv1d (the A operand of cm3p_conv1d_k3_gelu_fwd's GEMM); the training
+ * path keeps them as the activation operand of the conv weight gradients.  Layouts as above. */
+int cm3p_im2col_k3(const void* x, int x_layout, void* ws, int64_t ld_ws, int batch, int c_in, int frames, int stride,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backward entry points.  The reference has no backward code of its own: these are the gradients
+ * torch autograd derives for the forward call sites cited above (loss.backward() in
+ * transformers.Trainer.training_step, reached from train.py:360-375).  Weight gradients are
+ * cm3p_gemm_bf16 calls on transposed operands (trans_a/trans_b, CM3P_EPI_SCALE_F32, accumulate=1).
+ */
+
+/* Gradient of cm3p_attn_varlen_fwd w.r.t. the un-rotated Wqkv output: dqkv [T,3,heads,64] bf16.
+ *   out/dout [T,heads*64] bf16; lse [heads,T] from the forward; delta [heads,T] fp32 workspace;
+ *   positions + rope_table (both or neither): dq/dk are rotated back (inverse of CM3P_EPI_ROPE). */
+int cm3p_attn_varlen_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
+                         const int32_t* cu_seqlens, const int32_t* positions, const float* rope_table,
+                         int64_t total_tokens, int batch, int heads, int head_dim, int max_seqlen, int window,
+                         void* stream);
+
+/* dx = LayerNorm'(x; gamma) . dy (+ dres, the gradient arriving through the residual connection);
+ * dgamma[H] fp32 += sum_rows dy * xhat (NULL to skip).  Statistics are recomputed from x. */
+int cm3p_layernorm_bwd(const void* x, const void* dy, const float* gamma, const void* dres, void* dx, float* dgamma,
+                       int64_t rows, int hidden, float eps, void* stream);
+
+/* Backward of cm3p_embed_gather_ln: token rows are atomically added into d_tok_emb [vocab,H] fp32,
+ * audio rows written to d_audio_embeds [n_audio,H] bf16 (either may be NULL); dgamma as above. */
+int cm3p_embed_gather_ln_bwd(const int64_t* ids, const int32_t* src_index, const int32_t* audio_slot,
+                             const void* tok_emb, const void* audio_embeds, const float* gamma, const void* dy,
+                             float* d_tok_emb, void* d_audio_embeds, float* dgamma, int64_t rows, int hidden, int vocab,
+                             float eps, void* stream);
+
+/* GeGLU backward on the interleaved pre-activation ug [rows,2I] kept by CM3P_EPI_GEGLU_SAVE:
+ * dug [rows,2I] (same interleaving), h [rows,I] = gelu(u)*g recomputed (NULL to skip). */
+int cm3p_geglu_bwd(const void* ug, const void* dh, void* dug, void* h, int64_t rows, int intermediate, void* stream);
+
+/* y = gelu_erf(z) and dz = dy * gelu_erf'(z) over n bf16 elements (n % 8 == 0). */
+int cm3p_gelu_fwd(const void* z, void* y, int64_t n, void* stream);
+int cm3p_gelu_bwd(const void* z, const void* dy, void* dz, int64_t n, void* stream);
+
+/* out[n] fp32 += sum_rows dy[rows,n] bf16 (bias gradients). */
+int cm3p_colsum_f32(const void* dy, float* out, int64_t rows, int n, void* stream);
+
+/* Backward of the pooling in cm3p_pool_project_normalize: dhidden [T,H] bf16 (overwritten, or added to
+ * when accumulate != 0) from dpooled [B,H] bf16; mode as in the forward. */
+int cm3p_pool_bwd(const void* dpooled, const int32_t* cu_seqlens, void* dhidden, int mode, int accumulate, int batch,
+                  int hidden, void* stream);
+
+/* Backward of embeds = e / |e|: dproj (bf16 [rows,P]) from proj_f32, inv_norm and dembeds (fp32). */
+int cm3p_l2norm_bwd(const float* proj_f32, const float* inv_norm, const float* dembeds, void* dproj_bf16, int rows,
+                    int proj_dim, void* stream);
+
+/* Backward of cm3p_clip_loss_fwd: dS [Bm*V, ld_ds] bf16 (ld_ds >= Bb) and dlogit_scale (fp32, += sum dS*S).
+ * grad_out: device scalar (upstream gradient of the loss) or NULL for 1. */
+int cm3p_clip_loss_bwd(const float* S, const int32_t* true_idx, const float* row_lse, const float* col_lse,
+                       const float* grad_out, void* dS, int64_t ld_ds, float* dlogit_scale, int Bm, int V, int Bb,
+                       void* stream);
+
+/* conv2 input gradient (col2im of dA2 [B*F/2, 3*C] onto [B,F,C]) fused with conv1's GELU backward:
+ * dz1 = col2im(dA2) * gelu'(z1).  Replaces autograd through cm3p/modeling_cm3p.py:501-502. */
+int cm3p_conv2_col2im_gelu_bwd(const void* da2, const void* z1, void* dz1, int batch, int frames, int channels,
+                               void* stream);
 
 #ifdef __cplusplus
 }
