@@ -1,7 +1,381 @@
-"""Explicit-backward training path (filled in by the backward kernels)."""
+"""Explicit forward + backward of the contrastive train step on the sm_100a kernels.
+
+The reference trains through torch autograd (`loss.backward()` inside
+`transformers.Trainer.training_step`, reached from /root/reference/train.py:360-375).  Here the
+forward pass keeps exactly the activations the backward kernels need, and the backward pass is a
+hand-scheduled sequence of C-ABI calls (cm3p_b200.ops): dgrad / wgrad tcgen05 GEMMs, the varlen
+attention backward, LayerNorm / GeGLU / GELU / pooling / loss backward kernels.  It is attached to
+autograd through ONE `torch.autograd.Function` whose inputs are the trainable parameters and whose
+output is the loss, so `loss.backward()`, gradient accumulation, `torch.nn.parallel.
+DistributedDataParallel` hooks (gradient all-reduce over NCCL) and optimizers work unchanged.
+
+Per encoder layer the forward keeps x_in, qkv (rotated), the attention output, the log-sum-exp,
+x_mid and the GeGLU pre-activation (13.8 KB / token / layer for the beatmap tower); LayerNorm
+outputs and the GeGLU product are recomputed in the backward pass.
+
+Numerics: bf16 activations and gradients of activations, fp32 accumulation, fp32 parameter
+gradients (what autocast-bf16 training in the reference produces up to rounding; north-star
+tolerance: loss / gradient norms within 1e-2 relative).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+BF16, F32 = torch.bfloat16, torch.float32
 
 
-def forward_with_grad(model, **kwargs):
-    raise NotImplementedError(
-        "cm3p_b200: the training (gradient) path is not built yet; call the model under torch.no_grad() "
-        "for inference")
+class GradStore:
+    """fp32 gradient buffers, one per parameter, carved out of a single zero-filled allocation."""
+
+    def __init__(self, params):
+        self.params = list(params)
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4  # keep every view 16-byte aligned
+        dev = self.params[0].device
+        self.flat = torch.zeros(total, device=dev, dtype=F32)
+        self.views = {id(p): self.flat[o:o + p.numel()].view(p.shape) for p, o in zip(self.params, offs)}
+
+    def __call__(self, p: torch.Tensor) -> torch.Tensor:
+        return self.views[id(p)]
+
+
+def _wgrad(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor) -> None:
+    """out[N_out, K_in] (fp32) += dy[T, N_out]^T . x[T, K_in]  (K of the GEMM = tokens, split across CTAs)."""
+    ops.gemm(dy, x, trans_a=True, trans_b=True, epilogue=ops.EPI_SCALE_F32, accumulate=True, out=out)
+
+
+def _dgrad(dy: torch.Tensor, w: torch.Tensor, out: torch.Tensor | None = None, **kw) -> torch.Tensor:
+    """dx[T, K_in] = dy[T, N_out] . w[N_out, K_in]."""
+    return ops.gemm(dy, w, trans_b=True, out=out, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# ModernBERT trunk
+
+def encoder_forward(enc, x0: torch.Tensor, cu_seqlens, max_seqlen: int, positions):
+    """x0 [T,H] = normalised embeddings.  -> (final-normed hidden [T,H], saved activations)."""
+    cfg, pk = enc.config, enc.packed()
+    T, H = x0.shape
+    heads, I = cfg.num_attention_heads, int(cfg.intermediate_size)
+    dev = x0.device
+    tab_g = ops.rope_table(cfg.global_rope_theta, cfg.max_position_embeddings, dev)
+    tab_l = ops.rope_table(cfg.local_rope_theta, cfg.max_position_embeddings, dev)
+    a = torch.empty_like(x0)
+    layers = []
+    x = x0
+    for i, w in enumerate(pk["layers"]):
+        is_global = cfg.layer_is_global(i)
+        tab = tab_g if is_global else tab_l
+        src = x if i == 0 else ops.layernorm(x, w["attn_norm"], cfg.norm_eps, out=a)
+        qkv = ops.gemm(src, w["wqkv"], epilogue=ops.EPI_ROPE, positions=positions, rope_table=tab, rope_cols=2 * H)
+        lse = torch.empty((heads, T), device=dev, dtype=F32)
+        o = ops.attn_varlen_fwd(qkv, cu_seqlens, max_seqlen, heads, -1 if is_global else cfg.window_half, lse=lse)
+        x1 = ops.gemm(o, w["wo"], epilogue=ops.EPI_RESIDUAL, aux=x)
+        ops.layernorm(x1, w["mlp_norm"], cfg.norm_eps, out=a)
+        ug = torch.empty((T, 2 * I), device=dev, dtype=BF16)
+        h = ops.gemm(a, w["wi"], epilogue=ops.EPI_GEGLU_SAVE, c2=ug)
+        x2 = ops.gemm(h, w["wo2"], epilogue=ops.EPI_RESIDUAL, aux=x1)
+        layers.append(dict(x_in=x, qkv=qkv, o=o, lse=lse, x1=x1, ug=ug, window=-1 if is_global else cfg.window_half,
+                           tab=tab))
+        x = x2
+    last = ops.layernorm(x, pk["final_norm"], cfg.norm_eps)
+    saved = dict(layers=layers, x_final=x, cu=cu_seqlens, max_seqlen=max_seqlen, positions=positions)
+    return last, saved
+
+
+def encoder_backward(enc, saved, dlast: torch.Tensor, g: GradStore) -> torch.Tensor:
+    """dlast = gradient of the final-normed hidden states.  Accumulates every weight gradient of the
+    trunk into `g` and returns the gradient w.r.t. x0 (the normalised embeddings)."""
+    cfg, pk = enc.config, enc.packed()
+    T, H = dlast.shape
+    heads, I = cfg.num_attention_heads, int(cfg.intermediate_size)
+    dev = dlast.device
+    eps = cfg.norm_eps
+    cu, max_seqlen, positions = saved["cu"], saved["max_seqlen"], saved["positions"]
+
+    dx = ops.layernorm_bwd(saved["x_final"], dlast, pk["final_norm"], eps, dgamma=g(enc.final_norm.weight))
+    saved["x_final"] = None
+    # scratch reused by every layer
+    dh = torch.empty((T, I), device=dev, dtype=BF16)
+    dug = torch.empty((T, 2 * I), device=dev, dtype=BF16)
+    h = torch.empty((T, I), device=dev, dtype=BF16)
+    norm = torch.empty((T, H), device=dev, dtype=BF16)
+    dtmp = torch.empty((T, H), device=dev, dtype=BF16)
+    dqkv = torch.empty((T, 3 * H), device=dev, dtype=BF16)
+    delta = torch.empty((heads, T), device=dev, dtype=F32)
+    g_wi_il = torch.empty((2 * I, H), device=dev, dtype=F32)
+
+    for i in reversed(range(len(pk["layers"]))):
+        w, layer, s = pk["layers"][i], enc.layers[i], saved["layers"][i]
+        # ---- MLP:  x2 = x1 + (gelu(u) * gate) Wo2^T,  [u | gate] = LN_m(x1) Wi^T
+        _dgrad(dx, w["wo2"], out=dh)
+        ops.geglu_bwd(s["ug"], dh, dug=dug, h=h)
+        _wgrad(dx, h, g(layer.mlp.Wo.weight))
+        ops.layernorm(s["x1"], w["mlp_norm"], eps, out=norm)
+        g_wi_il.zero_()
+        _wgrad(dug, norm, g_wi_il)
+        g(layer.mlp.Wi.weight).add_(ops.deinterleave_wi(g_wi_il))
+        _dgrad(dug, w["wi"], out=dtmp)
+        ops.layernorm_bwd(s["x1"], dtmp, w["mlp_norm"], eps, dres=dx, dx=dx, dgamma=g(layer.mlp_norm.weight))
+        # ---- attention:  x1 = x_in + Attn(RoPE(LN_a(x_in) Wqkv^T)) Wo^T
+        _dgrad(dx, w["wo"], out=dtmp)  # d(attention output)
+        _wgrad(dx, s["o"], g(layer.attn.Wo.weight))
+        ops.attn_varlen_bwd(s["qkv"], s["o"], dtmp, s["lse"], cu, max_seqlen, heads, s["window"],
+                            positions=positions, rope_table=s["tab"], dqkv=dqkv, delta=delta)
+        if i == 0:
+            _wgrad(dqkv, s["x_in"], g(layer.attn.Wqkv.weight))
+            _dgrad(dqkv, w["wqkv"], out=dx, epilogue=ops.EPI_RESIDUAL, aux=dx)
+        else:
+            ops.layernorm(s["x_in"], w["attn_norm"], eps, out=norm)
+            _wgrad(dqkv, norm, g(layer.attn.Wqkv.weight))
+            _dgrad(dqkv, w["wqkv"], out=dtmp)
+            ops.layernorm_bwd(s["x_in"], dtmp, w["attn_norm"], eps, dres=dx, dx=dx,
+                              dgamma=g(layer.attn_norm.weight))
+        saved["layers"][i] = None  # release this layer's activations
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# audio encoder (conv front-end + trunk + 4:1 projector)
+
+def audio_forward(audio, input_features: torch.Tensor):
+    cfg, pk = audio.config, audio.packed()
+    B, _, Fr = input_features.shape
+    C = cfg.hidden_size
+    feats = input_features.float().contiguous()
+    a1 = ops.im2col_k3(feats, 1)
+    z1 = ops.gemm(a1, pk["w1"], epilogue=ops.EPI_BIAS, aux=pk["b1"])
+    y1 = ops.gelu_fwd(z1).view(B, Fr, C)
+    a2 = ops.im2col_k3(y1, 2)
+    del y1
+    z2 = ops.gemm(a2, pk["w2"], epilogue=ops.EPI_BIAS, aux=pk["b2"])
+    y2 = ops.gelu_fwd(z2)
+    T2 = Fr // 2
+    dev = feats.device
+    x0 = ops.layernorm(y2, audio.encoder.packed()["emb_norm"], cfg.norm_eps)
+    cu = torch.arange(0, B * T2 + 1, T2, device=dev, dtype=torch.int32)
+    pos = torch.remainder(torch.arange(B * T2, device=dev, dtype=torch.int32), T2).to(torch.int32)
+    last, enc_saved = encoder_forward(audio.encoder, x0, cu, T2, pos)
+    grouped = last.view(-1, cfg.projector_intermediate_size)
+    zp = ops.gemm(grouped, pk["p1"])
+    hp = ops.gelu_fwd(zp)
+    audio_embeds = ops.gemm(hp, pk["p2"])
+    saved = dict(a1=a1, z1=z1, a2=a2, z2=z2, y2=y2, enc=enc_saved, last=last, zp=zp, hp=hp, B=B, Fr=Fr)
+    return audio_embeds, last.view(B, T2, -1), saved
+
+
+def audio_backward(audio, saved, d_audio_embeds: torch.Tensor, g: GradStore) -> None:
+    cfg, pk = audio.config, audio.packed()
+    B, Fr, C = saved["B"], saved["Fr"], cfg.hidden_size
+    proj = audio.multi_modal_projector
+    _wgrad(d_audio_embeds, saved["hp"], g(proj.linear_2.weight))
+    dhp = _dgrad(d_audio_embeds, pk["p2"])
+    dzp = ops.gelu_bwd(saved["zp"], dhp)
+    grouped = saved["last"].view(-1, cfg.projector_intermediate_size)
+    _wgrad(dzp, grouped, g(proj.linear_1.weight))
+    dlast = _dgrad(dzp, pk["p1"]).view(-1, C)
+    dx0 = encoder_backward(audio.encoder, saved["enc"], dlast, g)
+    dy2 = ops.layernorm_bwd(saved["y2"], dx0, audio.encoder.packed()["emb_norm"], cfg.norm_eps,
+                            dgamma=g(audio.encoder.embeddings.norm.weight))
+    dz2 = ops.gelu_bwd(saved["z2"], dy2)
+    ops.colsum_f32(dz2, g(audio.conv2.bias))
+    g_w2p = torch.zeros((C, 3 * C), device=dz2.device, dtype=F32)
+    _wgrad(dz2, saved["a2"], g_w2p)
+    g(audio.conv2.weight).add_(g_w2p.view(C, 3, C).permute(0, 2, 1))  # (out, tap, in) -> (out, in, tap)
+    da2 = _dgrad(dz2, pk["w2"])
+    dz1 = ops.conv2_col2im_gelu_bwd(da2, saved["z1"].view(B, Fr, C)).view(B * Fr, C)
+    ops.colsum_f32(dz1, g(audio.conv1.bias))
+    _wgrad(dz1, saved["a1"], g(audio.conv1.weight).view(C, -1))
+
+
+# ------------------------------------------------------------------------------------------------
+# towers
+
+def beatmap_forward(tower, input_ids, input_features, attention_mask):
+    from .modeling_cm3p import _unpad
+    B, L = input_ids.shape
+    dev = input_ids.device
+    up = _unpad(attention_mask, B, L, dev)
+    ids_flat = input_ids.reshape(-1).contiguous()
+    audio_embeds = slot = audio_last = audio_saved = None
+    if input_features is not None:
+        audio_embeds, audio_last, audio_saved = audio_forward(tower.audio_encoder, input_features)
+        is_audio = ids_flat == tower.config.audio_token_id
+        running = torch.cumsum(is_audio, dim=0, dtype=torch.int32) - 1
+        slot = torch.where(is_audio, running, torch.full_like(running, -1))
+        slot = slot.index_select(0, up.src_index.long()).contiguous()
+    pk = tower.encoder.packed()
+    x0 = ops.embed_gather_ln(ids_flat, up.src_index, slot, pk["tok_emb"], audio_embeds, pk["emb_norm"],
+                             tower.config.norm_eps, rows=up.total)
+    last, enc_saved = encoder_forward(tower.encoder, x0, up.cu_seqlens, up.max_len, up.positions)
+    saved = dict(ids=ids_flat, up=up, slot=slot, audio_embeds=audio_embeds, audio=audio_saved, enc=enc_saved)
+    return last, up, audio_last, saved
+
+
+def beatmap_backward(tower, saved, dlast, g: GradStore) -> None:
+    enc, up = tower.encoder, saved["up"]
+    pk = enc.packed()
+    dx0 = encoder_backward(enc, saved["enc"], dlast, g)
+    d_audio = None
+    if saved["audio_embeds"] is not None:
+        d_audio = torch.zeros_like(saved["audio_embeds"])
+    ops.embed_gather_ln_bwd(saved["ids"], up.src_index, saved["slot"], pk["tok_emb"], saved["audio_embeds"],
+                            pk["emb_norm"], dx0, tower.config.norm_eps, d_tok_emb=g(enc.embeddings.tok_embeddings.weight),
+                            d_audio_embeds=d_audio, dgamma=g(enc.embeddings.norm.weight))
+    if d_audio is not None:
+        audio_backward(tower.audio_encoder, saved["audio"], d_audio, g)
+
+
+def metadata_forward(tower, metadata_ids, attention_mask):
+    from .modeling_cm3p import _unpad
+    S = metadata_ids.shape[-1]
+    ids = metadata_ids.reshape(-1, S).contiguous()
+    up = _unpad(attention_mask, ids.shape[0], S, ids.device)
+    pk = tower.encoder.packed()
+    ids_flat = ids.reshape(-1)
+    x0 = ops.embed_gather_ln(ids_flat, up.src_index, None, pk["tok_emb"], None, pk["emb_norm"], tower.config.norm_eps,
+                             rows=up.total)
+    last, enc_saved = encoder_forward(tower.encoder, x0, up.cu_seqlens, up.max_len, up.positions)
+    return last, up, dict(ids=ids_flat, up=up, enc=enc_saved)
+
+
+def metadata_backward(tower, saved, dlast, g: GradStore) -> None:
+    enc, up = tower.encoder, saved["up"]
+    pk = enc.packed()
+    dx0 = encoder_backward(enc, saved["enc"], dlast, g)
+    ops.embed_gather_ln_bwd(saved["ids"], up.src_index, None, pk["tok_emb"], None, pk["emb_norm"], dx0,
+                            tower.config.norm_eps, d_tok_emb=g(enc.embeddings.tok_embeddings.weight),
+                            d_audio_embeds=None, dgamma=g(enc.embeddings.norm.weight))
+
+
+# ------------------------------------------------------------------------------------------------
+# projection head + loss
+
+def head_forward(last, cu_seqlens, mean_pool: bool, proj_w):
+    pooled, proj, inv, emb32, emb16 = ops.pool_project_normalize(last, cu_seqlens, mean_pool, proj_w)
+    return emb32, emb16, dict(pooled=pooled, proj=proj, inv=inv, cu=cu_seqlens, mean_pool=mean_pool, T=last.shape[0],
+                              H=last.shape[1])
+
+
+def head_backward(saved, demb32: torch.Tensor, proj_w: torch.Tensor, g_proj: torch.Tensor) -> torch.Tensor:
+    """demb32 [B,P] fp32 (gradient of the normalised embeddings) -> dlast [T,H] bf16."""
+    dproj = ops.l2norm_bwd(saved["proj"], saved["inv"], demb32)
+    _wgrad(dproj, saved["pooled"], g_proj)
+    dpooled = _dgrad(dproj, proj_w)
+    dlast = torch.empty((saved["T"], saved["H"]), device=demb32.device, dtype=BF16)
+    ops.pool_bwd(dpooled, saved["cu"], saved["mean_pool"], dlast, accumulate=False)
+    return dlast
+
+
+class _TrainStep(torch.autograd.Function):
+    """loss = f(parameters): forward already ran (state in `st`), backward runs the explicit pass."""
+
+    @staticmethod
+    def forward(ctx, st, loss_value, *params):
+        ctx.st = st
+        ctx.n = len(params)
+        return loss_value.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        st = ctx.st
+        ctx.st = None
+        grads = st.backward(grad_out)
+        return (None, None, *grads)
+
+
+class _StepState:
+    def __init__(self, model, params):
+        self.model = model
+        self.params = params
+        self.saved = {}
+
+    def backward(self, grad_out: torch.Tensor):
+        model, sv = self.model, self.saved
+        self.saved = None
+        if sv is None:
+            raise RuntimeError("cm3p_b200: backward called twice on the same training step")
+        g = GradStore(list(model.parameters()))
+        dev = sv["S"].device
+        gout = grad_out.detach().to(device=dev, dtype=F32).reshape(1).contiguous()
+        dls = g(model.logit_scale).view(1)
+        dS = ops.clip_loss_bwd(sv["S"], sv["true_idx"], sv["row_lse"], sv["col_lse"], sv["V"], gout, dls)
+        scale = sv["scale"]
+        dme = ops.gemm(dS, sv["be16"], trans_b=True, epilogue=ops.EPI_SCALE_F32, scale=scale)
+        dbe = ops.gemm(dS, sv["me16"], trans_a=True, trans_b=True, epilogue=ops.EPI_SCALE_F32, scale=scale)
+        del dS
+        # metadata tower first (small), then the beatmap tower
+        dlast_m = head_backward(sv["mhead"], dme, sv["w_mp"], g(model.metadata_projection.weight))
+        metadata_backward(model.metadata_model, sv["meta"], dlast_m, g)
+        del dlast_m
+        dlast_b = head_backward(sv["bhead"], dbe, sv["w_bp"], g(model.beatmap_projection.weight))
+        beatmap_backward(model.beatmap_model, sv["beat"], dlast_b, g)
+        return [g(p).to(p.dtype) if p.requires_grad else None for p in self.params]
+
+
+def forward_with_grad(model, *, input_ids=None, input_features=None, metadata_ids=None, attention_mask=None,
+                      metadata_attention_mask=None, metadata_variation_classes=None, labels=None,
+                      return_loss=True, output_logits=False, **kwargs):
+    """Training-mode `CM3PModel.forward` (reference: cm3p/modeling_cm3p.py:849-1012 under autograd)."""
+    from .modeling_cm3p import (BaseModelOutputWithPooling, CM3PBeatmapModelOutput, CM3POutput, _out_dtype,
+                                _pack_linear, _repad, _require_cuda)
+    cfg = model.config
+    if input_ids is None or metadata_ids is None or not return_loss:
+        raise NotImplementedError(
+            "cm3p_b200 training path: the contrastive step needs input_ids, metadata_ids and return_loss=True; "
+            "call single-tower / no-loss forwards under torch.no_grad()")
+    if cfg.has_decoder_head and labels is not None:
+        raise NotImplementedError("cm3p_b200: the MLM auxiliary loss is not part of the explicit backward yet")
+    _require_cuda(input_ids, "input_ids")
+    odt = _out_dtype(model)
+    pad_outputs = getattr(cfg, "_attn_implementation", None) != "flash_attention_2"
+    params = [p for p in model.parameters()]
+    st = _StepState(model, params)
+    sv = st.saved
+
+    last_b, up_b, audio_last, sv["beat"] = beatmap_forward(model.beatmap_model, input_ids, input_features,
+                                                           attention_mask)
+    sv["w_bp"] = _pack_linear(model.beatmap_projection, model._wcache, "bp")
+    be32, be16, sv["bhead"] = head_forward(last_b, up_b.cu_seqlens, not cfg.beatmap_config.cls_embed, sv["w_bp"])
+    last_m, up_m, sv["meta"] = metadata_forward(model.metadata_model, metadata_ids, metadata_attention_mask)
+    sv["w_mp"] = _pack_linear(model.metadata_projection, model._wcache, "mp")
+    me32, me16, sv["mhead"] = head_forward(last_m, up_m.cu_seqlens, not cfg.metadata_config.cls_embed, sv["w_mp"])
+
+    scale = float(model.logit_scale.detach().float().exp())
+    S = ops.gemm(me16, be16, epilogue=ops.EPI_SCALE_F32, scale=scale)
+    Bb = be16.shape[0]
+    if metadata_ids.dim() == 3:
+        Bm, V = metadata_ids.shape[:2]
+        if metadata_variation_classes is None:
+            raise ValueError("When providing multiple metadata variations, metadata_variation_classes must be "
+                             "provided in order to compute loss correctly.")
+        true_idx = (metadata_variation_classes == 0).int().argmax(dim=1).to(torch.int32).contiguous()
+        logits_per_metadata = S.view(Bm, V, Bb)
+        logits_per_beatmap = logits_per_metadata.permute(2, 0, 1)
+    else:
+        Bm, V = metadata_ids.shape[0], 1
+        true_idx = torch.zeros(Bm, device=S.device, dtype=torch.int32)
+        logits_per_metadata, logits_per_beatmap = S, S.t()
+    if Bm != Bb:
+        raise ValueError(f"metadata batch {Bm} != beatmap batch {Bb}")
+    loss_val, row_lse, col_lse = ops.clip_loss_fwd(S, true_idx, V)
+    sv.update(S=S, true_idx=true_idx, row_lse=row_lse, col_lse=col_lse, V=V, scale=scale, be16=be16, me16=me16)
+
+    loss = _TrainStep.apply(st, loss_val.reshape(()), *params)
+
+    lead = tuple(metadata_ids.shape[:-1])
+    hidden_b = (_repad(last_b, up_b) if pad_outputs else last_b).to(odt)
+    hidden_m = (_repad(last_m, up_m).view(*metadata_ids.shape, -1) if pad_outputs else last_m).to(odt)
+    from .modeling_cm3p import CM3PAudioModelOutput
+    audio_out = None if audio_last is None else CM3PAudioModelOutput(last_hidden_state=audio_last)
+    return CM3POutput(
+        loss=loss, logits_per_beatmap=logits_per_beatmap, logits_per_metadata=logits_per_metadata,
+        metadata_embeds=me32.view(*lead, -1).to(odt), beatmap_embeds=be32.to(odt), logits=None,
+        metadata_model_output=BaseModelOutputWithPooling(
+            last_hidden_state=hidden_m, pooler_output=sv["mhead"]["pooled"].view(*lead, -1).to(odt)),
+        beatmap_model_output=CM3PBeatmapModelOutput(
+            last_hidden_state=hidden_b, pooler_output=sv["bhead"]["pooled"].to(odt), audio_model_output=audio_out))
