@@ -1,14 +1,18 @@
 """bench.py — headline benchmark of the CM3P hot path on B200 (contract: see the build brief).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload infer|train]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload all|infer|train]
 
 One "step" = one pass of the hot path over one batch of synthetic input per GPU.
 
-  workload infer (default; BASELINE.json configs[1]): base CM3P, bf16, batch 64 windows/GPU of 16 s
-      (L = 2000 padded, real lengths U{600..2000}, 200 audio tokens + 80x1600 log-mel per window),
-      beatmap tower + audio encoder + metadata tower (V = 1) + projections + logits,
+  workload infer (BASELINE.json configs[1], the headline line): base CM3P, bf16, batch 64 windows/GPU
+      of 16 s (L = 2000 padded, real lengths U{600..2000}, 200 audio tokens + 80x1600 log-mel per
+      window), beatmap tower + audio encoder + metadata tower (V = 1) + projections + logits,
       `return_loss=False`  ->  beatmap embeds/s.
-  workload train (BASELINE.json configs[2]): the contrastive train step -> pairs/s.
+  workload train (BASELINE.json configs[2]): the contrastive train step, fp32 master weights / bf16
+      compute, batch 256 windows/GPU, V = 8 metadata variations, forward + explicit backward + ONE
+      gradient all-reduce (NCCL) when N > 1; optimizer step excluded -> pairs/s.
+      `--global-negatives` switches to configs[3] semantics (embedding all-gather, global loss).
+  workload all (default): the infer line with the train result attached under the key "train".
 
 Prints ONE JSON line on rank 0.  `value` is measured with inputs resident in HBM; `e2e` goes through
 the public `CM3PModel.__call__` with pinned host inputs (H2D inside the timed region) and a D2H
@@ -37,6 +41,7 @@ from cm3p_b200.configuration_cm3p import CM3PConfig, base_config_dict  # noqa: E
 from cm3p_b200.synthetic import synthetic_batch, synthetic_state_dict  # noqa: E402
 
 BATCH_PER_GPU = {"infer": 64, "train": 256}
+TRAIN_STEPS_CAP = 5  # a train step is ~0.6 s of device time; keep the default run short
 SEQ_LEN = 2000
 MIN_LEN = 600
 TRAIN_VARIATIONS = 8
@@ -133,42 +138,51 @@ def _algorithmic_flops_infer(cfg: CM3PConfig, batch: dict) -> float:
     return float(total)
 
 
-def _make_batch(cfg, workload, rank):
-    B = BATCH_PER_GPU[workload]
+def _make_batch(cfg, workload, rank, batch):
     V = 1 if workload == "infer" else TRAIN_VARIATIONS
-    return synthetic_batch(cfg, batch=B, seq_len=SEQ_LEN, variations=V, seed=1 + rank, min_len=MIN_LEN)
+    return synthetic_batch(cfg, batch=batch, seq_len=SEQ_LEN, variations=V, seed=1 + rank, min_len=MIN_LEN)
 
 
-def run_ours(args) -> dict:
-    import torch.distributed as dist
+WORKLOAD_TEXT = {
+    "infer": "BASELINE.json configs[1]: CM3P base inference, beatmap tower + audio encoder + metadata tower (V=1) "
+             "bf16, batch {B} synthetic 16 s windows per GPU (L=2000 padded, real lengths U{{600..2000}}), "
+             "return_loss=False",
+    "train": "BASELINE.json configs[2]: CM3P base contrastive train step (audio fusion + V=8 metadata variations), "
+             "fp32 master weights / bf16 compute, batch {B} synthetic 16 s windows per GPU (L=2000 padded, real "
+             "lengths U{{600..2000}}), forward + backward + gradient all-reduce, {neg} negatives; optimizer step "
+             "excluded",
+}
 
+
+def _bench_workload(workload, args, dist, dev, world, rank, local_rank) -> dict | None:
+    """Times one workload on this rank's GPU; returns the result dict on rank 0."""
+    from cm3p_b200 import distributed as dp_utils
     from cm3p_b200 import ops
     from cm3p_b200.modeling_cm3p import CM3PModel
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py (impl=ours) needs a CUDA sm_100a device; there is no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    workload = args.workload
-    if workload == "train":
-        raise SystemExit("bench.py: the train workload is enabled once the backward kernels land")
+    train = workload == "train"
+    B = args.train_batch if train else BATCH_PER_GPU["infer"]
     cfg = CM3PConfig(attn_implementation="flash_attention_2", **copy.deepcopy(base_config_dict()))
     model = CM3PModel(cfg)
     model.load_state_dict(synthetic_state_dict(cfg, seed=0), strict=True)
-    model = model.to(dev).to(torch.bfloat16).eval()
+    model = model.to(dev)
+    if train:
+        model.train()
+        if world > 1:
+            dp_utils.enable_data_parallel(model, global_negatives=args.global_negatives)
+    else:
+        model = model.to(torch.bfloat16).eval()
 
-    host = _make_batch(cfg, workload, rank)
+    host = _make_batch(cfg, workload, rank, B)
     pinned = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
-    B = BATCH_PER_GPU[workload]
 
     def step(feed):
+        if train:
+            model.zero_grad(set_to_none=True)
+            out = model(**feed)
+            out.loss.backward()  # explicit CUDA backward; includes the gradient all-reduce when world > 1
+            return out
         with torch.no_grad():
             return model(**feed, return_loss=False)
 
@@ -190,35 +204,37 @@ def run_ours(args) -> dict:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) / steps
 
-    # ---- device-resident timing (value)
+    steps = min(args.steps, TRAIN_STEPS_CAP) if (train and args.workload == "all") else args.steps
     n_warm = args.warmup if args.quick else max(args.warmup, 3)
+    torch.cuda.reset_peak_memory_stats()
     for _ in range(n_warm):
         step(resident)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = ops.LAUNCH_COUNT
-    ms_step = timed(lambda: step(resident), args.steps)
-    launches = (ops.LAUNCH_COUNT - launches0) // args.steps
+    ms_step = timed(lambda: step(resident), steps)
+    launches = (ops.LAUNCH_COUNT - launches0) // steps
     clocks = sampler.stop() if rank == 0 else None
     if args.quick:
-        if world > 1:
-            dist.destroy_process_group()
-        return {"quick": True, "ms_per_step": round(ms_step, 3), "gpu_launches": int(launches)} if rank == 0 else None
+        return {"quick": True, "workload": workload, "ms_per_step": round(ms_step, 3),
+                "gpu_launches": int(launches)} if rank == 0 else None
 
-    # ---- end-to-end through the public API with pinned host inputs
+    # ---- end-to-end through the public API with pinned host inputs and a D2H read of the result
     def e2e_step():
         feed = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
         out = step(feed)
-        return out.beatmap_embeds.float().cpu()  # D2H read of the result (synchronises)
+        if train:
+            return out.loss.detach().float().cpu()
+        return out.beatmap_embeds.float().cpu()
 
     for _ in range(2):
         e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    ms_e2e = timed(e2e_step, steps)
     h2d = sum(v.numel() * v.element_size() for v in pinned.values())
-    d2h = B * cfg.projection_dim * 4
+    d2h = 4 if train else B * cfg.projection_dim * 4
 
-    # ---- roofline of the dominant kernel (the tcgen05 GEMM), timed live with CUDA events around
+    # ---- roofline of the dominant kernel family (the tcgen05 GEMM), timed live with CUDA events around
     #      every GEMM launch of one extra step on the launching stream
     gemm_events = []
     orig_gemm = ops.gemm
@@ -233,38 +249,36 @@ def run_ours(args) -> dict:
         gemm_events.append((e0, e1, 2.0 * M * N * K))
         return out
 
-    import cm3p_b200.modeling_cm3p as mod
     ops.gemm = timed_gemm
     try:
         step(resident)
         torch.cuda.synchronize()
     finally:
         ops.gemm = orig_gemm
-    assert mod.ops.gemm is orig_gemm
     gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in gemm_events)
     gemm_flops = sum(f for _, _, f in gemm_events)
     peaks = _peaks()
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
 
-    total_flops = _algorithmic_flops_infer(cfg, host)
+    total_flops = _algorithmic_flops_infer(cfg, host) * (3.0 if train else 1.0)
     metric, unit = METRIC[workload]
+    neg = "global (embedding all-gather)" if (train and args.global_negatives and world > 1) else "local (per-rank)"
     result = {
         "metric": metric, "value": round(world * B / (ms_step * 1e-3), 2), "unit": unit, "n_gpus": world,
-        "steps": args.steps, "warmup": n_warm, "ms_per_step": round(ms_step, 3),
+        "steps": steps, "warmup": n_warm, "ms_per_step": round(ms_step, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "impl": "ours",
         "config": {
-            "workload": "BASELINE.json configs[1]: CM3P base inference, beatmap tower + audio encoder + metadata "
-                        "tower (V=1) bf16, batch 64 synthetic 16 s windows per GPU (L=2000 padded, real lengths "
-                        "U{600..2000}), return_loss=False",
+            "workload": WORKLOAD_TEXT[workload].format(B=B, neg=neg),
             "batch_per_gpu": B, "seq_len": SEQ_LEN, "real_tokens_per_step": int(host["attention_mask"].sum()),
             "weights": "random init (seeded), 136.9 M params",
-            "l2": "per-step working set (~1.5 GB of activations) exceeds the 126 MB L2; no explicit flush",
+            "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2; no explicit flush",
         },
         "e2e": {"value": round(world * B / (ms_e2e * 1e-3), 2), "unit": unit, "ms_per_step": round(ms_e2e, 3),
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "model_tflops": round(total_flops / (ms_step * 1e-3) / 1e12, 1),
+        "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
         "roofline": {"kernel": "gemm_bf16_sm100_kernel (all epilogues)", "bound": "tensor",
                      "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
                      "frac": round(achieved / peaks["tflops"], 4), "traffic": None,
@@ -274,12 +288,53 @@ def run_ours(args) -> dict:
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         result["cpu_baseline"] = cpu_baseline(cfg, workload, sample_batch=2, reps=1)
-    if world > 1:
-        dist.destroy_process_group()
+    del model, resident, pinned
+    torch.cuda.empty_cache()
     return result if rank == 0 else None
 
 
+def run_ours(args) -> dict | None:
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA sm_100a device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    try:
+        order = ["infer", "train"] if args.workload == "all" else [args.workload]
+        results = {w: _bench_workload(w, args, dist, dev, world, rank, local_rank) for w in order}
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+    if rank != 0:
+        return None
+    head = results[order[0]]
+    if len(order) > 1:
+        head["train"] = results["train"]
+    return head
+
+
 # ------------------------------------------------------------------------------------------------
+def _cpu_run(cfg, workload, sample_batch, sd):
+    """One pass of the reference's algorithm (CPU oracle) over `sample_batch` windows; returns seconds."""
+    from oracle import cm3p_oracle as O
+
+    V = 1 if workload == "infer" else TRAIN_VARIATIONS
+    batch = synthetic_batch(cfg, batch=sample_batch, seq_len=SEQ_LEN, variations=V, seed=1, min_len=MIN_LEN)
+    t0 = time.perf_counter()
+    if workload == "infer":
+        with torch.no_grad():
+            O.model_forward(sd, cfg, **batch, return_loss=False)
+    else:
+        O.forward_backward(sd, cfg, batch)
+    return time.perf_counter() - t0
+
+
 def cpu_baseline(cfg, workload, sample_batch, reps):
     """The reference's algorithm (CPU oracle, fp32, torch SDPA like the reference's `sdpa` path) on
     the host cores, on a bounded sample of the same workload."""
@@ -288,57 +343,57 @@ def cpu_baseline(cfg, workload, sample_batch, reps):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = synthetic_state_dict(cfg, seed=0)
-    V = 1 if workload == "infer" else TRAIN_VARIATIONS
-    batch = synthetic_batch(cfg, batch=sample_batch, seq_len=SEQ_LEN, variations=V, seed=1, min_len=MIN_LEN)
-    best = float("inf")
     with torch.no_grad():
         warm = synthetic_batch(cfg, batch=1, seq_len=256, variations=1, seed=5, min_len=220)
         O.model_forward(sd, cfg, **warm, return_loss=False)
-        for _ in range(reps):
-            t0 = time.perf_counter()
-            O.model_forward(sd, cfg, **batch, return_loss=False)
-            best = min(best, time.perf_counter() - t0)
+    best = min(_cpu_run(cfg, workload, sample_batch, sd) for _ in range(reps))
     metric, unit = METRIC[workload]
+    what = "forward" if workload == "infer" else "forward + autograd backward"
     return {"value": round(sample_batch / best, 4), "unit": unit, "cores": cores, "kind": "port",
-            "sample": f"{sample_batch} windows of the same workload (L={SEQ_LEN}), fp32, torch CPU SDPA, "
+            "sample": f"{sample_batch} windows of the same workload (L={SEQ_LEN}), {what}, fp32, torch CPU SDPA, "
                       f"{cores} threads, best of {reps}; {best:.2f} s"}
 
 
-def run_reference(args) -> dict | None:
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return None
-    from oracle import cm3p_oracle as O
-
-    workload = args.workload
+def _reference_workload(workload, args) -> dict:
     cfg = CM3PConfig(**copy.deepcopy(base_config_dict()))
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = synthetic_state_dict(cfg, seed=0)
     sample = 2
-    V = 1 if workload == "infer" else TRAIN_VARIATIONS
-    batch = synthetic_batch(cfg, batch=sample, seq_len=SEQ_LEN, variations=V, seed=1, min_len=MIN_LEN)
     times = []
-    with torch.no_grad():
-        for i in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            O.model_forward(sd, cfg, **batch, return_loss=False)
-            if i >= args.warmup:
-                times.append(time.perf_counter() - t0)
+    for i in range(args.warmup + args.steps):
+        dt = _cpu_run(cfg, workload, sample, sd)
+        if i >= args.warmup:
+            times.append(dt)
     ms = 1e3 * sum(times) / len(times)
     metric, unit = METRIC[workload]
     value = round(sample / (ms * 1e-3), 4)
+    what = "forward" if workload == "infer" else "forward + autograd backward"
     return {
         "impl": "reference", "metric": metric, "value": value, "unit": unit,
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE.json configs[1] (same as impl=ours), CPU: each step = a bounded sample of "
-                               f"{sample} windows", "seq_len": SEQ_LEN},
+        "config": {"workload": WORKLOAD_TEXT[workload].format(B=sample, neg="local (per-rank)")
+                   + f" -- CPU arm: each step = a bounded sample of {sample} windows, {what}", "seq_len": SEQ_LEN},
         "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port",
-                         "sample": f"{sample} windows/step (L={SEQ_LEN}), fp32, torch CPU SDPA, {cores} threads"},
+                         "sample": f"{sample} windows/step (L={SEQ_LEN}), {what}, fp32, torch CPU SDPA, "
+                                   f"{cores} threads"},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+
+
+def run_reference(args) -> dict | None:
+    """The reference's own CPU implementation of the path (oracle port: the reference is Python and does
+    not travel to the GPU box) on the host cores.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return None
+    order = ["infer", "train"] if args.workload == "all" else [args.workload]
+    res = {w: _reference_workload(w, args) for w in order}
+    head = res[order[0]]
+    if len(order) > 1:
+        head["train"] = res["train"]
+    return head
 
 
 def main():
@@ -347,7 +402,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["infer", "train"], default="infer")
+    ap.add_argument("--workload", choices=["all", "infer", "train"], default="all")
+    ap.add_argument("--train-batch", type=int, default=BATCH_PER_GPU["train"], help="train windows per GPU")
+    ap.add_argument("--global-negatives", action="store_true",
+                    help="train: all-gather embeddings and use the global loss (BASELINE.json configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true",
                     help="profiling aid: only the device-resident timed loop (no e2e / roofline / CPU legs)")

@@ -54,8 +54,8 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 // given, is the gradient that reached the same x through the residual connection and is added.
 // GATHER variant = embedding layer: the row is re-gathered exactly as in embed_gather_ln_kernel and
 // dx is scattered: audio rows -> d_audio[slot] (unique), token rows -> atomic add into d_tok[id].
-template <bool GATHER>
-__global__ void __launch_bounds__(256)
+template <bool GATHER, int NV>
+__global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                      const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dres,
                      __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, int64_t rows, int H, float eps,
@@ -64,19 +64,17 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
                      const int32_t* __restrict__ audio_slot, const __nv_bfloat16* __restrict__ tok_emb,
                      const __nv_bfloat16* __restrict__ audio_embeds, float* __restrict__ d_tok,
                      __nv_bfloat16* __restrict__ d_audio, int vocab) {
-  __shared__ float red[8][MAXV * 256];
+  // NV = vectors (8 columns) per lane: H <= NV * 256.  gamma is re-read per row (L1-resident) so that
+  // two CTAs fit the register file; only the running dgamma partial sums live across rows.
+  __shared__ float red[8][NV * 256];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nvec = H >> 3;
-  float gam[MAXV][8], dg[MAXV][8];
+  float dg[NV][8];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int vi = lane + i * 32;
+  for (int i = 0; i < NV; ++i) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      gam[i][k] = (vi < nvec) ? gamma[vi * 8 + k] : 0.f;
-      dg[i][k] = 0.f;
-    }
+    for (int k = 0; k < 8; ++k) dg[i][k] = 0.f;
   }
   const float invH = 1.f / H;
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp; row < rows; row += static_cast<int64_t>(gridDim.x) * 8) {
@@ -97,10 +95,10 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
     } else {
       src = x + row * H;
     }
-    float v[MAXV][8], g[MAXV][8];
+    float v[NV][8], g[NV][8];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int vi = lane + i * 32;
       if (vi < nvec) {
         unpack8(*reinterpret_cast<const uint4*>(src + vi * 8), v[i]);
@@ -112,7 +110,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
     const float mean = warp_sum(s) * invH;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i)
+    for (int i = 0; i < NV; ++i)
       if (lane + i * 32 < nvec) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -123,13 +121,16 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
     const float rstd = rsqrtf(warp_sum(q) * invH + eps);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i)
+    for (int i = 0; i < NV; ++i)
       if (lane + i * 32 < nvec) {
+        float gam[8];
+        *reinterpret_cast<float4*>(gam) = __ldg(reinterpret_cast<const float4*>(gamma + (lane + i * 32) * 8));
+        *reinterpret_cast<float4*>(gam + 4) = __ldg(reinterpret_cast<const float4*>(gamma + (lane + i * 32) * 8 + 4));
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float xh = (v[i][k] - mean) * rstd;
           dg[i][k] += g[i][k] * xh;
-          const float gg = g[i][k] * gam[i][k];
+          const float gg = g[i][k] * gam[k];
           v[i][k] = xh;
           g[i][k] = gg;
           s1 += gg;
@@ -139,7 +140,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
     s1 = warp_sum(s1) * invH;
     s2 = warp_sum(s2) * invH;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int vi = lane + i * 32;
       if (vi < nvec) {
         float o[8];
@@ -168,10 +169,10 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
   if (dgamma == nullptr) return;
   // per-CTA reduction of the gamma gradient, then one atomic per column
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int vi = lane + i * 32;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) red[warp][(vi * 8 + k) % (MAXV * 256)] = dg[i][k];
+    for (int k = 0; k < 8; ++k) red[warp][vi * 8 + k] = dg[i][k];
   }
   __syncthreads();
   for (int c = threadIdx.x; c < H; c += blockDim.x) {
@@ -403,11 +404,17 @@ int layernorm_bwd(const void* x, const void* dy, const float* gamma, const void*
                MAXV * 256);
   if (rows == 0) return kOk;
   const int64_t want = (rows + 7) / 8;
-  const int grid = static_cast<int>(want < 4LL * num_sms() ? want : 4LL * num_sms());
-  layernorm_bwd_kernel<false><<<grid, 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), gamma,
-      reinterpret_cast<const __nv_bfloat16*>(dres), reinterpret_cast<__nv_bfloat16*>(dx), dgamma, rows, H, eps, nullptr,
-      nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+  const int grid = static_cast<int>(want < 8LL * num_sms() ? want : 8LL * num_sms());
+#define CM3P_LN_BWD(NV)                                                                                             \
+  layernorm_bwd_kernel<false, NV><<<grid, 256, 0, stream>>>(                                                        \
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), gamma,                 \
+      reinterpret_cast<const __nv_bfloat16*>(dres), reinterpret_cast<__nv_bfloat16*>(dx), dgamma, rows, H, eps,     \
+      nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0)
+  if (H <= 256) CM3P_LN_BWD(1);
+  else if (H <= 512) CM3P_LN_BWD(2);
+  else if (H <= 768) CM3P_LN_BWD(3);
+  else CM3P_LN_BWD(4);
+#undef CM3P_LN_BWD
   CM3P_CUDA_TRY(cudaGetLastError());
   return kOk;
 }
@@ -420,11 +427,18 @@ int embed_gather_ln_bwd(const int64_t* ids, const int32_t* src_index, const int3
                MAXV * 256);
   if (rows == 0) return kOk;
   const int64_t want = (rows + 7) / 8;
-  const int grid = static_cast<int>(want < 4LL * num_sms() ? want : 4LL * num_sms());
-  layernorm_bwd_kernel<true><<<grid, 256, 0, stream>>>(
-      nullptr, reinterpret_cast<const __nv_bfloat16*>(dy), gamma, nullptr, nullptr, dgamma, rows, H, eps, ids, src_index,
-      audio_slot, reinterpret_cast<const __nv_bfloat16*>(tok_emb), reinterpret_cast<const __nv_bfloat16*>(audio_embeds),
-      d_tok_emb, reinterpret_cast<__nv_bfloat16*>(d_audio_embeds), vocab);
+  const int grid = static_cast<int>(want < 8LL * num_sms() ? want : 8LL * num_sms());
+#define CM3P_LN_BWD(NV)                                                                                            \
+  layernorm_bwd_kernel<true, NV><<<grid, 256, 0, stream>>>(                                                        \
+      nullptr, reinterpret_cast<const __nv_bfloat16*>(dy), gamma, nullptr, nullptr, dgamma, rows, H, eps, ids,     \
+      src_index, audio_slot, reinterpret_cast<const __nv_bfloat16*>(tok_emb),                                      \
+      reinterpret_cast<const __nv_bfloat16*>(audio_embeds), d_tok_emb,                                             \
+      reinterpret_cast<__nv_bfloat16*>(d_audio_embeds), vocab)
+  if (H <= 256) CM3P_LN_BWD(1);
+  else if (H <= 512) CM3P_LN_BWD(2);
+  else if (H <= 768) CM3P_LN_BWD(3);
+  else CM3P_LN_BWD(4);
+#undef CM3P_LN_BWD
   CM3P_CUDA_TRY(cudaGetLastError());
   return kOk;
 }

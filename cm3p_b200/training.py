@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import torch
 
+from . import distributed as dp_utils
 from . import ops
 
 BF16, F32 = torch.bfloat16, torch.float32
@@ -308,12 +309,22 @@ class _StepState:
         dme = ops.gemm(dS, sv["be16"], trans_b=True, epilogue=ops.EPI_SCALE_F32, scale=scale)
         dbe = ops.gemm(dS, sv["me16"], trans_a=True, trans_b=True, epilogue=ops.EPI_SCALE_F32, scale=scale)
         del dS
+        dp = sv["dp"]
+        if dp is not None and dp.global_negatives:
+            # every rank holds d(global loss)/d(all embeddings); its own rows are its row block
+            dme = dp_utils.local_rows(dme, dp).contiguous()
+            dbe = dp_utils.local_rows(dbe, dp).contiguous()
         # metadata tower first (small), then the beatmap tower
         dlast_m = head_backward(sv["mhead"], dme, sv["w_mp"], g(model.metadata_projection.weight))
         metadata_backward(model.metadata_model, sv["meta"], dlast_m, g)
         del dlast_m
         dlast_b = head_backward(sv["bhead"], dbe, sv["w_bp"], g(model.beatmap_projection.weight))
         beatmap_backward(model.beatmap_model, sv["beat"], dlast_b, g)
+        if dp is not None:
+            if dp.global_negatives:
+                # every rank evaluated the full loss, so d(logit_scale) is already complete on each rank
+                g(model.logit_scale).div_(dp.world_size)
+            dp_utils.reduce_gradients(g.flat, dp)  # ONE all-reduce for every parameter gradient
         return [g(p).to(p.dtype) if p.requires_grad else None for p in self.params]
 
 
@@ -346,22 +357,31 @@ def forward_with_grad(model, *, input_ids=None, input_features=None, metadata_id
     me32, me16, sv["mhead"] = head_forward(last_m, up_m.cu_seqlens, not cfg.metadata_config.cls_embed, sv["w_mp"])
 
     scale = float(model.logit_scale.detach().float().exp())
-    S = ops.gemm(me16, be16, epilogue=ops.EPI_SCALE_F32, scale=scale)
-    Bb = be16.shape[0]
     if metadata_ids.dim() == 3:
         Bm, V = metadata_ids.shape[:2]
         if metadata_variation_classes is None:
             raise ValueError("When providing multiple metadata variations, metadata_variation_classes must be "
                              "provided in order to compute loss correctly.")
         true_idx = (metadata_variation_classes == 0).int().argmax(dim=1).to(torch.int32).contiguous()
+    else:
+        Bm, V = metadata_ids.shape[0], 1
+        true_idx = torch.zeros(Bm, device=be16.device, dtype=torch.int32)
+    if Bm != be16.shape[0]:
+        raise ValueError(f"metadata batch {Bm} != beatmap batch {be16.shape[0]}")
+    dp = getattr(model, "_dp", None)
+    sv["dp"] = dp
+    if dp is not None and dp.global_negatives and dp.world_size > 1:
+        # global negatives: all-gather the normalised embeddings (rank-major == concatenated batch order)
+        be16, me16 = dp_utils.all_gather_rows(be16, dp), dp_utils.all_gather_rows(me16, dp)
+        true_idx = dp_utils.all_gather_rows(true_idx, dp)
+        Bm = Bm * dp.world_size
+    S = ops.gemm(me16, be16, epilogue=ops.EPI_SCALE_F32, scale=scale)
+    Bb = be16.shape[0]
+    if metadata_ids.dim() == 3:
         logits_per_metadata = S.view(Bm, V, Bb)
         logits_per_beatmap = logits_per_metadata.permute(2, 0, 1)
     else:
-        Bm, V = metadata_ids.shape[0], 1
-        true_idx = torch.zeros(Bm, device=S.device, dtype=torch.int32)
         logits_per_metadata, logits_per_beatmap = S, S.t()
-    if Bm != Bb:
-        raise ValueError(f"metadata batch {Bm} != beatmap batch {Bb}")
     loss_val, row_lse, col_lse = ops.clip_loss_fwd(S, true_idx, V)
     sv.update(S=S, true_idx=true_idx, row_lse=row_lse, col_lse=col_lse, V=V, scale=scale, be16=be16, me16=me16)
 
