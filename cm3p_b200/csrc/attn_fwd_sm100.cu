@@ -18,6 +18,7 @@
 //        5 = MMA issuer.
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "attn.h"
 #include "common.h"
@@ -281,6 +282,294 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params 
   }
 }
 
+
+// ================================================================================================
+// v2: one CTA = 256 queries (two 128-row Q tiles A and B), one CTA per SM, 10 warps:
+//   warps 0-3 softmax group A, warps 4-7 softmax group B (thread <-> query row <-> TMEM lane),
+//   warp 8 TMA producer (+ TMEM alloc), warp 9 MMA issuer.
+// K/V tiles (128 rows) stream through a 3-stage ring shared by both Q tiles.  The two tiles
+// ping-pong on the tensor core: while group A runs exp on S_A(u+1), the MMA pipe executes PV_B(u)
+// and S_B(u+1), and vice versa.  O_A / O_B stay in TMEM for the whole KV loop (tcgen05.mma
+// accumulate); the running maximum is only raised when it grows by more than 2^8 (then the owning
+// warp rescales its 32 O rows in TMEM with tcgen05.ld/st), so the common iteration is: one
+// TMEM read of the 128 scores, max, exp2, bf16 pack into swizzled smem, one mbarrier arrive.
+// Masking (-inf) is only applied on tiles that need it (sequence tail, window band).
+// TMEM columns: S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384).
+namespace v2 {
+
+constexpr int KV_STAGES2 = 3;
+constexpr int THREADS2 = 384;  // 3 warpgroups: softmax A, softmax B, {TMA, MMA, 2 idle warps}
+constexpr int SMEM_TILES2 = 2 * Q_BYTES + KV_STAGES2 * 2 * KV_TILE_BYTES + 2 * P_BYTES;  // 32 + 96 + 64 = 192 KB
+constexpr int SMEM_BYTES2 = SMEM_TILES2 + 256;
+constexpr uint32_t TM_S = 0, TM_O = 256;  // + 128 * x for S, + 64 * x for O
+constexpr float RESCALE_LOG2 = 8.0f;
+
+__global__ void __launch_bounds__(THREADS2, 1)
+attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int seq = blockIdx.z, head = blockIdx.y;
+  const int seq_start = p.cu_seqlens[seq];
+  const int len = p.cu_seqlens[seq + 1] - seq_start;
+  const int q0 = blockIdx.x * 2 * BQ;
+  if (q0 >= len) return;
+  const bool act_b = q0 + BQ < len;
+
+  uint8_t* smem_q = smem;                                   // [2][16 KB]
+  uint8_t* smem_k = smem + 2 * Q_BYTES;                     // [3][16 KB]
+  uint8_t* smem_v = smem_k + KV_STAGES2 * KV_TILE_BYTES;    // [3][16 KB]
+  uint8_t* smem_p = smem_v + KV_STAGES2 * KV_TILE_BYTES;    // [2][32 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_TILES2);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;   // [3]
+  uint64_t* kv_empty = bars + 4;  // [3]
+  uint64_t* s_full = bars + 7;    // [2]
+  uint64_t* p_full = bars + 9;    // [2] 128 arrivals each
+  uint64_t* o_full = bars + 11;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
+
+  // KV stream: tiles u = 0..U-1 at sequence rows kv_base + 128 u; Q tile x consumes u in [lo[x], hi[x])
+  int kv_base = 0;
+  if (p.window >= 0) kv_base = max(0, q0 - p.window);
+  auto tile_range = [&](int qx, bool active, int& lo_out, int& hi_out) {
+    int first = 0, last = len - 1;
+    if (p.window >= 0) {
+      first = max(0, qx - p.window);
+      last = min(len - 1, qx + BQ - 1 + p.window);
+    }
+    lo_out = (first - kv_base) / BKV;
+    hi_out = active ? (last - kv_base) / BKV + 1 : lo_out;
+  };
+  int lo0, hi0, lo1, hi1;
+  tile_range(q0, true, lo0, hi0);
+  tile_range(q0 + BQ, act_b, lo1, hi1);
+  const int U = max(hi0, hi1);
+
+  if (warp == 9 && lane == 0) {
+    ptx::mbar_init(q_full, 1);
+    for (int s = 0; s < KV_STAGES2; ++s) {
+      ptx::mbar_init(&kv_full[s], 1);
+      ptx::mbar_init(&kv_empty[s], 1);
+    }
+    for (int x = 0; x < 2; ++x) {
+      ptx::mbar_init(&s_full[x], 1);
+      ptx::mbar_init(&p_full[x], 128);
+      ptx::mbar_init(&o_full[x], 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 8) {
+    if (lane == 0) ptx::prefetch_tmap(&tma_qkv);
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // 12 warps x 168 registers at launch; the data-movement warpgroup hands registers to the softmax ones
+  if (warp >= 8) {
+    ptx::setmaxnreg_dec<96>();
+    if (warp == 8 && lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      const int col_q = head * D, col_k = p.hidden + head * D, col_v = 2 * p.hidden + head * D;
+      ptx::mbar_arrive_expect_tx(q_full, 2 * Q_BYTES);
+      ptx::tma_load_2d(smem_q, &tma_qkv, q_full, col_q, seq_start + q0);
+      ptx::tma_load_2d(smem_q + Q_BYTES, &tma_qkv, q_full, col_q, seq_start + q0 + BQ);
+      for (int u = 0; u < U; ++u) {
+        const int s = u % KV_STAGES2;
+        ptx::mbar_wait(&kv_empty[s], ((u / KV_STAGES2) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&kv_full[s], 2 * KV_TILE_BYTES);
+        const int row = seq_start + kv_base + u * BKV;
+        ptx::tma_load_2d(smem_k + s * KV_TILE_BYTES, &tma_qkv, &kv_full[s], col_k, row);
+        ptx::tma_load_2d(smem_v + s * KV_TILE_BYTES, &tma_qkv, &kv_full[s], col_v, row);
+      }
+    } else if (warp == 9 && lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer
+      const uint32_t idesc_s = ptx::umma_idesc_bf16(BQ, BKV, 0, 0);
+      const uint32_t idesc_o = ptx::umma_idesc_bf16(BQ, D, 0, 1);  // V is MN-major
+      auto issue_s = [&](int x, int u) {
+        const int s = u % KV_STAGES2;
+        ptx::mbar_wait(&kv_full[s], (u / KV_STAGES2) & 1);
+        ptx::tc_fence_after();
+        const uint32_t q_addr = ptx::smem_u32(smem_q + x * Q_BYTES);
+        const uint32_t k_addr = ptx::smem_u32(smem_k + s * KV_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          ptx::umma_bf16(tmem_base + TM_S + x * 128, ptx::umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                         ptx::umma_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+        ptx::umma_commit(&s_full[x]);
+      };
+      int j0 = 0, j1 = 0;
+      ptx::mbar_wait(q_full, 0);
+      if (hi0 > lo0) issue_s(0, lo0);
+      if (hi1 > lo1) issue_s(1, lo1);
+      for (int u = 0; u < U; ++u) {
+        const int s = u % KV_STAGES2;
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          const int lo_x = x ? lo1 : lo0, hi_x = x ? hi1 : hi0;
+          int& jx = x ? j1 : j0;
+          if (u < lo_x || u >= hi_x) continue;
+          ptx::mbar_wait(&p_full[x], jx & 1);  // P_x(u) in smem, S_x(u) consumed, O_x rescaled if needed
+          ptx::tc_fence_after();
+          const uint32_t p_addr = ptx::smem_u32(smem_p + x * P_BYTES);
+          const uint32_t v_addr = ptx::smem_u32(smem_v + s * KV_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k)
+            ptx::umma_bf16(tmem_base + TM_O + x * 64,
+                           ptx::umma_smem_desc_sw128(p_addr + (k >> 2) * (BQ * 128) + (k & 3) * 32, 16, 1024),
+                           ptx::umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_o,
+                           (jx | k) != 0 ? 1u : 0u);
+          ++jx;
+          // S of the next tile goes in behind this PV: its commit also tells group x that the PV has
+          // retired (P buffer reusable, O stable for a rescale).
+          if (u + 1 < hi_x) issue_s(x, u + 1);
+          else ptx::umma_commit(&o_full[x]);
+        }
+        ptx::umma_commit(&kv_empty[s]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax groups
+    ptx::setmaxnreg_inc<200>();
+    const int x = warp >> 2;            // 0 = A, 1 = B
+    const int r = threadIdx.x & 127;    // query row inside the tile == TMEM lane
+    const int qi = q0 + x * BQ + r;
+    const bool valid = qi < len;
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t t_s = tmem_base + TM_S + x * 128 + lane_off;
+    const uint32_t t_o = tmem_base + TM_O + x * 64 + lane_off;
+    uint8_t* my_p = smem_p + x * P_BYTES;
+    const float c = p.scale_log2;
+    float m_run = -INFINITY, l = 0.f;
+    const int lo_x = x ? lo1 : lo0;
+    const int n_iter = (x ? hi1 : hi0) - lo_x;
+
+    for (int jj = 0; jj < n_iter; ++jj) {
+      const int kv0 = kv_base + (lo_x + jj) * BKV;
+      ptx::mbar_wait(&s_full[x], jj & 1);
+      ptx::tc_fence_after();
+      uint32_t sr[4][32];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ptx::tmem_ld_32x32b_x32(t_s + q * 32, sr[q]);
+      ptx::tmem_ld_wait();
+      // masking only where needed (CTA-uniform test)
+      const bool need_mask = (p.window >= 0) || (kv0 + BKV > len);
+      if (need_mask) {
+        int a = 0, b = min(BKV, len - kv0);
+        if (p.window >= 0) {
+          a = max(a, qi - p.window - kv0);
+          b = min(b, qi + p.window + 1 - kv0);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int kj = q * 32 + i;
+            if (kj < a || kj >= b) sr[q][i] = 0xff800000u;  // -inf
+          }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
+        mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
+        mx2 = fmaxf(mx2, __uint_as_float(sr[2][i]));
+        mx3 = fmaxf(mx3, __uint_as_float(sr[3][i]));
+      }
+      const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+      if (jj == 0) {
+        m_run = m_new;
+      } else {
+        const bool grow = (m_new - m_run) * c > RESCALE_LOG2;  // also true for -inf -> finite
+        if (__any_sync(0xffffffffu, grow)) {
+          // the S commit this iteration waited on was issued behind PV(jj-1): O is stable
+          const float alpha = grow ? ptx::ex2_approx((m_run - m_new) * c) : 1.f;
+#pragma unroll 1
+          for (int h = 0; h < D; h += 16) {
+            uint32_t o[16];
+            ptx::tmem_ld_32x32b_x16(t_o + h, o);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            ptx::tmem_st_32x32b_x16(t_o + h, o);
+          }
+          ptx::tmem_st_wait();
+          l *= alpha;
+          if (grow) m_run = m_new;
+        }
+      }
+      const float mc = (m_run == -INFINITY) ? 0.f : m_run * c;
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ptx::ex2_approx(__uint_as_float(sr[q][i]) * c - mc);
+          const float p1 = ptx::ex2_approx(__uint_as_float(sr[q][i + 1]) * c - mc);
+          rs0 += p0;
+          rs1 += p1;
+          packed[i >> 1] = ptx::pack_bf16x2(p0, p1);
+        }
+        uint8_t* prow = my_p + (q >> 1) * (BQ * 128) + r * 128;
+        const int u0 = (q & 1) ? 4 : 0;
+#pragma unroll
+        for (int uu = 0; uu < 4; ++uu) {
+          const int unit = (u0 + uu) ^ (r & 7);
+          *reinterpret_cast<uint4*>(prow + unit * 16) =
+              make_uint4(packed[uu * 4], packed[uu * 4 + 1], packed[uu * 4 + 2], packed[uu * 4 + 3]);
+        }
+      }
+      l += rs0 + rs1;
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&p_full[x]);
+    }
+    if (n_iter > 0) {
+      ptx::mbar_wait(&o_full[x], 0);
+      ptx::tc_fence_after();
+      float o[D];
+#pragma unroll
+      for (int h = 0; h < D; h += 32) {
+        uint32_t rr[32];
+        ptx::tmem_ld_32x32b_x32(t_o + h, rr);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[h + i] = __uint_as_float(rr[i]);
+      }
+      if (valid) {
+        const float inv = 1.f / l;
+        const int64_t row = static_cast<int64_t>(seq_start) + qi;
+        __nv_bfloat16* dst = p.out + row * p.hidden + head * D;
+#pragma unroll
+        for (int i = 0; i < D; i += 8) {
+          uint4 uo;
+          uo.x = ptx::pack_bf16x2(o[i] * inv, o[i + 1] * inv);
+          uo.y = ptx::pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv);
+          uo.z = ptx::pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv);
+          uo.w = ptx::pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv);
+          *reinterpret_cast<uint4*>(dst + i) = uo;
+        }
+        if (p.lse) p.lse[static_cast<int64_t>(head) * p.total_tokens + row] = m_run * c + log2f(l);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace v2
 }  // namespace
 
 int attn_varlen_fwd(const AttnFwdArgs& a, cudaStream_t stream) {
@@ -309,8 +598,25 @@ int attn_varlen_fwd(const AttnFwdArgs& a, cudaStream_t stream) {
   p.hidden = H;
   p.window = a.window;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
-  dim3 grid((a.max_seqlen + BQ - 1) / BQ, a.heads, a.batch);
-  attn_fwd_sm100_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmap, p);
+  static int use_v1 = -1;
+  if (use_v1 < 0) {
+    const char* e = getenv("CM3P_ATTN_FWD_V1");
+    use_v1 = (e && e[0] == '1') ? 1 : 0;
+  }
+  // short sequences (metadata tower: ~20 tokens) fit one 128-row tile: the light 2-CTA/SM kernel wins there
+  if (use_v1 || a.max_seqlen <= BQ) {
+    dim3 grid((a.max_seqlen + BQ - 1) / BQ, a.heads, a.batch);
+    attn_fwd_sm100_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmap, p);
+  } else {
+    static bool configured2 = false;
+    if (!configured2) {
+      CM3P_CUDA_TRY(cudaFuncSetAttribute(v2::attn_fwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         v2::SMEM_BYTES2));
+      configured2 = true;
+    }
+    dim3 grid((a.max_seqlen + 2 * BQ - 1) / (2 * BQ), a.heads, a.batch);
+    v2::attn_fwd_v2_kernel<<<grid, v2::THREADS2, v2::SMEM_BYTES2, stream>>>(tmap, p);
+  }
   CM3P_CUDA_TRY(cudaGetLastError());
   return kOk;
 }

@@ -49,7 +49,7 @@ def bench_gemm(M, N, K, epi=0, name=""):
 
 def bench_attn(B, L, heads, window):
     g = torch.Generator().manual_seed(0)
-    lens = torch.randint(600, L + 1, (B,), generator=g).tolist()
+    lens = torch.randint(min(600, max(1, L - 8)), L + 1, (B,), generator=g).tolist()
     lens[0] = L
     cu = [0]
     for n in lens:
@@ -76,6 +76,40 @@ def bench_attn(B, L, heads, window):
         print(json.dumps(dict(kernel="flash_attn2_ref", error=str(ex)[:200])), flush=True)
 
 
+def bench_attn_bwd(B, L, heads, window):
+    g = torch.Generator().manual_seed(0)
+    lens = torch.randint(600, L + 1, (B,), generator=g).tolist()
+    lens[0] = L
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    T = cu[-1]
+    qkv = torch.randn(T, 3 * heads * 64, device=DEV).bfloat16()
+    dout = torch.randn(T, heads * 64, device=DEV).bfloat16()
+    cu_t = torch.tensor(cu, dtype=torch.int32, device=DEV)
+    lse = torch.empty(heads, T, device=DEV)
+    out = ops.attn_varlen_fwd(qkv, cu_t, L, heads, window, lse=lse)
+    dqkv, delta = torch.empty_like(qkv), torch.empty_like(lse)
+    t = timeit(lambda: ops.attn_varlen_bwd(qkv, out, dout, lse, cu_t, L, heads, window, dqkv=dqkv, delta=delta))
+    if window < 0:
+        flops = sum(10.0 * n * n * 64 * heads for n in lens)
+    else:
+        flops = sum(10.0 * n * min(n, 2 * window + 1) * 64 * heads for n in lens)
+    print(json.dumps(dict(kernel="attn_bwd", B=B, L=L, T=T, heads=heads, window=window, ms=round(t * 1e3, 4),
+                          tflops_5gemm=round(flops / t / 1e12, 1))), flush=True)
+    try:
+        from flash_attn import flash_attn_varlen_qkvpacked_func
+        q4 = qkv.view(T, 3, heads, 64).clone().requires_grad_(True)
+        ws = (window, window) if window >= 0 else (-1, -1)
+        o = flash_attn_varlen_qkvpacked_func(q4, cu_t, L, window_size=ws)
+        do4 = dout.view(T, heads, 64)
+        t2 = timeit(lambda: torch.autograd.grad(o, q4, do4, retain_graph=True))
+        print(json.dumps(dict(kernel="flash_attn2_bwd_ref", window=window, ms=round(t2 * 1e3, 4),
+                              tflops_5gemm=round(flops / t2 / 1e12, 1))), flush=True)
+    except Exception as ex:  # library comparison only
+        print(json.dumps(dict(kernel="flash_attn2_bwd_ref", error=str(ex)[:200])), flush=True)
+
+
 def bench_ln(T, H):
     x = torch.randn(T, H, device=DEV).bfloat16()
     g = torch.ones(H, device=DEV)
@@ -86,6 +120,15 @@ def bench_ln(T, H):
 
 
 if __name__ == "__main__":
+    if "attn" in sys.argv[1:]:
+        bench_attn(64, 2000, 12, -1)
+        bench_attn(64, 2000, 12, 64)
+        bench_attn(64, 800, 8, -1)
+        bench_attn(512, 25, 4, -1)
+        if "bwd" in sys.argv[1:]:
+            bench_attn_bwd(64, 2000, 12, -1)
+            bench_attn_bwd(64, 2000, 12, 64)
+        sys.exit(0)
     T = 64 * 1300
     for (N, K, epi, name) in [(2304, 768, ops.EPI_ROPE, "_wqkv_rope"), (2304, 768, 0, "_wqkv_plain"),
                               (768, 768, ops.EPI_RESIDUAL, "_wo_res"), (2304, 768, ops.EPI_GEGLU, "_wi_geglu"),
