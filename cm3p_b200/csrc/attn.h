@@ -39,5 +39,6 @@ struct AttnBwdArgs {
 };
 
 int attn_varlen_bwd(const AttnBwdArgs& args, cudaStream_t stream);
+int attn_varlen_bwd_v2(const AttnBwdArgs& args, cudaStream_t stream);  // 1 CTA/SM ping-pong kernels (long sequences)
 
 }  // namespace cm3p

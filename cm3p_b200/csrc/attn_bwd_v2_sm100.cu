@@ -1,0 +1,637 @@
+// Attention backward, second generation: same math and data layout as attn_bwd_sm100.cu (see its
+// header for the formulas and the reference call sites), restructured so that one CTA per SM keeps
+// the tensor pipe and the exp units busy at the same time.
+//
+// One CTA = 3 warpgroups (384 threads):
+//   WG0 / WG1  element-wise groups.  They take ALTERNATE inner tiles (WG g handles tiles g, g+2, ...)
+//              of the same outer tile, each with its own S / dP buffers in TMEM and its own bf16
+//              staging buffers in shared memory, so while one group is computing exp / dZ for tile i
+//              the MMA pipe is already producing S / dP of tile i+1 for the other group and draining
+//              the accumulating GEMMs of tile i-1.  Accumulators (dQ, or dK and dV) stay in TMEM.
+//   WG2        warp 8 = TMA producer (4-stage ring; also stages lse/delta rows for the dKV kernel),
+//              warp 9 = MMA issuer, warps 10-11 idle.  WG2 hands registers to WG0/1 (setmaxnreg).
+// Window layers: a warp skips the exp work of 32-column chunks that are outside the band for all of
+// its 32 rows (5 of every 8 chunks remain for window 64).
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "attn.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace cm3p {
+namespace {
+
+constexpr int BT = 128;  // outer tile rows == TMEM lanes
+constexpr int BI = 64;   // inner (streamed) tile rows
+constexpr int D = 64;
+constexpr int OUTER_BYTES = BT * D * 2;  // 16 KB
+constexpr int INNER_BYTES = BI * D * 2;  // 8 KB
+constexpr int NS = 4;                    // ring stages of the streamed operands
+constexpr int THREADS = 384;
+
+struct BwdParams {
+  const int32_t* cu_seqlens;
+  const __nv_bfloat16* out;
+  const __nv_bfloat16* dout;
+  const float* lse;
+  float* delta;
+  __nv_bfloat16* dqkv;
+  const int32_t* positions;
+  const float2* rope_table;
+  int64_t total_tokens;
+  int heads;
+  int hidden;
+  int window;
+  float scale_log2;
+  float scale;
+};
+
+__device__ __forceinline__ uint4 pack8f(const float* v) {
+  return make_uint4(ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]), ptx::pack_bf16x2(v[4], v[5]),
+                    ptx::pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ void unpack8f(const uint4& u, float* f) {
+  float2 t;
+  t = ptx::unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = ptx::unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = ptx::unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = ptx::unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ void store_row_units(uint8_t* tile, int t, int first_unit, const uint32_t (&packed)[16]) {
+  uint8_t* row = tile + t * 128;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int unit = (first_unit + u) ^ (t & 7);
+    *reinterpret_cast<uint4*>(row + unit * 16) =
+        make_uint4(packed[u * 4], packed[u * 4 + 1], packed[u * 4 + 2], packed[u * 4 + 3]);
+  }
+}
+__device__ __forceinline__ void store_zero_units(uint8_t* tile, int t, int first_unit) {
+  uint8_t* row = tile + t * 128;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(row + (((first_unit + u) ^ (t & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+}
+// accumulator row (64 fp32 columns) -> optional inverse RoPE -> bf16 -> global
+__device__ __forceinline__ void store_grad_row(uint32_t taddr, __nv_bfloat16* dst, const float2* cs, bool valid) {
+  uint32_t r1[32], r2[32];
+  ptx::tmem_ld_32x32b_x32(taddr, r1);
+  ptx::tmem_ld_32x32b_x32(taddr + 32, r2);
+  ptx::tmem_ld_wait();
+  if (!valid) return;
+  float o1[32], o2[32];
+  if (cs) {
+    const float4* tab = reinterpret_cast<const float4*>(cs);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 f = __ldg(tab + k);
+      const float a0 = __uint_as_float(r1[2 * k]), b0 = __uint_as_float(r2[2 * k]);
+      const float a1 = __uint_as_float(r1[2 * k + 1]), b1 = __uint_as_float(r2[2 * k + 1]);
+      o1[2 * k] = a0 * f.x + b0 * f.y;
+      o2[2 * k] = b0 * f.x - a0 * f.y;
+      o1[2 * k + 1] = a1 * f.z + b1 * f.w;
+      o2[2 * k + 1] = b1 * f.z - a1 * f.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      o1[k] = __uint_as_float(r1[k]);
+      o2[k] = __uint_as_float(r2[k]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    *reinterpret_cast<uint4*>(dst + i * 8) = pack8f(o1 + i * 8);
+    *reinterpret_cast<uint4*>(dst + 32 + i * 8) = pack8f(o2 + i * 8);
+  }
+}
+
+// Allowed inner-tile columns for one row ([a,b)) and chunk states for its warp.
+//   row_pos / warp_pos: sequence position of the thread's row / of the warp's first row
+//   t0: sequence position of inner-tile column 0.  state: 0 skip, 1 mask per element, 2 no mask
+struct Band {
+  int a, b;
+  int state[2];
+};
+__device__ __forceinline__ Band band_of(int row_pos, int warp_pos, int t0, int len, int window, bool row_valid) {
+  Band r;
+  int a = 0, b = min(BI, len - t0);
+  int wa = 0, wb = b, ia = 0, ib = b;
+  if (window >= 0) {
+    a = max(a, row_pos - window - t0);
+    b = min(b, row_pos + window + 1 - t0);
+    wa = max(wa, warp_pos - window - t0);
+    wb = min(wb, warp_pos + 31 + window + 1 - t0);
+    ia = max(ia, warp_pos + 31 - window - t0);
+    ib = min(ib, warp_pos + window + 1 - t0);
+  }
+  // rows past the end of the sequence inside the warp: never "fully allowed"
+  if (warp_pos + 31 >= len) { ia = BI; ib = 0; }
+  if (warp_pos >= len) { wa = BI; wb = 0; }
+  if (!row_valid) b = 0;
+  r.a = a;
+  r.b = b;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int c0 = q * 32, c1 = q * 32 + 32;
+    r.state[q] = (c1 <= wa || c0 >= wb) ? 0 : ((c0 >= ia && c1 <= ib) ? 2 : 1);
+  }
+  return r;
+}
+
+// ================================================================================================
+// dQ kernel.  smem: Q 16K | dO 16K | K 4x8K | V 4x8K | dZ[2] 2x16K.
+// TMEM: S[g] = g*64, dP[g] = 128 + g*64, dQ = 256.
+constexpr int DQ_TILES = 2 * OUTER_BYTES + NS * 2 * INNER_BYTES + 2 * OUTER_BYTES;  // 128 KB
+constexpr int DQ_SMEM = DQ_TILES + 256;
+
+__global__ void __launch_bounds__(THREADS, 1)
+attn_bwd_dq_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __grid_constant__ CUtensorMap tma_qkv64,
+                      const __grid_constant__ CUtensorMap tma_do128, const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int seq = blockIdx.z, head = blockIdx.y;
+  const int seq_start = p.cu_seqlens[seq];
+  const int len = p.cu_seqlens[seq + 1] - seq_start;
+  const int q0 = blockIdx.x * BT;
+  if (q0 >= len) return;
+
+  uint8_t* smem_q = smem;
+  uint8_t* smem_do = smem + OUTER_BYTES;
+  uint8_t* smem_k = smem + 2 * OUTER_BYTES;
+  uint8_t* smem_v = smem_k + NS * INNER_BYTES;
+  uint8_t* smem_dz = smem_v + NS * INNER_BYTES;  // [2][16K]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_TILES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;         // [4]
+  uint64_t* kv_empty = bars + 1 + NS;   // [4]
+  uint64_t* s_full = bars + 1 + 2 * NS; // [2]
+  uint64_t* dz_full = s_full + 2;       // [2]
+  uint64_t* acc_full = dz_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
+
+  int kv_lo = 0, kv_hi = len - 1;
+  if (p.window >= 0) {
+    kv_lo = max(0, q0 - p.window);
+    kv_hi = min(len - 1, q0 + BT - 1 + p.window);
+  }
+  const int tile_lo = kv_lo / BI;
+  const int n_tiles = kv_hi / BI - tile_lo + 1;
+
+  if (warp == 9 && lane == 0) {
+    ptx::mbar_init(q_full, 1);
+    for (int s = 0; s < NS; ++s) {
+      ptx::mbar_init(&kv_full[s], 1);
+      ptx::mbar_init(&kv_empty[s], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      ptx::mbar_init(&s_full[g], 1);
+      ptx::mbar_init(&dz_full[g], 128);
+    }
+    ptx::mbar_init(acc_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 8) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tma_qkv128);
+      ptx::prefetch_tmap(&tma_qkv64);
+      ptx::prefetch_tmap(&tma_do128);
+    }
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DQ = 256;
+
+  if (warp >= 8) {
+    ptx::setmaxnreg_dec<96>();
+    if (warp == 8 && lane == 0) {
+      const int col_q = head * D, col_k = p.hidden + head * D, col_v = 2 * p.hidden + head * D;
+      ptx::mbar_arrive_expect_tx(q_full, 2 * OUTER_BYTES);
+      ptx::tma_load_2d(smem_q, &tma_qkv128, q_full, col_q, seq_start + q0);
+      ptx::tma_load_2d(smem_do, &tma_do128, q_full, head * D, seq_start + q0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % NS;
+        ptx::mbar_wait(&kv_empty[s], ((j / NS) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&kv_full[s], 2 * INNER_BYTES);
+        const int row = seq_start + (tile_lo + j) * BI;
+        ptx::tma_load_2d(smem_k + s * INNER_BYTES, &tma_qkv64, &kv_full[s], col_k, row);
+        ptx::tma_load_2d(smem_v + s * INNER_BYTES, &tma_qkv64, &kv_full[s], col_v, row);
+      }
+    } else if (warp == 9 && lane == 0) {
+      const uint32_t idesc_s = ptx::umma_idesc_bf16(BT, BI, 0, 0);
+      const uint32_t idesc_dq = ptx::umma_idesc_bf16(BT, D, 0, 1);
+      const uint32_t q_addr = ptx::smem_u32(smem_q), do_addr = ptx::smem_u32(smem_do);
+      auto issue_s_dp = [&](int j) {
+        const int s = j % NS, g = j & 1;
+        ptx::mbar_wait(&kv_full[s], (j / NS) & 1);
+        ptx::tc_fence_after();
+        const uint32_t k_addr = ptx::smem_u32(smem_k + s * INNER_BYTES);
+        const uint32_t v_addr = ptx::smem_u32(smem_v + s * INNER_BYTES);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          ptx::umma_bf16(tmem_base + TM_S + g * 64, ptx::umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                         ptx::umma_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          ptx::umma_bf16(tmem_base + TM_DP + g * 64, ptx::umma_smem_desc_sw128(do_addr + k * 32, 16, 1024),
+                         ptx::umma_smem_desc_sw128(v_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+        ptx::umma_commit(&s_full[g]);
+      };
+      ptx::mbar_wait(q_full, 0);
+      issue_s_dp(0);
+      if (n_tiles > 1) issue_s_dp(1);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % NS, g = j & 1;
+        ptx::mbar_wait(&dz_full[g], (j >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t k_addr = ptx::smem_u32(smem_k + s * INNER_BYTES);
+        const uint32_t dz_addr = ptx::smem_u32(smem_dz + g * OUTER_BYTES);
+#pragma unroll
+        for (int k = 0; k < BI / 16; ++k)
+          ptx::umma_bf16(tmem_base + TM_DQ, ptx::umma_smem_desc_sw128(dz_addr + k * 32, 16, 1024),
+                         ptx::umma_smem_desc_sw128(k_addr + k * 2048, 8192, 1024), idesc_dq, (j | k) != 0 ? 1u : 0u);
+        ptx::umma_commit(&kv_empty[s]);
+        // S/dP of tile j+2 reuse group g's TMEM buffers; their commit also retires the dZ[g] reads above
+        if (j + 2 < n_tiles) issue_s_dp(j + 2);
+      }
+      ptx::umma_commit(acc_full);
+    }
+  } else {
+    ptx::setmaxnreg_inc<200>();
+    const int g = warp >> 2;
+    const int t = threadIdx.x & 127;  // query row inside the tile == TMEM lane
+    const int qi = q0 + t;
+    const bool valid = qi < len;
+    const int64_t row = static_cast<int64_t>(seq_start) + qi;
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int warp_pos = q0 + (warp & 3) * 32;
+    float delta = 0.f, lse = 0.f;
+    if (valid) {
+      const uint4* po = reinterpret_cast<const uint4*>(p.out + row * p.hidden + head * D);
+      const uint4* pd = reinterpret_cast<const uint4*>(p.dout + row * p.hidden + head * D);
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i) {
+        float a[8], b[8];
+        unpack8f(__ldg(po + i), a);
+        unpack8f(__ldg(pd + i), b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) delta += a[k] * b[k];
+      }
+      lse = p.lse[static_cast<int64_t>(head) * p.total_tokens + row];
+      if (g == 0) p.delta[static_cast<int64_t>(head) * p.total_tokens + row] = delta;
+    }
+    const float c = p.scale_log2;
+    const float dsc = delta * p.scale;  // dZ = P * (dP*scale - delta*scale)
+    uint8_t* my_dz = smem_dz + g * OUTER_BYTES;
+    for (int j = g; j < n_tiles; j += 2) {
+      const int kv0 = (tile_lo + j) * BI;
+      ptx::mbar_wait(&s_full[g], (j >> 1) & 1);
+      ptx::tc_fence_after();
+      const Band bd = band_of(qi, warp_pos, kv0, len, p.window, valid);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (bd.state[q] == 0) {
+          store_zero_units(my_dz, t, q * 4);
+          continue;
+        }
+        uint32_t rs[32], rp[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + TM_S + g * 64 + lane_off + q * 32, rs);
+        ptx::tmem_ld_32x32b_x32(tmem_base + TM_DP + g * 64 + lane_off + q * 32, rp);
+        ptx::tmem_ld_wait();
+        uint32_t packed[16];
+        if (bd.state[q] == 2) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ptx::ex2_approx(__uint_as_float(rs[i]) * c - lse);
+            const float p1 = ptx::ex2_approx(__uint_as_float(rs[i + 1]) * c - lse);
+            packed[i >> 1] = ptx::pack_bf16x2(p0 * (__uint_as_float(rp[i]) * p.scale - dsc),
+                                              p1 * (__uint_as_float(rp[i + 1]) * p.scale - dsc));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const int kj = q * 32 + i;
+            const float p0 = (kj >= bd.a && kj < bd.b) ? ptx::ex2_approx(__uint_as_float(rs[i]) * c - lse) : 0.f;
+            const float p1 =
+                (kj + 1 >= bd.a && kj + 1 < bd.b) ? ptx::ex2_approx(__uint_as_float(rs[i + 1]) * c - lse) : 0.f;
+            packed[i >> 1] = ptx::pack_bf16x2(p0 * (__uint_as_float(rp[i]) * p.scale - dsc),
+                                              p1 * (__uint_as_float(rp[i + 1]) * p.scale - dsc));
+          }
+        }
+        store_row_units(my_dz, t, q * 4, packed);
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&dz_full[g]);
+    }
+    if (g == 0) {
+      ptx::mbar_wait(acc_full, 0);
+      ptx::tc_fence_after();
+      const float2* cs = nullptr;
+      if (p.rope_table && p.positions && valid) cs = p.rope_table + static_cast<int64_t>(p.positions[row]) * 32;
+      store_grad_row(tmem_base + TM_DQ + lane_off, p.dqkv + row * 3 * p.hidden + head * D, cs, valid);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ================================================================================================
+// dKV kernel.  smem: K 16K | V 16K | Q 4x8K | dO 4x8K | P^T[2] 2x16K | dZ^T[2] 2x16K | lse/delta 4x512 B
+// TMEM: S^T[g] = g*64, dP^T[g] = 128 + g*64, dK = 256, dV = 320.
+constexpr int DKV_TILES = 2 * OUTER_BYTES + NS * 2 * INNER_BYTES + 4 * OUTER_BYTES;  // 160 KB
+constexpr int DKV_VEC = NS * 2 * BI * 4;                                             // 2 KB
+constexpr int DKV_SMEM = DKV_TILES + DKV_VEC + 256;
+
+__global__ void __launch_bounds__(THREADS, 1)
+attn_bwd_dkv_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __grid_constant__ CUtensorMap tma_qkv64,
+                       const __grid_constant__ CUtensorMap tma_do64, const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int seq = blockIdx.z, head = blockIdx.y;
+  const int seq_start = p.cu_seqlens[seq];
+  const int len = p.cu_seqlens[seq + 1] - seq_start;
+  const int k0 = blockIdx.x * BT;
+  if (k0 >= len) return;
+
+  uint8_t* smem_k = smem;
+  uint8_t* smem_v = smem + OUTER_BYTES;
+  uint8_t* smem_q = smem + 2 * OUTER_BYTES;
+  uint8_t* smem_do = smem_q + NS * INNER_BYTES;
+  uint8_t* smem_pt = smem_do + NS * INNER_BYTES;  // [2][16K]
+  uint8_t* smem_dzt = smem_pt + 2 * OUTER_BYTES;  // [2][16K]
+  float* smem_vec = reinterpret_cast<float*>(smem + DKV_TILES);  // [stage][lse 64 | delta 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DKV_TILES + DKV_VEC);
+  uint64_t* kv_full = bars;
+  uint64_t* qdo_full = bars + 1;            // [4] TMA bytes + 32 staging-lane arrivals
+  uint64_t* qdo_empty = bars + 1 + NS;      // [4]
+  uint64_t* s_full = bars + 1 + 2 * NS;     // [2]
+  uint64_t* pz_full = s_full + 2;           // [2]
+  uint64_t* acc_full = pz_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
+
+  int q_lo = 0, q_hi = len - 1;
+  if (p.window >= 0) {
+    q_lo = max(0, k0 - p.window);
+    q_hi = min(len - 1, k0 + BT - 1 + p.window);
+  }
+  const int tile_lo = q_lo / BI;
+  const int n_tiles = q_hi / BI - tile_lo + 1;
+
+  if (warp == 9 && lane == 0) {
+    ptx::mbar_init(kv_full, 1);
+    for (int s = 0; s < NS; ++s) {
+      ptx::mbar_init(&qdo_full[s], 33);
+      ptx::mbar_init(&qdo_empty[s], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      ptx::mbar_init(&s_full[g], 1);
+      ptx::mbar_init(&pz_full[g], 128);
+    }
+    ptx::mbar_init(acc_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 8) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tma_qkv128);
+      ptx::prefetch_tmap(&tma_qkv64);
+      ptx::prefetch_tmap(&tma_do64);
+    }
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t TM_ST = 0, TM_DPT = 128, TM_DK = 256, TM_DV = 320;
+
+  if (warp >= 8) {
+    ptx::setmaxnreg_dec<96>();
+    if (warp == 8) {
+      // ------------------------------------------------------------------ producer (whole warp)
+      const int col_q = head * D, col_k = p.hidden + head * D, col_v = 2 * p.hidden + head * D;
+      if (lane == 0) {
+        ptx::mbar_arrive_expect_tx(kv_full, 2 * OUTER_BYTES);
+        ptx::tma_load_2d(smem_k, &tma_qkv128, kv_full, col_k, seq_start + k0);
+        ptx::tma_load_2d(smem_v, &tma_qkv128, kv_full, col_v, seq_start + k0);
+      }
+      const float* lse_h = p.lse + static_cast<int64_t>(head) * p.total_tokens;
+      const float* delta_h = p.delta + static_cast<int64_t>(head) * p.total_tokens;
+      for (int i = 0; i < n_tiles; ++i) {
+        const int s = i % NS;
+        ptx::mbar_wait(&qdo_empty[s], ((i / NS) & 1) ^ 1);
+        const int64_t row = static_cast<int64_t>(seq_start) + (tile_lo + i) * BI;
+        if (lane == 0) {
+          ptx::mbar_arrive_expect_tx(&qdo_full[s], 2 * INNER_BYTES);
+          ptx::tma_load_2d(smem_q + s * INNER_BYTES, &tma_qkv64, &qdo_full[s], col_q, static_cast<int32_t>(row));
+          ptx::tma_load_2d(smem_do + s * INNER_BYTES, &tma_do64, &qdo_full[s], col_q, static_cast<int32_t>(row));
+        }
+        float* vec = smem_vec + s * 2 * BI;
+#pragma unroll
+        for (int h = 0; h < BI; h += 32) {
+          const int64_t r = row + h + lane;
+          const bool ok = r < p.total_tokens;
+          vec[h + lane] = ok ? lse_h[r] : 0.f;
+          vec[BI + h + lane] = ok ? delta_h[r] * p.scale : 0.f;  // pre-scaled: dZ = P * (dP*scale - delta*scale)
+        }
+        ptx::mbar_arrive(&qdo_full[s]);
+      }
+    } else if (warp == 9 && lane == 0) {
+      const uint32_t idesc_s = ptx::umma_idesc_bf16(BT, BI, 0, 0);
+      const uint32_t idesc_acc = ptx::umma_idesc_bf16(BT, D, 0, 1);
+      const uint32_t k_addr = ptx::smem_u32(smem_k), v_addr = ptx::smem_u32(smem_v);
+      auto issue_s_dp = [&](int i) {
+        const int s = i % NS, g = i & 1;
+        ptx::mbar_wait(&qdo_full[s], (i / NS) & 1);
+        ptx::tc_fence_after();
+        const uint32_t q_addr = ptx::smem_u32(smem_q + s * INNER_BYTES);
+        const uint32_t do_addr = ptx::smem_u32(smem_do + s * INNER_BYTES);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          ptx::umma_bf16(tmem_base + TM_ST + g * 64, ptx::umma_smem_desc_sw128(k_addr + k * 32, 16, 1024),
+                         ptx::umma_smem_desc_sw128(q_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          ptx::umma_bf16(tmem_base + TM_DPT + g * 64, ptx::umma_smem_desc_sw128(v_addr + k * 32, 16, 1024),
+                         ptx::umma_smem_desc_sw128(do_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+        ptx::umma_commit(&s_full[g]);
+      };
+      ptx::mbar_wait(kv_full, 0);
+      issue_s_dp(0);
+      if (n_tiles > 1) issue_s_dp(1);
+      for (int i = 0; i < n_tiles; ++i) {
+        const int s = i % NS, g = i & 1;
+        ptx::mbar_wait(&pz_full[g], (i >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t q_addr = ptx::smem_u32(smem_q + s * INNER_BYTES);
+        const uint32_t do_addr = ptx::smem_u32(smem_do + s * INNER_BYTES);
+        const uint32_t pt_addr = ptx::smem_u32(smem_pt + g * OUTER_BYTES);
+        const uint32_t dzt_addr = ptx::smem_u32(smem_dzt + g * OUTER_BYTES);
+#pragma unroll
+        for (int k = 0; k < BI / 16; ++k)
+          ptx::umma_bf16(tmem_base + TM_DV, ptx::umma_smem_desc_sw128(pt_addr + k * 32, 16, 1024),
+                         ptx::umma_smem_desc_sw128(do_addr + k * 2048, 8192, 1024), idesc_acc, (i | k) != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < BI / 16; ++k)
+          ptx::umma_bf16(tmem_base + TM_DK, ptx::umma_smem_desc_sw128(dzt_addr + k * 32, 16, 1024),
+                         ptx::umma_smem_desc_sw128(q_addr + k * 2048, 8192, 1024), idesc_acc, (i | k) != 0 ? 1u : 0u);
+        ptx::umma_commit(&qdo_empty[s]);
+        if (i + 2 < n_tiles) issue_s_dp(i + 2);
+      }
+      ptx::umma_commit(acc_full);
+    }
+  } else {
+    ptx::setmaxnreg_inc<200>();
+    const int g = warp >> 2;
+    const int t = threadIdx.x & 127;  // key row inside the tile == TMEM lane
+    const int kj = k0 + t;
+    const bool valid = kj < len;
+    const int64_t row = static_cast<int64_t>(seq_start) + kj;
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int warp_pos = k0 + (warp & 3) * 32;
+    const float c = p.scale_log2;
+    uint8_t* my_pt = smem_pt + g * OUTER_BYTES;
+    uint8_t* my_dzt = smem_dzt + g * OUTER_BYTES;
+    for (int i = g; i < n_tiles; i += 2) {
+      const int s = i % NS;
+      const int q0i = (tile_lo + i) * BI;
+      ptx::mbar_wait(&s_full[g], (i >> 1) & 1);
+      ptx::mbar_wait(&qdo_full[s], (i / NS) & 1);  // already complete: orders the lse/delta staging writes
+      ptx::tc_fence_after();
+      const Band bd = band_of(kj, warp_pos, q0i, len, p.window, valid);
+      const float4* lse4 = reinterpret_cast<const float4*>(smem_vec + s * 2 * BI);
+      const float4* del4 = lse4 + BI / 4;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (bd.state[q] == 0) {
+          store_zero_units(my_pt, t, q * 4);
+          store_zero_units(my_dzt, t, q * 4);
+          continue;
+        }
+        uint32_t rs[32], rp[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + TM_ST + g * 64 + lane_off + q * 32, rs);
+        ptx::tmem_ld_32x32b_x32(tmem_base + TM_DPT + g * 64 + lane_off + q * 32, rp);
+        ptx::tmem_ld_wait();
+        uint32_t pp[16], pz[16];
+        if (bd.state[q] == 2) {
+          // every column allowed for every row of this warp: no predicates
+#pragma unroll
+          for (int i4 = 0; i4 < 32; i4 += 4) {
+            const float4 l4 = lse4[(q * 32 + i4) >> 2];
+            const float4 d4 = del4[(q * 32 + i4) >> 2];  // delta * scale
+            const float p0 = ptx::ex2_approx(__uint_as_float(rs[i4]) * c - l4.x);
+            const float p1 = ptx::ex2_approx(__uint_as_float(rs[i4 + 1]) * c - l4.y);
+            const float p2 = ptx::ex2_approx(__uint_as_float(rs[i4 + 2]) * c - l4.z);
+            const float p3 = ptx::ex2_approx(__uint_as_float(rs[i4 + 3]) * c - l4.w);
+            pp[i4 >> 1] = ptx::pack_bf16x2(p0, p1);
+            pp[(i4 >> 1) + 1] = ptx::pack_bf16x2(p2, p3);
+            pz[i4 >> 1] = ptx::pack_bf16x2(p0 * (__uint_as_float(rp[i4]) * p.scale - d4.x),
+                                           p1 * (__uint_as_float(rp[i4 + 1]) * p.scale - d4.y));
+            pz[(i4 >> 1) + 1] = ptx::pack_bf16x2(p2 * (__uint_as_float(rp[i4 + 2]) * p.scale - d4.z),
+                                                 p3 * (__uint_as_float(rp[i4 + 3]) * p.scale - d4.w));
+          }
+        } else {
+#pragma unroll
+          for (int i4 = 0; i4 < 32; i4 += 4) {
+            const float4 l4 = lse4[(q * 32 + i4) >> 2];
+            const float4 d4 = del4[(q * 32 + i4) >> 2];
+            const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
+            const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
+            float pv[4], zv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int qj = q * 32 + i4 + e;
+              const float ex = ptx::ex2_approx(__uint_as_float(rs[i4 + e]) * c - ls[e]);
+              pv[e] = (qj >= bd.a && qj < bd.b) ? ex : 0.f;
+              zv[e] = pv[e] * (__uint_as_float(rp[i4 + e]) * p.scale - dl[e]);
+            }
+            pp[i4 >> 1] = ptx::pack_bf16x2(pv[0], pv[1]);
+            pp[(i4 >> 1) + 1] = ptx::pack_bf16x2(pv[2], pv[3]);
+            pz[i4 >> 1] = ptx::pack_bf16x2(zv[0], zv[1]);
+            pz[(i4 >> 1) + 1] = ptx::pack_bf16x2(zv[2], zv[3]);
+          }
+        }
+        store_row_units(my_pt, t, q * 4, pp);
+        store_row_units(my_dzt, t, q * 4, pz);
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&pz_full[g]);
+    }
+    ptx::mbar_wait(acc_full, 0);
+    ptx::tc_fence_after();
+    __nv_bfloat16* base = p.dqkv + row * 3 * p.hidden + head * D;
+    if (g == 0) {
+      const float2* cs = nullptr;
+      if (p.rope_table && p.positions && valid) cs = p.rope_table + static_cast<int64_t>(p.positions[row]) * 32;
+      store_grad_row(tmem_base + TM_DK + lane_off, base + p.hidden, cs, valid);
+    } else {
+      store_grad_row(tmem_base + TM_DV + lane_off, base + 2 * p.hidden, nullptr, valid);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+int attn_varlen_bwd_v2(const AttnBwdArgs& a, cudaStream_t stream) {
+  const uint64_t H = static_cast<uint64_t>(a.heads) * 64;
+  const uint64_t T = static_cast<uint64_t>(a.total_tokens);
+  CUtensorMap qkv128, qkv64, do128, do64;
+  int rc;
+  if ((rc = encode_tmap_2d_bf16(&qkv128, a.qkv, 3 * H, T, 3 * H * 2, 64, BT)) != kOk) return rc;
+  if ((rc = encode_tmap_2d_bf16(&qkv64, a.qkv, 3 * H, T, 3 * H * 2, 64, BI)) != kOk) return rc;
+  if ((rc = encode_tmap_2d_bf16(&do128, a.dout, H, T, H * 2, 64, BT)) != kOk) return rc;
+  if ((rc = encode_tmap_2d_bf16(&do64, a.dout, H, T, H * 2, 64, BI)) != kOk) return rc;
+  static bool configured = false;
+  if (!configured) {
+    CM3P_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dq_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    CM3P_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dkv_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    configured = true;
+  }
+  BwdParams p;
+  p.cu_seqlens = a.cu_seqlens;
+  p.out = reinterpret_cast<const __nv_bfloat16*>(a.out);
+  p.dout = reinterpret_cast<const __nv_bfloat16*>(a.dout);
+  p.lse = a.lse;
+  p.delta = a.delta;
+  p.dqkv = reinterpret_cast<__nv_bfloat16*>(a.dqkv);
+  p.positions = a.positions;
+  p.rope_table = reinterpret_cast<const float2*>(a.rope_table);
+  p.total_tokens = a.total_tokens;
+  p.heads = a.heads;
+  p.hidden = static_cast<int>(H);
+  p.window = a.window;
+  p.scale = 0.125f;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  dim3 grid((a.max_seqlen + BT - 1) / BT, a.heads, a.batch);
+  attn_bwd_dq_v2_kernel<<<grid, THREADS, DQ_SMEM, stream>>>(qkv128, qkv64, do128, p);
+  CM3P_CUDA_TRY(cudaGetLastError());
+  attn_bwd_dkv_v2_kernel<<<grid, THREADS, DKV_SMEM, stream>>>(qkv128, qkv64, do64, p);
+  CM3P_CUDA_TRY(cudaGetLastError());
+  return kOk;
+}
+
+}  // namespace cm3p

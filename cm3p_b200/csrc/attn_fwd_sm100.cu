@@ -458,29 +458,52 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
 #pragma unroll
       for (int q = 0; q < 4; ++q) ptx::tmem_ld_32x32b_x32(t_s + q * 32, sr[q]);
       ptx::tmem_ld_wait();
-      // masking only where needed (CTA-uniform test)
-      const bool need_mask = (p.window >= 0) || (kv0 + BKV > len);
-      if (need_mask) {
+      // Masking state per 32-column chunk and per warp (32 consecutive query rows): 0 = no allowed key
+      // for any row of the warp (skip: no exp, P = 0), 1 = some rows partially masked, 2 = fully allowed.
+      // Interior tiles of global layers take the branch-free path (every chunk fully allowed).
+      const bool masked_tile = (p.window >= 0) || (kv0 + BKV > len);  // CTA-uniform
+      int state[4] = {2, 2, 2, 2};
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      if (!masked_tile) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
+          mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
+          mx2 = fmaxf(mx2, __uint_as_float(sr[2][i]));
+          mx3 = fmaxf(mx3, __uint_as_float(sr[3][i]));
+        }
+      } else {
         int a = 0, b = min(BKV, len - kv0);
+        const int qw = q0 + x * BQ + (warp & 3) * 32;  // first query row of this warp
+        int wa = 0, wb = b;                            // union of the warp's allowed ranges
+        int ia = 0, ib = b;                            // intersection
         if (p.window >= 0) {
           a = max(a, qi - p.window - kv0);
           b = min(b, qi + p.window + 1 - kv0);
+          wa = max(wa, qw - p.window - kv0);
+          wb = min(wb, qw + 31 + p.window + 1 - kv0);
+          ia = max(ia, qw + 31 - p.window - kv0);
+          ib = min(ib, qw + p.window + 1 - kv0);
         }
+        float mxq[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < 4; ++q) {
+          const int c0 = q * 32, c1 = q * 32 + 32;
+          state[q] = (c1 <= wa || c0 >= wb) ? 0 : ((c0 >= ia && c1 <= ib) ? 2 : 1);
+          mxq[q] = -INFINITY;
+          if (state[q] == 1) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int kj = q * 32 + i;
-            if (kj < a || kj >= b) sr[q][i] = 0xff800000u;  // -inf
+            for (int i = 0; i < 32; ++i) {
+              const int kj = q * 32 + i;
+              if (kj < a || kj >= b) sr[q][i] = 0xff800000u;  // -inf
+            }
           }
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+          if (state[q] != 0) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
-        mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
-        mx2 = fmaxf(mx2, __uint_as_float(sr[2][i]));
-        mx3 = fmaxf(mx3, __uint_as_float(sr[3][i]));
+            for (int i = 0; i < 32; ++i) mxq[q] = fmaxf(mxq[q], __uint_as_float(sr[q][i]));
+          }
+        }
+        mx0 = mxq[0]; mx1 = mxq[1]; mx2 = mxq[2]; mx3 = mxq[3];
       }
       const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
       if (jj == 0) {
@@ -506,16 +529,20 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
       }
       const float mc = (m_run == -INFINITY) ? 0.f : m_run * c;
       float rs0 = 0.f, rs1 = 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      auto exp_chunk = [&](int q, bool on) {
         uint32_t packed[16];
+        if (on) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = ptx::ex2_approx(__uint_as_float(sr[q][i]) * c - mc);
-          const float p1 = ptx::ex2_approx(__uint_as_float(sr[q][i + 1]) * c - mc);
-          rs0 += p0;
-          rs1 += p1;
-          packed[i >> 1] = ptx::pack_bf16x2(p0, p1);
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ptx::ex2_approx(__uint_as_float(sr[q][i]) * c - mc);
+            const float p1 = ptx::ex2_approx(__uint_as_float(sr[q][i + 1]) * c - mc);
+            rs0 += p0;
+            rs1 += p1;
+            packed[i >> 1] = ptx::pack_bf16x2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) packed[i] = 0u;
         }
         uint8_t* prow = my_p + (q >> 1) * (BQ * 128) + r * 128;
         const int u0 = (q & 1) ? 4 : 0;
@@ -525,6 +552,13 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
           *reinterpret_cast<uint4*>(prow + unit * 16) =
               make_uint4(packed[uu * 4], packed[uu * 4 + 1], packed[uu * 4 + 2], packed[uu * 4 + 3]);
         }
+      };
+      if (!masked_tile) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) exp_chunk(q, true);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) exp_chunk(q, state[q] != 0);
       }
       l += rs0 + rs1;
       ptx::tc_fence_before();
