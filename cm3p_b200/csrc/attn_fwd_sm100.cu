@@ -528,7 +528,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
         }
       }
       const float mc = (m_run == -INFINITY) ? 0.f : m_run * c;
-      float rs0 = 0.f, rs1 = 0.f;
+      float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // independent partial row sums (ILP)
       auto exp_chunk = [&](int q, bool on) {
         uint32_t packed[16];
         if (on) {
@@ -536,8 +536,8 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
           for (int i = 0; i < 32; i += 2) {
             const float p0 = ptx::ex2_approx(__uint_as_float(sr[q][i]) * c - mc);
             const float p1 = ptx::ex2_approx(__uint_as_float(sr[q][i + 1]) * c - mc);
-            rs0 += p0;
-            rs1 += p1;
+            rs[i & 7] += p0;
+            rs[(i & 7) + 1] += p1;
             packed[i >> 1] = ptx::pack_bf16x2(p0, p1);
           }
         } else {
@@ -560,7 +560,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
 #pragma unroll
         for (int q = 0; q < 4; ++q) exp_chunk(q, state[q] != 0);
       }
-      l += rs0 + rs1;
+      l += ((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + (rs[6] + rs[7]));
       ptx::tc_fence_before();
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(&p_full[x]);
