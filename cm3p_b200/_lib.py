@@ -42,6 +42,10 @@ SIGNATURES = {
     "cm3p_l2norm_bwd": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "cm3p_clip_loss_bwd": (_I, [_P, _P, _P, _P, _P, _P, _L, _P, _I, _I, _I, _P]),
     "cm3p_conv2_col2im_gelu_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "cm3p_vocab_ce_fwd": (_I, [_P, _L, _P, _P, _I, _P, _P, _P, _L, _I, _P]),
+    "cm3p_vocab_ce_bwd": (_I, [_P, _L, _P, _P, _I, _P, _P, _L, _I, _P]),
+    "cm3p_gather_rows": (_I, [_P, _P, _P, _L, _I, _P]),
+    "cm3p_scatter_add_rows": (_I, [_P, _P, _P, _L, _I, _P]),
 }
 
 _lib = None

@@ -214,4 +214,29 @@ int cm3p_conv2_col2im_gelu_bwd(const void* da2, const void* z1, void* dz1, int b
   return conv2_col2im_gelu_bwd(da2, z1, dz1, batch, frames, channels, as_stream(stream));
 }
 
+int cm3p_vocab_ce_fwd(const void* logits, int64_t ld, const int64_t* labels, const int32_t* src_index,
+                      int ignore_index, float* row_lse, float* loss_sum, float* count, int64_t rows, int vocab,
+                      void* stream) {
+  CM3P_ARCH_GUARD();
+  return vocab_ce_fwd(logits, ld, labels, src_index, ignore_index, row_lse, loss_sum, count, rows, vocab,
+                      as_stream(stream));
+}
+
+int cm3p_vocab_ce_bwd(void* logits, int64_t ld, const int64_t* labels, const int32_t* src_index, int ignore_index,
+                      const float* row_lse, const float* scale, int64_t rows, int vocab, void* stream) {
+  CM3P_ARCH_GUARD();
+  return vocab_ce_bwd(logits, ld, labels, src_index, ignore_index, row_lse, scale, rows, vocab, as_stream(stream));
+}
+
+int cm3p_gather_rows(const void* x, const int32_t* index, void* out, int64_t rows, int hidden, void* stream) {
+  CM3P_ARCH_GUARD();
+  return gather_rows_i32(x, index, out, rows, hidden, as_stream(stream));
+}
+
+int cm3p_scatter_add_rows(const void* dx_rows, const int32_t* index, void* dx, int64_t rows, int hidden,
+                          void* stream) {
+  CM3P_ARCH_GUARD();
+  return scatter_add_rows(dx_rows, index, dx, rows, hidden, as_stream(stream));
+}
+
 }  // extern "C"

@@ -37,6 +37,12 @@ int l2norm_bwd(const float* e, const float* inv_norm, const float* dembeds, void
 int clip_loss_bwd(const float* S, const int32_t* true_idx, const float* row_lse, const float* col_lse,
                   const float* grad_out, void* dS, int64_t ld_ds, float* dlogit_scale, int Bm, int V, int Bb,
                   cudaStream_t stream);
+int vocab_ce_fwd(const void* logits, int64_t ld, const int64_t* labels, const int32_t* src_index, int ignore_index,
+                 float* row_lse, float* loss_sum, float* count, int64_t rows, int V, cudaStream_t stream);
+int vocab_ce_bwd(void* logits, int64_t ld, const int64_t* labels, const int32_t* src_index, int ignore_index,
+                 const float* row_lse, const float* scale, int64_t rows, int V, cudaStream_t stream);
+int gather_rows_i32(const void* x, const int32_t* index, void* out, int64_t rows, int H, cudaStream_t stream);
+int scatter_add_rows(const void* dx_rows, const int32_t* index, void* dx, int64_t rows, int H, cudaStream_t stream);
 int conv2_col2im_gelu_bwd(const void* da2, const void* z1, void* dz1, int B, int F, int C, cudaStream_t stream);
 
 }  // namespace cm3p

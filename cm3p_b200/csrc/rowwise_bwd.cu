@@ -388,6 +388,97 @@ conv2_col2im_gelu_bwd_kernel(const __nv_bfloat16* __restrict__ da2, const __nv_b
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cross-entropy over a vocabulary (MLM head, cm3p/modeling_cm3p.py:994-996 / :1365-1367 ->
+// transformers ForMaskedLMLoss: F.cross_entropy(logits.float(), labels, ignore_index=-100)) and the
+// 2..n-way classifier loss (:1196-1212).  One warp per row, online max / sum-exp in fp32.
+//   target(row) = labels[src_index ? src_index[row] : row]; rows whose target == ignore_index are skipped.
+//   fwd: row_lse[row]; loss_sum += lse - x[target]; count += 1
+//   bwd: logits <- (softmax(x) - onehot(target)) * scale  in place (0 for ignored rows and pad columns)
+__global__ void __launch_bounds__(256)
+vocab_ce_fwd_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels,
+                    const int32_t* __restrict__ src_index, int ignore_index, float* __restrict__ row_lse,
+                    float* __restrict__ loss_sum, float* __restrict__ count, int64_t rows, int V) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int64_t tgt = labels[src_index ? src_index[row] : row];
+  if (tgt == ignore_index || tgt < 0 || tgt >= V) {
+    if (lane == 0) row_lse[row] = 0.f;
+    return;
+  }
+  const __nv_bfloat16* x = logits + row * ld;
+  float m = -INFINITY, s = 0.f;
+  for (int c = lane; c < V; c += 32) {
+    const float v = __bfloat162float(x[c]);
+    const float mn = fmaxf(m, v);
+    s = s * __expf(m - mn) + __expf(v - mn);
+    m = mn;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    const float mn = fmaxf(m, m2);
+    s = ((m == -INFINITY) ? 0.f : s * __expf(m - mn)) + ((m2 == -INFINITY) ? 0.f : s2 * __expf(m2 - mn));
+    m = mn;
+  }
+  if (lane == 0) {
+    const float lse = m + logf(s);
+    row_lse[row] = lse;
+    atomicAdd(loss_sum, lse - __bfloat162float(x[tgt]));
+    atomicAdd(count, 1.f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+vocab_ce_bwd_kernel(__nv_bfloat16* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels,
+                    const int32_t* __restrict__ src_index, int ignore_index, const float* __restrict__ row_lse,
+                    const float* __restrict__ scale, int64_t rows, int V) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int64_t tgt = labels[src_index ? src_index[row] : row];
+  __nv_bfloat16* x = logits + row * ld;
+  const bool skip = (tgt == ignore_index || tgt < 0 || tgt >= V);
+  const float lse = row_lse[row], sc = *scale;
+  for (int c = lane; c < ld; c += 32) {
+    float g = 0.f;
+    if (!skip && c < V) g = (__expf(__bfloat162float(x[c]) - lse) - ((c == tgt) ? 1.f : 0.f)) * sc;
+    x[c] = __float2bfloat16(g);
+  }
+}
+
+// out[r] = x[index[r]] and x[index[r]] += dx[r] (unique indices): sparse MLM prediction (:1349-1357)
+__global__ void __launch_bounds__(256)
+gather_rows_i32_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ index,
+                       __nv_bfloat16* __restrict__ out, int64_t rows, int H) {
+  const int nvec = H >> 3;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows * nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / nvec;
+    const int v = static_cast<int>(i % nvec);
+    *reinterpret_cast<uint4*>(out + r * H + v * 8) =
+        *reinterpret_cast<const uint4*>(x + static_cast<int64_t>(index[r]) * H + v * 8);
+  }
+}
+__global__ void __launch_bounds__(256)
+scatter_add_rows_kernel(const __nv_bfloat16* __restrict__ dx_rows, const int32_t* __restrict__ index,
+                        __nv_bfloat16* __restrict__ dx, int64_t rows, int H) {
+  const int nvec = H >> 3;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows * nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / nvec;
+    const int v = static_cast<int>(i % nvec);
+    __nv_bfloat16* dst = dx + static_cast<int64_t>(index[r]) * H + v * 8;
+    float a[8], b[8];
+    unpack8(*reinterpret_cast<const uint4*>(dst), a);
+    unpack8(*reinterpret_cast<const uint4*>(dx_rows + r * H + v * 8), b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += b[k];
+    *reinterpret_cast<uint4*>(dst) = pack8(a);
+  }
+}
+
 inline int grid_for(int64_t work_items, int threads) {
   int64_t g = (work_items + threads - 1) / threads;
   const int64_t cap = static_cast<int64_t>(num_sms() > 0 ? num_sms() : 148) * 16;
@@ -525,6 +616,45 @@ int conv2_col2im_gelu_bwd(const void* da2, const void* z1, void* dz1, int B, int
   conv2_col2im_gelu_bwd_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(da2), reinterpret_cast<const __nv_bfloat16*>(z1),
       reinterpret_cast<__nv_bfloat16*>(dz1), B, F, C);
+  CM3P_CUDA_TRY(cudaGetLastError());
+  return kOk;
+}
+
+int vocab_ce_fwd(const void* logits, int64_t ld, const int64_t* labels, const int32_t* src_index, int ignore_index,
+                 float* row_lse, float* loss_sum, float* count, int64_t rows, int V, cudaStream_t stream) {
+  CM3P_REQUIRE(ld >= V && V > 0, kBadShape, "vocab_ce: ld %lld < V %d", (long long)ld, V);
+  if (rows == 0) return kOk;
+  vocab_ce_fwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(logits), ld, labels, src_index, ignore_index, row_lse, loss_sum, count, rows,
+      V);
+  CM3P_CUDA_TRY(cudaGetLastError());
+  return kOk;
+}
+
+int vocab_ce_bwd(void* logits, int64_t ld, const int64_t* labels, const int32_t* src_index, int ignore_index,
+                 const float* row_lse, const float* scale, int64_t rows, int V, cudaStream_t stream) {
+  CM3P_REQUIRE(ld >= V && V > 0 && scale != nullptr, kBadShape, "vocab_ce_bwd: bad arguments");
+  if (rows == 0) return kOk;
+  vocab_ce_bwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
+      reinterpret_cast<__nv_bfloat16*>(logits), ld, labels, src_index, ignore_index, row_lse, scale, rows, V);
+  CM3P_CUDA_TRY(cudaGetLastError());
+  return kOk;
+}
+
+int gather_rows_i32(const void* x, const int32_t* index, void* out, int64_t rows, int H, cudaStream_t stream) {
+  CM3P_REQUIRE(H % 8 == 0, kBadShape, "gather_rows: H %% 8 required");
+  if (rows == 0) return kOk;
+  gather_rows_i32_kernel<<<grid_for(rows * (H / 8), 256), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), index, reinterpret_cast<__nv_bfloat16*>(out), rows, H);
+  CM3P_CUDA_TRY(cudaGetLastError());
+  return kOk;
+}
+
+int scatter_add_rows(const void* dx_rows, const int32_t* index, void* dx, int64_t rows, int H, cudaStream_t stream) {
+  CM3P_REQUIRE(H % 8 == 0, kBadShape, "scatter_add_rows: H %% 8 required");
+  if (rows == 0) return kOk;
+  scatter_add_rows_kernel<<<grid_for(rows * (H / 8), 256), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dx_rows), index, reinterpret_cast<__nv_bfloat16*>(dx), rows, H);
   CM3P_CUDA_TRY(cudaGetLastError());
   return kOk;
 }

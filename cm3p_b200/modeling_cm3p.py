@@ -24,8 +24,8 @@ from typing import Any, Optional
 
 import torch
 from torch import nn
-from transformers import AutoModel
-from transformers.modeling_outputs import BaseModelOutput, BaseModelOutputWithPooling
+from transformers import AutoModel, AutoModelForMaskedLM, AutoModelForSequenceClassification
+from transformers.modeling_outputs import BaseModelOutput, BaseModelOutputWithPooling, MaskedLMOutput
 from transformers.modeling_utils import PreTrainedModel
 from transformers.utils import ModelOutput
 
@@ -693,6 +693,73 @@ class CM3PBeatmapModelWithProjection(CM3PPreTrainedModel):
                                       last_hidden_state=_repad(last, up).to(odt))
 
 
+def _trains(module: nn.Module) -> bool:
+    return torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters())
+
+
+class CM3PForMaskedLM(CM3PPreTrainedModel):
+    """reference :1241-1379 — beatmap tower + prediction head + decoder, MLM cross-entropy (ignore -100),
+    optional `sparse_prediction` (only labelled positions go through the head)."""
+    config_class = CM3PBeatmapConfig
+    base_model_prefix = "beatmap_model"
+    _tied_weights_keys = ["decoder.weight"]
+
+    def __init__(self, config: CM3PBeatmapConfig):
+        super().__init__(config)
+        self.config = config
+        self.beatmap_model = CM3PBeatmapTransformer(config)
+        self.head = CM3PPredictionHead(config)
+        self.decoder = nn.Linear(config.hidden_size, config.vocab_size, bias=config.decoder_bias)
+        self.sparse_prediction = config.sparse_prediction
+        self.sparse_pred_ignore_index = config.sparse_pred_ignore_index
+        self._wcache: dict = {}
+        self.post_init()
+
+    def get_output_embeddings(self):
+        return self.decoder
+
+    def set_output_embeddings(self, new_embeddings: nn.Linear):
+        self.decoder = new_embeddings
+
+    def get_input_embeddings(self):
+        return self.beatmap_model.get_input_embeddings()
+
+    def forward(self, input_ids=None, input_features=None, attention_mask=None, sliding_window_mask=None,
+                position_ids=None, inputs_embeds=None, labels=None, indices=None, cu_seqlens=None, max_seqlen=None,
+                batch_size=None, seq_len=None, output_attentions=None, output_hidden_states=None,
+                **kwargs) -> MaskedLMOutput:
+        if inputs_embeds is not None or position_ids is not None or indices is not None or cu_seqlens is not None:
+            raise NotImplementedError("cm3p_b200 unpads internally; pass padded input_ids + attention_mask")
+        from .training import masked_lm_forward
+        loss, logits = masked_lm_forward(self, input_ids=input_ids, input_features=input_features,
+                                         attention_mask=attention_mask, labels=labels, train=_trains(self), **kwargs)
+        return MaskedLMOutput(loss=loss, logits=logits)
+
+
+class CM3PForBeatmapClassification(CM3PPreTrainedModel):
+    """reference :1137-1226 — classifier on the pooled beatmap representation (e.g. the ranked classifier)."""
+    config_class = CM3PBeatmapConfig
+    base_model_prefix = "beatmap_model"
+
+    def __init__(self, config: CM3PBeatmapConfig):
+        super().__init__(config)
+        self.num_labels = config.num_labels
+        self.beatmap_model = CM3PBeatmapTransformer(config)
+        self.classifier = nn.Linear(config.hidden_size, config.num_labels) if config.num_labels > 0 else nn.Identity()
+        self._wcache: dict = {}
+        self.post_init()
+
+    def forward(self, input_ids=None, input_features=None, attention_mask=None, position_ids=None,
+                inputs_embeds=None, labels=None, output_attentions=None,
+                output_hidden_states=None) -> BeatmapClassifierOutput:
+        if inputs_embeds is not None or position_ids is not None:
+            raise NotImplementedError("custom inputs_embeds / position_ids are not supported by the fused kernels")
+        from .training import classification_forward
+        loss, logits = classification_forward(self, input_ids=input_ids, input_features=input_features,
+                                              attention_mask=attention_mask, labels=labels, train=_trains(self))
+        return BeatmapClassifierOutput(loss=loss, logits=logits)
+
+
 def _register():
     for cfg_cls, model_cls in ((CM3PMetadataConfig, CM3PMetadataModel), (CM3PBeatmapConfig, CM3PBeatmapModel),
                                (CM3PConfig, CM3PModel)):
@@ -700,9 +767,16 @@ def _register():
             AutoModel.register(cfg_cls, model_cls)
         except ValueError:
             pass
+    for auto_cls, model_cls in ((AutoModelForSequenceClassification, CM3PForBeatmapClassification),
+                                (AutoModelForMaskedLM, CM3PForMaskedLM)):
+        try:
+            auto_cls.register(CM3PBeatmapConfig, model_cls)
+        except ValueError:
+            pass
 
 
 _register()
 
 __all__ = ["CM3PModel", "CM3PPreTrainedModel", "CM3PMetadataModel", "CM3PMetadataModelWithProjection",
-           "CM3PBeatmapModel", "CM3PBeatmapModelWithProjection", "CM3POutput"]
+           "CM3PBeatmapModel", "CM3PBeatmapModelWithProjection", "CM3PForBeatmapClassification", "CM3PForMaskedLM",
+           "CM3POutput"]

@@ -369,6 +369,59 @@ def conv2_col2im_gelu_bwd(da2: torch.Tensor, z1: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def vocab_ce_fwd(logits: torch.Tensor, vocab: int, labels: torch.Tensor, src_index: torch.Tensor | None,
+                 ignore_index: int = -100):
+    """logits bf16 [rows, ld>=vocab]; labels int64 (padded, flat).  -> (row_lse [rows], loss_sum [1], count [1])."""
+    _req(logits, torch.bfloat16, "logits")
+    _req(labels, torch.int64, "labels")
+    assert logits.dim() == 2 and logits.stride(1) == 1
+    rows = logits.shape[0]
+    row_lse = torch.empty((rows,), device=logits.device, dtype=torch.float32)
+    acc = torch.zeros((2,), device=logits.device, dtype=torch.float32)
+    rc = _lib.load().cm3p_vocab_ce_fwd(logits.data_ptr(), logits.stride(0), labels.data_ptr(), _ptr(src_index),
+                                       int(ignore_index), row_lse.data_ptr(), acc[0:1].data_ptr(), acc[1:2].data_ptr(),
+                                       rows, int(vocab), _stream())
+    _lib.check(rc, "cm3p_vocab_ce_fwd")
+    _count("rowwise")
+    return row_lse, acc[0:1], acc[1:2]
+
+
+def vocab_ce_bwd(logits: torch.Tensor, vocab: int, labels: torch.Tensor, src_index: torch.Tensor | None,
+                 row_lse: torch.Tensor, scale: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
+    """Overwrites logits [rows, ld] with d(loss)/d(logits) * scale (device scalar) and returns it."""
+    _req(logits, torch.bfloat16, "logits")
+    _req(scale, torch.float32, "scale")
+    rc = _lib.load().cm3p_vocab_ce_bwd(logits.data_ptr(), logits.stride(0), labels.data_ptr(), _ptr(src_index),
+                                       int(ignore_index), row_lse.data_ptr(), scale.data_ptr(), logits.shape[0],
+                                       int(vocab), _stream())
+    _lib.check(rc, "cm3p_vocab_ce_bwd")
+    _count("rowwise")
+    return logits
+
+
+def gather_rows(x: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    _req(x, torch.bfloat16, "x")
+    _req(index, torch.int32, "index")
+    assert x.is_contiguous()
+    out = torch.empty((index.numel(), x.shape[1]), device=x.device, dtype=torch.bfloat16)
+    rc = _lib.load().cm3p_gather_rows(x.data_ptr(), index.data_ptr(), out.data_ptr(), index.numel(), x.shape[1],
+                                      _stream())
+    _lib.check(rc, "cm3p_gather_rows")
+    _count("rowwise")
+    return out
+
+
+def scatter_add_rows(dx_rows: torch.Tensor, index: torch.Tensor, dx: torch.Tensor) -> torch.Tensor:
+    _req(dx_rows, torch.bfloat16, "dx_rows")
+    _req(dx, torch.bfloat16, "dx")
+    assert dx_rows.is_contiguous() and dx.is_contiguous() and dx_rows.shape[1] == dx.shape[1]
+    rc = _lib.load().cm3p_scatter_add_rows(dx_rows.data_ptr(), index.data_ptr(), dx.data_ptr(), index.numel(),
+                                           dx.shape[1], _stream())
+    _lib.check(rc, "cm3p_scatter_add_rows")
+    _count("rowwise")
+    return dx
+
+
 # ------------------------------------------------------------------------------------------------
 # host-side preparation helpers (layout only, no arithmetic on the hot path)
 

@@ -262,14 +262,77 @@ def head_forward(last, cu_seqlens, mean_pool: bool, proj_w):
                               H=last.shape[1])
 
 
-def head_backward(saved, demb32: torch.Tensor, proj_w: torch.Tensor, g_proj: torch.Tensor) -> torch.Tensor:
-    """demb32 [B,P] fp32 (gradient of the normalised embeddings) -> dlast [T,H] bf16."""
+def head_backward(saved, demb32: torch.Tensor, proj_w: torch.Tensor, g_proj: torch.Tensor,
+                  dlast: torch.Tensor | None = None) -> torch.Tensor:
+    """demb32 [B,P] fp32 (gradient of the normalised embeddings) -> dlast [T,H] bf16 (added to `dlast` if given)."""
     dproj = ops.l2norm_bwd(saved["proj"], saved["inv"], demb32)
     _wgrad(dproj, saved["pooled"], g_proj)
     dpooled = _dgrad(dproj, proj_w)
-    dlast = torch.empty((saved["T"], saved["H"]), device=demb32.device, dtype=BF16)
-    ops.pool_bwd(dpooled, saved["cu"], saved["mean_pool"], dlast, accumulate=False)
+    return pooled_backward(saved, dpooled, dlast)
+
+
+def pooled_backward(saved, dpooled: torch.Tensor, dlast: torch.Tensor | None = None) -> torch.Tensor:
+    accumulate = dlast is not None
+    if dlast is None:
+        dlast = torch.empty((saved["T"], saved["H"]), device=dpooled.device, dtype=BF16)
+    ops.pool_bwd(dpooled, saved["cu"], saved["mean_pool"], dlast, accumulate=accumulate)
     return dlast
+
+
+# ------------------------------------------------------------------------------------------------
+# MLM prediction head + vocabulary cross-entropy (reference: CM3PPredictionHead :1229-1238, decoder,
+# ForMaskedLMLoss via self.loss_function :994-996 / :1365-1367)
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(F32).contiguous()
+
+
+def mlm_head_forward(head, decoder, norm_eps: float, hidden: torch.Tensor, wcache: dict):
+    """hidden [M,H] bf16 -> (logits view [M,V] of a [M, ld] buffer, saved)."""
+    from .modeling_cm3p import _pack_linear
+    wd = _pack_linear(head.dense, wcache, "hd")
+    wv = _pack_linear(decoder, wcache, "dec")
+    gamma = _f32(head.norm.weight)
+    zd = ops.gemm(hidden, wd)
+    yd = ops.gelu_fwd(zd)
+    n = ops.layernorm(yd, gamma, norm_eps)
+    M, V = hidden.shape[0], wv.shape[0]
+    ld = (V + 7) // 8 * 8
+    buf = torch.empty((M, ld), device=hidden.device, dtype=BF16)
+    logits = buf[:, :V]
+    if decoder.bias is not None:
+        ops.gemm(n, wv, epilogue=ops.EPI_BIAS, aux=_f32(decoder.bias), out=logits)
+    else:
+        ops.gemm(n, wv, out=logits)
+    return logits, dict(zd=zd, hidden=hidden, buf=buf, V=V, wd=wd, wv=wv, gamma=gamma, eps=norm_eps)
+
+
+def mlm_head_backward(head, decoder, saved, g: GradStore) -> torch.Tensor:
+    """saved["buf"] holds d(loss)/d(logits) (written in place by vocab_ce_bwd) -> d(hidden) [M,H]."""
+    buf, V = saved["buf"], saved["V"]
+    dl = buf[:, :V]
+    yd = ops.gelu_fwd(saved["zd"])
+    n = ops.layernorm(yd, saved["gamma"], saved["eps"])
+    _wgrad(dl, n, g(decoder.weight))
+    if decoder.bias is not None:
+        tmp = torch.zeros((buf.shape[1],), device=buf.device, dtype=F32)
+        ops.colsum_f32(buf, tmp)
+        g(decoder.bias).add_(tmp[:V])
+    dn = _dgrad(dl, saved["wv"])
+    dyd = ops.layernorm_bwd(yd, dn, saved["gamma"], saved["eps"], dgamma=g(head.norm.weight))
+    dzd = ops.gelu_bwd(saved["zd"], dyd)
+    _wgrad(dzd, saved["hidden"], g(head.dense.weight))
+    return _dgrad(dzd, saved["wd"])
+
+
+def mlm_loss_forward(logits, vocab, labels_flat, src_index, num_items_in_batch):
+    """-> (mean CE over labelled rows as a device scalar, saved for the backward)."""
+    row_lse, loss_sum, count = ops.vocab_ce_fwd(logits, vocab, labels_flat, src_index)
+    if num_items_in_batch is None:
+        denom = count
+    else:
+        denom = torch.as_tensor(num_items_in_batch, device=logits.device, dtype=F32).reshape(1)
+    return loss_sum / denom, dict(row_lse=row_lse, denom=denom, labels=labels_flat, src_index=src_index, vocab=vocab)
 
 
 class _TrainStep(torch.autograd.Function):
@@ -290,9 +353,13 @@ class _TrainStep(torch.autograd.Function):
 
 
 class _StepState:
-    def __init__(self, model, params):
+    """Everything the backward pass of one training step needs; `backward_fn(saved, grad_out, g)` is the
+    model-specific schedule (contrastive / masked-LM / classification)."""
+
+    def __init__(self, model, params, backward_fn):
         self.model = model
         self.params = params
+        self.backward_fn = backward_fn
         self.saved = {}
 
     def backward(self, grad_out: torch.Tensor):
@@ -300,32 +367,44 @@ class _StepState:
         self.saved = None
         if sv is None:
             raise RuntimeError("cm3p_b200: backward called twice on the same training step")
-        g = GradStore(list(model.parameters()))
-        dev = sv["S"].device
-        gout = grad_out.detach().to(device=dev, dtype=F32).reshape(1).contiguous()
-        dls = g(model.logit_scale).view(1)
-        dS = ops.clip_loss_bwd(sv["S"], sv["true_idx"], sv["row_lse"], sv["col_lse"], sv["V"], gout, dls)
-        scale = sv["scale"]
-        dme = ops.gemm(dS, sv["be16"], trans_b=True, epilogue=ops.EPI_SCALE_F32, scale=scale)
-        dbe = ops.gemm(dS, sv["me16"], trans_a=True, trans_b=True, epilogue=ops.EPI_SCALE_F32, scale=scale)
-        del dS
-        dp = sv["dp"]
-        if dp is not None and dp.global_negatives:
-            # every rank holds d(global loss)/d(all embeddings); its own rows are its row block
-            dme = dp_utils.local_rows(dme, dp).contiguous()
-            dbe = dp_utils.local_rows(dbe, dp).contiguous()
-        # metadata tower first (small), then the beatmap tower
-        dlast_m = head_backward(sv["mhead"], dme, sv["w_mp"], g(model.metadata_projection.weight))
-        metadata_backward(model.metadata_model, sv["meta"], dlast_m, g)
-        del dlast_m
-        dlast_b = head_backward(sv["bhead"], dbe, sv["w_bp"], g(model.beatmap_projection.weight))
-        beatmap_backward(model.beatmap_model, sv["beat"], dlast_b, g)
+        g = GradStore(self.params)
+        gout = grad_out.detach().to(device=self.params[0].device, dtype=F32).reshape(1).contiguous()
+        self.backward_fn(model, sv, gout, g)
+        dp = getattr(model, "_dp", None)
         if dp is not None:
-            if dp.global_negatives:
+            if dp.global_negatives and hasattr(model, "logit_scale"):
                 # every rank evaluated the full loss, so d(logit_scale) is already complete on each rank
                 g(model.logit_scale).div_(dp.world_size)
             dp_utils.reduce_gradients(g.flat, dp)  # ONE all-reduce for every parameter gradient
         return [g(p).to(p.dtype) if p.requires_grad else None for p in self.params]
+
+
+def _contrastive_backward(model, sv, gout, g: GradStore) -> None:
+    dls = g(model.logit_scale).view(1)
+    dS = ops.clip_loss_bwd(sv["S"], sv["true_idx"], sv["row_lse"], sv["col_lse"], sv["V"], gout, dls)
+    scale = sv["scale"]
+    dme = ops.gemm(dS, sv["be16"], trans_b=True, epilogue=ops.EPI_SCALE_F32, scale=scale)
+    dbe = ops.gemm(dS, sv["me16"], trans_a=True, trans_b=True, epilogue=ops.EPI_SCALE_F32, scale=scale)
+    del dS
+    dp = sv["dp"]
+    if dp is not None and dp.global_negatives:
+        # every rank holds d(global loss)/d(all embeddings); its own rows are its row block
+        dme = dp_utils.local_rows(dme, dp).contiguous()
+        dbe = dp_utils.local_rows(dbe, dp).contiguous()
+    # metadata tower first (small), then the beatmap tower
+    dlast_m = head_backward(sv["mhead"], dme, sv["w_mp"], g(model.metadata_projection.weight))
+    metadata_backward(model.metadata_model, sv["meta"], dlast_m, g)
+    del dlast_m
+    dlast_b = None
+    if sv.get("mlm") is not None:
+        # auxiliary masked-LM loss: loss += 0.5 * CE  (modeling_cm3p.py:994-996)
+        ce = sv["mlm_ce"]
+        ops.vocab_ce_bwd(sv["mlm"]["buf"], ce["vocab"], ce["labels"], ce["src_index"], ce["row_lse"],
+                         (gout * 0.5 / ce["denom"]).contiguous())
+        dlast_b = mlm_head_backward(model.head, model.decoder, sv["mlm"], g)
+        sv["mlm"] = None
+    dlast_b = head_backward(sv["bhead"], dbe, sv["w_bp"], g(model.beatmap_projection.weight), dlast=dlast_b)
+    beatmap_backward(model.beatmap_model, sv["beat"], dlast_b, g)
 
 
 def forward_with_grad(model, *, input_ids=None, input_features=None, metadata_ids=None, attention_mask=None,
@@ -339,13 +418,11 @@ def forward_with_grad(model, *, input_ids=None, input_features=None, metadata_id
         raise NotImplementedError(
             "cm3p_b200 training path: the contrastive step needs input_ids, metadata_ids and return_loss=True; "
             "call single-tower / no-loss forwards under torch.no_grad()")
-    if cfg.has_decoder_head and labels is not None:
-        raise NotImplementedError("cm3p_b200: the MLM auxiliary loss is not part of the explicit backward yet")
     _require_cuda(input_ids, "input_ids")
     odt = _out_dtype(model)
     pad_outputs = getattr(cfg, "_attn_implementation", None) != "flash_attention_2"
     params = [p for p in model.parameters()]
-    st = _StepState(model, params)
+    st = _StepState(model, params, _contrastive_backward)
     sv = st.saved
 
     last_b, up_b, audio_last, sv["beat"] = beatmap_forward(model.beatmap_model, input_ids, input_features,
@@ -385,6 +462,19 @@ def forward_with_grad(model, *, input_ids=None, input_features=None, metadata_id
     loss_val, row_lse, col_lse = ops.clip_loss_fwd(S, true_idx, V)
     sv.update(S=S, true_idx=true_idx, row_lse=row_lse, col_lse=col_lse, V=V, scale=scale, be16=be16, me16=me16)
 
+    logits_out = None
+    if cfg.has_decoder_head and (output_logits or labels is not None):
+        # decoder(head(last_hidden)) on every real token (:987-993); bf16 like the reference under autocast
+        bc = cfg.beatmap_config
+        logits_u, mlm_saved = mlm_head_forward(model.head, model.decoder, bc.norm_eps, last_b, model._wcache)
+        if labels is not None:
+            mlm, sv["mlm_ce"] = mlm_loss_forward(logits_u, mlm_saved["V"], labels.reshape(-1).contiguous(),
+                                                 up_b.src_index, kwargs.get("num_items_in_batch"))
+            sv["mlm"] = mlm_saved
+            loss_val = loss_val + 0.5 * mlm
+        if output_logits:
+            logits_out = _repad(logits_u, up_b)  # a copy: the unpadded buffer is overwritten in the backward
+
     loss = _TrainStep.apply(st, loss_val.reshape(()), *params)
 
     lead = tuple(metadata_ids.shape[:-1])
@@ -394,8 +484,118 @@ def forward_with_grad(model, *, input_ids=None, input_features=None, metadata_id
     audio_out = None if audio_last is None else CM3PAudioModelOutput(last_hidden_state=audio_last)
     return CM3POutput(
         loss=loss, logits_per_beatmap=logits_per_beatmap, logits_per_metadata=logits_per_metadata,
-        metadata_embeds=me32.view(*lead, -1).to(odt), beatmap_embeds=be32.to(odt), logits=None,
+        metadata_embeds=me32.view(*lead, -1).to(odt), beatmap_embeds=be32.to(odt), logits=logits_out,
         metadata_model_output=BaseModelOutputWithPooling(
             last_hidden_state=hidden_m, pooler_output=sv["mhead"]["pooled"].view(*lead, -1).to(odt)),
         beatmap_model_output=CM3PBeatmapModelOutput(
             last_hidden_state=hidden_b, pooler_output=sv["bhead"]["pooled"].to(odt), audio_model_output=audio_out))
+
+
+# ------------------------------------------------------------------------------------------------
+# CM3PForMaskedLM / CM3PForBeatmapClassification (reference :1241-1379, :1137-1226)
+
+def _mlm_backward(model, sv, gout, g: GradStore) -> None:
+    ce = sv["mlm_ce"]
+    ops.vocab_ce_bwd(sv["mlm"]["buf"], ce["vocab"], ce["labels"], ce["src_index"], ce["row_lse"],
+                     (gout / ce["denom"]).contiguous())
+    dh = mlm_head_backward(model.head, model.decoder, sv["mlm"], g)
+    if sv["rows"] is not None:  # sparse prediction: only the labelled rows went through the head
+        dlast = torch.zeros((sv["T"], dh.shape[1]), device=dh.device, dtype=BF16)
+        ops.scatter_add_rows(dh, sv["rows"], dlast)
+    else:
+        dlast = dh
+    beatmap_backward(model.beatmap_model, sv["beat"], dlast, g)
+
+
+def masked_lm_forward(model, *, input_ids, input_features, attention_mask, labels, train: bool, **kwargs):
+    """CM3PForMaskedLM.forward.  -> (loss | None, padded logits) ; with `train` the loss carries the backward."""
+    from .modeling_cm3p import _repad, _require_cuda
+    cfg = model.config
+    _require_cuda(input_ids, "input_ids")
+    params = list(model.parameters())
+    st = _StepState(model, params, _mlm_backward)
+    sv = st.saved
+    if train:
+        last, up, _, sv["beat"] = beatmap_forward(model.beatmap_model, input_ids, input_features, attention_mask)
+    else:
+        last, up, _ = model.beatmap_model.encode(input_ids, input_features, attention_mask)
+    rows, hidden, src = None, last, up.src_index
+    labels_flat = labels.reshape(-1).contiguous() if labels is not None else None
+    if cfg.sparse_prediction and labels is not None:
+        # only tokens whose label is not the ignore index go through the head (:1349-1357)
+        lab_u = labels_flat.index_select(0, up.src_index.long())
+        rows = torch.nonzero(lab_u != cfg.sparse_pred_ignore_index).reshape(-1).to(torch.int32)
+        hidden = ops.gather_rows(last, rows)
+        src = up.src_index.index_select(0, rows.long()).contiguous()
+    logits_u, mlm_saved = mlm_head_forward(model.head, model.decoder, cfg.norm_eps, hidden, model._wcache)
+    loss = None
+    if labels is not None:
+        mlm, sv["mlm_ce"] = mlm_loss_forward(logits_u, mlm_saved["V"], labels_flat, src,
+                                             kwargs.get("num_items_in_batch"))
+        loss = mlm.reshape(())
+    if rows is not None:
+        logits_out = logits_u.clone()  # the reference returns the (n_masked, vocab) logits in this mode
+    else:
+        logits_out = _repad(logits_u, up)
+    if train and loss is not None:
+        sv.update(mlm=mlm_saved, rows=rows, T=last.shape[0])
+        loss = _TrainStep.apply(st, loss, *params)
+    return loss, logits_out
+
+
+def _cls_backward(model, sv, gout, g: GradStore) -> None:
+    ce = sv["ce"]
+    buf = sv["buf"]
+    ops.vocab_ce_bwd(buf, ce["vocab"], ce["labels"], None, ce["row_lse"], (gout / ce["denom"]).contiguous())
+    dl = buf[:, :ce["vocab"]]
+    _wgrad(dl, sv["pooled"], g(model.classifier.weight))
+    tmp = torch.zeros((buf.shape[1],), device=buf.device, dtype=F32)
+    ops.colsum_f32(buf, tmp)
+    g(model.classifier.bias).add_(tmp[:ce["vocab"]])
+    dpooled = _dgrad(dl, sv["wc"])
+    dlast = pooled_backward(sv["head"], dpooled)
+    beatmap_backward(model.beatmap_model, sv["beat"], dlast, g)
+
+
+def classification_forward(model, *, input_ids, input_features, attention_mask, labels, train: bool):
+    """CM3PForBeatmapClassification.forward: logits = classifier(pooled); single-label CE when labels given."""
+    from .modeling_cm3p import _pack_linear, _require_cuda
+    cfg = model.config
+    _require_cuda(input_ids, "input_ids")
+    params = list(model.parameters())
+    st = _StepState(model, params, _cls_backward)
+    sv = st.saved
+    if train:
+        last, up, _, sv["beat"] = beatmap_forward(model.beatmap_model, input_ids, input_features, attention_mask)
+    else:
+        last, up, _ = model.beatmap_model.encode(input_ids, input_features, attention_mask)
+    mean_pool = not cfg.cls_embed
+    pooled = ops.pool_project_normalize(last, up.cu_seqlens, mean_pool, None)[0]
+    if not isinstance(model.classifier, torch.nn.Linear):
+        return None, pooled.float()
+    wc = _pack_linear(model.classifier, model._wcache, "cls")
+    C = wc.shape[0]
+    ld = (C + 7) // 8 * 8
+    buf = torch.zeros((pooled.shape[0], ld), device=pooled.device, dtype=BF16)
+    logits = buf[:, :C]
+    ops.gemm(pooled, wc, epilogue=ops.EPI_BIAS, aux=_f32(model.classifier.bias), out=logits)
+    logits_out = logits.float()
+    loss = None
+    if labels is not None:
+        problem = cfg.problem_type
+        if problem is None:
+            problem = "regression" if C == 1 else (
+                "single_label_classification" if labels.dtype in (torch.long, torch.int) else
+                "multi_label_classification")
+            cfg.problem_type = problem
+        if problem != "single_label_classification":
+            raise NotImplementedError(f"cm3p_b200: problem_type {problem!r} has no CUDA loss kernel (only "
+                                      "single_label_classification, the reference's ranked classifier)")
+        lab = labels.reshape(-1).to(torch.int64).contiguous()
+        row_lse, loss_sum, count = ops.vocab_ce_fwd(logits, C, lab, None)
+        loss = (loss_sum / count).reshape(())
+        if train:
+            sv.update(ce=dict(row_lse=row_lse, denom=count, labels=lab, vocab=C), buf=buf, pooled=pooled, wc=wc,
+                      head=dict(cu=up.cu_seqlens, mean_pool=mean_pool, T=last.shape[0], H=last.shape[1]))
+            loss = _TrainStep.apply(st, loss, *params)
+    return loss, logits_out

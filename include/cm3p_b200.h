@@ -171,6 +171,24 @@ int cm3p_clip_loss_bwd(const float* S, const int32_t* true_idx, const float* row
 int cm3p_conv2_col2im_gelu_bwd(const void* da2, const void* z1, void* dz1, int batch, int frames, int channels,
                                void* stream);
 
+/* Cross-entropy over a vocabulary / class set on bf16 logits [rows, ld] (ld >= vocab).  Replaces
+ * `self.loss_function(logits, labels, vocab_size)` = transformers ForMaskedLMLoss (cm3p/modeling_cm3p.py:994-996,
+ * :1365-1367; ignore_index -100) and the classifier CrossEntropyLoss (:1207-1209).
+ *   target(row) = labels[src_index ? src_index[row] : row]  (labels: padded int64; src_index as in cm3p_embed_gather_ln)
+ *   fwd: row_lse [rows]; loss_sum (fp32, +=) = sum over non-ignored rows of (lse - x[target]); count (fp32, +=)
+ *   bwd: logits are overwritten by (softmax - onehot) * (*scale) (device scalar), zeros for ignored rows / pad columns */
+int cm3p_vocab_ce_fwd(const void* logits, int64_t ld, const int64_t* labels, const int32_t* src_index,
+                      int ignore_index, float* row_lse, float* loss_sum, float* count, int64_t rows, int vocab,
+                      void* stream);
+int cm3p_vocab_ce_bwd(void* logits, int64_t ld, const int64_t* labels, const int32_t* src_index, int ignore_index,
+                      const float* row_lse, const float* scale, int64_t rows, int vocab, void* stream);
+
+/* out[r] = x[index[r]];  dx[index[r]] += dx_rows[r] (unique indices).  Sparse MLM prediction,
+ * cm3p/modeling_cm3p.py:1349-1357 (`last_hidden_state[mask_tokens]`) and its gradient. */
+int cm3p_gather_rows(const void* x, const int32_t* index, void* out, int64_t rows, int hidden, void* stream);
+int cm3p_scatter_add_rows(const void* dx_rows, const int32_t* index, void* dx, int64_t rows, int hidden,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -299,3 +299,42 @@ def test_conv_training_path():
     _relerr("conv dw2", dw2p.view(Co, 3, Co).permute(0, 2, 1), w2r.grad, 2e-2)
     _relerr("conv db1", db1, b1r.grad, 3e-2)
     _relerr("conv dw1", dw1p.view(Co, C, 3), w1r.grad, 3e-2)
+
+
+@pytest.mark.parametrize("V", [3968, 500, 2])
+def test_vocab_cross_entropy_fwd_bwd(V):
+    ops = _ops()
+    rows, L = 900, 1000
+    ld = (V + 7) // 8 * 8
+    buf = torch.full((rows, ld), 3.0, device=DEV, dtype=torch.bfloat16)
+    logits = buf[:, :V]
+    logits.copy_(_rand((rows, V), 2.0, seed=1))
+    g = torch.Generator().manual_seed(3)
+    labels = torch.randint(0, V, (L,), generator=g)
+    labels[torch.rand(L, generator=g) < 0.7] = -100
+    src = torch.randperm(L, generator=g)[:rows].sort().values.to(torch.int32)
+    tgt = labels[src.long()].to(DEV)
+    ref = logits.float().clone().requires_grad_(True)
+    want = F.cross_entropy(ref, tgt, ignore_index=-100, reduction="sum")
+    (want * 0.37).backward()
+    row_lse, loss_sum, count = ops.vocab_ce_fwd(logits, V, labels.to(DEV), src.to(DEV))
+    assert abs(float(loss_sum) - float(want)) <= 2e-3 * abs(float(want)) + 1e-3
+    assert int(count) == int((tgt != -100).sum())
+    ops.vocab_ce_bwd(logits, V, labels.to(DEV), src.to(DEV), row_lse, torch.tensor([0.37], device=DEV))
+    torch.cuda.synchronize()
+    _close("vocab_ce_bwd", logits, ref.grad, 2e-3, 2e-2)
+    if ld > V:
+        assert float(buf[:, V:].abs().max()) == 0.0
+
+
+def test_gather_scatter_rows():
+    ops = _ops()
+    x = _rand((500, 128), seed=1)
+    idx = torch.tensor([3, 7, 8, 250, 499], dtype=torch.int32, device=DEV)
+    rows = ops.gather_rows(x, idx)
+    assert torch.equal(rows, x[idx.long()])
+    dx = _rand((500, 128), seed=2)
+    want = dx.float().clone()
+    want[idx.long()] += rows.float()
+    ops.scatter_add_rows(rows, idx, dx)
+    _close("scatter_add_rows", dx, want, 2e-2, 1e-2)

@@ -117,3 +117,110 @@ def test_gradient_accumulation_and_frozen_tower():
     for k, p in model.named_parameters():
         if p.grad is not None:
             torch.testing.assert_close(p.grad, g1[k] * 1.5, rtol=2e-2, atol=1e-3 * float(g1[k].abs().max()) + 1e-8)
+
+
+def test_train_step_with_mlm_head_matches_reference_goldens(golden_dir):
+    """has_decoder_head + labels: loss = contrastive + 0.5 * MLM (modeling_cm3p.py:994-996)."""
+    from oracle import cm3p_oracle as O
+    name = "small_b3_l320_mlm"
+    case = CASES[name]
+    gold = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    cfg, sd, model = _build(case["cfg"], case["wseed"], case["gain"])
+    batch = synthetic_batch(cfg, **case["batch"])
+    out = model(**{k: v.cuda() for k, v in batch.items()})
+    out.loss.backward()
+    torch.cuda.synchronize()
+    got = _grads(model)
+    assert abs(float(out.loss.detach()) - float(gold["loss"])) <= 1e-2 * abs(float(gold["loss"]))
+    assert out.logits is not None and out.logits.shape == (3, 320, cfg.beatmap_config.vocab_size)
+    probe = out.logits[:, 205:213, :16].float().cpu()
+    want = torch.from_numpy(gold["mlm_logits_probe"])
+    assert float(torch.nn.functional.cosine_similarity(probe.flatten(1).double(), want.flatten(1), dim=-1).min()) >= 0.99
+    names = [str(n) for n in gold["grad_names"]]
+    gnorm = float(np.sqrt(sum(float(got[n].norm()) ** 2 for n in names)))
+    assert abs(gnorm - float(gold["grad_global_norm"])) <= 1e-2 * float(gold["grad_global_norm"])
+    sd64 = {k: v.double() for k, v in sd.items()}
+    feed = {k: (v.double() if v.is_floating_point() else v) for k, v in batch.items()}
+    _, wgrads = O.forward_backward(sd64, cfg, feed)
+    _check_against_oracle(got, wgrads)
+
+
+@pytest.mark.parametrize("sparse", [False, True])
+def test_masked_lm_model_train_and_eval(sparse):
+    """CM3PForMaskedLM (reference :1241-1379): MLM loss + gradients vs the oracle's beatmap tower + head."""
+    import torch.nn.functional as F
+    from cm3p_b200.modeling_cm3p import CM3PForMaskedLM
+    from oracle import cm3p_oracle as O
+    case = CASES["small_b3_l320_mlm"]
+    full_cfg = CM3PConfig(**copy.deepcopy(case["cfg"]))
+    bc = copy.deepcopy(full_cfg.beatmap_config)
+    bc.sparse_prediction = sparse
+    sd_full = synthetic_state_dict(full_cfg, seed=case["wseed"], gain=case["gain"])
+    sd = {k: v for k, v in sd_full.items() if k.startswith(("beatmap_model.", "head.", "decoder."))}
+    model = CM3PForMaskedLM(bc)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    batch = synthetic_batch(full_cfg, **case["batch"])
+    feed = dict(input_ids=batch["input_ids"], input_features=batch["input_features"],
+                attention_mask=batch["attention_mask"], labels=batch["labels"])
+    out = model(**{k: v.cuda() for k, v in feed.items()})
+    out.loss.backward()
+    torch.cuda.synchronize()
+    # oracle
+    leaves = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+    last, _, _ = O.beatmap_tower(leaves, bc, feed["input_ids"], feed["attention_mask"], feed["input_features"].double())
+    logits = O.mlm_head(leaves, bc, last)
+    want = F.cross_entropy(logits.reshape(-1, logits.shape[-1]), feed["labels"].reshape(-1), ignore_index=-100)
+    want.backward()
+    assert abs(float(out.loss.detach()) - float(want)) <= 1e-2 * abs(float(want))
+    _check_against_oracle(_grads(model), {k: v.grad for k, v in leaves.items() if v.grad is not None})
+    n_lab = int((feed["labels"] != -100).sum())
+    if sparse:
+        assert out.logits.shape == (n_lab, bc.vocab_size)
+    else:
+        assert out.logits.shape == (3, 320, bc.vocab_size)
+        m = feed["attention_mask"].bool()
+        cos = torch.nn.functional.cosine_similarity(out.logits.float().cpu()[m].double(), logits.detach()[m], dim=-1)
+        assert float(cos.min()) >= 0.99
+    # eval path (no grad): same loss value, no autograd graph
+    model.eval()
+    with torch.no_grad():
+        ev = model(**{k: v.cuda() for k, v in feed.items()})
+    assert not ev.loss.requires_grad
+    assert abs(float(ev.loss) - float(want)) <= 1e-2 * abs(float(want))
+
+
+def test_beatmap_classification_model():
+    """CM3PForBeatmapClassification (reference :1137-1226), 2-way single-label head."""
+    import torch.nn.functional as F
+    from cm3p_b200.modeling_cm3p import CM3PForBeatmapClassification
+    from oracle import cm3p_oracle as O
+    case = CASES["small_b4_l400_v3_grads"]
+    full_cfg = CM3PConfig(**copy.deepcopy(case["cfg"]))
+    bc = copy.deepcopy(full_cfg.beatmap_config)
+    bc.num_labels = 2
+    sd_full = synthetic_state_dict(full_cfg, seed=case["wseed"], gain=case["gain"])
+    sd = {k: v for k, v in sd_full.items() if k.startswith("beatmap_model.")}
+    g = torch.Generator().manual_seed(5)
+    sd["classifier.weight"] = torch.randn(2, bc.hidden_size, generator=g) * 0.3
+    sd["classifier.bias"] = torch.randn(2, generator=g) * 0.1
+    model = CM3PForBeatmapClassification(bc)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    batch = synthetic_batch(full_cfg, **case["batch"])
+    labels = torch.tensor([1, 0, 1, 1])
+    out = model(input_ids=batch["input_ids"].cuda(), input_features=batch["input_features"].cuda(),
+                attention_mask=batch["attention_mask"].cuda(), labels=labels.cuda())
+    out.loss.backward()
+    torch.cuda.synchronize()
+    leaves = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+    _, pooled, _ = O.beatmap_tower(leaves, bc, batch["input_ids"], batch["attention_mask"],
+                                   batch["input_features"].double())
+    logits = F.linear(pooled, leaves["classifier.weight"], leaves["classifier.bias"])
+    want = F.cross_entropy(logits, labels)
+    want.backward()
+    assert out.logits.shape == (4, 2)
+    assert float((out.logits.cpu().double() - logits.detach()).abs().max()) <= 0.05 * float(logits.detach().abs().max()) + 0.02
+    assert abs(float(out.loss.detach()) - float(want)) <= 2e-2 * abs(float(want)) + 1e-3
+    _check_against_oracle(_grads(model), {k: v.grad for k, v in leaves.items() if v.grad is not None},
+                          min_cos=0.98, norm_tol=8e-2)
