@@ -5,6 +5,7 @@
 #include "attn.h"
 #include "common.h"
 #include "gemm.h"
+#include "optim.h"
 #include "rowwise.h"
 
 using namespace cm3p;
@@ -237,6 +238,31 @@ int cm3p_scatter_add_rows(const void* dx_rows, const int32_t* index, void* dx, i
                           void* stream) {
   CM3P_ARCH_GUARD();
   return scatter_add_rows(dx_rows, index, dx, rows, hidden, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------------ optimizer
+int cm3p_muon_momentum(const float* grad, float* momentum_buffer, void* x_bf16, int64_t n, float momentum,
+                       int nesterov, float* sumsq, void* stream) {
+  CM3P_ARCH_GUARD();
+  return muon_momentum(grad, momentum_buffer, x_bf16, n, momentum, nesterov, sumsq, as_stream(stream));
+}
+int cm3p_bf16_normalize(void* x_bf16, int64_t n, const float* sumsq, float eps, void* stream) {
+  CM3P_ARCH_GUARD();
+  return bf16_normalize(x_bf16, n, sumsq, eps, as_stream(stream));
+}
+int cm3p_bf16_axpy(void* out, int64_t ld_out, float a, const void* x, int64_t ld_x, const void* y, int64_t ld_y,
+                   int64_t rows, int64_t cols, void* stream) {
+  CM3P_ARCH_GUARD();
+  return bf16_axpy(out, ld_out, a, x, ld_x, y, ld_y, rows, cols, as_stream(stream));
+}
+int cm3p_muon_apply(float* param, const void* x_bf16, int64_t n, float post_scale, float alpha, void* stream) {
+  CM3P_ARCH_GUARD();
+  return muon_apply(param, x_bf16, n, post_scale, alpha, as_stream(stream));
+}
+int cm3p_adamw_step(float* param, const float* grad, float* moment1, float* moment2, int64_t n, float beta1,
+                    float beta2, float eps, float decay, float step_size, void* stream) {
+  CM3P_ARCH_GUARD();
+  return adamw_step(param, grad, moment1, moment2, n, beta1, beta2, eps, decay, step_size, as_stream(stream));
 }
 
 }  // extern "C"

@@ -702,7 +702,10 @@ class CM3PForMaskedLM(CM3PPreTrainedModel):
     optional `sparse_prediction` (only labelled positions go through the head)."""
     config_class = CM3PBeatmapConfig
     base_model_prefix = "beatmap_model"
-    _tied_weights_keys = ["decoder.weight"]
+    # The reference declares `_tied_weights_keys = ["decoder.weight"]` (:1244).  With the installed
+    # transformers the tie only happens when `config.tie_word_embeddings` is true (default: untied, which is
+    # what the oracle does, SURVEY.md quirk Q7); checkpoints with or without a separate decoder.weight load.
+    _tied_weights_keys = {"decoder.weight": "beatmap_model.encoder.embeddings.tok_embeddings.weight"}
 
     def __init__(self, config: CM3PBeatmapConfig):
         super().__init__(config)

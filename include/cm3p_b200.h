@@ -189,6 +189,25 @@ int cm3p_gather_rows(const void* x, const int32_t* index, void* out, int64_t row
 int cm3p_scatter_add_rows(const void* dx_rows, const int32_t* index, void* dx, int64_t rows, int hidden,
                           void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer step of the reference's Muon (utils/muon_utils.py).  The three GEMMs of every Newton-Schulz
+ * iteration (:50-53) are cm3p_gemm_bf16 calls; these are the element-wise pieces, with the reference's
+ * bf16 roundings.
+ *   cm3p_muon_momentum : buf = buf*momentum + g; x = bf16(nesterov ? g + momentum*buf : buf); sumsq += |x|^2   (:152-156, :47)
+ *   cm3p_bf16_normalize: x /= (bf16(sqrt(sumsq)) + eps)                                                     (:48)
+ *   cm3p_bf16_axpy     : out = bf16(bf16(a*x) + y) over [rows, cols] with pitches (y may be NULL)          (:51-53)
+ *   cm3p_muon_apply    : param += alpha * bf16(x * post_scale)                                             (:164-167)
+ *   cm3p_adamw_step    : the internal AdamW for embeddings / vectors (:179-203):
+ *                        m1 = lerp(m1,g,1-b1); m2 = lerp(m2,g^2,1-b2); p = p*decay - step_size * m1/(eps+sqrt(m2)) */
+int cm3p_muon_momentum(const float* grad, float* momentum_buffer, void* x_bf16, int64_t n, float momentum,
+                       int nesterov, float* sumsq, void* stream);
+int cm3p_bf16_normalize(void* x_bf16, int64_t n, const float* sumsq, float eps, void* stream);
+int cm3p_bf16_axpy(void* out, int64_t ld_out, float a, const void* x, int64_t ld_x, const void* y, int64_t ld_y,
+                   int64_t rows, int64_t cols, void* stream);
+int cm3p_muon_apply(float* param, const void* x_bf16, int64_t n, float post_scale, float alpha, void* stream);
+int cm3p_adamw_step(float* param, const float* grad, float* moment1, float* moment2, int64_t n, float beta1,
+                    float beta2, float eps, float decay, float step_size, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

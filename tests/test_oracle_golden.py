@@ -76,3 +76,18 @@ def test_loss_quirk_padding_variations_are_negatives():
     ml = torch.nn.functional.cross_entropy(rows, torch.arange(3))
     bl = torch.nn.functional.cross_entropy(sim.permute(2, 0, 1).reshape(3, 12), torch.arange(3) * 4 + t)
     assert abs(float(full) - float((ml + bl) / 2)) < 1e-12
+
+
+def test_muon_oracle_matches_reference(golden_dir):
+    """oracle/muon_oracle.py vs three steps of the unmodified utils/muon_utils.Muon (bit-exact on CPU)."""
+    from oracle import muon_oracle as M
+    from oracle.make_golden_muon import HYPER, SPECS, STEPS, seeded
+    torch.set_num_threads(1)
+    gold = np.load(os.path.join(golden_dir, "muon_steps.npz"))
+    params, grads = seeded()
+    state, use = {}, {n: m for n, _, m in SPECS}
+    for t in range(STEPS):
+        M.muon_step(params, grads[t], state, use, lr=HYPER["lr"], adamw_lr=HYPER["adamw_lr"],
+                    adamw_betas=HYPER["adamw_betas"], adamw_wd=HYPER["adamw_wd"], adamw_eps=HYPER["adamw_eps"])
+        for n in params:
+            np.testing.assert_allclose(params[n].numpy(), gold[f"step{t}/{n}"], rtol=0, atol=1e-7, err_msg=f"{t}/{n}")
