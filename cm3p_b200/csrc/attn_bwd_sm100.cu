@@ -81,6 +81,44 @@ __device__ __forceinline__ void store_row_units(uint8_t* tile, int t, int first_
   }
 }
 
+__device__ __forceinline__ void store_zero_units(uint8_t* tile, int t, int first_unit) {
+  uint8_t* row = tile + t * 128;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(row + (((first_unit + u) ^ (t & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+}
+
+// Allowed inner-tile columns [a,b) of one row and, per 32-column chunk, the state of its warp (32 rows):
+// 0 = no row of the warp needs the chunk (skip the exp work, write zeros), 1 = per-element masking,
+// 2 = every column allowed for every row (no predicates).
+struct Band {
+  int a, b;
+  int state[2];
+};
+__device__ __forceinline__ Band band_of(int row_pos, int warp_pos, int t0, int len, int window, bool row_valid) {
+  Band r;
+  int a = 0, b = min(BI, len - t0);
+  int wa = 0, wb = b, ia = 0, ib = b;
+  if (window >= 0) {
+    a = max(a, row_pos - window - t0);
+    b = min(b, row_pos + window + 1 - t0);
+    wa = max(wa, warp_pos - window - t0);
+    wb = min(wb, warp_pos + 31 + window + 1 - t0);
+    ia = max(ia, warp_pos + 31 - window - t0);
+    ib = min(ib, warp_pos + window + 1 - t0);
+  }
+  if (warp_pos + 31 >= len) { ia = BI; ib = 0; }
+  if (warp_pos >= len) { wa = BI; wb = 0; }
+  if (!row_valid) b = 0;
+  r.a = a;
+  r.b = b;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int c0 = q * 32, c1 = q * 32 + 32;
+    r.state[q] = (c1 <= wa || c0 >= wb) ? 0 : ((c0 >= ia && c1 <= ib) ? 2 : 1);
+  }
+  return r;
+}
+
 // TMEM accumulator row (64 fp32 columns) -> optional inverse RoPE -> bf16 -> global.
 //   forward: y1 = x1 c - x2 s, y2 = x2 c + x1 s   =>   dx1 = dy1 c + dy2 s, dx2 = dy2 c - dy1 s
 __device__ __forceinline__ void store_grad_row(uint32_t taddr, __nv_bfloat16* dst, const float2* cs, bool valid) {
@@ -261,32 +299,44 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __grid_
       p.delta[static_cast<int64_t>(head) * p.total_tokens + row] = delta;
     }
     const float c = p.scale_log2;
+    const float dsc = delta * p.scale;  // dZ = P * (dP*scale - delta*scale)
+    const int warp_pos = q0 + warp * 32;
     for (int j = 0; j < n_tiles; ++j) {
       const int kv0 = (tile_lo + j) * BI;
       ptx::mbar_wait(s_full, j & 1);
       ptx::tc_fence_after();
-      int a = 0, b = valid ? min(BI, len - kv0) : 0;
-      if (p.window >= 0) {
-        a = max(a, qi - p.window - kv0);
-        b = min(b, qi + p.window + 1 - kv0);
-      }
+      const Band bd = band_of(qi, warp_pos, kv0, len, p.window, valid);
 #pragma unroll
-      for (int cidx = 0; cidx < BI; cidx += 32) {
+      for (int q = 0; q < 2; ++q) {
+        if (bd.state[q] == 0) {
+          store_zero_units(smem_dz, t, q * 4);
+          continue;
+        }
         uint32_t rs[32], rp[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + TM_S + lane_off + cidx, rs);
-        ptx::tmem_ld_32x32b_x32(tmem_base + TM_DP + lane_off + cidx, rp);
+        ptx::tmem_ld_32x32b_x32(tmem_base + TM_S + lane_off + q * 32, rs);
+        ptx::tmem_ld_32x32b_x32(tmem_base + TM_DP + lane_off + q * 32, rp);
         ptx::tmem_ld_wait();
         uint32_t packed[16];
+        if (bd.state[q] == 2) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const int kj = cidx + i;
-          const float p0 = (kj >= a && kj < b) ? ptx::ex2_approx(__uint_as_float(rs[i]) * c - lse) : 0.f;
-          const float p1 = (kj + 1 >= a && kj + 1 < b) ? ptx::ex2_approx(__uint_as_float(rs[i + 1]) * c - lse) : 0.f;
-          const float z0 = p0 * (__uint_as_float(rp[i]) - delta) * p.scale;
-          const float z1 = p1 * (__uint_as_float(rp[i + 1]) - delta) * p.scale;
-          packed[i >> 1] = ptx::pack_bf16x2(z0, z1);
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ptx::ex2_approx(__uint_as_float(rs[i]) * c - lse);
+            const float p1 = ptx::ex2_approx(__uint_as_float(rs[i + 1]) * c - lse);
+            packed[i >> 1] = ptx::pack_bf16x2(p0 * (__uint_as_float(rp[i]) * p.scale - dsc),
+                                              p1 * (__uint_as_float(rp[i + 1]) * p.scale - dsc));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const int kj = q * 32 + i;
+            const float p0 = (kj >= bd.a && kj < bd.b) ? ptx::ex2_approx(__uint_as_float(rs[i]) * c - lse) : 0.f;
+            const float p1 =
+                (kj + 1 >= bd.a && kj + 1 < bd.b) ? ptx::ex2_approx(__uint_as_float(rs[i + 1]) * c - lse) : 0.f;
+            packed[i >> 1] = ptx::pack_bf16x2(p0 * (__uint_as_float(rp[i]) * p.scale - dsc),
+                                              p1 * (__uint_as_float(rp[i + 1]) * p.scale - dsc));
+          }
         }
-        store_row_units(smem_dz, t, cidx >> 3, packed);
+        store_row_units(smem_dz, t, q * 4, packed);
       }
       ptx::tc_fence_before();
       ptx::fence_proxy_async_smem();
@@ -403,7 +453,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __grid
         const int64_t r = row + h + lane;
         const bool ok = r < p.total_tokens;
         vec[h + lane] = ok ? lse_h[r] : 0.f;
-        vec[BI + h + lane] = ok ? delta_h[r] : 0.f;
+        vec[BI + h + lane] = ok ? delta_h[r] * p.scale : 0.f;  // pre-scaled
       }
       ptx::mbar_arrive(&qdo_full[s]);
     }
@@ -457,46 +507,67 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __grid
     const int64_t row = static_cast<int64_t>(seq_start) + kj;
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
     const float c = p.scale_log2;
+    const int warp_pos = k0 + warp * 32;
     for (int i = 0; i < n_tiles; ++i) {
       const int s = i & 1;
       const int q0i = (tile_lo + i) * BI;
       ptx::mbar_wait(s_full, i & 1);
       ptx::mbar_wait(&qdo_full[s], (i >> 1) & 1);  // already complete: orders the lse/delta staging writes
       ptx::tc_fence_after();
-      int a = 0, b = valid ? min(BI, len - q0i) : 0;
-      if (p.window >= 0) {
-        a = max(a, kj - p.window - q0i);
-        b = min(b, kj + p.window + 1 - q0i);
-      }
+      const Band bd = band_of(kj, warp_pos, q0i, len, p.window, valid);
       const float4* lse4 = reinterpret_cast<const float4*>(smem_vec + s * 2 * BI);
-      const float4* del4 = lse4 + BI / 4;
+      const float4* del4 = lse4 + BI / 4;  // delta * scale
 #pragma unroll
-      for (int cidx = 0; cidx < BI; cidx += 32) {
+      for (int q = 0; q < 2; ++q) {
+        if (bd.state[q] == 0) {
+          store_zero_units(smem_pt, t, q * 4);
+          store_zero_units(smem_dzt, t, q * 4);
+          continue;
+        }
         uint32_t rs[32], rp[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + TM_ST + lane_off + cidx, rs);
-        ptx::tmem_ld_32x32b_x32(tmem_base + TM_DPT + lane_off + cidx, rp);
+        ptx::tmem_ld_32x32b_x32(tmem_base + TM_ST + lane_off + q * 32, rs);
+        ptx::tmem_ld_32x32b_x32(tmem_base + TM_DPT + lane_off + q * 32, rp);
         ptx::tmem_ld_wait();
         uint32_t pp[16], pz[16];
+        if (bd.state[q] == 2) {
 #pragma unroll
-        for (int i4 = 0; i4 < 32; i4 += 4) {
-          const float4 l4 = lse4[(cidx + i4) >> 2];
-          const float4 d4 = del4[(cidx + i4) >> 2];
-          const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
-          const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
-          float pv[4], zv[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int qj = cidx + i4 + e;
-            pv[e] = (qj >= a && qj < b) ? ptx::ex2_approx(__uint_as_float(rs[i4 + e]) * c - ls[e]) : 0.f;
-            zv[e] = pv[e] * (__uint_as_float(rp[i4 + e]) - dl[e]) * p.scale;
+          for (int i4 = 0; i4 < 32; i4 += 4) {
+            const float4 l4 = lse4[(q * 32 + i4) >> 2];
+            const float4 d4 = del4[(q * 32 + i4) >> 2];
+            const float p0 = ptx::ex2_approx(__uint_as_float(rs[i4]) * c - l4.x);
+            const float p1 = ptx::ex2_approx(__uint_as_float(rs[i4 + 1]) * c - l4.y);
+            const float p2 = ptx::ex2_approx(__uint_as_float(rs[i4 + 2]) * c - l4.z);
+            const float p3 = ptx::ex2_approx(__uint_as_float(rs[i4 + 3]) * c - l4.w);
+            pp[i4 >> 1] = ptx::pack_bf16x2(p0, p1);
+            pp[(i4 >> 1) + 1] = ptx::pack_bf16x2(p2, p3);
+            pz[i4 >> 1] = ptx::pack_bf16x2(p0 * (__uint_as_float(rp[i4]) * p.scale - d4.x),
+                                           p1 * (__uint_as_float(rp[i4 + 1]) * p.scale - d4.y));
+            pz[(i4 >> 1) + 1] = ptx::pack_bf16x2(p2 * (__uint_as_float(rp[i4 + 2]) * p.scale - d4.z),
+                                                 p3 * (__uint_as_float(rp[i4 + 3]) * p.scale - d4.w));
           }
-          pp[i4 >> 1] = ptx::pack_bf16x2(pv[0], pv[1]);
-          pp[(i4 >> 1) + 1] = ptx::pack_bf16x2(pv[2], pv[3]);
-          pz[i4 >> 1] = ptx::pack_bf16x2(zv[0], zv[1]);
-          pz[(i4 >> 1) + 1] = ptx::pack_bf16x2(zv[2], zv[3]);
+        } else {
+#pragma unroll
+          for (int i4 = 0; i4 < 32; i4 += 4) {
+            const float4 l4 = lse4[(q * 32 + i4) >> 2];
+            const float4 d4 = del4[(q * 32 + i4) >> 2];
+            const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
+            const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
+            float pv[4], zv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int qj = q * 32 + i4 + e;
+              const float ex = ptx::ex2_approx(__uint_as_float(rs[i4 + e]) * c - ls[e]);
+              pv[e] = (qj >= bd.a && qj < bd.b) ? ex : 0.f;
+              zv[e] = pv[e] * (__uint_as_float(rp[i4 + e]) * p.scale - dl[e]);
+            }
+            pp[i4 >> 1] = ptx::pack_bf16x2(pv[0], pv[1]);
+            pp[(i4 >> 1) + 1] = ptx::pack_bf16x2(pv[2], pv[3]);
+            pz[i4 >> 1] = ptx::pack_bf16x2(zv[0], zv[1]);
+            pz[(i4 >> 1) + 1] = ptx::pack_bf16x2(zv[2], zv[3]);
+          }
         }
-        store_row_units(smem_pt, t, cidx >> 3, pp);
-        store_row_units(smem_dzt, t, cidx >> 3, pz);
+        store_row_units(smem_pt, t, q * 4, pp);
+        store_row_units(smem_dzt, t, q * 4, pz);
       }
       ptx::tc_fence_before();
       ptx::fence_proxy_async_smem();

@@ -169,7 +169,8 @@ attn_bwd_dq_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
   uint64_t* s_full = bars + 1 + 2 * NS; // [2]
   uint64_t* dz_full = s_full + 2;       // [2]
   uint64_t* acc_full = dz_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* dz_free = acc_full + 1;     // [2] the dQ MMAs that read dZ[g] have retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dz_free + 2);
 
   if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
 
@@ -190,6 +191,7 @@ attn_bwd_dq_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
     for (int g = 0; g < 2; ++g) {
       ptx::mbar_init(&s_full[g], 1);
       ptx::mbar_init(&dz_full[g], 128);
+      ptx::mbar_init(&dz_free[g], 1);
     }
     ptx::mbar_init(acc_full, 1);
     ptx::fence_barrier_init();
@@ -251,6 +253,9 @@ attn_bwd_dq_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
         const int s = j % NS, g = j & 1;
         ptx::mbar_wait(&dz_full[g], (j >> 1) & 1);
         ptx::tc_fence_after();
+        // S/dP of tile j+2 (group g's TMEM buffers are free again) go in FIRST, so group g can start on
+        // them while the tensor pipe is still busy with the accumulating GEMM of tile j
+        if (j + 2 < n_tiles) issue_s_dp(j + 2);
         const uint32_t k_addr = ptx::smem_u32(smem_k + s * INNER_BYTES);
         const uint32_t dz_addr = ptx::smem_u32(smem_dz + g * OUTER_BYTES);
 #pragma unroll
@@ -258,8 +263,7 @@ attn_bwd_dq_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
           ptx::umma_bf16(tmem_base + TM_DQ, ptx::umma_smem_desc_sw128(dz_addr + k * 32, 16, 1024),
                          ptx::umma_smem_desc_sw128(k_addr + k * 2048, 8192, 1024), idesc_dq, (j | k) != 0 ? 1u : 0u);
         ptx::umma_commit(&kv_empty[s]);
-        // S/dP of tile j+2 reuse group g's TMEM buffers; their commit also retires the dZ[g] reads above
-        if (j + 2 < n_tiles) issue_s_dp(j + 2);
+        ptx::umma_commit(&dz_free[g]);
       }
       ptx::umma_commit(acc_full);
     }
@@ -295,6 +299,7 @@ attn_bwd_dq_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
       ptx::mbar_wait(&s_full[g], (j >> 1) & 1);
       ptx::tc_fence_after();
       const Band bd = band_of(qi, warp_pos, kv0, len, p.window, valid);
+      ptx::mbar_wait(&dz_free[g], ((j >> 1) & 1) ^ 1);  // dZ[g] of tile j-2 consumed (passes at once for the first)
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         if (bd.state[q] == 0) {
@@ -381,7 +386,8 @@ attn_bwd_dkv_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __g
   uint64_t* s_full = bars + 1 + 2 * NS;     // [2]
   uint64_t* pz_full = s_full + 2;           // [2]
   uint64_t* acc_full = pz_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* pz_free = acc_full + 1;         // [2] the dV/dK MMAs that read P^T[g] / dZ^T[g] have retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pz_free + 2);
 
   if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
 
@@ -402,6 +408,7 @@ attn_bwd_dkv_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __g
     for (int g = 0; g < 2; ++g) {
       ptx::mbar_init(&s_full[g], 1);
       ptx::mbar_init(&pz_full[g], 128);
+      ptx::mbar_init(&pz_free[g], 1);
     }
     ptx::mbar_init(acc_full, 1);
     ptx::fence_barrier_init();
@@ -479,6 +486,7 @@ attn_bwd_dkv_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __g
         const int s = i % NS, g = i & 1;
         ptx::mbar_wait(&pz_full[g], (i >> 1) & 1);
         ptx::tc_fence_after();
+        if (i + 2 < n_tiles) issue_s_dp(i + 2);  // next S^T/dP^T of group g ahead of the accumulating GEMMs
         const uint32_t q_addr = ptx::smem_u32(smem_q + s * INNER_BYTES);
         const uint32_t do_addr = ptx::smem_u32(smem_do + s * INNER_BYTES);
         const uint32_t pt_addr = ptx::smem_u32(smem_pt + g * OUTER_BYTES);
@@ -492,7 +500,7 @@ attn_bwd_dkv_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __g
           ptx::umma_bf16(tmem_base + TM_DK, ptx::umma_smem_desc_sw128(dzt_addr + k * 32, 16, 1024),
                          ptx::umma_smem_desc_sw128(q_addr + k * 2048, 8192, 1024), idesc_acc, (i | k) != 0 ? 1u : 0u);
         ptx::umma_commit(&qdo_empty[s]);
-        if (i + 2 < n_tiles) issue_s_dp(i + 2);
+        ptx::umma_commit(&pz_free[g]);
       }
       ptx::umma_commit(acc_full);
     }
@@ -517,6 +525,7 @@ attn_bwd_dkv_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __g
       const Band bd = band_of(kj, warp_pos, q0i, len, p.window, valid);
       const float4* lse4 = reinterpret_cast<const float4*>(smem_vec + s * 2 * BI);
       const float4* del4 = lse4 + BI / 4;
+      ptx::mbar_wait(&pz_free[g], ((i >> 1) & 1) ^ 1);  // P^T[g]/dZ^T[g] of tile i-2 consumed
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         if (bd.state[q] == 0) {

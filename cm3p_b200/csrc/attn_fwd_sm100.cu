@@ -327,7 +327,8 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
   uint64_t* s_full = bars + 7;    // [2]
   uint64_t* p_full = bars + 9;    // [2] 128 arrivals each
   uint64_t* o_full = bars + 11;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* pv_done = bars + 13;  // [2] PV_x(u) retired: P_x buffer reusable, O_x stable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
 
@@ -358,6 +359,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
       ptx::mbar_init(&s_full[x], 1);
       ptx::mbar_init(&p_full[x], 128);
       ptx::mbar_init(&o_full[x], 1);
+      ptx::mbar_init(&pv_done[x], 1);
     }
     ptx::fence_barrier_init();
   }
@@ -417,6 +419,8 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
           if (u < lo_x || u >= hi_x) continue;
           ptx::mbar_wait(&p_full[x], jx & 1);  // P_x(u) in smem, S_x(u) consumed, O_x rescaled if needed
           ptx::tc_fence_after();
+          // S of the next tile first: group x can start on it while the tensor pipe is still busy with PV_x(u)
+          if (u + 1 < hi_x) issue_s(x, u + 1);
           const uint32_t p_addr = ptx::smem_u32(smem_p + x * P_BYTES);
           const uint32_t v_addr = ptx::smem_u32(smem_v + s * KV_TILE_BYTES);
 #pragma unroll
@@ -426,9 +430,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
                            ptx::umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_o,
                            (jx | k) != 0 ? 1u : 0u);
           ++jx;
-          // S of the next tile goes in behind this PV: its commit also tells group x that the PV has
-          // retired (P buffer reusable, O stable for a rescale).
-          if (u + 1 < hi_x) issue_s(x, u + 1);
+          if (u + 1 < hi_x) ptx::umma_commit(&pv_done[x]);
           else ptx::umma_commit(&o_full[x]);
         }
         ptx::umma_commit(&kv_empty[s]);
@@ -509,9 +511,11 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
       if (jj == 0) {
         m_run = m_new;
       } else {
+        // PV(jj-1) was issued behind S(jj): wait for it before rescaling O or overwriting the P buffer
+        ptx::mbar_wait(&pv_done[x], (jj - 1) & 1);
+        ptx::tc_fence_after();
         const bool grow = (m_new - m_run) * c > RESCALE_LOG2;  // also true for -inf -> finite
         if (__any_sync(0xffffffffu, grow)) {
-          // the S commit this iteration waited on was issued behind PV(jj-1): O is stable
           const float alpha = grow ? ptx::ex2_approx((m_run - m_new) * c) : 1.f;
 #pragma unroll 1
           for (int h = 0; h < D; h += 16) {

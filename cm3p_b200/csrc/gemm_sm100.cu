@@ -658,10 +658,25 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
     // weight gradients: few output tiles, K = number of tokens.  Split K so that ~4 work units per SM
     // exist; partial sums meet in C through fp32 atomics.
     const int64_t tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
-    int64_t want = (4LL * num_sms()) / tiles;
-    if (want > num_kb / 8) want = num_kb / 8;
-    if (want < 1) want = 1;
-    p.kb_per_split = static_cast<int>((num_kb + want - 1) / want);
+    // Pick the split count that minimises (waves of work units) x (K per unit): e.g. 54 output tiles on 148
+    // SMs -> 8 or 19 splits fill whole waves, where a plain "4 units per SM" rule leaves the last wave 65% full.
+    const int sms = num_sms() > 0 ? num_sms() : 148;
+    int64_t max_splits = num_kb / 8;  // at least 8 k-blocks (512 K elements) per unit
+    if (max_splits > (8LL * sms) / tiles + 1) max_splits = (8LL * sms) / tiles + 1;
+    if (max_splits < 1) max_splits = 1;
+    int64_t best = 1;
+    double best_cost = 1e30;
+    for (int64_t sp = 1; sp <= max_splits; ++sp) {
+      const int64_t kb_per = (num_kb + sp - 1) / sp;
+      const int64_t units = tiles * ((num_kb + kb_per - 1) / kb_per);
+      const int64_t waves = (units + sms - 1) / sms;
+      const double cost = static_cast<double>(waves) * (static_cast<double>(kb_per) + 6.0);  // +6: per-unit prologue/epilogue
+      if (cost < best_cost * 0.995) {
+        best_cost = cost;
+        best = sp;
+      }
+    }
+    p.kb_per_split = static_cast<int>((num_kb + best - 1) / best);
     p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
   }
 

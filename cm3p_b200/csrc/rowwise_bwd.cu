@@ -55,7 +55,7 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 // GATHER variant = embedding layer: the row is re-gathered exactly as in embed_gather_ln_kernel and
 // dx is scattered: audio rows -> d_audio[slot] (unique), token rows -> atomic add into d_tok[id].
 template <bool GATHER, int NV>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                      const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dres,
                      __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, int64_t rows, int H, float eps,
@@ -64,17 +64,21 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
                      const int32_t* __restrict__ audio_slot, const __nv_bfloat16* __restrict__ tok_emb,
                      const __nv_bfloat16* __restrict__ audio_embeds, float* __restrict__ d_tok,
                      __nv_bfloat16* __restrict__ d_audio, int vocab) {
-  // NV = vectors (8 columns) per lane: H <= NV * 256.  gamma is re-read per row (L1-resident) so that
-  // two CTAs fit the register file; only the running dgamma partial sums live across rows.
-  __shared__ float red[8][NV * 256];
+  // NV = 16-byte vectors per lane (H <= NV * 256).  The kernel is latency-bound unless enough rows are in
+  // flight (ncu: 3 TB/s with 16 warps/SM and two dependent DRAM round trips per row), so: every load of a
+  // row (x, dy, residual gradient) is issued up front and kept PACKED (bf16) in registers, statistics use
+  // two shuffle rounds (sum & sum-of-squares, then the two dx moments), and the register budget allows
+  // three CTAs (24 warps) per SM.  Only the dgamma partial sums live across rows.
+  // dgamma partial sums: one private shared-memory row per warp (keeps 8*NV registers free for occupancy)
+  __shared__ __align__(16) float red[8][NV * 256];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nvec = H >> 3;
-  float dg[NV][8];
+  float* my_dg = red[warp];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) dg[i][k] = 0.f;
+    *reinterpret_cast<float4*>(my_dg + (lane + i * 32) * 8) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(my_dg + (lane + i * 32) * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float invH = 1.f / H;
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp; row < rows; row += static_cast<int64_t>(gridDim.x) * 8) {
@@ -95,57 +99,80 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
     } else {
       src = x + row * H;
     }
-    float v[NV][8], g[NV][8];
-    float s = 0.f;
+    uint4 px[NV], pg[NV], pr[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      px[i] = pg[i] = pr[i] = make_uint4(0, 0, 0, 0);
+      if (vi < nvec) {
+        px[i] = *reinterpret_cast<const uint4*>(src + vi * 8);
+        pg[i] = *reinterpret_cast<const uint4*>(dy + row * H + vi * 8);
+        if constexpr (!GATHER) {
+          if (dres) pr[i] = *reinterpret_cast<const uint4*>(dres + row * H + vi * 8);
+        }
+      }
+    }
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float v[8];
+      unpack8(px[i], v);  // zeros beyond nvec contribute nothing
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s += v[k];
+        q += v[k] * v[k];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    const float mean = s * invH;
+    const float rstd = rsqrtf(fmaxf(q * invH - mean * mean, 0.f) + eps);
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + i * 32;
       if (vi < nvec) {
-        unpack8(*reinterpret_cast<const uint4*>(src + vi * 8), v[i]);
-        unpack8(*reinterpret_cast<const uint4*>(dy + row * H + vi * 8), g[i]);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s += v[i][k];
-      }
-    }
-    const float mean = warp_sum(s) * invH;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i)
-      if (lane + i * 32 < nvec) {
+        float v[8], g[8], gam[8];
+        unpack8(px[i], v);
+        unpack8(pg[i], g);
+        *reinterpret_cast<float4*>(gam) = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+        *reinterpret_cast<float4*>(gam + 4) = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+        float d[8];
+        *reinterpret_cast<float4*>(d) = *reinterpret_cast<const float4*>(my_dg + vi * 8);
+        *reinterpret_cast<float4*>(d + 4) = *reinterpret_cast<const float4*>(my_dg + vi * 8 + 4);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float d = v[i][k] - mean;
-          q += d * d;
-        }
-      }
-    const float rstd = rsqrtf(warp_sum(q) * invH + eps);
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i)
-      if (lane + i * 32 < nvec) {
-        float gam[8];
-        *reinterpret_cast<float4*>(gam) = __ldg(reinterpret_cast<const float4*>(gamma + (lane + i * 32) * 8));
-        *reinterpret_cast<float4*>(gam + 4) = __ldg(reinterpret_cast<const float4*>(gamma + (lane + i * 32) * 8 + 4));
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float xh = (v[i][k] - mean) * rstd;
-          dg[i][k] += g[i][k] * xh;
-          const float gg = g[i][k] * gam[k];
-          v[i][k] = xh;
-          g[i][k] = gg;
+          const float xh = (v[k] - mean) * rstd;
+          d[k] += g[k] * xh;
+          const float gg = g[k] * gam[k];
           s1 += gg;
           s2 += gg * xh;
         }
+        *reinterpret_cast<float4*>(my_dg + vi * 8) = *reinterpret_cast<const float4*>(d);
+        *reinterpret_cast<float4*>(my_dg + vi * 8 + 4) = *reinterpret_cast<const float4*>(d + 4);
       }
-    s1 = warp_sum(s1) * invH;
-    s2 = warp_sum(s2) * invH;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    s1 *= invH;
+    s2 *= invH;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + i * 32;
       if (vi < nvec) {
-        float o[8];
+        float v[8], g[8], gam[8], o[8];
+        unpack8(px[i], v);
+        unpack8(pg[i], g);
+        *reinterpret_cast<float4*>(gam) = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+        *reinterpret_cast<float4*>(gam + 4) = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = rstd * (g[i][k] - s1 - v[i][k] * s2);
+        for (int k = 0; k < 8; ++k) o[k] = rstd * (g[k] * gam[k] - s1 - (v[k] - mean) * rstd * s2);
         if constexpr (GATHER) {
           if (slot >= 0) {
             if (d_audio) *reinterpret_cast<uint4*>(d_audio + static_cast<int64_t>(slot) * H + vi * 8) = pack8(o);
@@ -157,7 +184,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
         } else {
           if (dres) {
             float r[8];
-            unpack8(*reinterpret_cast<const uint4*>(dres + row * H + vi * 8), r);
+            unpack8(pr[i], r);
 #pragma unroll
             for (int k = 0; k < 8; ++k) o[k] += r[k];
           }
@@ -168,12 +195,6 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
   }
   if (dgamma == nullptr) return;
   // per-CTA reduction of the gamma gradient, then one atomic per column
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int vi = lane + i * 32;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) red[warp][vi * 8 + k] = dg[i][k];
-  }
   __syncthreads();
   for (int c = threadIdx.x; c < H; c += blockDim.x) {
     float t = 0.f;
@@ -495,7 +516,7 @@ int layernorm_bwd(const void* x, const void* dy, const float* gamma, const void*
                MAXV * 256);
   if (rows == 0) return kOk;
   const int64_t want = (rows + 7) / 8;
-  const int grid = static_cast<int>(want < 8LL * num_sms() ? want : 8LL * num_sms());
+  const int grid = static_cast<int>(want < 6LL * num_sms() ? want : 6LL * num_sms());
 #define CM3P_LN_BWD(NV)                                                                                             \
   layernorm_bwd_kernel<false, NV><<<grid, 256, 0, stream>>>(                                                        \
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), gamma,                 \
@@ -518,7 +539,7 @@ int embed_gather_ln_bwd(const int64_t* ids, const int32_t* src_index, const int3
                MAXV * 256);
   if (rows == 0) return kOk;
   const int64_t want = (rows + 7) / 8;
-  const int grid = static_cast<int>(want < 8LL * num_sms() ? want : 8LL * num_sms());
+  const int grid = static_cast<int>(want < 6LL * num_sms() ? want : 6LL * num_sms());
 #define CM3P_LN_BWD(NV)                                                                                            \
   layernorm_bwd_kernel<true, NV><<<grid, 256, 0, stream>>>(                                                        \
       nullptr, reinterpret_cast<const __nv_bfloat16*>(dy), gamma, nullptr, nullptr, dgamma, rows, H, eps, ids,     \
