@@ -12,6 +12,8 @@ One "step" = one pass of the hot path over one batch of synthetic input per GPU.
       compute, batch 256 windows/GPU, V = 8 metadata variations, forward + explicit backward + ONE
       gradient all-reduce (NCCL) when N > 1; optimizer step excluded -> pairs/s.
       `--global-negatives` switches to configs[3] semantics (embedding all-gather, global loss).
+  workload mlm (BASELINE.json configs[4], not part of the default run): CM3PForMaskedLM train step on
+      8192-token windows, 8 windows/GPU, 15 % masked -> real tokens/s.
   workload all (default): the infer line with the train result attached under the key "train".
 
 Prints ONE JSON line on rank 0.  `value` is measured with inputs resident in HBM; `e2e` goes through
@@ -45,7 +47,9 @@ TRAIN_STEPS_CAP = 5  # a train step is ~0.6 s of device time; keep the default r
 SEQ_LEN = 2000
 MIN_LEN = 600
 TRAIN_VARIATIONS = 8
-METRIC = {"infer": ("beatmap_embeds_per_sec", "embeds/s"), "train": ("train_pairs_per_sec", "pairs/s")}
+METRIC = {"infer": ("beatmap_embeds_per_sec", "embeds/s"), "train": ("train_pairs_per_sec", "pairs/s"),
+          "mlm": ("mlm_train_tokens_per_sec", "tokens/s")}
+MLM_SEQ_LEN, MLM_BATCH = 8192, 8
 
 
 def _peaks():
@@ -139,6 +143,10 @@ def _algorithmic_flops_infer(cfg: CM3PConfig, batch: dict) -> float:
 
 
 def _make_batch(cfg, workload, rank, batch):
+    if workload == "mlm":
+        b = synthetic_batch(cfg, batch=batch, seq_len=MLM_SEQ_LEN, seed=1 + rank, min_len=MLM_SEQ_LEN // 2,
+                            with_labels=True)
+        return {k: b[k] for k in ("input_ids", "attention_mask", "input_features", "labels")}
     V = 1 if workload == "infer" else TRAIN_VARIATIONS
     return synthetic_batch(cfg, batch=batch, seq_len=SEQ_LEN, variations=V, seed=1 + rank, min_len=MIN_LEN)
 
@@ -151,6 +159,9 @@ WORKLOAD_TEXT = {
              "fp32 master weights / bf16 compute, batch {B} synthetic 16 s windows per GPU (L=2000 padded, real "
              "lengths U{{600..2000}}), forward + backward + gradient all-reduce, {neg} negatives; optimizer step "
              "excluded",
+    "mlm": "BASELINE.json configs[4]: CM3PForMaskedLM train step (beatmap tower + audio encoder + MLM head), fp32 "
+           "master weights / bf16 compute, {B} windows of L=8192 per GPU (real lengths U{{4096..8192}}), 15 % masked, "
+           "forward + backward + gradient all-reduce ({neg}); value = real tokens/s; optimizer step excluded",
 }
 
 
@@ -160,11 +171,18 @@ def _bench_workload(workload, args, dist, dev, world, rank, local_rank) -> dict 
     from cm3p_b200 import ops
     from cm3p_b200.modeling_cm3p import CM3PModel
 
-    train = workload == "train"
-    B = args.train_batch if train else BATCH_PER_GPU["infer"]
-    cfg = CM3PConfig(attn_implementation="flash_attention_2", **copy.deepcopy(base_config_dict()))
-    model = CM3PModel(cfg)
-    model.load_state_dict(synthetic_state_dict(cfg, seed=0), strict=True)
+    train = workload in ("train", "mlm")
+    B = MLM_BATCH if workload == "mlm" else (args.train_batch if train else BATCH_PER_GPU["infer"])
+    cfg = CM3PConfig(attn_implementation="flash_attention_2",
+                     **copy.deepcopy(base_config_dict(has_decoder_head=(workload == "mlm"))))
+    if workload == "mlm":
+        from cm3p_b200.modeling_cm3p import CM3PForMaskedLM
+        model = CM3PForMaskedLM(cfg.beatmap_config)
+        model.load_state_dict({k: v for k, v in synthetic_state_dict(cfg, seed=0).items()
+                               if k.startswith(("beatmap_model.", "head.", "decoder."))}, strict=True)
+    else:
+        model = CM3PModel(cfg)
+        model.load_state_dict(synthetic_state_dict(cfg, seed=0), strict=True)
     model = model.to(dev)
     if train:
         model.train()
@@ -260,21 +278,22 @@ def _bench_workload(workload, args, dist, dev, world, rank, local_rank) -> dict 
     peaks = _peaks()
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
 
-    total_flops = _algorithmic_flops_infer(cfg, host) * (3.0 if train else 1.0)
+    units = float(host["attention_mask"].sum()) if workload == "mlm" else float(B)  # tokens or windows per step
+    total_flops = 0.0 if workload == "mlm" else _algorithmic_flops_infer(cfg, host) * (3.0 if train else 1.0)
     metric, unit = METRIC[workload]
     neg = "global (embedding all-gather)" if (train and args.global_negatives and world > 1) else "local (per-rank)"
     result = {
-        "metric": metric, "value": round(world * B / (ms_step * 1e-3), 2), "unit": unit, "n_gpus": world,
+        "metric": metric, "value": round(world * units / (ms_step * 1e-3), 2), "unit": unit, "n_gpus": world,
         "steps": steps, "warmup": n_warm, "ms_per_step": round(ms_step, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "impl": "ours",
         "config": {
             "workload": WORKLOAD_TEXT[workload].format(B=B, neg=neg),
-            "batch_per_gpu": B, "seq_len": SEQ_LEN, "real_tokens_per_step": int(host["attention_mask"].sum()),
+            "batch_per_gpu": B, "seq_len": MLM_SEQ_LEN if workload == "mlm" else SEQ_LEN, "real_tokens_per_step": int(host["attention_mask"].sum()),
             "weights": "random init (seeded), 136.9 M params",
             "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2; no explicit flush",
         },
-        "e2e": {"value": round(world * B / (ms_e2e * 1e-3), 2), "unit": unit, "ms_per_step": round(ms_e2e, 3),
+        "e2e": {"value": round(world * units / (ms_e2e * 1e-3), 2), "unit": unit, "ms_per_step": round(ms_e2e, 3),
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "model_tflops": round(total_flops / (ms_step * 1e-3) / 1e12, 1),
@@ -286,7 +305,7 @@ def _bench_workload(workload, args, dist, dev, world, rank, local_rank) -> dict 
                      "peak_source": peaks["source"]},
         "clocks": clocks,
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and workload != "mlm":
         result["cpu_baseline"] = cpu_baseline(cfg, workload, sample_batch=2, reps=1)
     del model, resident, pinned
     torch.cuda.empty_cache()
@@ -402,7 +421,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["all", "infer", "train"], default="all")
+    ap.add_argument("--workload", choices=["all", "infer", "train", "mlm"], default="all")
     ap.add_argument("--train-batch", type=int, default=BATCH_PER_GPU["train"], help="train windows per GPU")
     ap.add_argument("--global-negatives", action="store_true",
                     help="train: all-gather embeddings and use the global loss (BASELINE.json configs[3])")
