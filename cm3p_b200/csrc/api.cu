@@ -240,6 +240,16 @@ int cm3p_scatter_add_rows(const void* dx_rows, const int32_t* index, void* dx, i
   return scatter_add_rows(dx_rows, index, dx, rows, hidden, as_stream(stream));
 }
 
+int cm3p_segment_accumulate(const float* embeds, const int32_t* slot, float* sums, float* counts, int rows,
+                            int proj_dim, void* stream) {
+  CM3P_ARCH_GUARD();
+  return segment_accumulate(embeds, slot, sums, counts, rows, proj_dim, as_stream(stream));
+}
+int cm3p_mean_renormalize(const float* sums, const float* counts, float* out, int rows, int proj_dim, void* stream) {
+  CM3P_ARCH_GUARD();
+  return mean_renormalize(sums, counts, out, rows, proj_dim, as_stream(stream));
+}
+
 // ------------------------------------------------------------------------------------------ optimizer
 int cm3p_muon_momentum(const float* grad, float* momentum_buffer, void* x_bf16, int64_t n, float momentum,
                        int nesterov, float* sumsq, void* stream) {

@@ -19,6 +19,10 @@ int l2norm_rows(const float* e, float* out_f32, void* out_bf16, float* inv_norm,
 int clip_loss_fwd(const float* S, const int32_t* true_idx, float* row_lse, float* col_lse, float* loss, int Bm, int V,
                   int Bb, cudaStream_t stream);
 
+int segment_accumulate(const float* e, const int32_t* slot, float* sums, float* counts, int rows, int P,
+                       cudaStream_t stream);
+int mean_renormalize(const float* sums, const float* counts, float* out, int rows, int P, cudaStream_t stream);
+
 // ---- backward (rowwise_bwd.cu)
 int layernorm_bwd(const void* x, const void* dy, const float* gamma, const void* dres, void* dx, float* dgamma,
                   int64_t rows, int H, float eps, cudaStream_t stream);

@@ -293,7 +293,52 @@ clip_loss_finalize_kernel(const float* __restrict__ S, const int32_t* __restrict
   }
 }
 
+// Embedding extraction (extract_beatmap_embeddings.py:243-262): window embeddings are summed per beatmap
+// (sums[slot[i]] += e[i], counts[slot[i]] += 1) and finalised as mean / |mean| (left as the mean when its norm is 0).
+__global__ void __launch_bounds__(256)
+segment_accumulate_kernel(const float* __restrict__ e, const int32_t* __restrict__ slot, float* __restrict__ sums,
+                          float* __restrict__ counts, int rows, int P) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int s = slot[row];
+  if (s < 0) return;
+  for (int i = lane; i < P; i += 32) atomicAdd(sums + static_cast<int64_t>(s) * P + i, e[static_cast<int64_t>(row) * P + i]);
+  if (lane == 0) atomicAdd(counts + s, 1.f);
+}
+__global__ void __launch_bounds__(256)
+mean_renormalize_kernel(const float* __restrict__ sums, const float* __restrict__ counts, float* __restrict__ out,
+                        int rows, int P) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float inv_n = 1.f / fmaxf(counts[row], 1.f);
+  float ss = 0.f;
+  for (int i = lane; i < P; i += 32) {
+    const float m = sums[static_cast<int64_t>(row) * P + i] * inv_n;
+    ss += m * m;
+  }
+  ss = warp_sum(ss);
+  const float norm = sqrtf(ss);
+  const float sc = norm > 0.f ? inv_n / norm : inv_n;
+  for (int i = lane; i < P; i += 32) out[static_cast<int64_t>(row) * P + i] = sums[static_cast<int64_t>(row) * P + i] * sc;
+}
+
 }  // namespace
+
+int segment_accumulate(const float* e, const int32_t* slot, float* sums, float* counts, int rows, int P,
+                       cudaStream_t stream) {
+  if (rows == 0) return kOk;
+  segment_accumulate_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(e, slot, sums, counts, rows, P);
+  CM3P_CUDA_TRY(cudaGetLastError());
+  return kOk;
+}
+int mean_renormalize(const float* sums, const float* counts, float* out, int rows, int P, cudaStream_t stream) {
+  if (rows == 0) return kOk;
+  mean_renormalize_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(sums, counts, out, rows, P);
+  CM3P_CUDA_TRY(cudaGetLastError());
+  return kOk;
+}
 
 int layernorm_fwd(const void* x, const float* gamma, void* y, float* stats, int64_t rows, int H, float eps,
                   cudaStream_t stream) {

@@ -189,6 +189,13 @@ int cm3p_gather_rows(const void* x, const int32_t* index, void* out, int64_t row
 int cm3p_scatter_add_rows(const void* dx_rows, const int32_t* index, void* dx, int64_t rows, int hidden,
                           void* stream);
 
+/* Per-beatmap aggregation of window embeddings (extract_beatmap_embeddings.py:243-262):
+ *   cm3p_segment_accumulate: sums[slot[i]] += embeds[i] (fp32 [rows,P]), counts[slot[i]] += 1; slot < 0 skipped
+ *   cm3p_mean_renormalize  : out[b] = mean_b / |mean_b|  (mean_b = sums[b]/counts[b]; left un-normalised if 0) */
+int cm3p_segment_accumulate(const float* embeds, const int32_t* slot, float* sums, float* counts, int rows,
+                            int proj_dim, void* stream);
+int cm3p_mean_renormalize(const float* sums, const float* counts, float* out, int rows, int proj_dim, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Optimizer step of the reference's Muon (utils/muon_utils.py).  The three GEMMs of every Newton-Schulz
  * iteration (:50-53) are cm3p_gemm_bf16 calls; these are the element-wise pieces, with the reference's
