@@ -50,6 +50,12 @@ TRAIN_VARIATIONS = 8
 METRIC = {"infer": ("beatmap_embeds_per_sec", "embeds/s"), "train": ("train_pairs_per_sec", "pairs/s"),
           "mlm": ("mlm_train_tokens_per_sec", "tokens/s")}
 MLM_SEQ_LEN, MLM_BATCH = 8192, 8
+# dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch (average over the GEMM launches of one step), from
+# the ncu launch lists committed under profiles/ (it cannot be measured from inside this script)
+GEMM_TRAFFIC = {
+    "infer": (263.5e6, "profiles/r1_infer_launch_summary_v2.txt (ncu, batch 64)"),
+    "train": (1254.0e6, "profiles/r1_train256_launch_summary.txt (ncu, batch 256)"),
+}
 
 
 def _peaks():
@@ -255,6 +261,7 @@ def _bench_workload(workload, args, dist, dev, world, rank, local_rank) -> dict 
     # ---- roofline of the dominant kernel family (the tcgen05 GEMM), timed live with CUDA events around
     #      every GEMM launch of one extra step on the launching stream
     gemm_events = []
+    gemm_bytes_box = [0.0]
     orig_gemm = ops.gemm
 
     def timed_gemm(a, b, **kw):
@@ -265,16 +272,44 @@ def _bench_workload(workload, args, dist, dev, world, rank, local_rank) -> dict 
         out = orig_gemm(a, b, **kw)
         e1.record()
         gemm_events.append((e0, e1, 2.0 * M * N * K))
+        gemm_bytes_box[0] += a.numel() * 2 + b.numel() * 2 + out.numel() * out.element_size()
         return out
 
-    ops.gemm = timed_gemm
+    attn_events = []
+    orig_fwd, orig_bwd = ops.attn_varlen_fwd, ops.attn_varlen_bwd
+
+    def _attn_flops(cu_seqlens, heads, window, factor):
+        lens = (cu_seqlens[1:] - cu_seqlens[:-1]).double()
+        keys = lens if window < 0 else torch.clamp(lens, max=2 * window + 1)
+        return factor * float((lens * keys).sum()) * 64 * heads
+
+    def timed_attn_fwd(qkv, cu_seqlens, max_seqlen, heads, window=-1, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig_fwd(qkv, cu_seqlens, max_seqlen, heads, window, **kw)
+        e1.record()
+        attn_events.append((e0, e1, cu_seqlens, heads, window, 4.0))
+        return out
+
+    def timed_attn_bwd(qkv, out, dout, lse, cu_seqlens, max_seqlen, heads, window=-1, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig_bwd(qkv, out, dout, lse, cu_seqlens, max_seqlen, heads, window, **kw)
+        e1.record()
+        attn_events.append((e0, e1, cu_seqlens, heads, window, 10.0))
+        return r
+
+    ops.gemm, ops.attn_varlen_fwd, ops.attn_varlen_bwd = timed_gemm, timed_attn_fwd, timed_attn_bwd
     try:
         step(resident)
         torch.cuda.synchronize()
     finally:
-        ops.gemm = orig_gemm
+        ops.gemm, ops.attn_varlen_fwd, ops.attn_varlen_bwd = orig_gemm, orig_fwd, orig_bwd
+    attn_ms = sum(e0.elapsed_time(e1) for e0, e1, *_ in attn_events)
+    attn_flops = sum(_attn_flops(cu, h, w, f) for _, _, cu, h, w, f in attn_events)
     gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in gemm_events)
     gemm_flops = sum(f for _, _, f in gemm_events)
+    gemm_bytes = gemm_bytes_box[0]
     peaks = _peaks()
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
 
@@ -300,9 +335,18 @@ def _bench_workload(workload, args, dist, dev, world, rank, local_rank) -> dict 
         "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
         "roofline": {"kernel": "gemm_bf16_sm100_kernel (all epilogues)", "bound": "tensor",
                      "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
-                     "frac": round(achieved / peaks["tflops"], 4), "traffic": None,
+                     "frac": round(achieved / peaks["tflops"], 4),
+                     "traffic": GEMM_TRAFFIC[workload][0] if (workload in GEMM_TRAFFIC and B == BATCH_PER_GPU.get(workload)) else None,
+                     "traffic_source": GEMM_TRAFFIC[workload][1] if workload in GEMM_TRAFFIC else None,
+                     "algorithmic_bytes_per_launch": round(gemm_bytes / max(1, len(gemm_events))),
                      "launches_per_step": len(gemm_events), "share_of_step": round(gemm_ms / ms_step, 3),
                      "peak_source": peaks["source"]},
+        "roofline_attention": {"kernel": "attn_fwd_v2 / attn_bwd_dq + attn_bwd_dkv (varlen, D=64)", "bound": "tensor",
+                               "achieved": round(attn_flops / (attn_ms * 1e-3) / 1e12, 1) if attn_ms > 0 else 0.0,
+                               "peak": peaks["tflops"], "unit": "TFLOP/s",
+                               "frac": round(attn_flops / (attn_ms * 1e-3) / 1e12 / peaks["tflops"], 4) if attn_ms > 0 else 0.0,
+                               "flops": "algorithmic: 4*l*keys*64 per head forward, 10*l*keys*64 backward (5 GEMMs)",
+                               "launches_per_step": len(attn_events), "share_of_step": round(attn_ms / ms_step, 3)},
         "clocks": clocks,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline and workload != "mlm":

@@ -48,6 +48,9 @@ SIGNATURES = {
     "cm3p_scatter_add_rows": (_I, [_P, _P, _P, _L, _I, _P]),
     "cm3p_segment_accumulate": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "cm3p_mean_renormalize": (_I, [_P, _P, _P, _I, _I, _P]),
+    "cm3p_logmel_frames": (_I, [_P, _P, _P, _P, _I, _L, _I, _I, _I, _I, _P]),
+    "cm3p_logmel_power_mel": (_I, [_P, _L, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "cm3p_logmel_finalize": (_I, [_P, _P, _I, _L, _P]),
     "cm3p_muon_momentum": (_I, [_P, _P, _P, _L, _F, _I, _P, _P]),
     "cm3p_bf16_normalize": (_I, [_P, _L, _P, _F, _P]),
     "cm3p_bf16_axpy": (_I, [_P, _L, _F, _P, _L, _P, _L, _L, _L, _P]),

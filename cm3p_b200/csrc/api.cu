@@ -5,6 +5,7 @@
 #include "attn.h"
 #include "common.h"
 #include "gemm.h"
+#include "logmel.h"
 #include "optim.h"
 #include "rowwise.h"
 
@@ -248,6 +249,22 @@ int cm3p_segment_accumulate(const float* embeds, const int32_t* slot, float* sum
 int cm3p_mean_renormalize(const float* sums, const float* counts, float* out, int rows, int proj_dim, void* stream) {
   CM3P_ARCH_GUARD();
   return mean_renormalize(sums, counts, out, rows, proj_dim, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------------ log-mel
+int cm3p_logmel_frames(const float* wave, const float* window, void* frames_hi, void* frames_lo, int batch,
+                       int64_t samples, int frames, int n_fft, int hop, int ld, void* stream) {
+  CM3P_ARCH_GUARD();
+  return logmel_frames(wave, window, frames_hi, frames_lo, batch, samples, frames, n_fft, hop, ld, as_stream(stream));
+}
+int cm3p_logmel_power_mel(const float* spec, int64_t ld_spec, const float* mel_filters, float* out, float* clip_max,
+                          int batch, int frames, int bins, int mels, void* stream) {
+  CM3P_ARCH_GUARD();
+  return logmel_power_mel(spec, ld_spec, mel_filters, out, clip_max, batch, frames, bins, mels, as_stream(stream));
+}
+int cm3p_logmel_finalize(float* out, const float* clip_max, int batch, int64_t per_clip, void* stream) {
+  CM3P_ARCH_GUARD();
+  return logmel_finalize(out, clip_max, batch, per_clip, as_stream(stream));
 }
 
 // ------------------------------------------------------------------------------------------ optimizer

@@ -196,6 +196,19 @@ int cm3p_segment_accumulate(const float* embeds, const int32_t* slot, float* sum
                             int proj_dim, void* stream);
 int cm3p_mean_renormalize(const float* sums, const float* counts, float* out, int rows, int proj_dim, void* stream);
 
+/* Log-mel front-end on the GPU: replaces `WhisperFeatureExtractor.__call__` as used by the reference's
+ * processor (cm3p/processing_cm3p.py:284-304; n_fft 400, hop 160, 80 slaney mel bins).  The DFT between the two
+ * kernels is three cm3p_gemm_bf16 calls on hi/lo-split bf16 operands (CM3P_EPI_SCALE_F32, accumulate).
+ *   cm3p_logmel_frames   : reflect-centred, Hann-windowed frames [batch*frames, ld] as bf16 hi + lo parts
+ *   cm3p_logmel_power_mel: spec [batch*frames, ld_spec] fp32 = (re[0..bins) | im[0..bins)) -> out [batch, mels, frames]
+ *                          = log10(max(mel(|.|^2), 1e-10)); clip_max[batch] = running max (init to -inf)
+ *   cm3p_logmel_finalize : out = (max(out, clip_max - 8) + 4) / 4 */
+int cm3p_logmel_frames(const float* wave, const float* window, void* frames_hi, void* frames_lo, int batch,
+                       int64_t samples, int frames, int n_fft, int hop, int ld, void* stream);
+int cm3p_logmel_power_mel(const float* spec, int64_t ld_spec, const float* mel_filters, float* out, float* clip_max,
+                          int batch, int frames, int bins, int mels, void* stream);
+int cm3p_logmel_finalize(float* out, const float* clip_max, int batch, int64_t per_clip, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Optimizer step of the reference's Muon (utils/muon_utils.py).  The three GEMMs of every Newton-Schulz
  * iteration (:50-53) are cm3p_gemm_bf16 calls; these are the element-wise pieces, with the reference's
