@@ -15,6 +15,7 @@
 //   warp 0 lane 0 : TMA producer            warp 1 lane 0 : MMA issuer
 //   warp 2        : TMEM alloc / dealloc    warps 4..7    : epilogue (TMEM lane quadrant = warp - 4)
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "gemm.h"
@@ -54,6 +55,7 @@ struct Params {
   int vec_c;       // C (and C2 / aux) rows allow 16-byte accesses
   int splits;        // split-K factor (>1 only with the atomic F32 epilogue: weight gradients, K = tokens)
   int kb_per_split;  // k-blocks per split
+  int cluster;       // 1, or 2: CTA pairs on adjacent M tiles share every B tile through TMA multicast
 };
 
 __device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
@@ -396,7 +398,8 @@ template <int EPI, bool STAGED>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                        const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_c2,
-                       const __grid_constant__ CUtensorMap tma_aux, const Params p) {
+                       const __grid_constant__ CUtensorMap tma_aux, const __grid_constant__ CUtensorMap tma_bh,
+                       const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -417,10 +420,13 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     ptx::prefetch_tmap(&tma_a);
     ptx::prefetch_tmap(&tma_b);
   }
+  // cluster mode: the pair's two CTAs each load half of every B tile and multicast it to both, so a
+  // stage may only be refilled once BOTH tensor pipes have drained it (empty barriers count 2 arrivals)
+  const uint32_t crank = p.cluster > 1 ? ptx::cluster_ctarank() : 0u;
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full[s], 1);
-      ptx::mbar_init(&empty[s], 1);
+      ptx::mbar_init(&empty[s], p.cluster);
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
@@ -434,24 +440,31 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (p.cluster > 1) ptx::cluster_sync_all();  // barrier inits visible to the peer before any remote arrive
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int64_t tiles_m = (p.M + BM - 1) / BM;
   const int64_t tiles_n = (p.N + BN - 1) / BN;
-  const int64_t mn_tiles = tiles_m * tiles_n;
-  const int64_t num_tiles = mn_tiles * p.splits;  // work units: (output tile, K split)
+  // work units: (group of `cluster` adjacent M tiles, N tile, K split); CTA `crank` of the cluster takes M tile
+  // group*cluster + crank (possibly past the end of M: it then only serves its half of the B loads)
+  const int64_t mn_tiles = ((tiles_m + p.cluster - 1) / p.cluster) * tiles_n;
+  const int64_t num_tiles = mn_tiles * p.splits;
+  const int64_t unit0 = blockIdx.x / p.cluster, unit_step = gridDim.x / p.cluster;
   const int num_kb_total = static_cast<int>((p.K + BK - 1) / BK);
+  auto tile_m0 = [&](int64_t t) { return (((t % mn_tiles) / tiles_n) * p.cluster + crank) * BM; };
+  auto tile_n0 = [&](int64_t t) { return ((t % mn_tiles) % tiles_n) * BN; };
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
     int s = 0;
     uint32_t ph = 0;
-    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int64_t mn = t % mn_tiles;
-      const int32_t m0 = static_cast<int32_t>((mn / tiles_n) * BM);
-      const int32_t n0 = static_cast<int32_t>((mn % tiles_n) * BN);
+    // (An L2 prefetch cursor running 8 k-blocks ahead of the loads was tried here and measured 40% SLOWER:
+    //  cp.async.bulk.prefetch.tensor competes with the real loads for the same TMA issue slot.)
+    for (int64_t t = unit0; t < num_tiles; t += unit_step) {
+      const int32_t m0 = static_cast<int32_t>(tile_m0(t));
+      const int32_t n0 = static_cast<int32_t>(tile_n0(t));
       const int kb0 = static_cast<int>(t / mn_tiles) * p.kb_per_split;
       const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -466,12 +479,26 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
           for (int i = 0; i < BM / 64; ++i)  // box {64 m, 64 k} per 64-wide M chunk
             ptx::tma_load_2d(sa + i * (BK * 128), &tma_a, &full[s], m0 + i * 64, kb * BK);
         }
-        if (!p.trans_b) {
-          ptx::tma_load_2d(sb, &tma_b, &full[s], kb * BK, n0);  // box {64 k, 256 n}
-        } else {
+        if (p.cluster == 1) {
+          if (!p.trans_b) {
+            ptx::tma_load_2d(sb, &tma_b, &full[s], kb * BK, n0);  // box {64 k, 256 n}
+          } else {
 #pragma unroll
-          for (int i = 0; i < BN / 64; ++i)  // box {64 n, 64 k}
-            ptx::tma_load_2d(sb + i * (BK * 128), &tma_b, &full[s], n0 + i * 64, kb * BK);
+            for (int i = 0; i < BN / 64; ++i)  // box {64 n, 64 k}
+              ptx::tma_load_2d(sb + i * (BK * 128), &tma_b, &full[s], n0 + i * 64, kb * BK);
+          }
+        } else {
+          // this CTA's half of the B tile, delivered to both CTAs of the pair
+          if (!p.trans_b) {
+            ptx::tma_load_2d_multicast(sb + crank * (B_STAGE_BYTES / 2), &tma_bh, &full[s], kb * BK,
+                                       n0 + static_cast<int32_t>(crank) * (BN / 2), 0x3);  // box {64 k, 128 n}
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 128; ++i) {
+              const int j = static_cast<int>(crank) * (BN / 128) + i;
+              ptx::tma_load_2d_multicast(sb + j * (BK * 128), &tma_b, &full[s], n0 + j * 64, kb * BK, 0x3);
+            }
+          }
         }
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
@@ -487,7 +514,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     uint32_t ph = 0;
     int as = 0;
     uint32_t aph = 0;
-    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int64_t t = unit0; t < num_tiles; t += unit_step) {
       ptx::mbar_wait(&tmem_empty[as], aph ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
@@ -504,7 +531,9 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
           const uint64_t db = ptx::umma_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
           ptx::umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
         }
-        ptx::umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+        // frees the smem stage once these MMAs have read it (in both CTAs of a pair: either may refill it)
+        if (p.cluster > 1) ptx::umma_commit_multicast(&empty[s], 0x3);
+        else ptx::umma_commit(&empty[s]);
         if (kb == kb1 - 1) ptx::umma_commit(&tmem_full[as]);
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
@@ -518,23 +547,21 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     EpiState st;
     if constexpr (STAGED && EPI == EPI_RESIDUAL) {
       // residual slab of the very first output slab
-      if (quad == 0 && lane == 0 && static_cast<int64_t>(blockIdx.x) < num_tiles) {
-        const int64_t t0 = blockIdx.x % mn_tiles;
+      if (quad == 0 && lane == 0 && unit0 < num_tiles) {
         ptx::mbar_arrive_expect_tx(&res_full[0], SLAB_BYTES);
-        ptx::tma_load_2d(slabs, &tma_aux, &res_full[0], static_cast<int32_t>((t0 % tiles_n) * BN),
-                         static_cast<int32_t>((t0 / tiles_n) * BM));
+        ptx::tma_load_2d(slabs, &tma_aux, &res_full[0], static_cast<int32_t>(tile_n0(unit0)),
+                         static_cast<int32_t>(tile_m0(unit0)));
       }
     }
-    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int64_t mn = t % mn_tiles;
-      const int64_t m0 = (mn / tiles_n) * BM;
-      const int64_t n0 = (mn % tiles_n) * BN;
+    for (int64_t t = unit0; t < num_tiles; t += unit_step) {
+      const int64_t m0 = tile_m0(t);
+      const int64_t n0 = tile_n0(t);
       ptx::mbar_wait(&tmem_full[as], aph);
       ptx::tc_fence_after();
       if constexpr (STAGED) {
-        const int64_t tn = t + gridDim.x;  // staged epilogues never split K: unit index == tile index
+        const int64_t tn = t + unit_step;
         epilogue_tile_staged<EPI>(p, &tma_c, &tma_c2, &tma_aux, slabs, res_full, st, tmem_base + as * BN, quad, m0,
-                                  n0, (tn / tiles_n) * BM, (tn % tiles_n) * BN, tn < num_tiles);
+                                  n0, tile_m0(tn), tile_n0(tn), tn < num_tiles);
       } else {
         epilogue_tile<EPI>(p, tmem_base + as * BN, quad, m0, n0);
       }
@@ -549,7 +576,8 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (p.cluster > 1) ptx::cluster_sync_all();  // the peer may still multicast into / signal this CTA
+  else __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
@@ -558,28 +586,42 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
 
 template <int EPI, bool STAGED>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2,
-           const CUtensorMap& taux, const Params& p, cudaStream_t stream) {
+           const CUtensorMap& taux, const CUtensorMap& tbh, const Params& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     CM3P_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_sm100_kernel<EPI, STAGED>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
-  const int64_t tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.splits;
-  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-  gemm_bf16_sm100_kernel<EPI, STAGED><<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, tc, tc2, taux, p);
-  CM3P_CUDA_TRY(cudaGetLastError());
+  const int64_t tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  const int64_t units = ((tiles_m + p.cluster - 1) / p.cluster) * tiles_n * p.splits;
+  const int64_t max_clusters = num_sms() / p.cluster;
+  const int grid = static_cast<int>((units < max_clusters ? units : max_clusters) * p.cluster);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CM3P_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_bf16_sm100_kernel<EPI, STAGED>, ta, tb, tc, tc2, taux, tbh, p));
   return kOk;
 }
 
 template <int EPI>
 int launch_any(bool staged, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
-               const CUtensorMap& tc2, const CUtensorMap& taux, const Params& p, cudaStream_t stream) {
+               const CUtensorMap& tc2, const CUtensorMap& taux, const CUtensorMap& tbh, const Params& p,
+               cudaStream_t stream) {
   if constexpr (EPI == EPI_SCALE_F32) {
-    return launch<EPI, false>(ta, tb, tc, tc2, taux, p, stream);
+    return launch<EPI, false>(ta, tb, tc, tc2, taux, tbh, p, stream);
   } else {
-    return staged ? launch<EPI, true>(ta, tb, tc, tc2, taux, p, stream)
-                  : launch<EPI, false>(ta, tb, tc, tc2, taux, p, stream);
+    return staged ? launch<EPI, true>(ta, tb, tc, tc2, taux, tbh, p, stream)
+                  : launch<EPI, false>(ta, tb, tc, tc2, taux, tbh, p, stream);
   }
 }
 
@@ -680,16 +722,32 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
     p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
   }
 
+  // CTA pairs (2-CTA clusters) on adjacent M tiles share each B tile through TMA multicast: a third less
+  // L2 -> SM traffic per CTA (ncu: the MMA thread waited ~30% of the time for operands without it).
+  static int cluster_mode = -1;
+  if (cluster_mode < 0) {
+    const char* e = getenv("CM3P_GEMM_CLUSTER");
+    cluster_mode = e ? atoi(e) : 2;
+    if (cluster_mode != 1 && cluster_mode != 2) cluster_mode = 2;
+  }
+  const int64_t tiles_m_total = (g.M + BM - 1) / BM;
+  p.cluster = (cluster_mode == 2 && tiles_m_total >= 2 && g.N > BN / 2) ? 2 : 1;
+  CUtensorMap tbh = tb;
+  if (p.cluster == 2 && !g.trans_b) {
+    rc = encode_tmap_2d_bf16(&tbh, g.b, g.K, g.N, g.ldb * 2, BK, BN / 2);
+    if (rc != kOk) return rc;
+  }
+
   switch (g.epilogue) {
-    case EPI_STORE: return launch_any<EPI_STORE>(staged, ta, tb, tc, tc2, taux, p, stream);
-    case EPI_RESIDUAL: return launch_any<EPI_RESIDUAL>(staged, ta, tb, tc, tc2, taux, p, stream);
-    case EPI_GELU: return launch_any<EPI_GELU>(staged, ta, tb, tc, tc2, taux, p, stream);
-    case EPI_BIAS_GELU: return launch_any<EPI_BIAS_GELU>(staged, ta, tb, tc, tc2, taux, p, stream);
-    case EPI_BIAS: return launch_any<EPI_BIAS>(staged, ta, tb, tc, tc2, taux, p, stream);
-    case EPI_GEGLU: return launch_any<EPI_GEGLU>(staged, ta, tb, tc, tc2, taux, p, stream);
-    case EPI_GEGLU_SAVE: return launch_any<EPI_GEGLU_SAVE>(staged, ta, tb, tc, tc2, taux, p, stream);
-    case EPI_ROPE: return launch_any<EPI_ROPE>(staged, ta, tb, tc, tc2, taux, p, stream);
-    case EPI_SCALE_F32: return launch_any<EPI_SCALE_F32>(staged, ta, tb, tc, tc2, taux, p, stream);
+    case EPI_STORE: return launch_any<EPI_STORE>(staged, ta, tb, tc, tc2, taux, tbh, p, stream);
+    case EPI_RESIDUAL: return launch_any<EPI_RESIDUAL>(staged, ta, tb, tc, tc2, taux, tbh, p, stream);
+    case EPI_GELU: return launch_any<EPI_GELU>(staged, ta, tb, tc, tc2, taux, tbh, p, stream);
+    case EPI_BIAS_GELU: return launch_any<EPI_BIAS_GELU>(staged, ta, tb, tc, tc2, taux, tbh, p, stream);
+    case EPI_BIAS: return launch_any<EPI_BIAS>(staged, ta, tb, tc, tc2, taux, tbh, p, stream);
+    case EPI_GEGLU: return launch_any<EPI_GEGLU>(staged, ta, tb, tc, tc2, taux, tbh, p, stream);
+    case EPI_GEGLU_SAVE: return launch_any<EPI_GEGLU_SAVE>(staged, ta, tb, tc, tc2, taux, tbh, p, stream);
+    case EPI_ROPE: return launch_any<EPI_ROPE>(staged, ta, tb, tc, tc2, taux, tbh, p, stream);
+    case EPI_SCALE_F32: return launch_any<EPI_SCALE_F32>(staged, ta, tb, tc, tc2, taux, tbh, p, stream);
   }
   return set_error(kBadShape, "gemm: unreachable epilogue %d", g.epilogue);
 }

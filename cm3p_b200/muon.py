@@ -145,6 +145,8 @@ class Muon(torch.optim.Optimizer):
                     post = max(1.0, R / C) ** 0.5
                     _lib.check(lib.cm3p_muon_apply(p.data_ptr(), upd.data_ptr(), R * C, float(post), float(-lr),
                                                    _stream()), "cm3p_muon_apply")
+                    # the kernels write through raw pointers: tell autograd / the bf16 weight-pack caches
+                    torch.autograd.graph.increment_version(p)
                 else:
                     if "step" not in state:
                         state["step"] = 0
@@ -158,6 +160,7 @@ class Muon(torch.optim.Optimizer):
                                                    state["moment2"].data_ptr(), p.numel(), float(b1), float(b2),
                                                    float(group["adamw_eps"]), float(1 - adamw_lr * group["adamw_wd"]),
                                                    float(lr / scale), _stream()), "cm3p_adamw_step")
+                    torch.autograd.graph.increment_version(p)
         return loss
 
 

@@ -63,3 +63,33 @@ def test_newton_schulz_production_shapes(shape):
     d_got, d_want = p.detach().cpu() - p0, ref["w"] - p0
     assert _cos(d_got, d_want) >= 0.99
     assert abs(float(d_got.norm()) - float(d_want.norm())) <= 0.05 * float(d_want.norm())
+
+
+def test_optimizer_step_invalidates_weight_packs():
+    """The kernels update parameters through raw pointers; the model's bf16 weight packs must notice
+    (regression test: a stale pack would make training a silent no-op)."""
+    import copy
+    from cm3p_b200.configuration_cm3p import CM3PConfig, small_config_dict
+    from cm3p_b200.modeling_cm3p import CM3PModel
+    from cm3p_b200.muon import Muon, split_muon_adamw
+    from cm3p_b200.synthetic import synthetic_batch, synthetic_state_dict
+    cfg = CM3PConfig(**copy.deepcopy(small_config_dict()))
+    model = CM3PModel(cfg)
+    model.load_state_dict(synthetic_state_dict(cfg, seed=0), strict=True)
+    model = model.cuda().train()
+    muon, adamw = split_muon_adamw(model)
+    opt = Muon(muon_params=muon, adamw_params=adamw, lr=5e-3, adamw_lr=1e-3)
+    batch = {k: v.cuda() for k, v in synthetic_batch(cfg, batch=4, seq_len=320, variations=2, seed=1).items()}
+    losses = []
+    for _ in range(6):
+        opt.zero_grad(set_to_none=True)
+        out = model(**batch)
+        out.loss.backward()
+        opt.step()
+        losses.append(float(out.loss.detach()))
+    assert losses[-1] < losses[0] - 0.05, losses  # far beyond atomics noise: the updated weights are being used
+    v0 = [p._version for p in model.parameters()]
+    opt.zero_grad(set_to_none=True)
+    model(**batch).loss.backward()
+    opt.step()
+    assert all(b > a for a, b in zip(v0, [p._version for p in model.parameters()]))
