@@ -24,6 +24,7 @@ SIGNATURES = {
     "cm3p_version": (_I, []),
     "cm3p_num_sms": (_I, []),
     "cm3p_gemm_bf16": (_I, [_P, _L, _I, _P, _L, _I, _P, _L, _L, _L, _L, _I, _P, _L, _P, _L, _F, _I, _P, _P, _L, _P]),
+    "cm3p_gemm_bf16_ln": (_I, [_P, _L, _P, _L, _P, _L, _L, _L, _L, _I, _P, _L, _P, _L, _P, _P, _L, _P, _P, _P, _F, _P]),
     "cm3p_attn_varlen_fwd": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
     "cm3p_layernorm_fwd": (_I, [_P, _P, _P, _P, _L, _I, _F, _P]),
     "cm3p_embed_gather_ln": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _F, _P]),

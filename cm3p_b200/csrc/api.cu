@@ -36,6 +36,23 @@ int cm3p_gemm_bf16(const void* a, int64_t lda, int trans_a, const void* b, int64
   return gemm_bf16(g, as_stream(stream));
 }
 
+int cm3p_gemm_bf16_ln(const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t M, int64_t N,
+                      int64_t K, int epilogue, const void* aux, int64_t ld_aux, void* c2, int64_t ldc2,
+                      const int32_t* positions, const float* rope_table, int64_t rope_cols, float* stats_out,
+                      const float* row_stats, const float* col_corr, float ln_eps, void* stream) {
+  GemmArgs g;
+  g.a = a; g.lda = lda;
+  g.b = b; g.ldb = ldb;
+  g.c = c; g.ldc = ldc;
+  g.M = M; g.N = N; g.K = K;
+  g.epilogue = epilogue;
+  g.aux = aux; g.ld_aux = ld_aux;
+  g.c2 = c2; g.ldc2 = ldc2;
+  g.positions = positions; g.rope_table = rope_table; g.rope_cols = rope_cols;
+  g.stats_out = stats_out; g.row_stats = row_stats; g.col_corr = col_corr; g.ln_eps = ln_eps;
+  return gemm_bf16(g, as_stream(stream));
+}
+
 int cm3p_attn_varlen_fwd(const void* qkv, void* out, float* lse, const int32_t* cu_seqlens, int64_t total_tokens,
                          int batch, int heads, int head_dim, int max_seqlen, int window, void* stream) {
   AttnFwdArgs a;

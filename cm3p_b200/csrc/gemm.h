@@ -38,6 +38,14 @@ struct GemmArgs {
   int64_t rope_cols = 0;
   int trans_a = 0, trans_b = 0;
   int accumulate = 0;
+  // LayerNorm folded into the GEMMs on both sides of it (bf16 staged epilogues only):
+  //   producer (EPI_RESIDUAL): stats_out[M][2] += (sum, sum of squares) of the bf16 rows it writes
+  //   consumer (EPI_ROPE / EPI_GEGLU / EPI_GEGLU_SAVE), B = W . diag(gamma):
+  //       acc <- rstd_row * (acc - mean_row * col_corr[n]),  col_corr[n] = sum_k B[n][k]
+  float* stats_out = nullptr;
+  const float* row_stats = nullptr;
+  const float* col_corr = nullptr;
+  float ln_eps = 1e-5f;
 };
 
 int gemm_bf16(const GemmArgs& args, cudaStream_t stream);

@@ -56,6 +56,10 @@ struct Params {
   int splits;        // split-K factor (>1 only with the atomic F32 epilogue: weight gradients, K = tokens)
   int kb_per_split;  // k-blocks per split
   int cluster;       // 1, or 2: CTA pairs on adjacent M tiles share every B tile through TMA multicast
+  float* stats_out;        // RESIDUAL: per-row (sum, sum^2) of the written rows, or null
+  const float* row_stats;  // ROPE / GEGLU(_SAVE): per-row (sum, sum^2) of the A rows -> LayerNorm folded in, or null
+  const float* col_corr;   // [N] column sums of B (= W . diag(gamma))
+  float ln_eps;
 };
 
 __device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
@@ -266,6 +270,31 @@ __device__ __forceinline__ void epilogue_tile_staged(const Params& p, const CUte
   const bool leader = (quad == 0 && lane == 0);
   const uint32_t taddr_row = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16);
 
+  // LayerNorm folded into this GEMM (see GemmArgs): y = rstd * (x.W'^T - mean * colsum(W'))
+  float ln_mean = 0.f, ln_rstd = 1.f;
+  bool ln = false;
+  if constexpr (EPI == EPI_ROPE || EPI == EPI_GEGLU || EPI == EPI_GEGLU_SAVE) {
+    ln = p.row_stats != nullptr;
+    if (ln && row < p.M) {
+      const float2 sq = *reinterpret_cast<const float2*>(p.row_stats + row * 2);
+      const float inv_w = 1.f / static_cast<float>(p.K);
+      ln_mean = sq.x * inv_w;
+      ln_rstd = rsqrtf(fmaxf(sq.y * inv_w - ln_mean * ln_mean, 0.f) + p.ln_eps);
+    }
+  }
+  auto ln_fix = [&](auto& v, int64_t first_col) {  // all columns < N (N % 64 == 0 is required)
+    constexpr int COUNT = sizeof(v) / sizeof(float);
+#pragma unroll
+    for (int i = 0; i < COUNT; i += 4) {
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.col_corr + first_col + i));
+      v[i] = ln_rstd * (v[i] - ln_mean * c4.x);
+      v[i + 1] = ln_rstd * (v[i + 1] - ln_mean * c4.y);
+      v[i + 2] = ln_rstd * (v[i + 2] - ln_mean * c4.z);
+      v[i + 3] = ln_rstd * (v[i + 3] - ln_mean * c4.w);
+    }
+  };
+  float st_sum = 0.f, st_sq = 0.f;  // RESIDUAL: statistics of the rows written by this thread
+
   float2 cs[32];
   if constexpr (EPI == EPI_ROPE) {
     if (n0 < p.rope_cols) {
@@ -314,11 +343,21 @@ __device__ __forceinline__ void epilogue_tile_staged(const Params& p, const CUte
         ptx::tmem_ld_32x32b_x32(taddr_row + sl * ACC + h * 64, ra);
         ptx::tmem_ld_32x32b_x32(taddr_row + sl * ACC + h * 64 + 32, rb);
         ptx::tmem_ld_wait();
+        float fa[32], fb[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          fa[i] = __uint_as_float(ra[i]);
+          fb[i] = __uint_as_float(rb[i]);
+        }
+        if (ln) {
+          ln_fix(fa, col + h * 64);
+          ln_fix(fb, col + h * 64 + 32);
+        }
         float o[32];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          o[i] = ptx::gelu_erf(__uint_as_float(ra[i])) * __uint_as_float(ra[16 + i]);
-          o[16 + i] = ptx::gelu_erf(__uint_as_float(rb[i])) * __uint_as_float(rb[16 + i]);
+          o[i] = ptx::gelu_erf(fa[i]) * fa[16 + i];
+          o[16 + i] = ptx::gelu_erf(fb[i]) * fb[16 + i];
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) slab_write_row(slab, r, h * 4 + c, pack8f(o + c * 8));
@@ -334,6 +373,9 @@ __device__ __forceinline__ void epilogue_tile_staged(const Params& p, const CUte
         v[i] = __uint_as_float(r1[i]);
         v[32 + i] = __uint_as_float(r2[i]);
       }
+      if constexpr (EPI == EPI_ROPE || EPI == EPI_GEGLU_SAVE) {
+        if (ln) ln_fix(v, col);
+      }
       if constexpr (EPI == EPI_RESIDUAL) {
         ptx::mbar_wait(&res_full[buf], st.res_parity[buf]);
         st.res_parity[buf] ^= 1;
@@ -345,6 +387,17 @@ __device__ __forceinline__ void epilogue_tile_staged(const Params& p, const CUte
           f = ptx::unpack_bf16x2(u.y); v[c * 8 + 2] += f.x; v[c * 8 + 3] += f.y;
           f = ptx::unpack_bf16x2(u.z); v[c * 8 + 4] += f.x; v[c * 8 + 5] += f.y;
           f = ptx::unpack_bf16x2(u.w); v[c * 8 + 6] += f.x; v[c * 8 + 7] += f.y;
+        }
+        if (p.stats_out) {
+          // statistics of what is actually stored (bf16-rounded), for the LayerNorm folded into the next GEMM
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            if (col + i < p.N) {
+              const float rv = __bfloat162float(__float2bfloat16(v[i]));
+              st_sum += rv;
+              st_sq += rv * rv;
+            }
+          }
         }
       } else if constexpr (EPI == EPI_GELU) {
 #pragma unroll
@@ -391,6 +444,12 @@ __device__ __forceinline__ void epilogue_tile_staged(const Params& p, const CUte
       ptx::tma_store_commit();
     }
     ++st.g;
+  }
+  if constexpr (EPI == EPI_RESIDUAL) {
+    if (p.stats_out && row < p.M) {
+      atomicAdd(p.stats_out + row * 2, st_sum);
+      atomicAdd(p.stats_out + row * 2 + 1, st_sq);
+    }
   }
 }
 
@@ -693,6 +752,17 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   p.trans_a = g.trans_a; p.trans_b = g.trans_b;
   p.accumulate = g.accumulate;
   p.vec_c = vec ? 1 : 0;
+  p.stats_out = g.stats_out;
+  p.row_stats = g.row_stats;
+  p.col_corr = g.col_corr;
+  p.ln_eps = g.ln_eps;
+  if (g.stats_out)
+    CM3P_REQUIRE(g.epilogue == EPI_RESIDUAL && vec, kBadShape,
+                 "gemm: stats_out needs the staged EPI_RESIDUAL epilogue (16-byte aligned bf16 rows)");
+  if (g.row_stats)
+    CM3P_REQUIRE((g.epilogue == EPI_ROPE || g.epilogue == EPI_GEGLU || g.epilogue == EPI_GEGLU_SAVE) && vec &&
+                     g.col_corr != nullptr && g.N % 64 == 0,
+                 kBadShape, "gemm: row_stats needs a staged ROPE/GEGLU epilogue, col_corr and N %% 64 == 0");
   p.splits = 1;
   const int num_kb = static_cast<int>((g.K + BK - 1) / BK);
   p.kb_per_split = num_kb;

@@ -166,14 +166,23 @@ class ModernBertEncoder(nn.Module):
                     "layers": [],
                 }
                 for i, layer in enumerate(self.layers):
-                    pk["layers"].append({
+                    e = {
                         "attn_norm": None if i == 0 else layer.attn_norm.weight.detach().to(f32).contiguous(),
                         "wqkv": layer.attn.Wqkv.weight.detach().to(bf).contiguous(),
                         "wo": layer.attn.Wo.weight.detach().to(bf).contiguous(),
                         "mlp_norm": layer.mlp_norm.weight.detach().to(f32).contiguous(),
                         "wi": ops.interleave_wi(layer.mlp.Wi.weight.detach().to(bf)).contiguous(),
                         "wo2": layer.mlp.Wo.weight.detach().to(bf).contiguous(),
-                    })
+                    }
+                    # LayerNorm folded into the GEMM that consumes it (cm3p_gemm_bf16_ln): W' = W.diag(gamma)
+                    # in bf16 and its row sums (of the rounded W', which is what the tensor core multiplies)
+                    if i > 0:
+                        wq = (layer.attn.Wqkv.weight.detach().float() * e["attn_norm"][None, :]).to(bf).contiguous()
+                        e["wqkv_ln"], e["cqkv"] = wq, wq.float().sum(dim=1).contiguous()
+                    wi = (layer.mlp.Wi.weight.detach().float() * e["mlp_norm"][None, :]).to(bf)
+                    wi = ops.interleave_wi(wi).contiguous()
+                    e["wi_ln"], e["ci"] = wi, wi.float().sum(dim=1).contiguous()
+                    pk["layers"].append(e)
             self._packed, self._packed_key = pk, key
         return self._packed
 
@@ -190,16 +199,36 @@ class ModernBertEncoder(nn.Module):
         qkv = torch.empty((T, 3 * H), device=dev, dtype=torch.bfloat16)
         h = torch.empty((T, int(cfg.intermediate_size)), device=dev, dtype=torch.bfloat16)
         eps = cfg.norm_eps
+        n_layers = len(pk["layers"])
+        if ops.FUSE_LAYERNORM:
+            # The two pre-norm LayerNorms of every block are folded into the GEMMs around them: the residual
+            # GEMM that writes x also accumulates its row statistics, the consuming GEMM applies them.
+            stats = torch.zeros((2 * n_layers, T, 2), device=dev, dtype=torch.float32)
         for i, w in enumerate(pk["layers"]):
             is_global = cfg.layer_is_global(i)
-            src = x if i == 0 else ops.layernorm(x, w["attn_norm"], eps, out=a)
-            ops.gemm(src, w["wqkv"], epilogue=ops.EPI_ROPE, out=qkv, positions=positions,
-                     rope_table=tab_g if is_global else tab_l, rope_cols=2 * H)
+            tab = tab_g if is_global else tab_l
+            if i == 0:
+                ops.gemm(x, w["wqkv"], epilogue=ops.EPI_ROPE, out=qkv, positions=positions, rope_table=tab,
+                         rope_cols=2 * H)
+            elif ops.FUSE_LAYERNORM:
+                ops.gemm(x, w["wqkv_ln"], epilogue=ops.EPI_ROPE, out=qkv, positions=positions, rope_table=tab,
+                         rope_cols=2 * H, row_stats=stats[2 * i - 1], col_corr=w["cqkv"], ln_eps=eps)
+            else:
+                ops.layernorm(x, w["attn_norm"], eps, out=a)
+                ops.gemm(a, w["wqkv"], epilogue=ops.EPI_ROPE, out=qkv, positions=positions, rope_table=tab,
+                         rope_cols=2 * H)
             ops.attn_varlen_fwd(qkv, cu_seqlens, max_seqlen, heads, -1 if is_global else cfg.window_half, out=a)
-            ops.gemm(a, w["wo"], epilogue=ops.EPI_RESIDUAL, out=x, aux=x)
-            ops.layernorm(x, w["mlp_norm"], eps, out=a)
-            ops.gemm(a, w["wi"], epilogue=ops.EPI_GEGLU, out=h)
-            ops.gemm(h, w["wo2"], epilogue=ops.EPI_RESIDUAL, out=x, aux=x)
+            if ops.FUSE_LAYERNORM:
+                ops.gemm(a, w["wo"], epilogue=ops.EPI_RESIDUAL, out=x, aux=x, stats_out=stats[2 * i])
+                ops.gemm(x, w["wi_ln"], epilogue=ops.EPI_GEGLU, out=h, row_stats=stats[2 * i], col_corr=w["ci"],
+                         ln_eps=eps)
+                ops.gemm(h, w["wo2"], epilogue=ops.EPI_RESIDUAL, out=x, aux=x,
+                         stats_out=stats[2 * i + 1] if i + 1 < n_layers else None)
+            else:
+                ops.gemm(a, w["wo"], epilogue=ops.EPI_RESIDUAL, out=x, aux=x)
+                ops.layernorm(x, w["mlp_norm"], eps, out=a)
+                ops.gemm(a, w["wi"], epilogue=ops.EPI_GEGLU, out=h)
+                ops.gemm(h, w["wo2"], epilogue=ops.EPI_RESIDUAL, out=x, aux=x)
         return ops.layernorm(x, pk["final_norm"], eps, out=a)
 
 

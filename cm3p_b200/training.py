@@ -68,18 +68,35 @@ def encoder_forward(enc, x0: torch.Tensor, cu_seqlens, max_seqlen: int, position
     a = torch.empty_like(x0)
     layers = []
     x = x0
+    eps, n_layers = cfg.norm_eps, len(pk["layers"])
+    fuse = ops.FUSE_LAYERNORM  # LayerNorms folded into the neighbouring GEMMs (the backward recomputes them from x)
+    if fuse:
+        stats = torch.zeros((2 * n_layers, T, 2), device=dev, dtype=F32)
     for i, w in enumerate(pk["layers"]):
         is_global = cfg.layer_is_global(i)
         tab = tab_g if is_global else tab_l
-        src = x if i == 0 else ops.layernorm(x, w["attn_norm"], cfg.norm_eps, out=a)
-        qkv = ops.gemm(src, w["wqkv"], epilogue=ops.EPI_ROPE, positions=positions, rope_table=tab, rope_cols=2 * H)
+        if i == 0:
+            qkv = ops.gemm(x, w["wqkv"], epilogue=ops.EPI_ROPE, positions=positions, rope_table=tab, rope_cols=2 * H)
+        elif fuse:
+            qkv = ops.gemm(x, w["wqkv_ln"], epilogue=ops.EPI_ROPE, positions=positions, rope_table=tab,
+                           rope_cols=2 * H, row_stats=stats[2 * i - 1], col_corr=w["cqkv"], ln_eps=eps)
+        else:
+            ops.layernorm(x, w["attn_norm"], eps, out=a)
+            qkv = ops.gemm(a, w["wqkv"], epilogue=ops.EPI_ROPE, positions=positions, rope_table=tab, rope_cols=2 * H)
         lse = torch.empty((heads, T), device=dev, dtype=F32)
         o = ops.attn_varlen_fwd(qkv, cu_seqlens, max_seqlen, heads, -1 if is_global else cfg.window_half, lse=lse)
-        x1 = ops.gemm(o, w["wo"], epilogue=ops.EPI_RESIDUAL, aux=x)
-        ops.layernorm(x1, w["mlp_norm"], cfg.norm_eps, out=a)
         ug = torch.empty((T, 2 * I), device=dev, dtype=BF16)
-        h = ops.gemm(a, w["wi"], epilogue=ops.EPI_GEGLU_SAVE, c2=ug)
-        x2 = ops.gemm(h, w["wo2"], epilogue=ops.EPI_RESIDUAL, aux=x1)
+        if fuse:
+            x1 = ops.gemm(o, w["wo"], epilogue=ops.EPI_RESIDUAL, aux=x, stats_out=stats[2 * i])
+            h = ops.gemm(x1, w["wi_ln"], epilogue=ops.EPI_GEGLU_SAVE, c2=ug, row_stats=stats[2 * i], col_corr=w["ci"],
+                         ln_eps=eps)
+            x2 = ops.gemm(h, w["wo2"], epilogue=ops.EPI_RESIDUAL, aux=x1,
+                          stats_out=stats[2 * i + 1] if i + 1 < n_layers else None)
+        else:
+            x1 = ops.gemm(o, w["wo"], epilogue=ops.EPI_RESIDUAL, aux=x)
+            ops.layernorm(x1, w["mlp_norm"], eps, out=a)
+            h = ops.gemm(a, w["wi"], epilogue=ops.EPI_GEGLU_SAVE, c2=ug)
+            x2 = ops.gemm(h, w["wo2"], epilogue=ops.EPI_RESIDUAL, aux=x1)
         layers.append(dict(x_in=x, qkv=qkv, o=o, lse=lse, x1=x1, ug=ug, window=-1 if is_global else cfg.window_half,
                            tab=tab))
         x = x2

@@ -61,6 +61,18 @@ int cm3p_gemm_bf16(const void* a, int64_t lda, int trans_a, const void* b, int64
                    void* c2, int64_t ldc2, float scale, int accumulate, const int32_t* positions,
                    const float* rope_table, int64_t rope_cols, void* stream);
 
+/* The same GEMM with a LayerNorm folded into the GEMMs on both sides of it, so that the pre-norm blocks of
+ * ModernBERT (MB:313-342: `attn(attn_norm(x))`, `mlp(mlp_norm(x))`) need no LayerNorm pass at all:
+ *   producer, epilogue CM3P_EPI_RESIDUAL: stats_out [M][2] fp32 += (sum, sum of squares) of the bf16 rows written
+ *   consumer, epilogue CM3P_EPI_ROPE / CM3P_EPI_GEGLU(_SAVE), with b = W . diag(gamma) (bf16) and
+ *     col_corr [N] = row sums of b:   acc <- rstd_m * (acc - mean_m * col_corr[n])
+ *     where mean / rstd come from row_stats [M][2] (the producer's stats_out; width = K, eps = ln_eps).
+ * Operands K-major only; outputs must be 16-byte aligned bf16 rows. */
+int cm3p_gemm_bf16_ln(const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t M, int64_t N,
+                      int64_t K, int epilogue, const void* aux, int64_t ld_aux, void* c2, int64_t ldc2,
+                      const int32_t* positions, const float* rope_table, int64_t rope_cols, float* stats_out,
+                      const float* row_stats, const float* col_corr, float ln_eps, void* stream);
+
 /* Unpadded bidirectional attention, head_dim 64: out = softmax(q k^T / 8 | mask) v per sequence/head.
  * Replaces ALL_ATTENTION_FUNCTIONS[...] in MB:286-300 (sdpa / flash_attention_2 / eager) together
  * with the padding + sliding-window masks (transformers/masking_utils.py:121-131) and the

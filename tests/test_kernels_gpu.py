@@ -259,3 +259,47 @@ def test_clip_loss(B, V):
     bl = F.cross_entropy(S.permute(2, 0, 1).reshape(B, B * V), torch.arange(B, device=DEV) * V + t)
     _report("clip_loss", loss, ((ml + bl) / 2).reshape(1), 1e-4, 1e-4)
     _report("col_lse", col_lse, torch.logsumexp(S.view(B * V, B), 0), 1e-4, 1e-4)
+
+
+# ------------------------------------------------------------------- LayerNorm folded into GEMMs
+def test_gemm_layernorm_folding():
+    """residual GEMM emits row statistics; the next GEMM (RoPE / GeGLU epilogue) applies the LayerNorm:
+    rstd * (x . W'^T - mean * colsum(W')) == LN(x; gamma) . W^T."""
+    ops = _ops()
+    T, H, I, heads = 1000, 768, 1152, 12
+    a, wo = _rand((T, H), seed=1), _rand((H, H), 0.03, seed=2)
+    x0 = _rand((T, H), 2.0, seed=3) + 0.7  # non-zero mean rows
+    gamma = _rand((H,), 0.2, seed=4, dtype=torch.float32) + 1.0
+    stats = torch.zeros((T, 2), device=DEV)
+    x = ops.gemm(a, wo, epilogue=ops.EPI_RESIDUAL, aux=x0, stats_out=stats)
+    torch.cuda.synchronize()
+    xf = x.float()
+    _report("stats sum", stats[:, 0], xf.sum(-1), 5e-2, 1e-3)
+    _report("stats sumsq", stats[:, 1], (xf * xf).sum(-1), 5e-1, 1e-3)
+    ln = F.layer_norm(xf, (H,), gamma, None, 1e-5)
+    # --- GeGLU consumer
+    wi = _rand((2 * I, H), 0.05, seed=5)
+    wi_ln = ops.interleave_wi((wi.float() * gamma[None]).to(torch.bfloat16)).contiguous()
+    ci = wi_ln.float().sum(1).contiguous()
+    got = ops.gemm(x, wi_ln, epilogue=ops.EPI_GEGLU, row_stats=stats, col_corr=ci, ln_eps=1e-5)
+    acc = ln @ wi.float().t()
+    _report("geglu(LN folded)", got, F.gelu(acc[:, :I]) * acc[:, I:], 4e-2, 3e-2)
+    raw = torch.empty((T, 2 * I), device=DEV, dtype=torch.bfloat16)
+    got2 = ops.gemm(x, wi_ln, epilogue=ops.EPI_GEGLU_SAVE, c2=raw, row_stats=stats, col_corr=ci, ln_eps=1e-5)
+    _report("geglu_save(LN folded).raw", ops.deinterleave_wi(raw.t().contiguous()).t(), acc, 4e-2, 2e-2)
+    _report("geglu_save(LN folded).out", got2, F.gelu(acc[:, :I]) * acc[:, I:], 4e-2, 3e-2)
+    # --- RoPE consumer
+    wq = _rand((3 * H, H), 0.05, seed=6)
+    wq_ln = (wq.float() * gamma[None]).to(torch.bfloat16).contiguous()
+    cq = wq_ln.float().sum(1).contiguous()
+    pos = (torch.arange(T, dtype=torch.int32) % 333).to(DEV)
+    tab = ops.rope_table(160000.0, 512, DEV)
+    got3 = ops.gemm(x, wq_ln, epilogue=ops.EPI_ROPE, positions=pos, rope_table=tab, rope_cols=2 * H, row_stats=stats,
+                    col_corr=cq, ln_eps=1e-5)
+    accq = (ln @ wq.float().t()).view(T, 3, heads, 64)
+    cos, sin = tab[pos.long(), :, 0], tab[pos.long(), :, 1]
+    cos, sin = torch.cat((cos, cos), -1)[:, None, None], torch.cat((sin, sin), -1)[:, None, None]
+    rot = torch.cat((-accq[..., 32:], accq[..., :32]), dim=-1)
+    want = accq.clone()
+    want[:, :2] = (accq * cos + rot * sin)[:, :2]
+    _report("rope(LN folded)", got3, want.view(T, 3 * H), 5e-2, 2e-2)
