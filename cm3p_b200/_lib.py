@@ -11,7 +11,8 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcm3p_b200.so")
+# CM3P_LIB_PATH: load a differently-built copy of the same library (kernel ablation builds for profiling)
+LIB_PATH = os.environ.get("CM3P_LIB_PATH") or os.path.join(HERE, "libcm3p_b200.so")
 
 _P = c_void_p
 _I = c_int

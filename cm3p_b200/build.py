@@ -63,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if (not force and os.path.isfile(obj) and os.path.getmtime(obj) > os.path.getmtime(src)
                 and os.path.getmtime(obj) > newest_header):
             return obj
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("CM3P_NVCC_EXTRA", "").split(), "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
