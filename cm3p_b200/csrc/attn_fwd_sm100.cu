@@ -297,9 +297,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params 
 // TMEM columns: S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384).
 namespace v2 {
 
-constexpr int KV_STAGES2 = 3;
+constexpr int KV_STAGES2 = 4;
 constexpr int THREADS2 = 384;  // 3 warpgroups: softmax A, softmax B, {TMA, MMA, 2 idle warps}
-constexpr int SMEM_TILES2 = 2 * Q_BYTES + KV_STAGES2 * 2 * KV_TILE_BYTES + 2 * P_BYTES;  // 32 + 96 + 64 = 192 KB
+constexpr int SMEM_TILES2 = 2 * Q_BYTES + KV_STAGES2 * 2 * KV_TILE_BYTES + 2 * P_BYTES;  // 32 + 128 + 64 = 224 KB
 constexpr int SMEM_BYTES2 = SMEM_TILES2 + 256;
 constexpr uint32_t TM_S = 0, TM_O = 256;  // + 128 * x for S, + 64 * x for O
 constexpr float RESCALE_LOG2 = 8.0f;
@@ -317,20 +317,24 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
   const bool act_b = q0 + BQ < len;
 
   uint8_t* smem_q = smem;                                   // [2][16 KB]
-  uint8_t* smem_k = smem + 2 * Q_BYTES;                     // [3][16 KB]
-  uint8_t* smem_v = smem_k + KV_STAGES2 * KV_TILE_BYTES;    // [3][16 KB]
+  uint8_t* smem_k = smem + 2 * Q_BYTES;                     // [4][16 KB]
+  uint8_t* smem_v = smem_k + KV_STAGES2 * KV_TILE_BYTES;    // [4][16 KB]
   uint8_t* smem_p = smem_v + KV_STAGES2 * KV_TILE_BYTES;    // [2][32 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_TILES2);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;   // [3]
-  uint64_t* kv_empty = bars + 4;  // [3]
-  uint64_t* s_full = bars + 7;    // [2]
-  uint64_t* p_full = bars + 9;    // [2] 128 arrivals each
-  uint64_t* o_full = bars + 11;   // [2]
-  uint64_t* pv_done = bars + 13;  // [2] PV_x(u) retired: P_x buffer reusable, O_x stable
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* kv_full = bars + 1;   // [4]
+  uint64_t* kv_empty = bars + 5;  // [4]
+  uint64_t* s_full = bars + 9;    // [2]
+  uint64_t* s_free = bars + 11;   // [2] 4 arrivals (one per warp): S_x is in registers, the buffer may be overwritten
+  uint64_t* p_full = bars + 13;   // [2][2] per 64-key half of P_x, 128 arrivals each
+  uint64_t* pv_done = bars + 17;  // [2][2] PV_x(u, half) retired: that half of the P_x buffer is reusable
+  uint64_t* o_full = bars + 21;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
 
   if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
+#ifdef CM3P_ATTN_PROF
+  __shared__ long long ev[4][40];  // x = 0 only: [0] p_full arrive (row 0), [1] issuer saw p_full, [2] pv_done seen, [3] S issue
+#endif
 
   // KV stream: tiles u = 0..U-1 at sequence rows kv_base + 128 u; Q tile x consumes u in [lo[x], hi[x])
   int kv_base = 0;
@@ -353,13 +357,16 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
     ptx::mbar_init(q_full, 1);
     for (int s = 0; s < KV_STAGES2; ++s) {
       ptx::mbar_init(&kv_full[s], 1);
-      ptx::mbar_init(&kv_empty[s], 1);
+      ptx::mbar_init(&kv_empty[s], 2);
     }
     for (int x = 0; x < 2; ++x) {
       ptx::mbar_init(&s_full[x], 1);
-      ptx::mbar_init(&p_full[x], 128);
+      ptx::mbar_init(&s_free[x], 4);
+      for (int h = 0; h < 2; ++h) {
+        ptx::mbar_init(&p_full[2 * x + h], 128);
+        ptx::mbar_init(&pv_done[2 * x + h], 1);
+      }
       ptx::mbar_init(&o_full[x], 1);
-      ptx::mbar_init(&pv_done[x], 1);
     }
     ptx::fence_barrier_init();
   }
@@ -390,50 +397,71 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
         ptx::tma_load_2d(smem_k + s * KV_TILE_BYTES, &tma_qkv, &kv_full[s], col_k, row);
         ptx::tma_load_2d(smem_v + s * KV_TILE_BYTES, &tma_qkv, &kv_full[s], col_v, row);
       }
-    } else if (warp == 9 && lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
+    } else if ((warp == 9 || warp == 10) && lane == 0) {
+      // ---------------------------------------------------------------- MMA issuers (one per Q tile)
+      // Each Q tile has its own issuing thread, so its MMAs follow the order in which its softmax group
+      // produces the events: "S_x buffer drained into registers" -> S_x(t+1) (runs on the tensor pipe WHILE
+      // the group is still exponentiating S_x(t)), "first / second 64-key half of P_x(t) written" -> PV on
+      // that half.  All waits are blocking mbarrier waits: a polling issuer steals issue slots from the
+      // softmax warps that share its scheduler (measured: -20 %).
+      const int x = warp - 9;
       const uint32_t idesc_s = ptx::umma_idesc_bf16(BQ, BKV, 0, 0);
       const uint32_t idesc_o = ptx::umma_idesc_bf16(BQ, D, 0, 1);  // V is MN-major
-      auto issue_s = [&](int x, int u) {
-        const int s = u % KV_STAGES2;
-        ptx::mbar_wait(&kv_full[s], (u / KV_STAGES2) & 1);
+      const int lo_x = x ? lo1 : lo0, hi_x = x ? hi1 : hi0;
+      const uint32_t q_addr = ptx::smem_u32(smem_q + x * Q_BYTES);
+      const uint32_t p_base = ptx::smem_u32(smem_p + x * P_BYTES);
+      const uint32_t t_s = tmem_base + TM_S + x * 128, t_o = tmem_base + TM_O + x * 64;
+      auto issue_s = [&](int t) {
+        const int s = t % KV_STAGES2;
+        ptx::mbar_wait(&kv_full[s], (t / KV_STAGES2) & 1);
         ptx::tc_fence_after();
-        const uint32_t q_addr = ptx::smem_u32(smem_q + x * Q_BYTES);
         const uint32_t k_addr = ptx::smem_u32(smem_k + s * KV_TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
-          ptx::umma_bf16(tmem_base + TM_S + x * 128, ptx::umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+          ptx::umma_bf16(t_s, ptx::umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
                          ptx::umma_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
         ptx::umma_commit(&s_full[x]);
       };
-      int j0 = 0, j1 = 0;
       ptx::mbar_wait(q_full, 0);
-      if (hi0 > lo0) issue_s(0, lo0);
-      if (hi1 > lo1) issue_s(1, lo1);
-      for (int u = 0; u < U; ++u) {
-        const int s = u % KV_STAGES2;
-#pragma unroll
-        for (int x = 0; x < 2; ++x) {
-          const int lo_x = x ? lo1 : lo0, hi_x = x ? hi1 : hi0;
-          int& jx = x ? j1 : j0;
-          if (u < lo_x || u >= hi_x) continue;
-          ptx::mbar_wait(&p_full[x], jx & 1);  // P_x(u) in smem, S_x(u) consumed, O_x rescaled if needed
-          ptx::tc_fence_after();
-          // S of the next tile first: group x can start on it while the tensor pipe is still busy with PV_x(u)
-          if (u + 1 < hi_x) issue_s(x, u + 1);
-          const uint32_t p_addr = ptx::smem_u32(smem_p + x * P_BYTES);
-          const uint32_t v_addr = ptx::smem_u32(smem_v + s * KV_TILE_BYTES);
-#pragma unroll
-          for (int k = 0; k < BKV / 16; ++k)
-            ptx::umma_bf16(tmem_base + TM_O + x * 64,
-                           ptx::umma_smem_desc_sw128(p_addr + (k >> 2) * (BQ * 128) + (k & 3) * 32, 16, 1024),
-                           ptx::umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_o,
-                           (jx | k) != 0 ? 1u : 0u);
-          ++jx;
-          if (u + 1 < hi_x) ptx::umma_commit(&pv_done[x]);
-          else ptx::umma_commit(&o_full[x]);
+      // the ring is released by BOTH issuers (kv_empty counts 2): tiles outside this Q tile's range are
+      // acknowledged as soon as they have landed
+      for (int u = 0; u < lo_x; ++u) {
+        ptx::mbar_wait(&kv_full[u % KV_STAGES2], (u / KV_STAGES2) & 1);
+        ptx::umma_commit(&kv_empty[u % KV_STAGES2]);
+      }
+      if (hi_x > lo_x) issue_s(lo_x);
+      for (int t = lo_x; t < hi_x; ++t) {
+        const int j = t - lo_x;
+        if (t + 1 < hi_x) {
+          ptx::mbar_wait(&s_free[x], j & 1);
+          issue_s(t + 1);
+#ifdef CM3P_ATTN_PROF
+          if (x == 0 && j < 19) ev[3][j + 1] = clock64();
+#endif
         }
-        ptx::umma_commit(&kv_empty[s]);
+        const uint32_t v_base = ptx::smem_u32(smem_v + (t % KV_STAGES2) * KV_TILE_BYTES);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          ptx::mbar_wait(&p_full[2 * x + h], j & 1);  // this half of P_x(t) is in smem (O_x rescaled if needed)
+#ifdef CM3P_ATTN_PROF
+          if (x == 0 && j < 20) ev[1][2 * j + h] = clock64();
+#endif
+          ptx::tc_fence_after();
+          const uint32_t p_addr = p_base + h * (BQ * 128);
+          const uint32_t v_addr = v_base + h * (64 * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16(t_o, ptx::umma_smem_desc_sw128(p_addr + k * 32, 16, 1024),
+                           ptx::umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_o,
+                           (j | h | k) != 0 ? 1u : 0u);
+          if (h == 1 && t + 1 == hi_x) ptx::umma_commit(&o_full[x]);
+          else ptx::umma_commit(&pv_done[2 * x + h]);
+        }
+        ptx::umma_commit(&kv_empty[t % KV_STAGES2]);
+      }
+      for (int u = max(hi_x, lo_x); u < U; ++u) {
+        ptx::mbar_wait(&kv_full[u % KV_STAGES2], (u / KV_STAGES2) & 1);
+        ptx::umma_commit(&kv_empty[u % KV_STAGES2]);
       }
     }
   } else {
@@ -448,31 +476,49 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
     const uint32_t t_o = tmem_base + TM_O + x * 64 + lane_off;
     uint8_t* my_p = smem_p + x * P_BYTES;
     const float c = p.scale_log2;
+    const float2 c2 = make_float2(c, c);
     float m_run = -INFINITY, l = 0.f;
     const int lo_x = x ? lo1 : lo0;
     const int n_iter = (x ? hi1 : hi0) - lo_x;
 
+#ifdef CM3P_ATTN_PROF
+    long long pf_s = 0, pf_ld = 0, pf_max = 0, pf_pv = 0, pf_exp = 0, pf_t0 = clock64(), pf_a, pf_b;
+#define PF_A() pf_a = clock64()
+#define PF_B(acc) do { pf_b = clock64(); acc += pf_b - pf_a; pf_a = pf_b; } while (0)
+#else
+#define PF_A()
+#define PF_B(acc)
+#endif
     for (int jj = 0; jj < n_iter; ++jj) {
       const int kv0 = kv_base + (lo_x + jj) * BKV;
+      PF_A();
       ptx::mbar_wait(&s_full[x], jj & 1);
+      PF_B(pf_s);
       ptx::tc_fence_after();
       uint32_t sr[4][32];
 #pragma unroll
       for (int q = 0; q < 4; ++q) ptx::tmem_ld_32x32b_x32(t_s + q * 32, sr[q]);
       ptx::tmem_ld_wait();
+      // the scores are in registers: hand the S buffer back so S_x(jj+1) overlaps this tile's softmax
+      ptx::tc_fence_before();
+      if (lane == 0) ptx::mbar_arrive(&s_free[x]);
+      PF_B(pf_ld);
       // Masking state per 32-column chunk and per warp (32 consecutive query rows): 0 = no allowed key
       // for any row of the warp (skip: no exp, P = 0), 1 = some rows partially masked, 2 = fully allowed.
       // Interior tiles of global layers take the branch-free path (every chunk fully allowed).
       const bool masked_tile = (p.window >= 0) || (kv0 + BKV > len);  // CTA-uniform
       int state[4] = {2, 2, 2, 2};
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      float mxq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       if (!masked_tile) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
-          mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
-          mx2 = fmaxf(mx2, __uint_as_float(sr[2][i]));
-          mx3 = fmaxf(mx3, __uint_as_float(sr[3][i]));
+        for (int q = 0; q < 4; ++q) {
+          float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            ma = ptx::max3(ma, __uint_as_float(sr[q][i]), __uint_as_float(sr[q][i + 1]));
+            mb = ptx::max3(mb, __uint_as_float(sr[q][i + 2]), __uint_as_float(sr[q][i + 3]));
+          }
+          mxq[q] = fmaxf(ma, mb);
         }
       } else {
         int a = 0, b = min(BKV, len - kv0);
@@ -487,12 +533,10 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
           ia = max(ia, qw + 31 - p.window - kv0);
           ib = min(ib, qw + p.window + 1 - kv0);
         }
-        float mxq[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int c0 = q * 32, c1 = q * 32 + 32;
           state[q] = (c1 <= wa || c0 >= wb) ? 0 : ((c0 >= ia && c1 <= ib) ? 2 : 1);
-          mxq[q] = -INFINITY;
           if (state[q] == 1) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -501,21 +545,27 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
             }
           }
           if (state[q] != 0) {
+            float ma = -INFINITY, mb = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mxq[q] = fmaxf(mxq[q], __uint_as_float(sr[q][i]));
+            for (int i = 0; i < 32; i += 4) {
+              ma = ptx::max3(ma, __uint_as_float(sr[q][i]), __uint_as_float(sr[q][i + 1]));
+              mb = ptx::max3(mb, __uint_as_float(sr[q][i + 2]), __uint_as_float(sr[q][i + 3]));
+            }
+            mxq[q] = fmaxf(ma, mb);
           }
         }
-        mx0 = mxq[0]; mx1 = mxq[1]; mx2 = mxq[2]; mx3 = mxq[3];
       }
-      const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+      const float m_new = ptx::max3(m_run, fmaxf(mxq[0], mxq[1]), fmaxf(mxq[2], mxq[3]));
+      PF_B(pf_max);
       if (jj == 0) {
         m_run = m_new;
       } else {
-        // PV(jj-1) was issued behind S(jj): wait for it before rescaling O or overwriting the P buffer
-        ptx::mbar_wait(&pv_done[x], (jj - 1) & 1);
-        ptx::tc_fence_after();
         const bool grow = (m_new - m_run) * c > RESCALE_LOG2;  // also true for -inf -> finite
         if (__any_sync(0xffffffffu, grow)) {
+          // both halves of PV(jj-1) must have retired before O is rescaled
+          ptx::mbar_wait(&pv_done[2 * x], (jj - 1) & 1);
+          ptx::mbar_wait(&pv_done[2 * x + 1], (jj - 1) & 1);
+          ptx::tc_fence_after();
           const float alpha = grow ? ptx::ex2_approx((m_run - m_new) * c) : 1.f;
 #pragma unroll 1
           for (int h = 0; h < D; h += 16) {
@@ -532,21 +582,33 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
         }
       }
       const float mc = (m_run == -INFINITY) ? 0.f : m_run * c;
-      float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // independent partial row sums (ILP)
+      const float2 nmc2 = make_float2(-mc, -mc);
+      float2 rs[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};  // independent partial row sums (ILP)
       auto exp_chunk = [&](int q, bool on) {
         uint32_t packed[16];
         if (on) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float p0 = ptx::ex2_approx(__uint_as_float(sr[q][i]) * c - mc);
-            const float p1 = ptx::ex2_approx(__uint_as_float(sr[q][i + 1]) * c - mc);
-            rs[i & 7] += p0;
-            rs[(i & 7) + 1] += p1;
-            packed[i >> 1] = ptx::pack_bf16x2(p0, p1);
+            const float2 t = ptx::fma2(make_float2(__uint_as_float(sr[q][i]), __uint_as_float(sr[q][i + 1])), c2, nmc2);
+            float2 e;
+            e.x = ptx::ex2_approx(t.x);
+            e.y = ptx::ex2_approx(t.y);
+            rs[(i >> 1) & 3] = ptx::add2(rs[(i >> 1) & 3], e);
+            packed[i >> 1] = ptx::pack_bf16x2(e.x, e.y);
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) packed[i] = 0u;
+        }
+        // half (q >> 1) of the P buffer is still being read by PV(jj-1, half) until pv_done fires; that MMA
+        // was issued half a tile ago, so this wait is normally already satisfied
+        if ((q & 1) == 0 && jj > 0) {
+          PF_B(pf_exp);
+          ptx::mbar_wait(&pv_done[2 * x + (q >> 1)], (jj - 1) & 1);
+          PF_B(pf_pv);
+#ifdef CM3P_ATTN_PROF
+          if (x == 0 && r == 0 && jj < 20) ev[2][2 * (jj - 1) + (q >> 1)] = clock64();
+#endif
         }
         uint8_t* prow = my_p + (q >> 1) * (BQ * 128) + r * 128;
         const int u0 = (q & 1) ? 4 : 0;
@@ -556,6 +618,14 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
           *reinterpret_cast<uint4*>(prow + unit * 16) =
               make_uint4(packed[uu * 4], packed[uu * 4 + 1], packed[uu * 4 + 2], packed[uu * 4 + 3]);
         }
+        if (q & 1) {  // a 64-key half of P is complete: PV on it can start while the other half is computed
+          ptx::tc_fence_before();
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(&p_full[2 * x + (q >> 1)]);
+#ifdef CM3P_ATTN_PROF
+          if (x == 0 && r == 0 && jj < 20) ev[0][2 * jj + (q >> 1)] = clock64();
+#endif
+        }
       };
       if (!masked_tile) {
 #pragma unroll
@@ -564,11 +634,20 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
 #pragma unroll
         for (int q = 0; q < 4; ++q) exp_chunk(q, state[q] != 0);
       }
-      l += ((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + (rs[6] + rs[7]));
-      ptx::tc_fence_before();
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&p_full[x]);
+      const float2 rsum = ptx::add2(ptx::add2(rs[0], rs[1]), ptx::add2(rs[2], rs[3]));
+      l += rsum.x + rsum.y;
+      PF_B(pf_exp);
     }
+#ifdef CM3P_ATTN_PROF
+    if (r == 0 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0) {
+      if (x == 0)
+        for (int i = 0; i < 2 * n_iter - 2 && i < 38; ++i)
+          printf("half %2d: arrive %6lld  seen +%5lld  done_seen +%5lld | S issue(%d) %6lld\n", i, ev[0][i] - pf_t0,
+                 ev[1][i] - ev[0][i], ev[2][i] - ev[0][i], i >> 1, ev[3][i >> 1] - pf_t0);
+      printf("attn prof x=%d iters=%d total=%lld wait_s=%lld ld=%lld max=%lld wait_pv=%lld exp=%lld\n", x, n_iter,
+             clock64() - pf_t0, pf_s, pf_ld, pf_max, pf_pv, pf_exp);
+    }
+#endif
     if (n_iter > 0) {
       ptx::mbar_wait(&o_full[x], 0);
       ptx::tc_fence_after();

@@ -1,0 +1,24 @@
+"""Single attention forward launch at the bench shape (used with profiling builds: CM3P_LIB_PATH=...)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cm3p_b200 import ops  # noqa: E402
+
+window = int(sys.argv[1]) if len(sys.argv) > 1 else -1
+B, L, heads = 64, 2000, 12
+g = torch.Generator().manual_seed(0)
+lens = torch.randint(600, L + 1, (B,), generator=g).tolist()
+lens[0] = L
+cu = [0]
+for n in lens:
+    cu.append(cu[-1] + n)
+T = cu[-1]
+qkv = torch.randn(T, 3 * heads * 64, device="cuda").bfloat16()
+cu_t = torch.tensor(cu, dtype=torch.int32, device="cuda")
+out = torch.empty(T, heads * 64, device="cuda", dtype=torch.bfloat16)
+for _ in range(2):
+    ops.attn_varlen_fwd(qkv, cu_t, L, heads, window, out=out)
+    torch.cuda.synchronize()
