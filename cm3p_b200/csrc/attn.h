@@ -39,6 +39,7 @@ struct AttnBwdArgs {
 };
 
 int attn_varlen_bwd(const AttnBwdArgs& args, cudaStream_t stream);
-int attn_varlen_bwd_v2(const AttnBwdArgs& args, cudaStream_t stream);  // 1 CTA/SM ping-pong kernels (long sequences)
+int attn_varlen_bwd_v2(const AttnBwdArgs& args, cudaStream_t stream);  // 1 CTA/SM ping-pong kernels (CM3P_ATTN_BWD=v2)
+int attn_varlen_bwd_v3(const AttnBwdArgs& args, cudaStream_t stream);  // 128x128 tiles, early S/dP issue (long sequences)
 
 }  // namespace cm3p

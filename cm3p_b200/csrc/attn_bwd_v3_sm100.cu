@@ -1,0 +1,720 @@
+// Attention backward, third generation (global layers over long sequences).  Same math and data layout
+// as attn_bwd_sm100.cu (formulas and reference call sites are in its header); what changed is how the
+// work is cut so that neither the tensor pipe nor the element-wise warps wait for each other:
+//
+//   * 128 x 128 tiles.  Every MMA is M128 x N128 (S, dP) or M128 x N64 over K = 128: with 64-wide inner
+//     tiles the 128-row operand was re-read from shared memory for every 64 columns (192 B/clk, above
+//     the 128 B/clk the SM delivers).
+//   * 16 element-wise warps share ONE tile: warp w owns TMEM lanes 32 (w & 3) .. +31 and the 32-column
+//     slice (w >> 2).  Four light warps per scheduler (about 100 registers each) hide the exp / TMEM /
+//     mbarrier latencies that two heavy ones could not (measured: 2 warps per scheduler ran the
+//     element-wise loop at 0.2 instructions per clock).  They copy their S and dP values into registers
+//     and release the TMEM buffers at once (s_free), so the S / dP GEMMs of the next tile run while
+//     exp / dZ of this tile are computed.
+//   * dZ (and P^T) never touch shared memory: the warps write them as packed bf16 into TMEM (tcgen05.st,
+//     thread = row = TMEM lane) and the accumulating GEMMs read their A operand from TMEM.  With both
+//     operands in shared memory those N = 64 MMAs needed 192 B/clk and the dK/dV kernel moved 256 KB of
+//     shared memory per tile (2048 clk at the SM's 128 B/clk).  They are handed over in the 32-column
+//     slices, each with its own mbarrier pair: the GEMM on a slice is issued as soon as it is written,
+//     and the slice is reusable by the time its warps get to it in the next tile.
+//   * all issuer / producer waits are blocking mbarrier waits (a polling issuer steals issue slots from
+//     the element-wise warps on its scheduler); packed f32x2 arithmetic in the element-wise loops.
+//
+// Two deterministic kernels as before (no atomics): dQ (outer = 128 queries, streams K/V) and dK/dV on
+// the transposed problem (outer = 128 keys as TMEM lanes, streams Q/dO with their lse / delta rows).
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "attn.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace cm3p {
+namespace {
+namespace v3 {
+
+constexpr int BT = 128;  // outer tile rows == TMEM lanes
+constexpr int BI = 128;  // inner (streamed) tile rows
+constexpr int HC = 32;   // columns per element-wise warp
+constexpr int D = 64;
+constexpr int TILE_BYTES = 128 * D * 2;  // 16 KB: one 128-row operand tile, or one 64-column block of dZ / P^T
+constexpr int NS = 3;                    // ring stages of the streamed operands
+constexpr int THREADS = 640;  // 16 element-wise warps, producer, issuer, 2 idle (warpgroup granularity)
+constexpr int EW_WARPS = 16;
+constexpr int REG_EW = 104, REG_AUX = 64;
+
+#ifdef CM3P_ATTN_PROF
+#define PF_DECL() long long pf_s = 0, pf_ld = 0, pf_cmp = 0, pf_free = 0, pf_st = 0, pf_t0 = clock64(), pf_a = pf_t0, pf_b
+#define PF_B(acc) do { pf_b = clock64(); acc += pf_b - pf_a; pf_a = pf_b; } while (0)
+#define PF_PRINT(name, n) \
+  if (lane == 0 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0) \
+    printf("%s warp %d tiles=%d total=%lld wait_s=%lld ld=%lld compute=%lld wait_free=%lld store=%lld\n", name, warp, n, \
+           clock64() - pf_t0, pf_s, pf_ld, pf_cmp, pf_free, pf_st)
+#else
+#define PF_DECL()
+#define PF_B(acc)
+#define PF_PRINT(name, n)
+#endif
+
+struct BwdParams {
+  const int32_t* cu_seqlens;
+  const __nv_bfloat16* out;
+  const __nv_bfloat16* dout;
+  const float* lse;
+  float* delta;
+  __nv_bfloat16* dqkv;
+  const int32_t* positions;
+  const float2* rope_table;
+  int64_t total_tokens;
+  int heads;
+  int hidden;
+  int window;
+  float scale_log2;
+  float scale;
+};
+
+__device__ __forceinline__ uint4 pack8f(const float* v) {
+  return make_uint4(ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]), ptx::pack_bf16x2(v[4], v[5]),
+                    ptx::pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ void unpack8f(const uint4& u, float* f) {
+  float2 t;
+  t = ptx::unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = ptx::unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = ptx::unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = ptx::unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+// accumulator row (64 fp32 columns) -> optional inverse RoPE -> bf16 -> global
+__device__ __forceinline__ void store_grad_row(uint32_t taddr, __nv_bfloat16* dst, const float2* cs, bool valid) {
+  uint32_t r1[32], r2[32];
+  ptx::tmem_ld_32x32b_x32(taddr, r1);
+  ptx::tmem_ld_32x32b_x32(taddr + 32, r2);
+  ptx::tmem_ld_wait();
+  if (!valid) return;
+  float o1[32], o2[32];
+  if (cs) {
+    const float4* tab = reinterpret_cast<const float4*>(cs);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 f = __ldg(tab + k);
+      const float a0 = __uint_as_float(r1[2 * k]), b0 = __uint_as_float(r2[2 * k]);
+      const float a1 = __uint_as_float(r1[2 * k + 1]), b1 = __uint_as_float(r2[2 * k + 1]);
+      o1[2 * k] = a0 * f.x + b0 * f.y;
+      o2[2 * k] = b0 * f.x - a0 * f.y;
+      o1[2 * k + 1] = a1 * f.z + b1 * f.w;
+      o2[2 * k + 1] = b1 * f.z - a1 * f.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      o1[k] = __uint_as_float(r1[k]);
+      o2[k] = __uint_as_float(r2[k]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    *reinterpret_cast<uint4*>(dst + i * 8) = pack8f(o1 + i * 8);
+    *reinterpret_cast<uint4*>(dst + 32 + i * 8) = pack8f(o2 + i * 8);
+  }
+}
+
+// Allowed columns [a,b) of one row inside a 32-column slice whose column 0 sits at sequence position t0,
+// and the state of the slice for the row's warp (0 skip, 1 mask per element, 2 no mask).
+struct Band {
+  int a, b;
+  int state;
+};
+__device__ __forceinline__ Band band_of(int row_pos, int warp_pos, int t0, int len, int window, bool row_valid) {
+  Band r;
+  int a = 0, b = max(0, min(HC, len - t0));
+  int wa = 0, wb = b, ia = 0, ib = b;
+  if (window >= 0) {
+    a = max(a, row_pos - window - t0);
+    b = min(b, row_pos + window + 1 - t0);
+    wa = max(wa, warp_pos - window - t0);
+    wb = min(wb, warp_pos + 31 + window + 1 - t0);
+    ia = max(ia, warp_pos + 31 - window - t0);
+    ib = min(ib, warp_pos + window + 1 - t0);
+  }
+  if (warp_pos + 31 >= len) { ia = HC; ib = 0; }  // rows past the end of the sequence: never "fully allowed"
+  if (warp_pos >= len) { wa = HC; wb = 0; }
+  if (!row_valid) b = 0;
+  r.a = a;
+  r.b = b;
+  r.state = (HC <= wa || 0 >= wb) ? 0 : ((0 >= ia && HC <= ib) ? 2 : 1);
+  return r;
+}
+
+// ================================================================================================
+// dQ kernel.  smem: Q 16K | dO 16K | K 3x16K | V 3x16K.
+// TMEM: S = [0,128)  dP = [128,256)  dZ (bf16 pairs) = [256,320)  dQ = [320,384).
+constexpr int DQ_TILES = 2 * TILE_BYTES + NS * 2 * TILE_BYTES;  // 128 KB
+constexpr int DQ_SMEM = DQ_TILES + 256 + 4 * BT * 4;  // + barriers + delta partial sums
+
+__global__ void __launch_bounds__(THREADS, 1)
+attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __grid_constant__ CUtensorMap tma_do128,
+                      const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int seq = blockIdx.z, head = blockIdx.y;
+  const int seq_start = p.cu_seqlens[seq];
+  const int len = p.cu_seqlens[seq + 1] - seq_start;
+  const int q0 = blockIdx.x * BT;
+  if (q0 >= len) return;
+
+  uint8_t* smem_q = smem;
+  uint8_t* smem_do = smem + TILE_BYTES;
+  uint8_t* smem_k = smem + 2 * TILE_BYTES;
+  uint8_t* smem_v = smem_k + NS * TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_TILES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;            // [NS]
+  uint64_t* kv_empty = kv_full + NS;       // [NS]
+  uint64_t* s_full = kv_empty + NS;        // S and dP of a tile are in TMEM
+  uint64_t* s_free = s_full + 1;           // 16 arrivals (one per warp): S / dP are in registers
+  uint64_t* dz_full = s_free + 1;          // [slice] 128 arrivals: a 32-column slice of dZ is in TMEM
+  uint64_t* dz_free = dz_full + 4;         // [slice] the dQ MMAs that read the piece have retired
+  uint64_t* acc_full = dz_free + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  float* delta_part = reinterpret_cast<float*>(smem + DQ_TILES + 256);  // [4][128]
+
+  if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
+
+  int kv_lo = 0, kv_hi = len - 1;
+  if (p.window >= 0) {
+    kv_lo = max(0, q0 - p.window);
+    kv_hi = min(len - 1, q0 + BT - 1 + p.window);
+  }
+  // inner tiles start AT the band (not on a 128 grid): a window layer streams 2 tiles per outer tile, not 3
+  const int kv_base = kv_lo;
+  const int n_tiles = (kv_hi - kv_base) / BI + 1;
+
+  if (warp == EW_WARPS + 1 && lane == 0) {
+    ptx::mbar_init(q_full, 1);
+    for (int s = 0; s < NS; ++s) {
+      ptx::mbar_init(&kv_full[s], 1);
+      ptx::mbar_init(&kv_empty[s], 1);
+    }
+    ptx::mbar_init(s_full, 1);
+    ptx::mbar_init(s_free, EW_WARPS);
+    for (int i = 0; i < 4; ++i) {
+      ptx::mbar_init(&dz_full[i], 128);
+      ptx::mbar_init(&dz_free[i], 1);
+    }
+    ptx::mbar_init(acc_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == EW_WARPS) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tma_qkv128);
+      ptx::prefetch_tmap(&tma_do128);
+    }
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DZ = 256, TM_DQ = 320;
+
+  if (warp >= EW_WARPS) {
+    ptx::setmaxnreg_dec<REG_AUX>();
+    if (warp == EW_WARPS && lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      const int col_q = head * D, col_k = p.hidden + head * D, col_v = 2 * p.hidden + head * D;
+      ptx::mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
+      ptx::tma_load_2d(smem_q, &tma_qkv128, q_full, col_q, seq_start + q0);
+      ptx::tma_load_2d(smem_do, &tma_do128, q_full, head * D, seq_start + q0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % NS;
+        ptx::mbar_wait(&kv_empty[s], ((j / NS) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+        const int row = seq_start + kv_base + j * BI;
+        ptx::tma_load_2d(smem_k + s * TILE_BYTES, &tma_qkv128, &kv_full[s], col_k, row);
+        ptx::tma_load_2d(smem_v + s * TILE_BYTES, &tma_qkv128, &kv_full[s], col_v, row);
+      }
+    } else if (warp == EW_WARPS + 1) {
+      // The whole warp runs the issuer loop (warp-uniform control flow keeps the descriptor arithmetic in the
+      // uniform datapath); one elected lane issues.  With a single active lane every MMA cost ~100 clk of
+      // address moves and the issuer, not the tensor pipe, set the pace (measured).
+      const bool leader = ptx::elect_one();
+      // ---------------------------------------------------------------- MMA issuer
+      const uint32_t idesc_s = ptx::umma_idesc_bf16(BT, BI, 0, 0);
+      const uint32_t idesc_dq = ptx::umma_idesc_bf16(BT, D, 0, 1);  // K as MN-major B operand
+      constexpr uint32_t HI = ptx::umma_desc_hi_sw128(1024);
+      const uint32_t q_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_q), 16);
+      const uint32_t do_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_do), 16);
+      auto issue_s_dp = [&](int j) {
+        const int s = j % NS;
+        ptx::mbar_wait(&kv_full[s], (j / NS) & 1);
+        ptx::tc_fence_after();
+        const uint32_t k_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_k + s * TILE_BYTES), 16);
+        const uint32_t v_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_v + s * TILE_BYTES), 16);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          if (leader) ptx::umma_bf16_split(tmem_base + TM_S, q_lo + k * 2, k_lo + k * 2, HI, idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          if (leader) ptx::umma_bf16_split(tmem_base + TM_DP, do_lo + k * 2, v_lo + k * 2, HI, idesc_s, k != 0 ? 1u : 0u);
+        if (leader) ptx::umma_commit(s_full);
+      };
+      ptx::mbar_wait(q_full, 0);
+      issue_s_dp(0);
+#pragma unroll 1
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % NS;
+        if (j + 1 < n_tiles) {
+          ptx::mbar_wait(s_free, j & 1);  // S(j) / dP(j) are in registers: overwrite them with tile j+1
+          issue_s_dp(j + 1);
+        }
+        // K tile as the MN-major B operand of dQ += dZ K (LBO = 8192: distance of 64-element MN chunks, unused)
+        const uint32_t kmn_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_k + s * TILE_BYTES), 8192);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {  // 32-column slices (their warps finish at about the same time)
+          ptx::mbar_wait(&dz_full[c], j & 1);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const int k = 2 * c + kk;  // 16-key step: 8 TMEM columns of dZ, 16 rows of K
+            if (leader) ptx::umma_bf16_ts(tmem_base + TM_DQ, tmem_base + TM_DZ + k * 8, kmn_lo + ((k * 2048) >> 4), HI, idesc_dq,
+                              (j | c | kk) != 0 ? 1u : 0u);
+          }
+          if (leader) ptx::umma_commit(&dz_free[c]);
+        }
+        if (leader) ptx::umma_commit(&kv_empty[s]);
+      }
+      if (leader) ptx::umma_commit(acc_full);
+    }
+  } else {
+    // ------------------------------------------------------------------ element-wise warps
+    ptx::setmaxnreg_inc<REG_EW>();
+    const int c = warp >> 2;                       // 32-column slice
+    const int t = (warp & 3) * 32 + lane;          // query row inside the tile == TMEM lane
+    const int qi = q0 + t;
+    const bool valid = qi < len;
+    const int64_t row = static_cast<int64_t>(seq_start) + qi;
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int warp_pos = q0 + (warp & 3) * 32;
+    // delta = <dO, O> of the row: each of the row's four threads takes 16 of the 64 columns
+    float delta = 0.f, lse = 0.f;
+    if (valid) {
+      const uint4* po = reinterpret_cast<const uint4*>(p.out + row * p.hidden + head * D + c * 16);
+      const uint4* pd = reinterpret_cast<const uint4*>(p.dout + row * p.hidden + head * D + c * 16);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float a[8], b[8];
+        unpack8f(__ldg(po + i), a);
+        unpack8f(__ldg(pd + i), b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) delta += a[k] * b[k];
+      }
+      lse = p.lse[static_cast<int64_t>(head) * p.total_tokens + row];
+    }
+    delta_part[c * BT + t] = delta;
+    ptx::named_bar_sync(1, EW_WARPS * 32);
+    delta = (delta_part[t] + delta_part[BT + t]) + (delta_part[2 * BT + t] + delta_part[3 * BT + t]);
+    if (valid && c == 0) p.delta[static_cast<int64_t>(head) * p.total_tokens + row] = delta;
+    const float2 c2 = make_float2(p.scale_log2, p.scale_log2);
+    const float2 nlse2 = make_float2(-lse, -lse);
+    const float2 sc2 = make_float2(p.scale, p.scale);
+    const float2 ndsc2 = make_float2(-delta * p.scale, -delta * p.scale);  // dZ = P * (dP*scale - delta*scale)
+    const uint32_t t_dz = tmem_base + TM_DZ + lane_off + c * (HC / 2);
+    const uint32_t t_s = tmem_base + TM_S + lane_off + c * HC;
+    const uint32_t t_dp = tmem_base + TM_DP + lane_off + c * HC;
+    PF_DECL();
+    for (int j = 0; j < n_tiles; ++j) {
+      const int kv0 = kv_base + j * BI + c * HC;
+      PF_B(pf_st);
+      ptx::mbar_wait(s_full, j & 1);
+      PF_B(pf_s);
+      ptx::tc_fence_after();
+      uint32_t rs[32], rp[32];
+      ptx::tmem_ld_32x32b_x32(t_s, rs);
+      ptx::tmem_ld_32x32b_x32(t_dp, rp);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      if (lane == 0) ptx::mbar_arrive(s_free);
+      PF_B(pf_ld);
+      const Band bd = band_of(qi, warp_pos, kv0, len, p.window, valid);
+      uint32_t packed[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) packed[i] = 0u;
+      if (bd.state == 2) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float2 e = ptx::fma2(make_float2(__uint_as_float(rs[i]), __uint_as_float(rs[i + 1])), c2, nlse2);
+          const float2 pr = make_float2(ptx::ex2_approx(e.x), ptx::ex2_approx(e.y));
+          const float2 u = ptx::fma2(make_float2(__uint_as_float(rp[i]), __uint_as_float(rp[i + 1])), sc2, ndsc2);
+          const float2 z = ptx::mul2(pr, u);
+          packed[i >> 1] = ptx::pack_bf16x2(z.x, z.y);
+        }
+      } else if (bd.state == 1) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float2 e = ptx::fma2(make_float2(__uint_as_float(rs[i]), __uint_as_float(rs[i + 1])), c2, nlse2);
+          const float p0 = (i >= bd.a && i < bd.b) ? ptx::ex2_approx(e.x) : 0.f;
+          const float p1 = (i + 1 >= bd.a && i + 1 < bd.b) ? ptx::ex2_approx(e.y) : 0.f;
+          const float2 u = ptx::fma2(make_float2(__uint_as_float(rp[i]), __uint_as_float(rp[i + 1])), sc2, ndsc2);
+          packed[i >> 1] = ptx::pack_bf16x2(p0 * u.x, p1 * u.y);
+        }
+      }
+      PF_B(pf_cmp);
+      // the slice still feeds the dQ MMAs of the previous tile until dz_free fires (issued a whole tile ago)
+      if (j > 0) ptx::mbar_wait(&dz_free[c], (j - 1) & 1);
+      PF_B(pf_free);
+      ptx::tc_fence_after();
+      ptx::tmem_st_32x32b_x16(t_dz, packed);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&dz_full[c]);
+    }
+    PF_B(pf_st);
+    PF_PRINT("dq", n_tiles);
+    if (c == 0) {
+      ptx::mbar_wait(acc_full, 0);
+      ptx::tc_fence_after();
+      const float2* cs = nullptr;
+      if (p.rope_table && p.positions && valid) cs = p.rope_table + static_cast<int64_t>(p.positions[row]) * 32;
+      store_grad_row(tmem_base + TM_DQ + lane_off, p.dqkv + row * 3 * p.hidden + head * D, cs, valid);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == EW_WARPS) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ================================================================================================
+// dKV kernel.  smem: K 16K | V 16K | Q 3x16K | dO 3x16K | -lse / -delta*scale 3x1 KB
+// TMEM: S^T = [0,128)  dP^T = [128,256)  P^T (bf16 pairs) = [256,320)  dZ^T = [320,384)  dK = [384,448)  dV = [448,512).
+constexpr int DKV_TILES = 2 * TILE_BYTES + NS * 2 * TILE_BYTES;  // 128 KB
+constexpr int DKV_VEC = NS * 2 * BI * 4;                                          // 3 KB
+constexpr int DKV_SMEM = DKV_TILES + DKV_VEC + 256;
+
+__global__ void __launch_bounds__(THREADS, 1)
+attn_bwd_dkv_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __grid_constant__ CUtensorMap tma_do128,
+                       const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int seq = blockIdx.z, head = blockIdx.y;
+  const int seq_start = p.cu_seqlens[seq];
+  const int len = p.cu_seqlens[seq + 1] - seq_start;
+  const int k0 = blockIdx.x * BT;
+  if (k0 >= len) return;
+
+  uint8_t* smem_k = smem;
+  uint8_t* smem_v = smem + TILE_BYTES;
+  uint8_t* smem_q = smem + 2 * TILE_BYTES;
+  uint8_t* smem_do = smem_q + NS * TILE_BYTES;
+  float* smem_vec = reinterpret_cast<float*>(smem + DKV_TILES);  // [stage][-lse 128 | -delta*scale 128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DKV_TILES + DKV_VEC);
+  uint64_t* kv_full = bars;
+  uint64_t* qdo_full = bars + 1;          // [NS] TMA bytes + 32 staging-lane arrivals
+  uint64_t* qdo_empty = qdo_full + NS;    // [NS]
+  uint64_t* s_full = qdo_empty + NS;
+  uint64_t* s_free = s_full + 1;          // 16 arrivals
+  uint64_t* pz_full = s_free + 1;         // [slice] 128 arrivals: 32-column pieces of P^T and dZ^T are in smem
+  uint64_t* pz_free = pz_full + 4;        // [slice]
+  uint64_t* acc_full = pz_free + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
+#ifdef CM3P_ATTN_PROF
+  __shared__ long long ev[8][20];  // per tile: 0 s_free seen, 1 S issued, 2..5 slice seen, 6 warp0 s_full seen, 7 warp0 arrive
+#define EV(k, i) do { if ((i) < 20) ev[k][i] = clock64(); } while (0)
+#else
+#define EV(k, i)
+#endif
+
+  int q_lo = 0, q_hi = len - 1;
+  if (p.window >= 0) {
+    q_lo = max(0, k0 - p.window);
+    q_hi = min(len - 1, k0 + BT - 1 + p.window);
+  }
+  const int q_base = q_lo;
+  const int n_tiles = (q_hi - q_base) / BI + 1;
+
+  if (warp == EW_WARPS + 1 && lane == 0) {
+    ptx::mbar_init(kv_full, 1);
+    for (int s = 0; s < NS; ++s) {
+      ptx::mbar_init(&qdo_full[s], 33);
+      ptx::mbar_init(&qdo_empty[s], 1);
+    }
+    ptx::mbar_init(s_full, 1);
+    ptx::mbar_init(s_free, EW_WARPS);
+    for (int i = 0; i < 4; ++i) {
+      ptx::mbar_init(&pz_full[i], 128);
+      ptx::mbar_init(&pz_free[i], 1);
+    }
+    ptx::mbar_init(acc_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == EW_WARPS) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tma_qkv128);
+      ptx::prefetch_tmap(&tma_do128);
+    }
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t TM_ST = 0, TM_DPT = 128, TM_PT = 256, TM_DZT = 320, TM_DK = 384, TM_DV = 448;
+
+  if (warp >= EW_WARPS) {
+    ptx::setmaxnreg_dec<REG_AUX>();
+    if (warp == EW_WARPS) {
+      // ------------------------------------------------------------------ producer (whole warp)
+      const int col_q = head * D, col_k = p.hidden + head * D, col_v = 2 * p.hidden + head * D;
+      if (lane == 0) {
+        ptx::mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
+        ptx::tma_load_2d(smem_k, &tma_qkv128, kv_full, col_k, seq_start + k0);
+        ptx::tma_load_2d(smem_v, &tma_qkv128, kv_full, col_v, seq_start + k0);
+      }
+      const float* lse_h = p.lse + static_cast<int64_t>(head) * p.total_tokens;
+      const float* delta_h = p.delta + static_cast<int64_t>(head) * p.total_tokens;
+      for (int i = 0; i < n_tiles; ++i) {
+        const int s = i % NS;
+        ptx::mbar_wait(&qdo_empty[s], ((i / NS) & 1) ^ 1);
+        const int64_t row = static_cast<int64_t>(seq_start) + q_base + i * BI;
+        if (lane == 0) {
+          ptx::mbar_arrive_expect_tx(&qdo_full[s], 2 * TILE_BYTES);
+          ptx::tma_load_2d(smem_q + s * TILE_BYTES, &tma_qkv128, &qdo_full[s], col_q, static_cast<int32_t>(row));
+          ptx::tma_load_2d(smem_do + s * TILE_BYTES, &tma_do128, &qdo_full[s], col_q, static_cast<int32_t>(row));
+        }
+        float* vec = smem_vec + s * 2 * BI;
+#pragma unroll
+        for (int hh = 0; hh < BI; hh += 32) {
+          const int64_t r = row + hh + lane;
+          const bool ok = r < p.total_tokens;
+          vec[hh + lane] = ok ? -lse_h[r] : 0.f;
+          vec[BI + hh + lane] = ok ? -delta_h[r] * p.scale : 0.f;  // dZ = P * (dP*scale - delta*scale)
+        }
+        ptx::mbar_arrive(&qdo_full[s]);
+      }
+    } else if (warp == EW_WARPS + 1) {
+      // The whole warp runs the issuer loop (warp-uniform control flow keeps the descriptor arithmetic in the
+      // uniform datapath); one elected lane issues.  With a single active lane every MMA cost ~100 clk of
+      // address moves and the issuer, not the tensor pipe, set the pace (measured).
+      const bool leader = ptx::elect_one();
+      // ------------------------------------------------------------------ MMA issuer
+      const uint32_t idesc_s = ptx::umma_idesc_bf16(BT, BI, 0, 0);
+      const uint32_t idesc_acc = ptx::umma_idesc_bf16(BT, D, 0, 1);
+      constexpr uint32_t HI = ptx::umma_desc_hi_sw128(1024);
+      const uint32_t k_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_k), 16);
+      const uint32_t v_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_v), 16);
+      auto issue_s_dp = [&](int i) {
+        const int s = i % NS;
+        ptx::mbar_wait(&qdo_full[s], (i / NS) & 1);
+        ptx::tc_fence_after();
+        const uint32_t q_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_q + s * TILE_BYTES), 16);
+        const uint32_t do_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_do + s * TILE_BYTES), 16);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          if (leader) ptx::umma_bf16_split(tmem_base + TM_ST, k_lo + k * 2, q_lo + k * 2, HI, idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          if (leader) ptx::umma_bf16_split(tmem_base + TM_DPT, v_lo + k * 2, do_lo + k * 2, HI, idesc_s, k != 0 ? 1u : 0u);
+        if (leader) ptx::umma_commit(s_full);
+      };
+      ptx::mbar_wait(kv_full, 0);
+      issue_s_dp(0);
+#pragma unroll 1
+      for (int i = 0; i < n_tiles; ++i) {
+        const int s = i % NS;
+        if (i + 1 < n_tiles) {
+          ptx::mbar_wait(s_free, i & 1);
+          if (leader) EV(0, i);
+          issue_s_dp(i + 1);
+          if (leader) EV(1, i);
+        }
+        const uint32_t qmn_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_q + s * TILE_BYTES), 8192);
+        const uint32_t domn_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_do + s * TILE_BYTES), 8192);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          ptx::mbar_wait(&pz_full[c], i & 1);
+          if (leader) EV(2 + c, i);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const int k = 2 * c + kk;  // 16-query step: 8 TMEM columns of P^T, 16 rows of dO
+            if (leader) ptx::umma_bf16_ts(tmem_base + TM_DV, tmem_base + TM_PT + k * 8, domn_lo + ((k * 2048) >> 4), HI, idesc_acc,
+                              (i | c | kk) != 0 ? 1u : 0u);
+          }
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const int k = 2 * c + kk;
+            if (leader) ptx::umma_bf16_ts(tmem_base + TM_DK, tmem_base + TM_DZT + k * 8, qmn_lo + ((k * 2048) >> 4), HI, idesc_acc,
+                              (i | c | kk) != 0 ? 1u : 0u);
+          }
+          if (leader) ptx::umma_commit(&pz_free[c]);
+        }
+        if (leader) ptx::umma_commit(&qdo_empty[s]);
+      }
+      if (leader) ptx::umma_commit(acc_full);
+    }
+  } else {
+    // ------------------------------------------------------------------ element-wise warps
+    ptx::setmaxnreg_inc<REG_EW>();
+    const int c = warp >> 2;                 // 32-column (query) slice
+    const int t = (warp & 3) * 32 + lane;    // key row inside the tile == TMEM lane
+    const int kj = k0 + t;
+    const bool valid = kj < len;
+    const int64_t row = static_cast<int64_t>(seq_start) + kj;
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int warp_pos = k0 + (warp & 3) * 32;
+    const float2 c2 = make_float2(p.scale_log2, p.scale_log2);
+    const float2 sc2 = make_float2(p.scale, p.scale);
+    const uint32_t t_pt = tmem_base + TM_PT + lane_off + c * (HC / 2);
+    const uint32_t t_dzt = tmem_base + TM_DZT + lane_off + c * (HC / 2);
+    const uint32_t t_s = tmem_base + TM_ST + lane_off + c * HC;
+    const uint32_t t_dp = tmem_base + TM_DPT + lane_off + c * HC;
+    PF_DECL();
+    for (int i = 0; i < n_tiles; ++i) {
+      const int s = i % NS;
+      const int q0i = q_base + i * BI + c * HC;
+      PF_B(pf_st);
+      ptx::mbar_wait(s_full, i & 1);
+      ptx::mbar_wait(&qdo_full[s], (i / NS) & 1);  // already complete: orders the lse / delta staging writes
+      PF_B(pf_s);
+      if (threadIdx.x == 0) EV(6, i);
+      ptx::tc_fence_after();
+      uint32_t rs[32], rp[32];
+      ptx::tmem_ld_32x32b_x32(t_s, rs);
+      ptx::tmem_ld_32x32b_x32(t_dp, rp);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      if (lane == 0) ptx::mbar_arrive(s_free);
+      PF_B(pf_ld);
+      const Band bd = band_of(kj, warp_pos, q0i, len, p.window, valid);
+      const float4* nlse4 = reinterpret_cast<const float4*>(smem_vec + s * 2 * BI + c * HC);
+      const float4* ndel4 = reinterpret_cast<const float4*>(smem_vec + s * 2 * BI + BI + c * HC);
+      uint32_t pp[16], pz[16];
+#pragma unroll
+      for (int i2 = 0; i2 < 16; ++i2) pp[i2] = pz[i2] = 0u;
+      if (bd.state == 2) {
+        // every column allowed for every row of this warp: no predicates
+#pragma unroll
+        for (int i2 = 0; i2 < 32; i2 += 4) {
+          const float4 l4 = nlse4[i2 >> 2];
+          const float4 d4 = ndel4[i2 >> 2];
+          const float2 e0 = ptx::fma2(make_float2(__uint_as_float(rs[i2]), __uint_as_float(rs[i2 + 1])), c2,
+                                      make_float2(l4.x, l4.y));
+          const float2 e1 = ptx::fma2(make_float2(__uint_as_float(rs[i2 + 2]), __uint_as_float(rs[i2 + 3])), c2,
+                                      make_float2(l4.z, l4.w));
+          const float2 p0 = make_float2(ptx::ex2_approx(e0.x), ptx::ex2_approx(e0.y));
+          const float2 p1 = make_float2(ptx::ex2_approx(e1.x), ptx::ex2_approx(e1.y));
+          const float2 u0 = ptx::fma2(make_float2(__uint_as_float(rp[i2]), __uint_as_float(rp[i2 + 1])), sc2,
+                                      make_float2(d4.x, d4.y));
+          const float2 u1 = ptx::fma2(make_float2(__uint_as_float(rp[i2 + 2]), __uint_as_float(rp[i2 + 3])), sc2,
+                                      make_float2(d4.z, d4.w));
+          const float2 z0 = ptx::mul2(p0, u0), z1 = ptx::mul2(p1, u1);
+          pp[i2 >> 1] = ptx::pack_bf16x2(p0.x, p0.y);
+          pp[(i2 >> 1) + 1] = ptx::pack_bf16x2(p1.x, p1.y);
+          pz[i2 >> 1] = ptx::pack_bf16x2(z0.x, z0.y);
+          pz[(i2 >> 1) + 1] = ptx::pack_bf16x2(z1.x, z1.y);
+        }
+      } else if (bd.state == 1) {
+        const float2* nlse2 = reinterpret_cast<const float2*>(nlse4);
+        const float2* ndel2 = reinterpret_cast<const float2*>(ndel4);
+#pragma unroll
+        for (int i2 = 0; i2 < 32; i2 += 2) {
+          const float2 l2 = nlse2[i2 >> 1];
+          const float2 d2 = ndel2[i2 >> 1];
+          const float2 e = ptx::fma2(make_float2(__uint_as_float(rs[i2]), __uint_as_float(rs[i2 + 1])), c2, l2);
+          const float p0 = (i2 >= bd.a && i2 < bd.b) ? ptx::ex2_approx(e.x) : 0.f;
+          const float p1 = (i2 + 1 >= bd.a && i2 + 1 < bd.b) ? ptx::ex2_approx(e.y) : 0.f;
+          const float2 u = ptx::fma2(make_float2(__uint_as_float(rp[i2]), __uint_as_float(rp[i2 + 1])), sc2, d2);
+          pp[i2 >> 1] = ptx::pack_bf16x2(p0, p1);
+          pz[i2 >> 1] = ptx::pack_bf16x2(p0 * u.x, p1 * u.y);
+        }
+      }
+      PF_B(pf_cmp);
+      if (i > 0) ptx::mbar_wait(&pz_free[c], (i - 1) & 1);
+      PF_B(pf_free);
+      ptx::tc_fence_after();
+      ptx::tmem_st_32x32b_x16(t_pt, pp);
+      ptx::tmem_st_32x32b_x16(t_dzt, pz);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&pz_full[c]);
+      if (threadIdx.x == 0) EV(7, i);
+    }
+    PF_B(pf_st);
+    PF_PRINT("dkv", n_tiles);
+#ifdef CM3P_ATTN_PROF
+    if (threadIdx.x == 0 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0)
+      for (int i = 1; i < n_tiles - 1 && i < 20; ++i)
+        printf("tile %2d: w0 s_full %6lld arrive +%5lld | issuer s_free +%5lld S issued +%5lld slices +%5lld +%5lld +%5lld +%5lld\n",
+               i, ev[6][i] - pf_t0, ev[7][i] - ev[6][i], ev[0][i] - ev[6][i], ev[1][i] - ev[6][i], ev[2][i] - ev[6][i],
+               ev[3][i] - ev[6][i], ev[4][i] - ev[6][i], ev[5][i] - ev[6][i]);
+#endif
+    ptx::mbar_wait(acc_full, 0);
+    ptx::tc_fence_after();
+    __nv_bfloat16* base = p.dqkv + row * 3 * p.hidden + head * D;
+    if (c == 0) {
+      const float2* cs = nullptr;
+      if (p.rope_table && p.positions && valid) cs = p.rope_table + static_cast<int64_t>(p.positions[row]) * 32;
+      store_grad_row(tmem_base + TM_DK + lane_off, base + p.hidden, cs, valid);
+    } else if (c == 1) {
+      store_grad_row(tmem_base + TM_DV + lane_off, base + 2 * p.hidden, nullptr, valid);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == EW_WARPS) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace v3
+}  // namespace
+
+int attn_varlen_bwd_v3(const AttnBwdArgs& a, cudaStream_t stream) {
+  using namespace v3;
+  const uint64_t H = static_cast<uint64_t>(a.heads) * 64;
+  const uint64_t T = static_cast<uint64_t>(a.total_tokens);
+  CUtensorMap qkv128, do128;
+  int rc;
+  if ((rc = encode_tmap_2d_bf16(&qkv128, a.qkv, 3 * H, T, 3 * H * 2, 64, BT)) != kOk) return rc;
+  if ((rc = encode_tmap_2d_bf16(&do128, a.dout, H, T, H * 2, 64, BT)) != kOk) return rc;
+  static bool configured = false;
+  if (!configured) {
+    CM3P_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dq_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    CM3P_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dkv_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    configured = true;
+  }
+  BwdParams p;
+  p.cu_seqlens = a.cu_seqlens;
+  p.out = reinterpret_cast<const __nv_bfloat16*>(a.out);
+  p.dout = reinterpret_cast<const __nv_bfloat16*>(a.dout);
+  p.lse = a.lse;
+  p.delta = a.delta;
+  p.dqkv = reinterpret_cast<__nv_bfloat16*>(a.dqkv);
+  p.positions = a.positions;
+  p.rope_table = reinterpret_cast<const float2*>(a.rope_table);
+  p.total_tokens = a.total_tokens;
+  p.heads = a.heads;
+  p.hidden = static_cast<int>(H);
+  p.window = a.window;
+  p.scale = 0.125f;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  dim3 grid((a.max_seqlen + BT - 1) / BT, a.heads, a.batch);
+  attn_bwd_dq_v3_kernel<<<grid, THREADS, DQ_SMEM, stream>>>(qkv128, do128, p);
+  CM3P_CUDA_TRY(cudaGetLastError());
+  attn_bwd_dkv_v3_kernel<<<grid, THREADS, DKV_SMEM, stream>>>(qkv128, do128, p);
+  CM3P_CUDA_TRY(cudaGetLastError());
+  return kOk;
+}
+
+}  // namespace cm3p

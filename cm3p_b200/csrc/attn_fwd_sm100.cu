@@ -397,13 +397,16 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
         ptx::tma_load_2d(smem_k + s * KV_TILE_BYTES, &tma_qkv, &kv_full[s], col_k, row);
         ptx::tma_load_2d(smem_v + s * KV_TILE_BYTES, &tma_qkv, &kv_full[s], col_v, row);
       }
-    } else if ((warp == 9 || warp == 10) && lane == 0) {
+    } else if (warp == 9 || warp == 10) {
       // ---------------------------------------------------------------- MMA issuers (one per Q tile)
       // Each Q tile has its own issuing thread, so its MMAs follow the order in which its softmax group
       // produces the events: "S_x buffer drained into registers" -> S_x(t+1) (runs on the tensor pipe WHILE
       // the group is still exponentiating S_x(t)), "first / second 64-key half of P_x(t) written" -> PV on
       // that half.  All waits are blocking mbarrier waits: a polling issuer steals issue slots from the
       // softmax warps that share its scheduler (measured: -20 %).
+      // The whole warp runs the loop (warp-uniform control flow keeps the descriptor arithmetic in the uniform
+      // datapath: back-to-back UTCHMMA instead of ~10 address-move instructions per MMA); one elected lane issues.
+      const bool leader = ptx::elect_one();
       const int x = warp - 9;
       const uint32_t idesc_s = ptx::umma_idesc_bf16(BQ, BKV, 0, 0);
       const uint32_t idesc_o = ptx::umma_idesc_bf16(BQ, D, 0, 1);  // V is MN-major
@@ -418,16 +421,16 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
         const uint32_t k_addr = ptx::smem_u32(smem_k + s * KV_TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
-          ptx::umma_bf16(t_s, ptx::umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+          if (leader) ptx::umma_bf16(t_s, ptx::umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
                          ptx::umma_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
-        ptx::umma_commit(&s_full[x]);
+        if (leader) ptx::umma_commit(&s_full[x]);
       };
       ptx::mbar_wait(q_full, 0);
       // the ring is released by BOTH issuers (kv_empty counts 2): tiles outside this Q tile's range are
       // acknowledged as soon as they have landed
       for (int u = 0; u < lo_x; ++u) {
         ptx::mbar_wait(&kv_full[u % KV_STAGES2], (u / KV_STAGES2) & 1);
-        ptx::umma_commit(&kv_empty[u % KV_STAGES2]);
+        if (leader) ptx::umma_commit(&kv_empty[u % KV_STAGES2]);
       }
       if (hi_x > lo_x) issue_s(lo_x);
       for (int t = lo_x; t < hi_x; ++t) {
@@ -436,7 +439,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
           ptx::mbar_wait(&s_free[x], j & 1);
           issue_s(t + 1);
 #ifdef CM3P_ATTN_PROF
-          if (x == 0 && j < 19) ev[3][j + 1] = clock64();
+          if (leader && x == 0 && j < 19) ev[3][j + 1] = clock64();
 #endif
         }
         const uint32_t v_base = ptx::smem_u32(smem_v + (t % KV_STAGES2) * KV_TILE_BYTES);
@@ -444,24 +447,26 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
         for (int h = 0; h < 2; ++h) {
           ptx::mbar_wait(&p_full[2 * x + h], j & 1);  // this half of P_x(t) is in smem (O_x rescaled if needed)
 #ifdef CM3P_ATTN_PROF
-          if (x == 0 && j < 20) ev[1][2 * j + h] = clock64();
+          if (leader && x == 0 && j < 20) ev[1][2 * j + h] = clock64();
 #endif
           ptx::tc_fence_after();
           const uint32_t p_addr = p_base + h * (BQ * 128);
           const uint32_t v_addr = v_base + h * (64 * 128);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            ptx::umma_bf16(t_o, ptx::umma_smem_desc_sw128(p_addr + k * 32, 16, 1024),
+            if (leader) ptx::umma_bf16(t_o, ptx::umma_smem_desc_sw128(p_addr + k * 32, 16, 1024),
                            ptx::umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_o,
                            (j | h | k) != 0 ? 1u : 0u);
-          if (h == 1 && t + 1 == hi_x) ptx::umma_commit(&o_full[x]);
-          else ptx::umma_commit(&pv_done[2 * x + h]);
+          if (leader) {
+            if (h == 1 && t + 1 == hi_x) ptx::umma_commit(&o_full[x]);
+            else ptx::umma_commit(&pv_done[2 * x + h]);
+          }
         }
-        ptx::umma_commit(&kv_empty[t % KV_STAGES2]);
+        if (leader) ptx::umma_commit(&kv_empty[t % KV_STAGES2]);
       }
       for (int u = max(hi_x, lo_x); u < U; ++u) {
         ptx::mbar_wait(&kv_full[u % KV_STAGES2], (u / KV_STAGES2) & 1);
-        ptx::umma_commit(&kv_empty[u % KV_STAGES2]);
+        if (leader) ptx::umma_commit(&kv_empty[u % KV_STAGES2]);
       }
     }
   } else {

@@ -1,4 +1,5 @@
-"""Single attention forward launch at the bench shape (used with profiling builds: CM3P_LIB_PATH=...)."""
+"""Single attention forward (+ backward with "bwd") launch at the bench shape; used with profiling builds
+(CM3P_LIB_PATH=variants/libprof.so, built with CM3P_NVCC_EXTRA=-DCM3P_ATTN_PROF)."""
 import os
 import sys
 
@@ -7,7 +8,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cm3p_b200 import ops  # noqa: E402
 
-window = int(sys.argv[1]) if len(sys.argv) > 1 else -1
+args = [a for a in sys.argv[1:] if a != "bwd"]
+window = int(args[0]) if args else -1
 B, L, heads = 64, 2000, 12
 g = torch.Generator().manual_seed(0)
 lens = torch.randint(600, L + 1, (B,), generator=g).tolist()
@@ -19,6 +21,12 @@ T = cu[-1]
 qkv = torch.randn(T, 3 * heads * 64, device="cuda").bfloat16()
 cu_t = torch.tensor(cu, dtype=torch.int32, device="cuda")
 out = torch.empty(T, heads * 64, device="cuda", dtype=torch.bfloat16)
+lse = torch.empty(heads, T, device="cuda")
 for _ in range(2):
-    ops.attn_varlen_fwd(qkv, cu_t, L, heads, window, out=out)
+    ops.attn_varlen_fwd(qkv, cu_t, L, heads, window, out=out, lse=lse)
+    torch.cuda.synchronize()
+if "bwd" in sys.argv[1:]:
+    dout = torch.randn(T, heads * 64, device="cuda").bfloat16()
+    dqkv, delta = torch.empty_like(qkv), torch.empty_like(lse)
+    ops.attn_varlen_bwd(qkv, out, dout, lse, cu_t, L, heads, window, dqkv=dqkv, delta=delta)
     torch.cuda.synchronize()
