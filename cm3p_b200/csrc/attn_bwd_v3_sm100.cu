@@ -345,7 +345,7 @@ attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const float2 e = ptx::fma2(make_float2(__uint_as_float(rs[i]), __uint_as_float(rs[i + 1])), c2, nlse2);
-          const float2 pr = make_float2(ptx::ex2_approx(e.x), ptx::ex2_approx(e.y));
+          const float2 pr = ptx::ex2_pair(e, i >> 1);
           const float2 u = ptx::fma2(make_float2(__uint_as_float(rp[i]), __uint_as_float(rp[i + 1])), sc2, ndsc2);
           const float2 z = ptx::mul2(pr, u);
           packed[i >> 1] = ptx::pack_bf16x2(z.x, z.y);
@@ -610,8 +610,8 @@ attn_bwd_dkv_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __g
                                       make_float2(l4.x, l4.y));
           const float2 e1 = ptx::fma2(make_float2(__uint_as_float(rs[i2 + 2]), __uint_as_float(rs[i2 + 3])), c2,
                                       make_float2(l4.z, l4.w));
-          const float2 p0 = make_float2(ptx::ex2_approx(e0.x), ptx::ex2_approx(e0.y));
-          const float2 p1 = make_float2(ptx::ex2_approx(e1.x), ptx::ex2_approx(e1.y));
+          const float2 p0 = ptx::ex2_pair(e0, i2 >> 1);
+          const float2 p1 = ptx::ex2_pair(e1, (i2 >> 1) + 1);
           const float2 u0 = ptx::fma2(make_float2(__uint_as_float(rp[i2]), __uint_as_float(rp[i2 + 1])), sc2,
                                       make_float2(d4.x, d4.y));
           const float2 u1 = ptx::fma2(make_float2(__uint_as_float(rp[i2 + 2]), __uint_as_float(rp[i2 + 3])), sc2,

@@ -595,9 +595,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const float2 t = ptx::fma2(make_float2(__uint_as_float(sr[q][i]), __uint_as_float(sr[q][i + 1])), c2, nmc2);
-            float2 e;
-            e.x = ptx::ex2_approx(t.x);
-            e.y = ptx::ex2_approx(t.y);
+            const float2 e = ptx::ex2_pair(t, i >> 1);
             rs[(i >> 1) & 3] = ptx::add2(rs[(i >> 1) & 3], e);
             packed[i >> 1] = ptx::pack_bf16x2(e.x, e.y);
           }

@@ -360,4 +360,33 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// 2^x for a pair on the FMA pipe instead of the 16-per-clock MUFU: Cody-Waite split x = n + f (round to
+// nearest through the 1.5 * 2^23 trick, f in [-0.5, 0.5]), degree-3 minimax polynomial for 2^f (max relative
+// error 7.5e-5, far below the bf16 rounding of the probabilities it feeds), n added into the exponent field.
+// Inputs below -126 are clamped (the result is then ~1e-38 instead of 0); inputs must stay below +100.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f);
+  const float2 r = add2(x, magic);
+  const float2 n = add2(r, make_float2(-12582912.f, -12582912.f));
+  const float2 f = fma2(n, make_float2(-1.f, -1.f), x);
+  float2 p = fma2(f, make_float2(0.0551716648f, 0.0551716648f), make_float2(0.2426111251f, 0.2426111251f));
+  p = fma2(p, f, make_float2(0.6932609677f, 0.6932609677f));
+  p = fma2(p, f, make_float2(0.9999280572f, 0.9999280572f));
+  float2 y;
+  y.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(r.x) << 23));
+  y.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(r.y) << 23));
+  return y;
+}
+// Pair exponential: pairs whose index has one of the low bits selected by CM3P_EXP_EMU_MASK take the
+// polynomial, the rest the MUFU (compile-time choice per call site: `idx` must be a constant after unrolling).
+#ifndef CM3P_EXP_EMU_MASK
+#define CM3P_EXP_EMU_MASK 0x11u  // bit k set: pairs with (idx & 7) == k are emulated (2 of 8 = 25 %)
+#endif
+__device__ __forceinline__ float2 ex2_pair(float2 x, int idx) {
+  if ((CM3P_EXP_EMU_MASK >> (idx & 7)) & 1u) return ex2_poly2(x);
+  return make_float2(ex2_approx(x.x), ex2_approx(x.y));
+}
+
 }  // namespace ptx
