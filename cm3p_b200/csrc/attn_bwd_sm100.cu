@@ -604,18 +604,17 @@ int attn_varlen_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
                "attn_bwd: null pointer");
   CM3P_REQUIRE((a.positions == nullptr) == (a.rope_table == nullptr), kBadShape,
                "attn_bwd: positions and rope_table must be given together");
-  static int use_v1 = -1, gen = 3, v3_window = 0;
+  static int use_v1 = -1, gen = 3, v3_window = 1;
   if (use_v1 < 0) {
     const char* e = getenv("CM3P_ATTN_BWD_V1");
     use_v1 = (e && e[0] == '1') ? 1 : 0;
     const char* g = getenv("CM3P_ATTN_BWD");  // "v2": previous generation (kept for A/B measurements)
     if (g && g[0] == 'v' && g[1] == '2') gen = 2;
     const char* w = getenv("CM3P_ATTN_BWD_V3_WINDOW");
-    v3_window = (w && w[0] == '1') ? 1 : 0;
+    v3_window = (w && w[0] == '0') ? 0 : 1;
   }
-  // global layers over long sequences: the 1-CTA/SM ping-pong kernels.  Window layers (4 inner tiles per
-  // outer tile) and short sequences (metadata tower) are faster in the light 2-CTA/SM form (measured:
-  // window 64, T=80k: 0.77 ms vs 0.95 ms).
+  // sequences longer than one tile: the streaming v3 kernels (attn_bwd_v3_sm100.cu).  Short sequences (metadata
+  // tower, ~20 tokens) stay on the light 2-CTA/SM kernels below.
   if (!use_v1 && a.max_seqlen > BT && (a.window < 0 || v3_window))
     return gen == 2 && a.window < 0 ? attn_varlen_bwd_v2(a, stream) : attn_varlen_bwd_v3(a, stream);
   const uint64_t H = static_cast<uint64_t>(a.heads) * 64;

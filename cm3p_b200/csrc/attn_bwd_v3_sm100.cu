@@ -24,6 +24,7 @@
 // the transposed problem (outer = 128 keys as TMEM lanes, streams Q/dO with their lse / delta rows).
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "attn.h"
 #include "common.h"
@@ -43,19 +44,6 @@ constexpr int THREADS = 640;  // 16 element-wise warps, producer, issuer, 2 idle
 constexpr int EW_WARPS = 16;
 constexpr int REG_EW = 104, REG_AUX = 64;
 
-#ifdef CM3P_ATTN_PROF
-#define PF_DECL() long long pf_s = 0, pf_ld = 0, pf_cmp = 0, pf_free = 0, pf_st = 0, pf_t0 = clock64(), pf_a = pf_t0, pf_b
-#define PF_B(acc) do { pf_b = clock64(); acc += pf_b - pf_a; pf_a = pf_b; } while (0)
-#define PF_PRINT(name, n) \
-  if (lane == 0 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0) \
-    printf("%s warp %d tiles=%d total=%lld wait_s=%lld ld=%lld compute=%lld wait_free=%lld store=%lld\n", name, warp, n, \
-           clock64() - pf_t0, pf_s, pf_ld, pf_cmp, pf_free, pf_st)
-#else
-#define PF_DECL()
-#define PF_B(acc)
-#define PF_PRINT(name, n)
-#endif
-
 struct BwdParams {
   const int32_t* cu_seqlens;
   const __nv_bfloat16* out;
@@ -71,6 +59,7 @@ struct BwdParams {
   int window;
   float scale_log2;
   float scale;
+  int outer_per_cta;
 };
 
 __device__ __forceinline__ uint4 pack8f(const float* v) {
@@ -84,13 +73,9 @@ __device__ __forceinline__ void unpack8f(const uint4& u, float* f) {
   t = ptx::unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
   t = ptx::unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
 }
-// accumulator row (64 fp32 columns) -> optional inverse RoPE -> bf16 -> global
-__device__ __forceinline__ void store_grad_row(uint32_t taddr, __nv_bfloat16* dst, const float2* cs, bool valid) {
-  uint32_t r1[32], r2[32];
-  ptx::tmem_ld_32x32b_x32(taddr, r1);
-  ptx::tmem_ld_32x32b_x32(taddr + 32, r2);
-  ptx::tmem_ld_wait();
-  if (!valid) return;
+// accumulator row (64 fp32 columns, already in registers) -> optional inverse RoPE -> bf16 -> global
+__device__ __forceinline__ void store_grad_regs(const uint32_t (&r1)[32], const uint32_t (&r2)[32], __nv_bfloat16* dst,
+                                                const float2* cs) {
   float o1[32], o2[32];
   if (cs) {
     const float4* tab = reinterpret_cast<const float4*>(cs);
@@ -145,11 +130,66 @@ __device__ __forceinline__ Band band_of(int row_pos, int warp_pos, int t0, int l
   return r;
 }
 
+// Both kernels walk OUTER_PER_CTA consecutive outer tiles of one (sequence, head) in a single CTA and treat
+// the (outer, inner) tile pairs as ONE stream: the producer runs ahead into the next outer tile (its 128-row
+// operands are double-buffered), the issuer chains the S / dP GEMM of the next outer tile's first inner tile
+// behind the current one, and the element-wise warps only swap their per-row constants.  A CTA per outer
+// tile paid ~9000 clk of launch / TMEM allocation / first-load / drain latency with nothing to overlap it
+// (1 CTA per SM): 35 % of a global-layer CTA and 70 % of a window-layer one (measured).
+// The count per CTA is chosen by the launcher (BwdParams::outer_per_cta): enough CTAs for ~8 (global) / ~4
+// (window) waves of uneven work, at most MAX_OUTER_PER_CTA tiles each.
+constexpr int MAX_OUTER_PER_CTA = 16;
+
+struct TileRange {
+  int base;  // sequence position of inner tile 0
+  int n;     // inner tiles
+};
+// inner tiles start AT the band (not on a 128 grid): a window layer streams 2 tiles per outer tile, not 3
+__device__ __forceinline__ TileRange tile_range(int o0, int len, int window) {
+  int lo = 0, hi = len - 1;
+  if (window >= 0) {
+    lo = max(0, o0 - window);
+    hi = min(len - 1, o0 + BT - 1 + window);
+  }
+  TileRange r;
+  r.base = lo;
+  r.n = (hi - lo) / BI + 1;
+  return r;
+}
+
+// delta[head, row] = <dO[row, head, :], O[row, head, :]>: 8 lanes per (row, head), one 16-byte load of each
+// operand per lane (HBM-bound pre-pass; both backward kernels read the result).
+__global__ void __launch_bounds__(256)
+attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                      float* __restrict__ delta, int64_t total_tokens, int heads) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;  // 16-byte unit of the [T, heads*64] matrix
+  const int64_t pair = idx >> 3;                                              // row * heads + head
+  const bool ok = pair < total_tokens * heads;
+  float acc = 0.f;
+  if (ok) {
+    float a[8], b[8];
+    unpack8f(__ldg(reinterpret_cast<const uint4*>(out) + idx), a);
+    unpack8f(__ldg(reinterpret_cast<const uint4*>(dout) + idx), b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += a[k] * b[k];
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (ok && (threadIdx.x & 7) == 0) {
+    const int64_t row = pair / heads;
+    const int head = static_cast<int>(pair - row * heads);
+    delta[static_cast<int64_t>(head) * total_tokens + row] = acc;
+  }
+}
+
 // ================================================================================================
-// dQ kernel.  smem: Q 16K | dO 16K | K 3x16K | V 3x16K.
-// TMEM: S = [0,128)  dP = [128,256)  dZ (bf16 pairs) = [256,320)  dQ = [320,384).
-constexpr int DQ_TILES = 2 * TILE_BYTES + NS * 2 * TILE_BYTES;  // 128 KB
-constexpr int DQ_SMEM = DQ_TILES + 256 + 4 * BT * 4;  // + barriers + delta partial sums
+// dQ kernel.  smem: Q 2x16K | dO 2x16K | K 3x16K | V 3x16K | per-row -lse / -delta*scale 2x1 KB.
+// TMEM: S = [0,128)  dP = [128,256)  dZ (bf16 pairs) = [256,320)  dQ[2] = [320,448) (double-buffered so the
+// next outer tile accumulates while the previous one is written out).
+constexpr int DQ_TILES = 4 * TILE_BYTES + NS * 2 * TILE_BYTES;  // 160 KB
+constexpr int DQ_VEC = 2 * 2 * BT * 4;                          // 2 KB
+constexpr int DQ_SMEM = DQ_TILES + DQ_VEC + 256;
 
 __global__ void __launch_bounds__(THREADS, 1)
 attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __grid_constant__ CUtensorMap tma_do128,
@@ -160,38 +200,37 @@ attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
   const int seq = blockIdx.z, head = blockIdx.y;
   const int seq_start = p.cu_seqlens[seq];
   const int len = p.cu_seqlens[seq + 1] - seq_start;
-  const int q0 = blockIdx.x * BT;
-  if (q0 >= len) return;
+  const int o_begin = blockIdx.x * p.outer_per_cta;
+  const int n_o = min(p.outer_per_cta, (len + BT - 1) / BT - o_begin);  // outer tiles of this CTA
+  if (n_o <= 0) return;
 
-  uint8_t* smem_q = smem;
-  uint8_t* smem_do = smem + TILE_BYTES;
-  uint8_t* smem_k = smem + 2 * TILE_BYTES;
-  uint8_t* smem_v = smem_k + NS * TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_TILES);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;            // [NS]
+  uint8_t* smem_q = smem;                       // [2][16K]
+  uint8_t* smem_do = smem + 2 * TILE_BYTES;     // [2][16K]
+  uint8_t* smem_k = smem + 4 * TILE_BYTES;      // [NS][16K]
+  uint8_t* smem_v = smem_k + NS * TILE_BYTES;   // [NS][16K]
+  float* smem_vec = reinterpret_cast<float*>(smem + DQ_TILES);  // [2][-lse 128 | -delta*scale 128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_TILES + DQ_VEC);
+  uint64_t* q_full = bars;                 // [2] TMA bytes + 32 staging-lane arrivals
+  uint64_t* q_empty = q_full + 2;          // [2] the S / dP MMAs of the outer tile have retired
+  uint64_t* kv_full = q_empty + 2;         // [NS]
   uint64_t* kv_empty = kv_full + NS;       // [NS]
   uint64_t* s_full = kv_empty + NS;        // S and dP of a tile are in TMEM
   uint64_t* s_free = s_full + 1;           // 16 arrivals (one per warp): S / dP are in registers
   uint64_t* dz_full = s_free + 1;          // [slice] 128 arrivals: a 32-column slice of dZ is in TMEM
-  uint64_t* dz_free = dz_full + 4;         // [slice] the dQ MMAs that read the piece have retired
-  uint64_t* acc_full = dz_free + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-  float* delta_part = reinterpret_cast<float*>(smem + DQ_TILES + 256);  // [4][128]
+  uint64_t* dz_free = dz_full + 4;         // [slice] the dQ MMAs that read the slice have retired
+  uint64_t* acc_full = dz_free + 4;        // [2]
+  uint64_t* acc_free = acc_full + 2;       // [2] 8 arrivals: the accumulator has been copied out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
 
   if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
 
-  int kv_lo = 0, kv_hi = len - 1;
-  if (p.window >= 0) {
-    kv_lo = max(0, q0 - p.window);
-    kv_hi = min(len - 1, q0 + BT - 1 + p.window);
-  }
-  // inner tiles start AT the band (not on a 128 grid): a window layer streams 2 tiles per outer tile, not 3
-  const int kv_base = kv_lo;
-  const int n_tiles = (kv_hi - kv_base) / BI + 1;
-
   if (warp == EW_WARPS + 1 && lane == 0) {
-    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&q_full[i], 33);
+      ptx::mbar_init(&q_empty[i], 1);
+      ptx::mbar_init(&acc_full[i], 1);
+      ptx::mbar_init(&acc_free[i], 8);
+    }
     for (int s = 0; s < NS; ++s) {
       ptx::mbar_init(&kv_full[s], 1);
       ptx::mbar_init(&kv_empty[s], 1);
@@ -202,7 +241,6 @@ attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
       ptx::mbar_init(&dz_full[i], 128);
       ptx::mbar_init(&dz_free[i], 1);
     }
-    ptx::mbar_init(acc_full, 1);
     ptx::fence_barrier_init();
   }
   if (warp == EW_WARPS) {
@@ -221,35 +259,59 @@ attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
 
   if (warp >= EW_WARPS) {
     ptx::setmaxnreg_dec<REG_AUX>();
-    if (warp == EW_WARPS && lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
+    if (warp == EW_WARPS) {
+      // ---------------------------------------------------------------- producer (whole warp)
       const int col_q = head * D, col_k = p.hidden + head * D, col_v = 2 * p.hidden + head * D;
-      ptx::mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
-      ptx::tma_load_2d(smem_q, &tma_qkv128, q_full, col_q, seq_start + q0);
-      ptx::tma_load_2d(smem_do, &tma_do128, q_full, head * D, seq_start + q0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % NS;
-        ptx::mbar_wait(&kv_empty[s], ((j / NS) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
-        const int row = seq_start + kv_base + j * BI;
-        ptx::tma_load_2d(smem_k + s * TILE_BYTES, &tma_qkv128, &kv_full[s], col_k, row);
-        ptx::tma_load_2d(smem_v + s * TILE_BYTES, &tma_qkv128, &kv_full[s], col_v, row);
+      const int64_t vec_off = static_cast<int64_t>(head) * p.total_tokens;
+      int it = 0;
+      for (int oi = 0; oi < n_o; ++oi) {
+        const int q0 = (o_begin + oi) * BT;
+        const int qb = oi & 1;
+        ptx::mbar_wait(&q_empty[qb], ((oi >> 1) & 1) ^ 1);
+        if (lane == 0) {
+          ptx::mbar_arrive_expect_tx(&q_full[qb], 2 * TILE_BYTES);
+          ptx::tma_load_2d(smem_q + qb * TILE_BYTES, &tma_qkv128, &q_full[qb], col_q, seq_start + q0);
+          ptx::tma_load_2d(smem_do + qb * TILE_BYTES, &tma_do128, &q_full[qb], head * D, seq_start + q0);
+        }
+        // per-row constants of the outer tile (delta = <dO, O> comes from attn_bwd_delta_kernel)
+        float* vec = smem_vec + qb * 2 * BT;
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int r = q0 + rr * 32 + lane;
+          const int64_t row = static_cast<int64_t>(seq_start) + r;
+          const bool ok = r < len;
+          vec[rr * 32 + lane] = ok ? -p.lse[vec_off + row] : 0.f;
+          vec[BT + rr * 32 + lane] = ok ? -p.delta[vec_off + row] * p.scale : 0.f;  // dZ = P * (dP*scale - delta*scale)
+        }
+        ptx::mbar_arrive(&q_full[qb]);
+        const TileRange tr = tile_range(q0, len, p.window);
+        for (int j = 0; j < tr.n; ++j, ++it) {
+          const int s = it % NS;
+          ptx::mbar_wait(&kv_empty[s], ((it / NS) & 1) ^ 1);
+          if (lane == 0) {
+            ptx::mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+            const int row = seq_start + tr.base + j * BI;
+            ptx::tma_load_2d(smem_k + s * TILE_BYTES, &tma_qkv128, &kv_full[s], col_k, row);
+            ptx::tma_load_2d(smem_v + s * TILE_BYTES, &tma_qkv128, &kv_full[s], col_v, row);
+          }
+        }
       }
     } else if (warp == EW_WARPS + 1) {
+      // ---------------------------------------------------------------- MMA issuer
       // The whole warp runs the issuer loop (warp-uniform control flow keeps the descriptor arithmetic in the
       // uniform datapath); one elected lane issues.  With a single active lane every MMA cost ~100 clk of
       // address moves and the issuer, not the tensor pipe, set the pace (measured).
       const bool leader = ptx::elect_one();
-      // ---------------------------------------------------------------- MMA issuer
       const uint32_t idesc_s = ptx::umma_idesc_bf16(BT, BI, 0, 0);
       const uint32_t idesc_dq = ptx::umma_idesc_bf16(BT, D, 0, 1);  // K as MN-major B operand
       constexpr uint32_t HI = ptx::umma_desc_hi_sw128(1024);
-      const uint32_t q_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_q), 16);
-      const uint32_t do_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_do), 16);
-      auto issue_s_dp = [&](int j) {
-        const int s = j % NS;
-        ptx::mbar_wait(&kv_full[s], (j / NS) & 1);
+      // S / dP of global tile t (stage t % NS) from the Q / dO buffer qb; `last` = last inner tile of its outer tile
+      auto issue_s_dp = [&](int t, int qb, bool last) {
+        const int s = t % NS;
+        ptx::mbar_wait(&kv_full[s], (t / NS) & 1);
         ptx::tc_fence_after();
+        const uint32_t q_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_q + qb * TILE_BYTES), 16);
+        const uint32_t do_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_do + qb * TILE_BYTES), 16);
         const uint32_t k_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_k + s * TILE_BYTES), 16);
         const uint32_t v_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_v + s * TILE_BYTES), 16);
 #pragma unroll
@@ -258,127 +320,181 @@ attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
           if (leader) ptx::umma_bf16_split(tmem_base + TM_DP, do_lo + k * 2, v_lo + k * 2, HI, idesc_s, k != 0 ? 1u : 0u);
-        if (leader) ptx::umma_commit(s_full);
+        if (leader) {
+          ptx::umma_commit(s_full);
+          if (last) ptx::umma_commit(&q_empty[qb]);  // Q / dO of this outer tile are not read again
+        }
       };
-      ptx::mbar_wait(q_full, 0);
-      issue_s_dp(0);
+      int it = 0;
+      ptx::mbar_wait(&q_full[0], 0);
+      issue_s_dp(0, 0, tile_range(o_begin * BT, len, p.window).n == 1);
 #pragma unroll 1
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % NS;
-        if (j + 1 < n_tiles) {
-          ptx::mbar_wait(s_free, j & 1);  // S(j) / dP(j) are in registers: overwrite them with tile j+1
-          issue_s_dp(j + 1);
-        }
-        // K tile as the MN-major B operand of dQ += dZ K (LBO = 8192: distance of 64-element MN chunks, unused)
-        const uint32_t kmn_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_k + s * TILE_BYTES), 8192);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {  // 32-column slices (their warps finish at about the same time)
-          ptx::mbar_wait(&dz_full[c], j & 1);
-          ptx::tc_fence_after();
-#pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            const int k = 2 * c + kk;  // 16-key step: 8 TMEM columns of dZ, 16 rows of K
-            if (leader) ptx::umma_bf16_ts(tmem_base + TM_DQ, tmem_base + TM_DZ + k * 8, kmn_lo + ((k * 2048) >> 4), HI, idesc_dq,
-                              (j | c | kk) != 0 ? 1u : 0u);
+      for (int oi = 0; oi < n_o; ++oi) {
+        const int n = tile_range((o_begin + oi) * BT, len, p.window).n;
+        const int qb = oi & 1;
+        const uint32_t t_acc = tmem_base + TM_DQ + qb * 64;
+#pragma unroll 1
+        for (int j = 0; j < n; ++j, ++it) {
+          const int s = it % NS;
+          // chain the S / dP GEMM of the next tile of the stream (same outer tile, or the next one's first)
+          if (j + 1 < n) {
+            ptx::mbar_wait(s_free, it & 1);  // S / dP of tile `it` are in registers
+            issue_s_dp(it + 1, qb, j + 2 == n);
+          } else if (oi + 1 < n_o) {
+            ptx::mbar_wait(&q_full[qb ^ 1], ((oi + 1) >> 1) & 1);
+            ptx::mbar_wait(s_free, it & 1);
+            issue_s_dp(it + 1, qb ^ 1, tile_range((o_begin + oi + 1) * BT, len, p.window).n == 1);
           }
-          if (leader) ptx::umma_commit(&dz_free[c]);
+          if (j == 0) {  // the accumulator buffer was last used two outer tiles ago: wait until it is copied out
+            ptx::mbar_wait(&acc_free[qb], ((oi >> 1) & 1) ^ 1);
+            ptx::tc_fence_after();
+          }
+          // K tile as the MN-major B operand of dQ += dZ K (LBO = 8192: distance of 64-element MN chunks, unused)
+          const uint32_t kmn_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_k + s * TILE_BYTES), 8192);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {  // 32-column slices (their warps finish at about the same time)
+            ptx::mbar_wait(&dz_full[c], it & 1);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const int k = 2 * c + kk;  // 16-key step: 8 TMEM columns of dZ, 16 rows of K
+              if (leader)
+                ptx::umma_bf16_ts(t_acc, tmem_base + TM_DZ + k * 8, kmn_lo + ((k * 2048) >> 4), HI, idesc_dq,
+                                  (j | c | kk) != 0 ? 1u : 0u);
+            }
+            if (leader) ptx::umma_commit(&dz_free[c]);
+          }
+          if (leader) {
+            ptx::umma_commit(&kv_empty[s]);
+            if (j + 1 == n) ptx::umma_commit(&acc_full[qb]);
+          }
         }
-        if (leader) ptx::umma_commit(&kv_empty[s]);
       }
-      if (leader) ptx::umma_commit(acc_full);
     }
   } else {
     // ------------------------------------------------------------------ element-wise warps
     ptx::setmaxnreg_inc<REG_EW>();
     const int c = warp >> 2;                       // 32-column slice
     const int t = (warp & 3) * 32 + lane;          // query row inside the tile == TMEM lane
-    const int qi = q0 + t;
-    const bool valid = qi < len;
-    const int64_t row = static_cast<int64_t>(seq_start) + qi;
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const int warp_pos = q0 + (warp & 3) * 32;
-    // delta = <dO, O> of the row: each of the row's four threads takes 16 of the 64 columns
-    float delta = 0.f, lse = 0.f;
-    if (valid) {
-      const uint4* po = reinterpret_cast<const uint4*>(p.out + row * p.hidden + head * D + c * 16);
-      const uint4* pd = reinterpret_cast<const uint4*>(p.dout + row * p.hidden + head * D + c * 16);
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        float a[8], b[8];
-        unpack8f(__ldg(po + i), a);
-        unpack8f(__ldg(pd + i), b);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) delta += a[k] * b[k];
-      }
-      lse = p.lse[static_cast<int64_t>(head) * p.total_tokens + row];
-    }
-    delta_part[c * BT + t] = delta;
-    ptx::named_bar_sync(1, EW_WARPS * 32);
-    delta = (delta_part[t] + delta_part[BT + t]) + (delta_part[2 * BT + t] + delta_part[3 * BT + t]);
-    if (valid && c == 0) p.delta[static_cast<int64_t>(head) * p.total_tokens + row] = delta;
     const float2 c2 = make_float2(p.scale_log2, p.scale_log2);
-    const float2 nlse2 = make_float2(-lse, -lse);
     const float2 sc2 = make_float2(p.scale, p.scale);
-    const float2 ndsc2 = make_float2(-delta * p.scale, -delta * p.scale);  // dZ = P * (dP*scale - delta*scale)
     const uint32_t t_dz = tmem_base + TM_DZ + lane_off + c * (HC / 2);
     const uint32_t t_s = tmem_base + TM_S + lane_off + c * HC;
     const uint32_t t_dp = tmem_base + TM_DP + lane_off + c * HC;
-    PF_DECL();
-    for (int j = 0; j < n_tiles; ++j) {
-      const int kv0 = kv_base + j * BI + c * HC;
-      PF_B(pf_st);
-      ptx::mbar_wait(s_full, j & 1);
-      PF_B(pf_s);
+    // dQ of outer tile `po`: slices 0 / 1 each take 16 + 16 columns (a RoPE pair is columns k and k + 32)
+    auto write_out = [&](int po) {
+      if (c >= 2) return;
+      const int ab = po & 1;
+      ptx::mbar_wait(&acc_full[ab], (po >> 1) & 1);
       ptx::tc_fence_after();
-      uint32_t rs[32], rp[32];
-      ptx::tmem_ld_32x32b_x32(t_s, rs);
-      ptx::tmem_ld_32x32b_x32(t_dp, rp);
+      uint32_t r1[16], r2[16];
+      const uint32_t t_acc = tmem_base + TM_DQ + ab * 64 + lane_off + c * 16;
+      ptx::tmem_ld_32x32b_x16(t_acc, r1);
+      ptx::tmem_ld_32x32b_x16(t_acc + 32, r2);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
-      if (lane == 0) ptx::mbar_arrive(s_free);
-      PF_B(pf_ld);
-      const Band bd = band_of(qi, warp_pos, kv0, len, p.window, valid);
-      uint32_t packed[16];
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_free[ab]);
+      const int qi = (o_begin + po) * BT + t;
+      if (qi >= len) return;
+      const int64_t row = static_cast<int64_t>(seq_start) + qi;
+      float o1[16], o2[16];
+      if (p.rope_table && p.positions) {
+        const float4* tab = reinterpret_cast<const float4*>(p.rope_table + static_cast<int64_t>(p.positions[row]) * 32) + c * 8;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) packed[i] = 0u;
-      if (bd.state == 2) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float2 e = ptx::fma2(make_float2(__uint_as_float(rs[i]), __uint_as_float(rs[i + 1])), c2, nlse2);
-          const float2 pr = ptx::ex2_pair(e, i >> 1);
-          const float2 u = ptx::fma2(make_float2(__uint_as_float(rp[i]), __uint_as_float(rp[i + 1])), sc2, ndsc2);
-          const float2 z = ptx::mul2(pr, u);
-          packed[i >> 1] = ptx::pack_bf16x2(z.x, z.y);
+        for (int k = 0; k < 8; ++k) {
+          const float4 f = __ldg(tab + k);
+          const float a0 = __uint_as_float(r1[2 * k]), b0 = __uint_as_float(r2[2 * k]);
+          const float a1 = __uint_as_float(r1[2 * k + 1]), b1 = __uint_as_float(r2[2 * k + 1]);
+          o1[2 * k] = a0 * f.x + b0 * f.y;
+          o2[2 * k] = b0 * f.x - a0 * f.y;
+          o1[2 * k + 1] = a1 * f.z + b1 * f.w;
+          o2[2 * k + 1] = b1 * f.z - a1 * f.w;
         }
-      } else if (bd.state == 1) {
+      } else {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float2 e = ptx::fma2(make_float2(__uint_as_float(rs[i]), __uint_as_float(rs[i + 1])), c2, nlse2);
-          const float p0 = (i >= bd.a && i < bd.b) ? ptx::ex2_approx(e.x) : 0.f;
-          const float p1 = (i + 1 >= bd.a && i + 1 < bd.b) ? ptx::ex2_approx(e.y) : 0.f;
-          const float2 u = ptx::fma2(make_float2(__uint_as_float(rp[i]), __uint_as_float(rp[i + 1])), sc2, ndsc2);
-          packed[i >> 1] = ptx::pack_bf16x2(p0 * u.x, p1 * u.y);
+        for (int k = 0; k < 16; ++k) {
+          o1[k] = __uint_as_float(r1[k]);
+          o2[k] = __uint_as_float(r2[k]);
         }
       }
-      PF_B(pf_cmp);
-      // the slice still feeds the dQ MMAs of the previous tile until dz_free fires (issued a whole tile ago)
-      if (j > 0) ptx::mbar_wait(&dz_free[c], (j - 1) & 1);
-      PF_B(pf_free);
-      ptx::tc_fence_after();
-      ptx::tmem_st_32x32b_x16(t_dz, packed);
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&dz_full[c]);
+      __nv_bfloat16* dst = p.dqkv + row * 3 * p.hidden + head * D + c * 16;
+      *reinterpret_cast<uint4*>(dst) = pack8f(o1);
+      *reinterpret_cast<uint4*>(dst + 8) = pack8f(o1 + 8);
+      *reinterpret_cast<uint4*>(dst + 32) = pack8f(o2);
+      *reinterpret_cast<uint4*>(dst + 40) = pack8f(o2 + 8);
+    };
+    int it = 0;
+#ifdef CM3P_ATTN_PROF
+    const long long pf0 = clock64();
+    __shared__ long long pf_ev[MAX_OUTER_PER_CTA];
+#endif
+    for (int oi = 0; oi < n_o; ++oi) {
+#ifdef CM3P_ATTN_PROF
+      if (threadIdx.x == 0) pf_ev[oi] = clock64();
+#endif
+      const int q0 = (o_begin + oi) * BT;
+      const int qi = q0 + t;
+      const bool valid = qi < len;
+      const int warp_pos = q0 + (warp & 3) * 32;
+      const TileRange tr = tile_range(q0, len, p.window);
+      ptx::mbar_wait(&q_full[oi & 1], (oi >> 1) & 1);
+      const float nlse = smem_vec[(oi & 1) * 2 * BT + t];
+      const float ndsc = smem_vec[(oi & 1) * 2 * BT + BT + t];
+      const float2 nlse2 = make_float2(nlse, nlse), ndsc2 = make_float2(ndsc, ndsc);
+      for (int j = 0; j < tr.n; ++j, ++it) {
+        const int kv0 = tr.base + j * BI + c * HC;
+        ptx::mbar_wait(s_full, it & 1);
+        ptx::tc_fence_after();
+        uint32_t rs[32], rp[32];
+        ptx::tmem_ld_32x32b_x32(t_s, rs);
+        ptx::tmem_ld_32x32b_x32(t_dp, rp);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        if (lane == 0) ptx::mbar_arrive(s_free);
+        const Band bd = band_of(qi, warp_pos, kv0, len, p.window, valid);
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) packed[i] = 0u;
+        if (bd.state == 2) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float2 e = ptx::fma2(make_float2(__uint_as_float(rs[i]), __uint_as_float(rs[i + 1])), c2, nlse2);
+            const float2 pr = ptx::ex2_pair(e, i >> 1);
+            const float2 u = ptx::fma2(make_float2(__uint_as_float(rp[i]), __uint_as_float(rp[i + 1])), sc2, ndsc2);
+            const float2 z = ptx::mul2(pr, u);
+            packed[i >> 1] = ptx::pack_bf16x2(z.x, z.y);
+          }
+        } else if (bd.state == 1) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float2 e = ptx::fma2(make_float2(__uint_as_float(rs[i]), __uint_as_float(rs[i + 1])), c2, nlse2);
+            const float p0 = (i >= bd.a && i < bd.b) ? ptx::ex2_approx(e.x) : 0.f;
+            const float p1 = (i + 1 >= bd.a && i + 1 < bd.b) ? ptx::ex2_approx(e.y) : 0.f;
+            const float2 u = ptx::fma2(make_float2(__uint_as_float(rp[i]), __uint_as_float(rp[i + 1])), sc2, ndsc2);
+            packed[i >> 1] = ptx::pack_bf16x2(p0 * u.x, p1 * u.y);
+          }
+        }
+        // the slice still feeds the dQ MMAs of the previous tile until dz_free fires (issued a whole tile ago)
+        if (it > 0) ptx::mbar_wait(&dz_free[c], (it - 1) & 1);
+        ptx::tc_fence_after();
+        ptx::tmem_st_32x32b_x16(t_dz, packed);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&dz_full[c]);
+        // the previous outer tile's accumulator is written out one tile late: its MMAs have drained by now
+        if (j == 0 && oi > 0) write_out(oi - 1);
+      }
     }
-    PF_B(pf_st);
-    PF_PRINT("dq", n_tiles);
-    if (c == 0) {
-      ptx::mbar_wait(acc_full, 0);
-      ptx::tc_fence_after();
-      const float2* cs = nullptr;
-      if (p.rope_table && p.positions && valid) cs = p.rope_table + static_cast<int64_t>(p.positions[row]) * 32;
-      store_grad_row(tmem_base + TM_DQ + lane_off, p.dqkv + row * 3 * p.hidden + head * D, cs, valid);
+    write_out(n_o - 1);
+#ifdef CM3P_ATTN_PROF
+    if (threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+      const long long pf1 = clock64();
+      for (int oi = 0; oi < n_o; ++oi) printf("dq cta %d outer %d start +%lld\n", blockIdx.x, oi, pf_ev[oi] - pf0);
+      printf("dq cta %d end +%lld tiles=%d\n", blockIdx.x, pf1 - pf0, it);
     }
+#endif
   }
 
   ptx::tc_fence_before();
@@ -390,10 +506,10 @@ attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
 }
 
 // ================================================================================================
-// dKV kernel.  smem: K 16K | V 16K | Q 3x16K | dO 3x16K | -lse / -delta*scale 3x1 KB
+// dKV kernel.  smem: K 2x16K | V 2x16K | Q 3x16K | dO 3x16K | -lse / -delta*scale 3x1 KB
 // TMEM: S^T = [0,128)  dP^T = [128,256)  P^T (bf16 pairs) = [256,320)  dZ^T = [320,384)  dK = [384,448)  dV = [448,512).
-constexpr int DKV_TILES = 2 * TILE_BYTES + NS * 2 * TILE_BYTES;  // 128 KB
-constexpr int DKV_VEC = NS * 2 * BI * 4;                                          // 3 KB
+constexpr int DKV_TILES = 4 * TILE_BYTES + NS * 2 * TILE_BYTES;  // 160 KB
+constexpr int DKV_VEC = NS * 2 * BI * 4;                         // 3 KB
 constexpr int DKV_SMEM = DKV_TILES + DKV_VEC + 256;
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -405,43 +521,35 @@ attn_bwd_dkv_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __g
   const int seq = blockIdx.z, head = blockIdx.y;
   const int seq_start = p.cu_seqlens[seq];
   const int len = p.cu_seqlens[seq + 1] - seq_start;
-  const int k0 = blockIdx.x * BT;
-  if (k0 >= len) return;
+  const int o_begin = blockIdx.x * p.outer_per_cta;
+  const int n_o = min(p.outer_per_cta, (len + BT - 1) / BT - o_begin);
+  if (n_o <= 0) return;
 
-  uint8_t* smem_k = smem;
-  uint8_t* smem_v = smem + TILE_BYTES;
-  uint8_t* smem_q = smem + 2 * TILE_BYTES;
-  uint8_t* smem_do = smem_q + NS * TILE_BYTES;
+  uint8_t* smem_k = smem;                       // [2][16K]
+  uint8_t* smem_v = smem + 2 * TILE_BYTES;      // [2][16K]
+  uint8_t* smem_q = smem + 4 * TILE_BYTES;      // [NS][16K]
+  uint8_t* smem_do = smem_q + NS * TILE_BYTES;  // [NS][16K]
   float* smem_vec = reinterpret_cast<float*>(smem + DKV_TILES);  // [stage][-lse 128 | -delta*scale 128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DKV_TILES + DKV_VEC);
-  uint64_t* kv_full = bars;
-  uint64_t* qdo_full = bars + 1;          // [NS] TMA bytes + 32 staging-lane arrivals
+  uint64_t* kv_full = bars;               // [2]
+  uint64_t* kv_empty = kv_full + 2;       // [2] the S^T / dP^T MMAs of the outer tile have retired
+  uint64_t* qdo_full = kv_empty + 2;      // [NS] TMA bytes + 32 staging-lane arrivals
   uint64_t* qdo_empty = qdo_full + NS;    // [NS]
   uint64_t* s_full = qdo_empty + NS;
   uint64_t* s_free = s_full + 1;          // 16 arrivals
-  uint64_t* pz_full = s_free + 1;         // [slice] 128 arrivals: 32-column pieces of P^T and dZ^T are in smem
+  uint64_t* pz_full = s_free + 1;         // [slice] 128 arrivals: 32-column slices of P^T and dZ^T are in TMEM
   uint64_t* pz_free = pz_full + 4;        // [slice]
   uint64_t* acc_full = pz_free + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* acc_free = acc_full + 1;      // 8 arrivals: dK and dV have been copied out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1);
 
   if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
-#ifdef CM3P_ATTN_PROF
-  __shared__ long long ev[8][20];  // per tile: 0 s_free seen, 1 S issued, 2..5 slice seen, 6 warp0 s_full seen, 7 warp0 arrive
-#define EV(k, i) do { if ((i) < 20) ev[k][i] = clock64(); } while (0)
-#else
-#define EV(k, i)
-#endif
-
-  int q_lo = 0, q_hi = len - 1;
-  if (p.window >= 0) {
-    q_lo = max(0, k0 - p.window);
-    q_hi = min(len - 1, k0 + BT - 1 + p.window);
-  }
-  const int q_base = q_lo;
-  const int n_tiles = (q_hi - q_base) / BI + 1;
 
   if (warp == EW_WARPS + 1 && lane == 0) {
-    ptx::mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&kv_full[i], 1);
+      ptx::mbar_init(&kv_empty[i], 1);
+    }
     for (int s = 0; s < NS; ++s) {
       ptx::mbar_init(&qdo_full[s], 33);
       ptx::mbar_init(&qdo_empty[s], 1);
@@ -453,6 +561,7 @@ attn_bwd_dkv_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __g
       ptx::mbar_init(&pz_free[i], 1);
     }
     ptx::mbar_init(acc_full, 1);
+    ptx::mbar_init(acc_free, 8);
     ptx::fence_barrier_init();
   }
   if (warp == EW_WARPS) {
@@ -474,47 +583,51 @@ attn_bwd_dkv_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __g
     if (warp == EW_WARPS) {
       // ------------------------------------------------------------------ producer (whole warp)
       const int col_q = head * D, col_k = p.hidden + head * D, col_v = 2 * p.hidden + head * D;
-      if (lane == 0) {
-        ptx::mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
-        ptx::tma_load_2d(smem_k, &tma_qkv128, kv_full, col_k, seq_start + k0);
-        ptx::tma_load_2d(smem_v, &tma_qkv128, kv_full, col_v, seq_start + k0);
-      }
       const float* lse_h = p.lse + static_cast<int64_t>(head) * p.total_tokens;
       const float* delta_h = p.delta + static_cast<int64_t>(head) * p.total_tokens;
-      for (int i = 0; i < n_tiles; ++i) {
-        const int s = i % NS;
-        ptx::mbar_wait(&qdo_empty[s], ((i / NS) & 1) ^ 1);
-        const int64_t row = static_cast<int64_t>(seq_start) + q_base + i * BI;
+      int it = 0;
+      for (int oi = 0; oi < n_o; ++oi) {
+        const int k0 = (o_begin + oi) * BT;
+        const int kb = oi & 1;
+        ptx::mbar_wait(&kv_empty[kb], ((oi >> 1) & 1) ^ 1);
         if (lane == 0) {
-          ptx::mbar_arrive_expect_tx(&qdo_full[s], 2 * TILE_BYTES);
-          ptx::tma_load_2d(smem_q + s * TILE_BYTES, &tma_qkv128, &qdo_full[s], col_q, static_cast<int32_t>(row));
-          ptx::tma_load_2d(smem_do + s * TILE_BYTES, &tma_do128, &qdo_full[s], col_q, static_cast<int32_t>(row));
+          ptx::mbar_arrive_expect_tx(&kv_full[kb], 2 * TILE_BYTES);
+          ptx::tma_load_2d(smem_k + kb * TILE_BYTES, &tma_qkv128, &kv_full[kb], col_k, seq_start + k0);
+          ptx::tma_load_2d(smem_v + kb * TILE_BYTES, &tma_qkv128, &kv_full[kb], col_v, seq_start + k0);
         }
-        float* vec = smem_vec + s * 2 * BI;
+        const TileRange tr = tile_range(k0, len, p.window);
+        for (int i = 0; i < tr.n; ++i, ++it) {
+          const int s = it % NS;
+          ptx::mbar_wait(&qdo_empty[s], ((it / NS) & 1) ^ 1);
+          const int64_t row = static_cast<int64_t>(seq_start) + tr.base + i * BI;
+          if (lane == 0) {
+            ptx::mbar_arrive_expect_tx(&qdo_full[s], 2 * TILE_BYTES);
+            ptx::tma_load_2d(smem_q + s * TILE_BYTES, &tma_qkv128, &qdo_full[s], col_q, static_cast<int32_t>(row));
+            ptx::tma_load_2d(smem_do + s * TILE_BYTES, &tma_do128, &qdo_full[s], col_q, static_cast<int32_t>(row));
+          }
+          float* vec = smem_vec + s * 2 * BI;
 #pragma unroll
-        for (int hh = 0; hh < BI; hh += 32) {
-          const int64_t r = row + hh + lane;
-          const bool ok = r < p.total_tokens;
-          vec[hh + lane] = ok ? -lse_h[r] : 0.f;
-          vec[BI + hh + lane] = ok ? -delta_h[r] * p.scale : 0.f;  // dZ = P * (dP*scale - delta*scale)
+          for (int hh = 0; hh < BI; hh += 32) {
+            const int64_t r = row + hh + lane;
+            const bool ok = r < p.total_tokens;
+            vec[hh + lane] = ok ? -lse_h[r] : 0.f;
+            vec[BI + hh + lane] = ok ? -delta_h[r] * p.scale : 0.f;  // dZ = P * (dP*scale - delta*scale)
+          }
+          ptx::mbar_arrive(&qdo_full[s]);
         }
-        ptx::mbar_arrive(&qdo_full[s]);
       }
     } else if (warp == EW_WARPS + 1) {
-      // The whole warp runs the issuer loop (warp-uniform control flow keeps the descriptor arithmetic in the
-      // uniform datapath); one elected lane issues.  With a single active lane every MMA cost ~100 clk of
-      // address moves and the issuer, not the tensor pipe, set the pace (measured).
+      // ------------------------------------------------------------------ MMA issuer (see the dQ kernel)
       const bool leader = ptx::elect_one();
-      // ------------------------------------------------------------------ MMA issuer
       const uint32_t idesc_s = ptx::umma_idesc_bf16(BT, BI, 0, 0);
       const uint32_t idesc_acc = ptx::umma_idesc_bf16(BT, D, 0, 1);
       constexpr uint32_t HI = ptx::umma_desc_hi_sw128(1024);
-      const uint32_t k_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_k), 16);
-      const uint32_t v_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_v), 16);
-      auto issue_s_dp = [&](int i) {
-        const int s = i % NS;
-        ptx::mbar_wait(&qdo_full[s], (i / NS) & 1);
+      auto issue_s_dp = [&](int t, int kb, bool last) {
+        const int s = t % NS;
+        ptx::mbar_wait(&qdo_full[s], (t / NS) & 1);
         ptx::tc_fence_after();
+        const uint32_t k_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_k + kb * TILE_BYTES), 16);
+        const uint32_t v_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_v + kb * TILE_BYTES), 16);
         const uint32_t q_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_q + s * TILE_BYTES), 16);
         const uint32_t do_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_do + s * TILE_BYTES), 16);
 #pragma unroll
@@ -523,149 +636,165 @@ attn_bwd_dkv_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __g
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
           if (leader) ptx::umma_bf16_split(tmem_base + TM_DPT, v_lo + k * 2, do_lo + k * 2, HI, idesc_s, k != 0 ? 1u : 0u);
-        if (leader) ptx::umma_commit(s_full);
+        if (leader) {
+          ptx::umma_commit(s_full);
+          if (last) ptx::umma_commit(&kv_empty[kb]);  // K / V of this outer tile are not read again
+        }
       };
-      ptx::mbar_wait(kv_full, 0);
-      issue_s_dp(0);
+      int it = 0;
+      ptx::mbar_wait(&kv_full[0], 0);
+      issue_s_dp(0, 0, tile_range(o_begin * BT, len, p.window).n == 1);
 #pragma unroll 1
-      for (int i = 0; i < n_tiles; ++i) {
-        const int s = i % NS;
-        if (i + 1 < n_tiles) {
-          ptx::mbar_wait(s_free, i & 1);
-          if (leader) EV(0, i);
-          issue_s_dp(i + 1);
-          if (leader) EV(1, i);
-        }
-        const uint32_t qmn_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_q + s * TILE_BYTES), 8192);
-        const uint32_t domn_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_do + s * TILE_BYTES), 8192);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          ptx::mbar_wait(&pz_full[c], i & 1);
-          if (leader) EV(2 + c, i);
-          ptx::tc_fence_after();
-#pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            const int k = 2 * c + kk;  // 16-query step: 8 TMEM columns of P^T, 16 rows of dO
-            if (leader) ptx::umma_bf16_ts(tmem_base + TM_DV, tmem_base + TM_PT + k * 8, domn_lo + ((k * 2048) >> 4), HI, idesc_acc,
-                              (i | c | kk) != 0 ? 1u : 0u);
+      for (int oi = 0; oi < n_o; ++oi) {
+        const int n = tile_range((o_begin + oi) * BT, len, p.window).n;
+        const int kb = oi & 1;
+#pragma unroll 1
+        for (int i = 0; i < n; ++i, ++it) {
+          const int s = it % NS;
+          if (i + 1 < n) {
+            ptx::mbar_wait(s_free, it & 1);
+            issue_s_dp(it + 1, kb, i + 2 == n);
+          } else if (oi + 1 < n_o) {
+            ptx::mbar_wait(&kv_full[kb ^ 1], ((oi + 1) >> 1) & 1);
+            ptx::mbar_wait(s_free, it & 1);
+            issue_s_dp(it + 1, kb ^ 1, tile_range((o_begin + oi + 1) * BT, len, p.window).n == 1);
           }
-#pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            const int k = 2 * c + kk;
-            if (leader) ptx::umma_bf16_ts(tmem_base + TM_DK, tmem_base + TM_DZT + k * 8, qmn_lo + ((k * 2048) >> 4), HI, idesc_acc,
-                              (i | c | kk) != 0 ? 1u : 0u);
+          if (i == 0 && oi > 0) {  // dK / dV of the previous outer tile must have been copied out
+            ptx::mbar_wait(acc_free, (oi - 1) & 1);
+            ptx::tc_fence_after();
           }
-          if (leader) ptx::umma_commit(&pz_free[c]);
+          const uint32_t qmn_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_q + s * TILE_BYTES), 8192);
+          const uint32_t domn_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_do + s * TILE_BYTES), 8192);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            ptx::mbar_wait(&pz_full[c], it & 1);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const int k = 2 * c + kk;  // 16-query step: 8 TMEM columns of P^T, 16 rows of dO
+              if (leader)
+                ptx::umma_bf16_ts(tmem_base + TM_DV, tmem_base + TM_PT + k * 8, domn_lo + ((k * 2048) >> 4), HI,
+                                  idesc_acc, (i | c | kk) != 0 ? 1u : 0u);
+            }
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const int k = 2 * c + kk;
+              if (leader)
+                ptx::umma_bf16_ts(tmem_base + TM_DK, tmem_base + TM_DZT + k * 8, qmn_lo + ((k * 2048) >> 4), HI,
+                                  idesc_acc, (i | c | kk) != 0 ? 1u : 0u);
+            }
+            if (leader) ptx::umma_commit(&pz_free[c]);
+          }
+          if (leader) {
+            ptx::umma_commit(&qdo_empty[s]);
+            if (i + 1 == n) ptx::umma_commit(acc_full);
+          }
         }
-        if (leader) ptx::umma_commit(&qdo_empty[s]);
       }
-      if (leader) ptx::umma_commit(acc_full);
     }
   } else {
     // ------------------------------------------------------------------ element-wise warps
     ptx::setmaxnreg_inc<REG_EW>();
     const int c = warp >> 2;                 // 32-column (query) slice
     const int t = (warp & 3) * 32 + lane;    // key row inside the tile == TMEM lane
-    const int kj = k0 + t;
-    const bool valid = kj < len;
-    const int64_t row = static_cast<int64_t>(seq_start) + kj;
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const int warp_pos = k0 + (warp & 3) * 32;
     const float2 c2 = make_float2(p.scale_log2, p.scale_log2);
     const float2 sc2 = make_float2(p.scale, p.scale);
     const uint32_t t_pt = tmem_base + TM_PT + lane_off + c * (HC / 2);
     const uint32_t t_dzt = tmem_base + TM_DZT + lane_off + c * (HC / 2);
     const uint32_t t_s = tmem_base + TM_ST + lane_off + c * HC;
     const uint32_t t_dp = tmem_base + TM_DPT + lane_off + c * HC;
-    PF_DECL();
-    for (int i = 0; i < n_tiles; ++i) {
-      const int s = i % NS;
-      const int q0i = q_base + i * BI + c * HC;
-      PF_B(pf_st);
-      ptx::mbar_wait(s_full, i & 1);
-      ptx::mbar_wait(&qdo_full[s], (i / NS) & 1);  // already complete: orders the lse / delta staging writes
-      PF_B(pf_s);
-      if (threadIdx.x == 0) EV(6, i);
-      ptx::tc_fence_after();
-      uint32_t rs[32], rp[32];
-      ptx::tmem_ld_32x32b_x32(t_s, rs);
-      ptx::tmem_ld_32x32b_x32(t_dp, rp);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      if (lane == 0) ptx::mbar_arrive(s_free);
-      PF_B(pf_ld);
-      const Band bd = band_of(kj, warp_pos, q0i, len, p.window, valid);
-      const float4* nlse4 = reinterpret_cast<const float4*>(smem_vec + s * 2 * BI + c * HC);
-      const float4* ndel4 = reinterpret_cast<const float4*>(smem_vec + s * 2 * BI + BI + c * HC);
-      uint32_t pp[16], pz[16];
+    int it = 0;
+    for (int oi = 0; oi < n_o; ++oi) {
+      const int k0 = (o_begin + oi) * BT;
+      const int kj = k0 + t;
+      const bool valid = kj < len;
+      const int warp_pos = k0 + (warp & 3) * 32;
+      const TileRange tr = tile_range(k0, len, p.window);
+      for (int i = 0; i < tr.n; ++i, ++it) {
+        const int s = it % NS;
+        const int q0i = tr.base + i * BI + c * HC;
+        ptx::mbar_wait(s_full, it & 1);
+        ptx::mbar_wait(&qdo_full[s], (it / NS) & 1);  // already complete: orders the lse / delta staging writes
+        ptx::tc_fence_after();
+        uint32_t rs[32], rp[32];
+        ptx::tmem_ld_32x32b_x32(t_s, rs);
+        ptx::tmem_ld_32x32b_x32(t_dp, rp);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        if (lane == 0) ptx::mbar_arrive(s_free);
+        const Band bd = band_of(kj, warp_pos, q0i, len, p.window, valid);
+        const float4* nlse4 = reinterpret_cast<const float4*>(smem_vec + s * 2 * BI + c * HC);
+        const float4* ndel4 = reinterpret_cast<const float4*>(smem_vec + s * 2 * BI + BI + c * HC);
+        uint32_t pp[16], pz[16];
 #pragma unroll
-      for (int i2 = 0; i2 < 16; ++i2) pp[i2] = pz[i2] = 0u;
-      if (bd.state == 2) {
-        // every column allowed for every row of this warp: no predicates
+        for (int i2 = 0; i2 < 16; ++i2) pp[i2] = pz[i2] = 0u;
+        if (bd.state == 2) {
+          // every column allowed for every row of this warp: no predicates
 #pragma unroll
-        for (int i2 = 0; i2 < 32; i2 += 4) {
-          const float4 l4 = nlse4[i2 >> 2];
-          const float4 d4 = ndel4[i2 >> 2];
-          const float2 e0 = ptx::fma2(make_float2(__uint_as_float(rs[i2]), __uint_as_float(rs[i2 + 1])), c2,
-                                      make_float2(l4.x, l4.y));
-          const float2 e1 = ptx::fma2(make_float2(__uint_as_float(rs[i2 + 2]), __uint_as_float(rs[i2 + 3])), c2,
-                                      make_float2(l4.z, l4.w));
-          const float2 p0 = ptx::ex2_pair(e0, i2 >> 1);
-          const float2 p1 = ptx::ex2_pair(e1, (i2 >> 1) + 1);
-          const float2 u0 = ptx::fma2(make_float2(__uint_as_float(rp[i2]), __uint_as_float(rp[i2 + 1])), sc2,
-                                      make_float2(d4.x, d4.y));
-          const float2 u1 = ptx::fma2(make_float2(__uint_as_float(rp[i2 + 2]), __uint_as_float(rp[i2 + 3])), sc2,
-                                      make_float2(d4.z, d4.w));
-          const float2 z0 = ptx::mul2(p0, u0), z1 = ptx::mul2(p1, u1);
-          pp[i2 >> 1] = ptx::pack_bf16x2(p0.x, p0.y);
-          pp[(i2 >> 1) + 1] = ptx::pack_bf16x2(p1.x, p1.y);
-          pz[i2 >> 1] = ptx::pack_bf16x2(z0.x, z0.y);
-          pz[(i2 >> 1) + 1] = ptx::pack_bf16x2(z1.x, z1.y);
+          for (int i2 = 0; i2 < 32; i2 += 4) {
+            const float4 l4 = nlse4[i2 >> 2];
+            const float4 d4 = ndel4[i2 >> 2];
+            const float2 e0 = ptx::fma2(make_float2(__uint_as_float(rs[i2]), __uint_as_float(rs[i2 + 1])), c2,
+                                        make_float2(l4.x, l4.y));
+            const float2 e1 = ptx::fma2(make_float2(__uint_as_float(rs[i2 + 2]), __uint_as_float(rs[i2 + 3])), c2,
+                                        make_float2(l4.z, l4.w));
+            const float2 p0 = ptx::ex2_pair(e0, i2 >> 1);
+            const float2 p1 = ptx::ex2_pair(e1, (i2 >> 1) + 1);
+            const float2 u0 = ptx::fma2(make_float2(__uint_as_float(rp[i2]), __uint_as_float(rp[i2 + 1])), sc2,
+                                        make_float2(d4.x, d4.y));
+            const float2 u1 = ptx::fma2(make_float2(__uint_as_float(rp[i2 + 2]), __uint_as_float(rp[i2 + 3])), sc2,
+                                        make_float2(d4.z, d4.w));
+            const float2 z0 = ptx::mul2(p0, u0), z1 = ptx::mul2(p1, u1);
+            pp[i2 >> 1] = ptx::pack_bf16x2(p0.x, p0.y);
+            pp[(i2 >> 1) + 1] = ptx::pack_bf16x2(p1.x, p1.y);
+            pz[i2 >> 1] = ptx::pack_bf16x2(z0.x, z0.y);
+            pz[(i2 >> 1) + 1] = ptx::pack_bf16x2(z1.x, z1.y);
+          }
+        } else if (bd.state == 1) {
+          const float2* nlse2 = reinterpret_cast<const float2*>(nlse4);
+          const float2* ndel2 = reinterpret_cast<const float2*>(ndel4);
+#pragma unroll
+          for (int i2 = 0; i2 < 32; i2 += 2) {
+            const float2 l2 = nlse2[i2 >> 1];
+            const float2 d2 = ndel2[i2 >> 1];
+            const float2 e = ptx::fma2(make_float2(__uint_as_float(rs[i2]), __uint_as_float(rs[i2 + 1])), c2, l2);
+            const float p0 = (i2 >= bd.a && i2 < bd.b) ? ptx::ex2_approx(e.x) : 0.f;
+            const float p1 = (i2 + 1 >= bd.a && i2 + 1 < bd.b) ? ptx::ex2_approx(e.y) : 0.f;
+            const float2 u = ptx::fma2(make_float2(__uint_as_float(rp[i2]), __uint_as_float(rp[i2 + 1])), sc2, d2);
+            pp[i2 >> 1] = ptx::pack_bf16x2(p0, p1);
+            pz[i2 >> 1] = ptx::pack_bf16x2(p0 * u.x, p1 * u.y);
+          }
         }
-      } else if (bd.state == 1) {
-        const float2* nlse2 = reinterpret_cast<const float2*>(nlse4);
-        const float2* ndel2 = reinterpret_cast<const float2*>(ndel4);
-#pragma unroll
-        for (int i2 = 0; i2 < 32; i2 += 2) {
-          const float2 l2 = nlse2[i2 >> 1];
-          const float2 d2 = ndel2[i2 >> 1];
-          const float2 e = ptx::fma2(make_float2(__uint_as_float(rs[i2]), __uint_as_float(rs[i2 + 1])), c2, l2);
-          const float p0 = (i2 >= bd.a && i2 < bd.b) ? ptx::ex2_approx(e.x) : 0.f;
-          const float p1 = (i2 + 1 >= bd.a && i2 + 1 < bd.b) ? ptx::ex2_approx(e.y) : 0.f;
-          const float2 u = ptx::fma2(make_float2(__uint_as_float(rp[i2]), __uint_as_float(rp[i2 + 1])), sc2, d2);
-          pp[i2 >> 1] = ptx::pack_bf16x2(p0, p1);
-          pz[i2 >> 1] = ptx::pack_bf16x2(p0 * u.x, p1 * u.y);
+        if (it > 0) ptx::mbar_wait(&pz_free[c], (it - 1) & 1);
+        ptx::tc_fence_after();
+        ptx::tmem_st_32x32b_x16(t_pt, pp);
+        ptx::tmem_st_32x32b_x16(t_dzt, pz);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&pz_full[c]);
+      }
+      // dK (slice-0 warps, inverse RoPE) and dV (slice-1 warps) of this outer tile; the accumulators are
+      // released as soon as they are in registers
+      if (c < 2) {
+        ptx::mbar_wait(acc_full, oi & 1);
+        ptx::tc_fence_after();
+        uint32_t r1[32], r2[32];
+        const uint32_t t_acc = tmem_base + (c == 0 ? TM_DK : TM_DV) + lane_off;
+        ptx::tmem_ld_32x32b_x32(t_acc, r1);
+        ptx::tmem_ld_32x32b_x32(t_acc + 32, r2);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(acc_free);
+        if (valid) {
+          const int64_t row = static_cast<int64_t>(seq_start) + kj;
+          __nv_bfloat16* base = p.dqkv + row * 3 * p.hidden + head * D;
+          const float2* cs = nullptr;
+          if (c == 0 && p.rope_table && p.positions) cs = p.rope_table + static_cast<int64_t>(p.positions[row]) * 32;
+          store_grad_regs(r1, r2, base + (c == 0 ? p.hidden : 2 * p.hidden), cs);
         }
       }
-      PF_B(pf_cmp);
-      if (i > 0) ptx::mbar_wait(&pz_free[c], (i - 1) & 1);
-      PF_B(pf_free);
-      ptx::tc_fence_after();
-      ptx::tmem_st_32x32b_x16(t_pt, pp);
-      ptx::tmem_st_32x32b_x16(t_dzt, pz);
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&pz_full[c]);
-      if (threadIdx.x == 0) EV(7, i);
-    }
-    PF_B(pf_st);
-    PF_PRINT("dkv", n_tiles);
-#ifdef CM3P_ATTN_PROF
-    if (threadIdx.x == 0 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0)
-      for (int i = 1; i < n_tiles - 1 && i < 20; ++i)
-        printf("tile %2d: w0 s_full %6lld arrive +%5lld | issuer s_free +%5lld S issued +%5lld slices +%5lld +%5lld +%5lld +%5lld\n",
-               i, ev[6][i] - pf_t0, ev[7][i] - ev[6][i], ev[0][i] - ev[6][i], ev[1][i] - ev[6][i], ev[2][i] - ev[6][i],
-               ev[3][i] - ev[6][i], ev[4][i] - ev[6][i], ev[5][i] - ev[6][i]);
-#endif
-    ptx::mbar_wait(acc_full, 0);
-    ptx::tc_fence_after();
-    __nv_bfloat16* base = p.dqkv + row * 3 * p.hidden + head * D;
-    if (c == 0) {
-      const float2* cs = nullptr;
-      if (p.rope_table && p.positions && valid) cs = p.rope_table + static_cast<int64_t>(p.positions[row]) * 32;
-      store_grad_row(tmem_base + TM_DK + lane_off, base + p.hidden, cs, valid);
-    } else if (c == 1) {
-      store_grad_row(tmem_base + TM_DV + lane_off, base + 2 * p.hidden, nullptr, valid);
     }
   }
 
@@ -709,7 +838,22 @@ int attn_varlen_bwd_v3(const AttnBwdArgs& a, cudaStream_t stream) {
   p.window = a.window;
   p.scale = 0.125f;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
-  dim3 grid((a.max_seqlen + BT - 1) / BT, a.heads, a.batch);
+  const int64_t vec_units = a.total_tokens * a.heads * 8;
+  attn_bwd_delta_kernel<<<static_cast<unsigned>((vec_units + 255) / 256), 256, 0, stream>>>(p.out, p.dout, p.delta,
+                                                                                       a.total_tokens, a.heads);
+  CM3P_CUDA_TRY(cudaGetLastError());
+  static int forced_opc = -1;
+  if (forced_opc < 0) {
+    const char* e = getenv("CM3P_BWD_OUTER_PER_CTA");
+    forced_opc = e ? atoi(e) : 0;
+  }
+  const int64_t units = (a.total_tokens / BT + a.batch / 2 + 1) * a.heads;  // ~ (sequence, head, outer tile) triples
+  const int64_t target_ctas = static_cast<int64_t>(num_sms()) * (a.window >= 0 ? 4 : 8);
+  int opc = static_cast<int>((units + target_ctas - 1) / target_ctas);
+  opc = opc < 2 ? 2 : (opc > MAX_OUTER_PER_CTA ? MAX_OUTER_PER_CTA : opc);
+  if (forced_opc > 0) opc = forced_opc > MAX_OUTER_PER_CTA ? MAX_OUTER_PER_CTA : forced_opc;
+  p.outer_per_cta = opc;
+  dim3 grid((a.max_seqlen + BT * opc - 1) / (BT * opc), a.heads, a.batch);
   attn_bwd_dq_v3_kernel<<<grid, THREADS, DQ_SMEM, stream>>>(qkv128, do128, p);
   CM3P_CUDA_TRY(cudaGetLastError());
   attn_bwd_dkv_v3_kernel<<<grid, THREADS, DKV_SMEM, stream>>>(qkv128, do128, p);
