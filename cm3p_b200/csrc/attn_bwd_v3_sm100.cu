@@ -136,7 +136,7 @@ __device__ __forceinline__ Band band_of(int row_pos, int warp_pos, int t0, int l
 // behind the current one, and the element-wise warps only swap their per-row constants.  A CTA per outer
 // tile paid ~9000 clk of launch / TMEM allocation / first-load / drain latency with nothing to overlap it
 // (1 CTA per SM): 35 % of a global-layer CTA and 70 % of a window-layer one (measured).
-// The count per CTA is chosen by the launcher (BwdParams::outer_per_cta): enough CTAs for ~8 (global) / ~4
+// The count per CTA is chosen by the launcher (BwdParams::outer_per_cta): enough CTAs for ~16 (global) / ~4
 // (window) waves of uneven work, at most MAX_OUTER_PER_CTA tiles each.
 constexpr int MAX_OUTER_PER_CTA = 16;
 
@@ -848,7 +848,7 @@ int attn_varlen_bwd_v3(const AttnBwdArgs& a, cudaStream_t stream) {
     forced_opc = e ? atoi(e) : 0;
   }
   const int64_t units = (a.total_tokens / BT + a.batch / 2 + 1) * a.heads;  // ~ (sequence, head, outer tile) triples
-  const int64_t target_ctas = static_cast<int64_t>(num_sms()) * (a.window >= 0 ? 4 : 8);
+  const int64_t target_ctas = static_cast<int64_t>(num_sms()) * (a.window >= 0 ? 4 : 16);
   int opc = static_cast<int>((units + target_ctas - 1) / target_ctas);
   opc = opc < 2 ? 2 : (opc > MAX_OUTER_PER_CTA ? MAX_OUTER_PER_CTA : opc);
   if (forced_opc > 0) opc = forced_opc > MAX_OUTER_PER_CTA ? MAX_OUTER_PER_CTA : forced_opc;

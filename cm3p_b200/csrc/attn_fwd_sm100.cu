@@ -50,6 +50,7 @@ struct Params {
   int hidden;  // H = heads * 64
   int window;  // < 0: global
   float scale_log2;  // (1/sqrt(64)) * log2(e)
+  int blocks_per_cta;  // v2: consecutive 256-query blocks streamed by one CTA
 };
 
 __global__ void __launch_bounds__(THREADS, 2)
@@ -297,12 +298,37 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params 
 // TMEM columns: S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384).
 namespace v2 {
 
-constexpr int KV_STAGES2 = 4;
-constexpr int THREADS2 = 384;  // 3 warpgroups: softmax A, softmax B, {TMA, MMA, 2 idle warps}
-constexpr int SMEM_TILES2 = 2 * Q_BYTES + KV_STAGES2 * 2 * KV_TILE_BYTES + 2 * P_BYTES;  // 32 + 128 + 64 = 224 KB
-constexpr int SMEM_BYTES2 = SMEM_TILES2 + 256;
-constexpr uint32_t TM_S = 0, TM_O = 256;  // + 128 * x for S, + 64 * x for O
+constexpr int KV_STAGES2 = 3;
+constexpr int THREADS2 = 384;  // 3 warpgroups: softmax A, softmax B, {TMA, MMA issuer A, MMA issuer B, idle}
+constexpr int SMEM_TILES2 = 2 * 2 * Q_BYTES + KV_STAGES2 * 2 * KV_TILE_BYTES + 2 * P_BYTES;  // 64 + 96 + 64 = 224 KB
+constexpr int SMEM_BYTES2 = SMEM_TILES2 + 512;
+constexpr uint32_t TM_S = 0, TM_O = 256;  // S: + 128 x;  O: + 128 (block parity) + 64 x
 constexpr float RESCALE_LOG2 = 8.0f;
+constexpr int MAX_BLOCKS_PER_CTA = 16;
+
+// KV stream of one 256-query block: tiles u = 0..U-1 at sequence rows kv_base + 128 u; Q tile x consumes
+// u in [lo[x], hi[x])
+struct BlockRange {
+  int kv_base, U;
+  int lo[2], hi[2];
+};
+__device__ __forceinline__ BlockRange block_range(int q0, int len, int window) {
+  BlockRange r;
+  r.kv_base = window >= 0 ? max(0, q0 - window) : 0;
+#pragma unroll
+  for (int x = 0; x < 2; ++x) {
+    const int qx = q0 + x * BQ;
+    int first = 0, last = len - 1;
+    if (window >= 0) {
+      first = max(0, qx - window);
+      last = min(len - 1, qx + BQ - 1 + window);
+    }
+    r.lo[x] = (first - r.kv_base) / BKV;
+    r.hi[x] = qx < len ? (last - r.kv_base) / BKV + 1 : r.lo[x];
+  }
+  r.U = max(r.hi[0], r.hi[1]);
+  return r;
+}
 
 __global__ void __launch_bounds__(THREADS2, 1)
 attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) {
@@ -312,61 +338,45 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
   const int seq = blockIdx.z, head = blockIdx.y;
   const int seq_start = p.cu_seqlens[seq];
   const int len = p.cu_seqlens[seq + 1] - seq_start;
-  const int q0 = blockIdx.x * 2 * BQ;
-  if (q0 >= len) return;
-  const bool act_b = q0 + BQ < len;
+  const int b_begin = blockIdx.x * p.blocks_per_cta;
+  const int n_b = min(p.blocks_per_cta, (len + 2 * BQ - 1) / (2 * BQ) - b_begin);  // 256-query blocks of this CTA
+  if (n_b <= 0) return;
 
-  uint8_t* smem_q = smem;                                   // [2][16 KB]
-  uint8_t* smem_k = smem + 2 * Q_BYTES;                     // [4][16 KB]
-  uint8_t* smem_v = smem_k + KV_STAGES2 * KV_TILE_BYTES;    // [4][16 KB]
+  uint8_t* smem_q = smem;                                   // [2 blocks][2 tiles][16 KB]
+  uint8_t* smem_k = smem + 4 * Q_BYTES;                     // [3][16 KB]
+  uint8_t* smem_v = smem_k + KV_STAGES2 * KV_TILE_BYTES;    // [3][16 KB]
   uint8_t* smem_p = smem_v + KV_STAGES2 * KV_TILE_BYTES;    // [2][32 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_TILES2);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;   // [4]
-  uint64_t* kv_empty = bars + 5;  // [4]
-  uint64_t* s_full = bars + 9;    // [2]
-  uint64_t* s_free = bars + 11;   // [2] 4 arrivals (one per warp): S_x is in registers, the buffer may be overwritten
-  uint64_t* p_full = bars + 13;   // [2][2] per 64-key half of P_x, 128 arrivals each
-  uint64_t* pv_done = bars + 17;  // [2][2] PV_x(u, half) retired: that half of the P_x buffer is reusable
-  uint64_t* o_full = bars + 21;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
+  uint64_t* q_full = bars;                 // [2]
+  uint64_t* q_empty = q_full + 2;          // [2] 2 arrivals: both issuers have retired their S MMAs of the block
+  uint64_t* kv_full = q_empty + 2;         // [3]
+  uint64_t* kv_empty = kv_full + KV_STAGES2;  // [3] 2 arrivals (both issuers)
+  uint64_t* s_full = kv_empty + KV_STAGES2;   // [2]
+  uint64_t* s_free = s_full + 2;           // [2] 4 arrivals (one per warp): S_x is in registers
+  uint64_t* p_full = s_free + 2;           // [2][2] per 64-key half of P_x, 128 arrivals each
+  uint64_t* pv_done = p_full + 4;          // [2][2] PV_x(u, half) retired: that half of the P_x buffer is reusable
+  uint64_t* o_full = pv_done + 4;          // [2][2] (x, block parity)
+  uint64_t* o_free = o_full + 4;           // [2][2] 4 arrivals: O_x of the block is in registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 4);
 
   if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
-#ifdef CM3P_ATTN_PROF
-  __shared__ long long ev[4][40];  // x = 0 only: [0] p_full arrive (row 0), [1] issuer saw p_full, [2] pv_done seen, [3] S issue
-#endif
-
-  // KV stream: tiles u = 0..U-1 at sequence rows kv_base + 128 u; Q tile x consumes u in [lo[x], hi[x])
-  int kv_base = 0;
-  if (p.window >= 0) kv_base = max(0, q0 - p.window);
-  auto tile_range = [&](int qx, bool active, int& lo_out, int& hi_out) {
-    int first = 0, last = len - 1;
-    if (p.window >= 0) {
-      first = max(0, qx - p.window);
-      last = min(len - 1, qx + BQ - 1 + p.window);
-    }
-    lo_out = (first - kv_base) / BKV;
-    hi_out = active ? (last - kv_base) / BKV + 1 : lo_out;
-  };
-  int lo0, hi0, lo1, hi1;
-  tile_range(q0, true, lo0, hi0);
-  tile_range(q0 + BQ, act_b, lo1, hi1);
-  const int U = max(hi0, hi1);
 
   if (warp == 9 && lane == 0) {
-    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&q_full[i], 1);
+      ptx::mbar_init(&q_empty[i], 2);
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&s_free[i], 4);
+    }
     for (int s = 0; s < KV_STAGES2; ++s) {
       ptx::mbar_init(&kv_full[s], 1);
       ptx::mbar_init(&kv_empty[s], 2);
     }
-    for (int x = 0; x < 2; ++x) {
-      ptx::mbar_init(&s_full[x], 1);
-      ptx::mbar_init(&s_free[x], 4);
-      for (int h = 0; h < 2; ++h) {
-        ptx::mbar_init(&p_full[2 * x + h], 128);
-        ptx::mbar_init(&pv_done[2 * x + h], 1);
-      }
-      ptx::mbar_init(&o_full[x], 1);
+    for (int i = 0; i < 4; ++i) {
+      ptx::mbar_init(&p_full[i], 128);
+      ptx::mbar_init(&pv_done[i], 1);
+      ptx::mbar_init(&o_full[i], 1);
+      ptx::mbar_init(&o_free[i], 4);
     }
     ptx::fence_barrier_init();
   }
@@ -386,87 +396,109 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
     if (warp == 8 && lane == 0) {
       // ---------------------------------------------------------------- TMA producer
       const int col_q = head * D, col_k = p.hidden + head * D, col_v = 2 * p.hidden + head * D;
-      ptx::mbar_arrive_expect_tx(q_full, 2 * Q_BYTES);
-      ptx::tma_load_2d(smem_q, &tma_qkv, q_full, col_q, seq_start + q0);
-      ptx::tma_load_2d(smem_q + Q_BYTES, &tma_qkv, q_full, col_q, seq_start + q0 + BQ);
-      for (int u = 0; u < U; ++u) {
-        const int s = u % KV_STAGES2;
-        ptx::mbar_wait(&kv_empty[s], ((u / KV_STAGES2) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(&kv_full[s], 2 * KV_TILE_BYTES);
-        const int row = seq_start + kv_base + u * BKV;
-        ptx::tma_load_2d(smem_k + s * KV_TILE_BYTES, &tma_qkv, &kv_full[s], col_k, row);
-        ptx::tma_load_2d(smem_v + s * KV_TILE_BYTES, &tma_qkv, &kv_full[s], col_v, row);
+      int ring = 0;
+      for (int bi = 0; bi < n_b; ++bi) {
+        const int q0 = (b_begin + bi) * 2 * BQ;
+        const int qb = bi & 1;
+        ptx::mbar_wait(&q_empty[qb], ((bi >> 1) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&q_full[qb], 2 * Q_BYTES);
+        ptx::tma_load_2d(smem_q + qb * 2 * Q_BYTES, &tma_qkv, &q_full[qb], col_q, seq_start + q0);
+        ptx::tma_load_2d(smem_q + qb * 2 * Q_BYTES + Q_BYTES, &tma_qkv, &q_full[qb], col_q, seq_start + q0 + BQ);
+        const BlockRange br = block_range(q0, len, p.window);
+        for (int u = 0; u < br.U; ++u, ++ring) {
+          const int s = ring % KV_STAGES2;
+          ptx::mbar_wait(&kv_empty[s], ((ring / KV_STAGES2) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&kv_full[s], 2 * KV_TILE_BYTES);
+          const int row = seq_start + br.kv_base + u * BKV;
+          ptx::tma_load_2d(smem_k + s * KV_TILE_BYTES, &tma_qkv, &kv_full[s], col_k, row);
+          ptx::tma_load_2d(smem_v + s * KV_TILE_BYTES, &tma_qkv, &kv_full[s], col_v, row);
+        }
       }
     } else if (warp == 9 || warp == 10) {
       // ---------------------------------------------------------------- MMA issuers (one per Q tile)
-      // Each Q tile has its own issuing thread, so its MMAs follow the order in which its softmax group
+      // Each Q tile has its own issuing warp, so its MMAs follow the order in which its softmax group
       // produces the events: "S_x buffer drained into registers" -> S_x(t+1) (runs on the tensor pipe WHILE
       // the group is still exponentiating S_x(t)), "first / second 64-key half of P_x(t) written" -> PV on
       // that half.  All waits are blocking mbarrier waits: a polling issuer steals issue slots from the
-      // softmax warps that share its scheduler (measured: -20 %).
-      // The whole warp runs the loop (warp-uniform control flow keeps the descriptor arithmetic in the uniform
-      // datapath: back-to-back UTCHMMA instead of ~10 address-move instructions per MMA); one elected lane issues.
+      // softmax warps that share its scheduler (measured: -20 %).  The whole warp runs the loop (warp-uniform
+      // control flow keeps the descriptor arithmetic in the uniform datapath: back-to-back UTCHMMA instead
+      // of ~10 address-move instructions per MMA); one elected lane issues.
       const bool leader = ptx::elect_one();
       const int x = warp - 9;
       const uint32_t idesc_s = ptx::umma_idesc_bf16(BQ, BKV, 0, 0);
       const uint32_t idesc_o = ptx::umma_idesc_bf16(BQ, D, 0, 1);  // V is MN-major
-      const int lo_x = x ? lo1 : lo0, hi_x = x ? hi1 : hi0;
-      const uint32_t q_addr = ptx::smem_u32(smem_q + x * Q_BYTES);
       const uint32_t p_base = ptx::smem_u32(smem_p + x * P_BYTES);
-      const uint32_t t_s = tmem_base + TM_S + x * 128, t_o = tmem_base + TM_O + x * 64;
-      auto issue_s = [&](int t) {
-        const int s = t % KV_STAGES2;
-        ptx::mbar_wait(&kv_full[s], (t / KV_STAGES2) & 1);
-        ptx::tc_fence_after();
-        const uint32_t k_addr = ptx::smem_u32(smem_k + s * KV_TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k)
-          if (leader) ptx::umma_bf16(t_s, ptx::umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                         ptx::umma_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
-        if (leader) ptx::umma_commit(&s_full[x]);
-      };
-      ptx::mbar_wait(q_full, 0);
-      // the ring is released by BOTH issuers (kv_empty counts 2): tiles outside this Q tile's range are
-      // acknowledged as soon as they have landed
-      for (int u = 0; u < lo_x; ++u) {
-        ptx::mbar_wait(&kv_full[u % KV_STAGES2], (u / KV_STAGES2) & 1);
-        if (leader) ptx::umma_commit(&kv_empty[u % KV_STAGES2]);
-      }
-      if (hi_x > lo_x) issue_s(lo_x);
-      for (int t = lo_x; t < hi_x; ++t) {
-        const int j = t - lo_x;
-        if (t + 1 < hi_x) {
-          ptx::mbar_wait(&s_free[x], j & 1);
-          issue_s(t + 1);
-#ifdef CM3P_ATTN_PROF
-          if (leader && x == 0 && j < 19) ev[3][j + 1] = clock64();
-#endif
-        }
-        const uint32_t v_base = ptx::smem_u32(smem_v + (t % KV_STAGES2) * KV_TILE_BYTES);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          ptx::mbar_wait(&p_full[2 * x + h], j & 1);  // this half of P_x(t) is in smem (O_x rescaled if needed)
-#ifdef CM3P_ATTN_PROF
-          if (leader && x == 0 && j < 20) ev[1][2 * j + h] = clock64();
-#endif
+      const uint32_t t_s = tmem_base + TM_S + x * 128;
+      int ring_base = 0;  // ring position of tile 0 of the current block
+      int it = 0;         // tiles this Q-tile stream has consumed so far (phase of its s / p barriers)
+#pragma unroll 1
+      for (int bi = 0; bi < n_b; ++bi) {
+        const BlockRange br = block_range((b_begin + bi) * 2 * BQ, len, p.window);
+        const int lo_x = br.lo[x], hi_x = br.hi[x];
+        const int qb = bi & 1;
+        const uint32_t q_addr = ptx::smem_u32(smem_q + qb * 2 * Q_BYTES + x * Q_BYTES);
+        const uint32_t t_o = tmem_base + TM_O + qb * 128 + x * 64;
+        auto issue_s = [&](int t) {
+          const int r = ring_base + t;
+          const int s = r % KV_STAGES2;
+          ptx::mbar_wait(&kv_full[s], (r / KV_STAGES2) & 1);
           ptx::tc_fence_after();
-          const uint32_t p_addr = p_base + h * (BQ * 128);
-          const uint32_t v_addr = v_base + h * (64 * 128);
+          const uint32_t k_addr = ptx::smem_u32(smem_k + s * KV_TILE_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (leader) ptx::umma_bf16(t_o, ptx::umma_smem_desc_sw128(p_addr + k * 32, 16, 1024),
-                           ptx::umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_o,
-                           (j | h | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < D / 16; ++k)
+            if (leader)
+              ptx::umma_bf16(t_s, ptx::umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                             ptx::umma_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
           if (leader) {
-            if (h == 1 && t + 1 == hi_x) ptx::umma_commit(&o_full[x]);
-            else ptx::umma_commit(&pv_done[2 * x + h]);
+            ptx::umma_commit(&s_full[x]);
+            if (t + 1 == hi_x) ptx::umma_commit(&q_empty[qb]);  // last S of the block: Q is not read again
           }
+        };
+        auto ack = [&](int u) {  // tile outside this Q tile's range: hand the stage back once it has landed
+          const int r = ring_base + u;
+          ptx::mbar_wait(&kv_full[r % KV_STAGES2], (r / KV_STAGES2) & 1);
+          if (leader) ptx::umma_commit(&kv_empty[r % KV_STAGES2]);
+        };
+        ptx::mbar_wait(&q_full[qb], (bi >> 1) & 1);
+        for (int u = 0; u < lo_x; ++u) ack(u);
+        if (hi_x > lo_x) {
+          // the S buffer was drained when the group loaded the last tile of the previous block (s_free of tile
+          // it-1 has completed long ago); O_x of two blocks ago must have been copied out
+          ptx::mbar_wait(&o_free[2 * x + qb], ((bi >> 1) & 1) ^ 1);
+          ptx::tc_fence_after();
+          issue_s(lo_x);
+        } else if (leader) {
+          ptx::umma_commit(&q_empty[qb]);
         }
-        if (leader) ptx::umma_commit(&kv_empty[t % KV_STAGES2]);
-      }
-      for (int u = max(hi_x, lo_x); u < U; ++u) {
-        ptx::mbar_wait(&kv_full[u % KV_STAGES2], (u / KV_STAGES2) & 1);
-        if (leader) ptx::umma_commit(&kv_empty[u % KV_STAGES2]);
+#pragma unroll 1
+        for (int t = lo_x; t < hi_x; ++t, ++it) {
+          const int j = t - lo_x;
+          if (t + 1 < hi_x) {
+            ptx::mbar_wait(&s_free[x], it & 1);
+            issue_s(t + 1);
+          }
+          const uint32_t v_base = ptx::smem_u32(smem_v + ((ring_base + t) % KV_STAGES2) * KV_TILE_BYTES);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            ptx::mbar_wait(&p_full[2 * x + h], it & 1);  // this half of P_x(t) is in smem (O_x rescaled if needed)
+            ptx::tc_fence_after();
+            const uint32_t p_addr = p_base + h * (BQ * 128);
+            const uint32_t v_addr = v_base + h * (64 * 128);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (leader)
+                ptx::umma_bf16(t_o, ptx::umma_smem_desc_sw128(p_addr + k * 32, 16, 1024),
+                               ptx::umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_o,
+                               (j | h | k) != 0 ? 1u : 0u);
+            if (leader) {
+              ptx::umma_commit(&pv_done[2 * x + h]);
+              if (h == 1 && t + 1 == hi_x) ptx::umma_commit(&o_full[2 * x + qb]);
+            }
+          }
+          if (leader) ptx::umma_commit(&kv_empty[(ring_base + t) % KV_STAGES2]);
+        }
+        for (int u = max(hi_x, lo_x); u < br.U; ++u) ack(u);
+        ring_base += br.U;
       }
     }
   } else {
@@ -474,82 +506,51 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
     ptx::setmaxnreg_inc<200>();
     const int x = warp >> 2;            // 0 = A, 1 = B
     const int r = threadIdx.x & 127;    // query row inside the tile == TMEM lane
-    const int qi = q0 + x * BQ + r;
-    const bool valid = qi < len;
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t t_s = tmem_base + TM_S + x * 128 + lane_off;
-    const uint32_t t_o = tmem_base + TM_O + x * 64 + lane_off;
     uint8_t* my_p = smem_p + x * P_BYTES;
     const float c = p.scale_log2;
     const float2 c2 = make_float2(c, c);
-    float m_run = -INFINITY, l = 0.f;
-    const int lo_x = x ? lo1 : lo0;
-    const int n_iter = (x ? hi1 : hi0) - lo_x;
-
+    int it = 0;  // tiles consumed so far by this group (phase of its barriers)
 #ifdef CM3P_ATTN_PROF
-    long long pf_s = 0, pf_ld = 0, pf_max = 0, pf_pv = 0, pf_exp = 0, pf_t0 = clock64(), pf_a, pf_b;
-#define PF_A() pf_a = clock64()
+    long long pf_s = 0, pf_ld = 0, pf_max = 0, pf_pv = 0, pf_exp = 0, pf_epi = 0, pf_t0 = clock64(), pf_a = pf_t0, pf_b;
 #define PF_B(acc) do { pf_b = clock64(); acc += pf_b - pf_a; pf_a = pf_b; } while (0)
 #else
-#define PF_A()
 #define PF_B(acc)
 #endif
-    for (int jj = 0; jj < n_iter; ++jj) {
-      const int kv0 = kv_base + (lo_x + jj) * BKV;
-      PF_A();
-      ptx::mbar_wait(&s_full[x], jj & 1);
-      PF_B(pf_s);
-      ptx::tc_fence_after();
-      uint32_t sr[4][32];
+    for (int bi = 0; bi < n_b; ++bi) {
+      const int q0 = (b_begin + bi) * 2 * BQ;
+      const BlockRange br = block_range(q0, len, p.window);
+      const int qi = q0 + x * BQ + r;
+      const bool valid = qi < len;
+      const uint32_t t_o = tmem_base + TM_O + (bi & 1) * 128 + x * 64 + lane_off;
+      float m_run = -INFINITY, l = 0.f;
+      const int lo_x = br.lo[x];
+      const int n_iter = br.hi[x] - lo_x;
+
+      for (int jj = 0; jj < n_iter; ++jj, ++it) {
+        const int kv0 = br.kv_base + (lo_x + jj) * BKV;
+        PF_B(pf_epi);
+        ptx::mbar_wait(&s_full[x], it & 1);
+        PF_B(pf_s);
+        ptx::tc_fence_after();
+        uint32_t sr[4][32];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) ptx::tmem_ld_32x32b_x32(t_s + q * 32, sr[q]);
-      ptx::tmem_ld_wait();
-      // the scores are in registers: hand the S buffer back so S_x(jj+1) overlaps this tile's softmax
-      ptx::tc_fence_before();
-      if (lane == 0) ptx::mbar_arrive(&s_free[x]);
-      PF_B(pf_ld);
-      // Masking state per 32-column chunk and per warp (32 consecutive query rows): 0 = no allowed key
-      // for any row of the warp (skip: no exp, P = 0), 1 = some rows partially masked, 2 = fully allowed.
-      // Interior tiles of global layers take the branch-free path (every chunk fully allowed).
-      const bool masked_tile = (p.window >= 0) || (kv0 + BKV > len);  // CTA-uniform
-      int state[4] = {2, 2, 2, 2};
-      float mxq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      if (!masked_tile) {
+        for (int q = 0; q < 4; ++q) ptx::tmem_ld_32x32b_x32(t_s + q * 32, sr[q]);
+        ptx::tmem_ld_wait();
+        // the scores are in registers: hand the S buffer back so S_x(jj+1) overlaps this tile's softmax
+        ptx::tc_fence_before();
+        if (lane == 0) ptx::mbar_arrive(&s_free[x]);
+        PF_B(pf_ld);
+        // Masking state per 32-column chunk and per warp (32 consecutive query rows): 0 = no allowed key
+        // for any row of the warp (skip: no exp, P = 0), 1 = some rows partially masked, 2 = fully allowed.
+        // Interior tiles of global layers take the branch-free path (every chunk fully allowed).
+        const bool masked_tile = (p.window >= 0) || (kv0 + BKV > len);  // CTA-uniform
+        int state[4] = {2, 2, 2, 2};
+        float mxq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (!masked_tile) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float ma = -INFINITY, mb = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            ma = ptx::max3(ma, __uint_as_float(sr[q][i]), __uint_as_float(sr[q][i + 1]));
-            mb = ptx::max3(mb, __uint_as_float(sr[q][i + 2]), __uint_as_float(sr[q][i + 3]));
-          }
-          mxq[q] = fmaxf(ma, mb);
-        }
-      } else {
-        int a = 0, b = min(BKV, len - kv0);
-        const int qw = q0 + x * BQ + (warp & 3) * 32;  // first query row of this warp
-        int wa = 0, wb = b;                            // union of the warp's allowed ranges
-        int ia = 0, ib = b;                            // intersection
-        if (p.window >= 0) {
-          a = max(a, qi - p.window - kv0);
-          b = min(b, qi + p.window + 1 - kv0);
-          wa = max(wa, qw - p.window - kv0);
-          wb = min(wb, qw + 31 + p.window + 1 - kv0);
-          ia = max(ia, qw + 31 - p.window - kv0);
-          ib = min(ib, qw + p.window + 1 - kv0);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int c0 = q * 32, c1 = q * 32 + 32;
-          state[q] = (c1 <= wa || c0 >= wb) ? 0 : ((c0 >= ia && c1 <= ib) ? 2 : 1);
-          if (state[q] == 1) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int kj = q * 32 + i;
-              if (kj < a || kj >= b) sr[q][i] = 0xff800000u;  // -inf
-            }
-          }
-          if (state[q] != 0) {
+          for (int q = 0; q < 4; ++q) {
             float ma = -INFINITY, mb = -INFINITY;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -558,127 +559,154 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
             }
             mxq[q] = fmaxf(ma, mb);
           }
+        } else {
+          int a = 0, b = min(BKV, len - kv0);
+          const int qw = q0 + x * BQ + (warp & 3) * 32;  // first query row of this warp
+          int wa = 0, wb = b;                            // union of the warp's allowed ranges
+          int ia = 0, ib = b;                            // intersection
+          if (p.window >= 0) {
+            a = max(a, qi - p.window - kv0);
+            b = min(b, qi + p.window + 1 - kv0);
+            wa = max(wa, qw - p.window - kv0);
+            wb = min(wb, qw + 31 + p.window + 1 - kv0);
+            ia = max(ia, qw + 31 - p.window - kv0);
+            ib = min(ib, qw + p.window + 1 - kv0);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int c0 = q * 32, c1 = q * 32 + 32;
+            state[q] = (c1 <= wa || c0 >= wb) ? 0 : ((c0 >= ia && c1 <= ib) ? 2 : 1);
+            if (state[q] == 1) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int kj = q * 32 + i;
+                if (kj < a || kj >= b) sr[q][i] = 0xff800000u;  // -inf
+              }
+            }
+            if (state[q] != 0) {
+              float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                ma = ptx::max3(ma, __uint_as_float(sr[q][i]), __uint_as_float(sr[q][i + 1]));
+                mb = ptx::max3(mb, __uint_as_float(sr[q][i + 2]), __uint_as_float(sr[q][i + 3]));
+              }
+              mxq[q] = fmaxf(ma, mb);
+            }
+          }
         }
-      }
-      const float m_new = ptx::max3(m_run, fmaxf(mxq[0], mxq[1]), fmaxf(mxq[2], mxq[3]));
-      PF_B(pf_max);
-      if (jj == 0) {
-        m_run = m_new;
-      } else {
-        const bool grow = (m_new - m_run) * c > RESCALE_LOG2;  // also true for -inf -> finite
-        if (__any_sync(0xffffffffu, grow)) {
-          // both halves of PV(jj-1) must have retired before O is rescaled
-          ptx::mbar_wait(&pv_done[2 * x], (jj - 1) & 1);
-          ptx::mbar_wait(&pv_done[2 * x + 1], (jj - 1) & 1);
-          ptx::tc_fence_after();
-          const float alpha = grow ? ptx::ex2_approx((m_run - m_new) * c) : 1.f;
+        const float m_new = ptx::max3(m_run, fmaxf(mxq[0], mxq[1]), fmaxf(mxq[2], mxq[3]));
+        PF_B(pf_max);
+        if (jj == 0) {
+          m_run = m_new;
+        } else {
+          const bool grow = (m_new - m_run) * c > RESCALE_LOG2;  // also true for -inf -> finite
+          if (__any_sync(0xffffffffu, grow)) {
+            // both halves of PV(jj-1) must have retired before O is rescaled
+            ptx::mbar_wait(&pv_done[2 * x], (it - 1) & 1);
+            ptx::mbar_wait(&pv_done[2 * x + 1], (it - 1) & 1);
+            ptx::tc_fence_after();
+            const float alpha = grow ? ptx::ex2_approx((m_run - m_new) * c) : 1.f;
 #pragma unroll 1
-          for (int h = 0; h < D; h += 16) {
-            uint32_t o[16];
-            ptx::tmem_ld_32x32b_x16(t_o + h, o);
-            ptx::tmem_ld_wait();
+            for (int h = 0; h < D; h += 16) {
+              uint32_t o[16];
+              ptx::tmem_ld_32x32b_x16(t_o + h, o);
+              ptx::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            ptx::tmem_st_32x32b_x16(t_o + h, o);
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              ptx::tmem_st_32x32b_x16(t_o + h, o);
+            }
+            ptx::tmem_st_wait();
+            l *= alpha;
+            if (grow) m_run = m_new;
           }
-          ptx::tmem_st_wait();
-          l *= alpha;
-          if (grow) m_run = m_new;
         }
-      }
-      const float mc = (m_run == -INFINITY) ? 0.f : m_run * c;
-      const float2 nmc2 = make_float2(-mc, -mc);
-      float2 rs[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};  // independent partial row sums (ILP)
-      auto exp_chunk = [&](int q, bool on) {
-        uint32_t packed[16];
-        if (on) {
+        const float mc = (m_run == -INFINITY) ? 0.f : m_run * c;
+        const float2 nmc2 = make_float2(-mc, -mc);
+        float2 rs[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};  // independent partial row sums (ILP)
+        auto exp_chunk = [&](int q, bool on) {
+          uint32_t packed[16];
+          if (on) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float2 t = ptx::fma2(make_float2(__uint_as_float(sr[q][i]), __uint_as_float(sr[q][i + 1])), c2, nmc2);
-            const float2 e = ptx::ex2_pair(t, i >> 1);
-            rs[(i >> 1) & 3] = ptx::add2(rs[(i >> 1) & 3], e);
-            packed[i >> 1] = ptx::pack_bf16x2(e.x, e.y);
+            for (int i = 0; i < 32; i += 2) {
+              const float2 t = ptx::fma2(make_float2(__uint_as_float(sr[q][i]), __uint_as_float(sr[q][i + 1])), c2, nmc2);
+              const float2 e = ptx::ex2_pair(t, i >> 1);
+              rs[(i >> 1) & 3] = ptx::add2(rs[(i >> 1) & 3], e);
+              packed[i >> 1] = ptx::pack_bf16x2(e.x, e.y);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) packed[i] = 0u;
           }
+          // half (q >> 1) of the P buffer is still being read by the PV of the previous tile until pv_done fires;
+          // that MMA was issued half a tile ago, so this wait is normally already satisfied
+          if ((q & 1) == 0 && it > 0) {
+            PF_B(pf_exp);
+            ptx::mbar_wait(&pv_done[2 * x + (q >> 1)], (it - 1) & 1);
+            PF_B(pf_pv);
+          }
+          uint8_t* prow = my_p + (q >> 1) * (BQ * 128) + r * 128;
+          const int u0 = (q & 1) ? 4 : 0;
+#pragma unroll
+          for (int uu = 0; uu < 4; ++uu) {
+            const int unit = (u0 + uu) ^ (r & 7);
+            *reinterpret_cast<uint4*>(prow + unit * 16) =
+                make_uint4(packed[uu * 4], packed[uu * 4 + 1], packed[uu * 4 + 2], packed[uu * 4 + 3]);
+          }
+          if (q & 1) {  // a 64-key half of P is complete: PV on it can start while the other half is computed
+            ptx::tc_fence_before();
+            ptx::fence_proxy_async_smem();
+            ptx::mbar_arrive(&p_full[2 * x + (q >> 1)]);
+          }
+        };
+        if (!masked_tile) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) exp_chunk(q, true);
         } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) packed[i] = 0u;
+          for (int q = 0; q < 4; ++q) exp_chunk(q, state[q] != 0);
         }
-        // half (q >> 1) of the P buffer is still being read by PV(jj-1, half) until pv_done fires; that MMA
-        // was issued half a tile ago, so this wait is normally already satisfied
-        if ((q & 1) == 0 && jj > 0) {
-          PF_B(pf_exp);
-          ptx::mbar_wait(&pv_done[2 * x + (q >> 1)], (jj - 1) & 1);
-          PF_B(pf_pv);
-#ifdef CM3P_ATTN_PROF
-          if (x == 0 && r == 0 && jj < 20) ev[2][2 * (jj - 1) + (q >> 1)] = clock64();
-#endif
-        }
-        uint8_t* prow = my_p + (q >> 1) * (BQ * 128) + r * 128;
-        const int u0 = (q & 1) ? 4 : 0;
-#pragma unroll
-        for (int uu = 0; uu < 4; ++uu) {
-          const int unit = (u0 + uu) ^ (r & 7);
-          *reinterpret_cast<uint4*>(prow + unit * 16) =
-              make_uint4(packed[uu * 4], packed[uu * 4 + 1], packed[uu * 4 + 2], packed[uu * 4 + 3]);
-        }
-        if (q & 1) {  // a 64-key half of P is complete: PV on it can start while the other half is computed
-          ptx::tc_fence_before();
-          ptx::fence_proxy_async_smem();
-          ptx::mbar_arrive(&p_full[2 * x + (q >> 1)]);
-#ifdef CM3P_ATTN_PROF
-          if (x == 0 && r == 0 && jj < 20) ev[0][2 * jj + (q >> 1)] = clock64();
-#endif
-        }
-      };
-      if (!masked_tile) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) exp_chunk(q, true);
-      } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) exp_chunk(q, state[q] != 0);
+        const float2 rsum = ptx::add2(ptx::add2(rs[0], rs[1]), ptx::add2(rs[2], rs[3]));
+        l += rsum.x + rsum.y;
+        PF_B(pf_exp);
       }
-      const float2 rsum = ptx::add2(ptx::add2(rs[0], rs[1]), ptx::add2(rs[2], rs[3]));
-      l += rsum.x + rsum.y;
-      PF_B(pf_exp);
-    }
-#ifdef CM3P_ATTN_PROF
-    if (r == 0 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0) {
-      if (x == 0)
-        for (int i = 0; i < 2 * n_iter - 2 && i < 38; ++i)
-          printf("half %2d: arrive %6lld  seen +%5lld  done_seen +%5lld | S issue(%d) %6lld\n", i, ev[0][i] - pf_t0,
-                 ev[1][i] - ev[0][i], ev[2][i] - ev[0][i], i >> 1, ev[3][i >> 1] - pf_t0);
-      printf("attn prof x=%d iters=%d total=%lld wait_s=%lld ld=%lld max=%lld wait_pv=%lld exp=%lld\n", x, n_iter,
-             clock64() - pf_t0, pf_s, pf_ld, pf_max, pf_pv, pf_exp);
-    }
-#endif
-    if (n_iter > 0) {
-      ptx::mbar_wait(&o_full[x], 0);
-      ptx::tc_fence_after();
-      float o[D];
+      if (n_iter > 0) {
+        // epilogue of the block; meanwhile the issuer already runs S of the next block's first tile
+        ptx::mbar_wait(&o_full[2 * x + (bi & 1)], (bi >> 1) & 1);
+        ptx::tc_fence_after();
+        float o[D];
 #pragma unroll
-      for (int h = 0; h < D; h += 32) {
-        uint32_t rr[32];
-        ptx::tmem_ld_32x32b_x32(t_o + h, rr);
-        ptx::tmem_ld_wait();
+        for (int h = 0; h < D; h += 32) {
+          uint32_t rr[32];
+          ptx::tmem_ld_32x32b_x32(t_o + h, rr);
+          ptx::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[h + i] = __uint_as_float(rr[i]);
-      }
-      if (valid) {
-        const float inv = 1.f / l;
-        const int64_t row = static_cast<int64_t>(seq_start) + qi;
-        __nv_bfloat16* dst = p.out + row * p.hidden + head * D;
-#pragma unroll
-        for (int i = 0; i < D; i += 8) {
-          uint4 uo;
-          uo.x = ptx::pack_bf16x2(o[i] * inv, o[i + 1] * inv);
-          uo.y = ptx::pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv);
-          uo.z = ptx::pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv);
-          uo.w = ptx::pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv);
-          *reinterpret_cast<uint4*>(dst + i) = uo;
+          for (int i = 0; i < 32; ++i) o[h + i] = __uint_as_float(rr[i]);
         }
-        if (p.lse) p.lse[static_cast<int64_t>(head) * p.total_tokens + row] = m_run * c + log2f(l);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&o_free[2 * x + (bi & 1)]);
+        if (valid) {
+          const float inv = 1.f / l;
+          const int64_t row = static_cast<int64_t>(seq_start) + qi;
+          __nv_bfloat16* dst = p.out + row * p.hidden + head * D;
+#pragma unroll
+          for (int i = 0; i < D; i += 8) {
+            uint4 uo;
+            uo.x = ptx::pack_bf16x2(o[i] * inv, o[i + 1] * inv);
+            uo.y = ptx::pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv);
+            uo.z = ptx::pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv);
+            uo.w = ptx::pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv);
+            *reinterpret_cast<uint4*>(dst + i) = uo;
+          }
+          if (p.lse) p.lse[static_cast<int64_t>(head) * p.total_tokens + row] = m_run * c + log2f(l);
+        }
       }
     }
+#ifdef CM3P_ATTN_PROF
+    if (r == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+      printf("attn prof x=%d blocks=%d tiles=%d total=%lld wait_s=%lld ld=%lld max=%lld wait_pv=%lld exp=%lld epilogue=%lld\n", x,
+             n_b, it, clock64() - pf_t0, pf_s, pf_ld, pf_max, pf_pv, pf_exp, pf_epi);
+#endif
   }
 
   ptx::tc_fence_before();
@@ -718,6 +746,7 @@ int attn_varlen_fwd(const AttnFwdArgs& a, cudaStream_t stream) {
   p.hidden = H;
   p.window = a.window;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
+  p.blocks_per_cta = 1;
   static int use_v1 = -1;
   if (use_v1 < 0) {
     const char* e = getenv("CM3P_ATTN_FWD_V1");
@@ -734,7 +763,19 @@ int attn_varlen_fwd(const AttnFwdArgs& a, cudaStream_t stream) {
                                          v2::SMEM_BYTES2));
       configured2 = true;
     }
-    dim3 grid((a.max_seqlen + 2 * BQ - 1) / (2 * BQ), a.heads, a.batch);
+    // blocks per CTA: enough CTAs for ~16 (global) / ~4 (window) waves of uneven work
+    static int forced_bpc = -1;
+    if (forced_bpc < 0) {
+      const char* e = getenv("CM3P_FWD_BLOCKS_PER_CTA");
+      forced_bpc = e ? atoi(e) : 0;
+    }
+    const int64_t units = (a.total_tokens / (2 * BQ) + a.batch / 2 + 1) * a.heads;
+    const int64_t target_ctas = static_cast<int64_t>(num_sms()) * (a.window >= 0 ? 4 : 16);
+    int bpc = static_cast<int>((units + target_ctas - 1) / target_ctas);
+    bpc = bpc < 1 ? 1 : (bpc > v2::MAX_BLOCKS_PER_CTA ? v2::MAX_BLOCKS_PER_CTA : bpc);
+    if (forced_bpc > 0) bpc = forced_bpc > v2::MAX_BLOCKS_PER_CTA ? v2::MAX_BLOCKS_PER_CTA : forced_bpc;
+    p.blocks_per_cta = bpc;
+    dim3 grid((a.max_seqlen + 2 * BQ * bpc - 1) / (2 * BQ * bpc), a.heads, a.batch);
     v2::attn_fwd_v2_kernel<<<grid, v2::THREADS2, v2::SMEM_BYTES2, stream>>>(tmap, p);
   }
   CM3P_CUDA_TRY(cudaGetLastError());

@@ -562,8 +562,11 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    // The whole warp runs the loop (warp-uniform control flow keeps the descriptor arithmetic in the uniform
+    // datapath); one elected lane issues the MMAs and commits.
+    const bool leader = ptx::elect_one();
     const uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, p.trans_a ? 1u : 0u, p.trans_b ? 1u : 0u);
     // K-major: 8-row groups 1024 B apart; one UMMA_K (16 elem) step = +32 B inside the swizzle row.
     // MN-major: 8-k groups 1024 B apart (SBO), 64-wide MN chunks BK*128 B apart (LBO); UMMA_K step = +2048 B.
@@ -588,12 +591,14 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         for (int k = 0; k < BK / 16; ++k) {
           const uint64_t da = ptx::umma_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
           const uint64_t db = ptx::umma_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
-          ptx::umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          if (leader) ptx::umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
         }
         // frees the smem stage once these MMAs have read it (in both CTAs of a pair: either may refill it)
-        if (p.cluster > 1) ptx::umma_commit_multicast(&empty[s], 0x3);
-        else ptx::umma_commit(&empty[s]);
-        if (kb == kb1 - 1) ptx::umma_commit(&tmem_full[as]);
+        if (leader) {
+          if (p.cluster > 1) ptx::umma_commit_multicast(&empty[s], 0x3);
+          else ptx::umma_commit(&empty[s]);
+          if (kb == kb1 - 1) ptx::umma_commit(&tmem_full[as]);
+        }
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
       if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
