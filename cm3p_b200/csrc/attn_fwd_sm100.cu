@@ -285,17 +285,22 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params 
 
 
 // ================================================================================================
-// v2: one CTA = 256 queries (two 128-row Q tiles A and B), one CTA per SM, 10 warps:
+// v2: one CTA per SM streams `blocks_per_cta` consecutive 256-query blocks of one (sequence, head); a block
+// is two 128-row Q tiles A and B.  12 warps:
 //   warps 0-3 softmax group A, warps 4-7 softmax group B (thread <-> query row <-> TMEM lane),
-//   warp 8 TMA producer (+ TMEM alloc), warp 9 MMA issuer.
-// K/V tiles (128 rows) stream through a 3-stage ring shared by both Q tiles.  The two tiles
-// ping-pong on the tensor core: while group A runs exp on S_A(u+1), the MMA pipe executes PV_B(u)
-// and S_B(u+1), and vice versa.  O_A / O_B stay in TMEM for the whole KV loop (tcgen05.mma
-// accumulate); the running maximum is only raised when it grows by more than 2^8 (then the owning
-// warp rescales its 32 O rows in TMEM with tcgen05.ld/st), so the common iteration is: one
-// TMEM read of the 128 scores, max, exp2, bf16 pack into swizzled smem, one mbarrier arrive.
-// Masking (-inf) is only applied on tiles that need it (sequence tail, window band).
-// TMEM columns: S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384).
+//   warp 8 TMA producer (+ TMEM alloc), warps 9 / 10 MMA issuers of tile A / B, warp 11 idle.
+// K/V tiles (128 rows) stream through a 3-stage ring shared by both Q tiles; Q and the O accumulators are
+// double-buffered across blocks, so the next block's loads and first S GEMM run under the current block's
+// epilogue.  Per Q tile the pipeline is decoupled in both directions: S_x(t+1) is issued as soon as group x
+// has copied S_x(t) into registers (s_free), and PV_x(t) is issued per 64-key half of P as soon as that half
+// is written (p_full / pv_done per half), so neither the group nor the tensor pipe waits for the other in
+// steady state (measured with the CM3P_ATTN_PROF clock64 counters: the exp phase is 75 % of a tile).
+// O_A / O_B stay in TMEM for the whole KV loop (tcgen05.mma accumulate); the running maximum is only raised
+// when it grows by more than 2^8 (then the owning warp rescales its 32 O rows in TMEM with tcgen05.ld/st),
+// so the common iteration is: one TMEM read of the 128 scores, max (3-input), exp2 (packed f32x2 arithmetic,
+// a quarter of the exponentials as a polynomial on the FMA pipe), bf16 pack into swizzled smem, mbarrier
+// arrives.  Masking (-inf) is only applied on tiles that need it (sequence tail, window band).
+// TMEM columns: S_A [0,128)  S_B [128,256)  O_A / O_B of even blocks [256,384), of odd blocks [384,512).
 namespace v2 {
 
 constexpr int KV_STAGES2 = 3;

@@ -20,6 +20,8 @@ EPI_GEGLU, EPI_GEGLU_SAVE, EPI_ROPE, EPI_SCALE_F32 = 5, 6, 7, 8
 import os as _os
 
 FUSE_LAYERNORM = _os.environ.get("CM3P_FUSE_LN", "0") == "1"
+# training: keep LayerNorm outputs for the backward ("1"), recompute them ("0"), or decide by free memory ("auto")
+SAVE_LAYERNORM = _os.environ.get("CM3P_SAVE_LN", "auto")
 
 # kernel launches issued through this module (bench.py reports it as `gpu_launches`)
 LAUNCH_COUNT = 0

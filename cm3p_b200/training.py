@@ -10,8 +10,10 @@ output is the loss, so `loss.backward()`, gradient accumulation, `torch.nn.paral
 DistributedDataParallel` hooks (gradient all-reduce over NCCL) and optimizers work unchanged.
 
 Per encoder layer the forward keeps x_in, qkv (rotated), the attention output, the log-sum-exp,
-x_mid and the GeGLU pre-activation (13.8 KB / token / layer for the beatmap tower); LayerNorm
-outputs and the GeGLU product are recomputed in the backward pass.
+x_mid and the GeGLU pre-activation (13.8 KB / token / layer for the beatmap tower); the GeGLU
+product is recomputed in the backward pass, and so are the LayerNorm outputs unless there is
+room to keep them (`CM3P_SAVE_LN`: "auto" keeps them when they fit in a quarter of the free
+device memory, +3 KB / token / layer; "1" / "0" force it).
 
 Numerics: bf16 activations and gradients of activations, fp32 accumulation, fp32 parameter
 gradients (what autocast-bf16 training in the reference produces up to rounding; north-star
@@ -57,6 +59,15 @@ def _dgrad(dy: torch.Tensor, w: torch.Tensor, out: torch.Tensor | None = None, *
 # ------------------------------------------------------------------------------------------------
 # ModernBERT trunk
 
+def _keep_layernorm_outputs(nbytes: int, dev) -> bool:
+    mode = ops.SAVE_LAYERNORM
+    if mode in ("0", "1"):
+        return mode == "1"
+    free, _ = torch.cuda.mem_get_info(dev)
+    free += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)  # cached blocks are reusable
+    return nbytes < free // 4
+
+
 def encoder_forward(enc, x0: torch.Tensor, cu_seqlens, max_seqlen: int, positions):
     """x0 [T,H] = normalised embeddings.  -> (final-normed hidden [T,H], saved activations)."""
     cfg, pk = enc.config, enc.packed()
@@ -72,17 +83,23 @@ def encoder_forward(enc, x0: torch.Tensor, cu_seqlens, max_seqlen: int, position
     fuse = ops.FUSE_LAYERNORM  # LayerNorms folded into the neighbouring GEMMs (the backward recomputes them from x)
     if fuse:
         stats = torch.zeros((2 * n_layers, T, 2), device=dev, dtype=F32)
+    # keep the LayerNorm outputs for the weight-gradient GEMMs instead of recomputing them in the backward
+    keep_ln = (not fuse) and _keep_layernorm_outputs(2 * n_layers * T * H * 2, dev)
     for i, w in enumerate(pk["layers"]):
         is_global = cfg.layer_is_global(i)
         tab = tab_g if is_global else tab_l
+        norm_a = norm_m = None
         if i == 0:
             qkv = ops.gemm(x, w["wqkv"], epilogue=ops.EPI_ROPE, positions=positions, rope_table=tab, rope_cols=2 * H)
         elif fuse:
             qkv = ops.gemm(x, w["wqkv_ln"], epilogue=ops.EPI_ROPE, positions=positions, rope_table=tab,
                            rope_cols=2 * H, row_stats=stats[2 * i - 1], col_corr=w["cqkv"], ln_eps=eps)
         else:
+            if keep_ln:
+                a = torch.empty_like(x0)
             ops.layernorm(x, w["attn_norm"], eps, out=a)
             qkv = ops.gemm(a, w["wqkv"], epilogue=ops.EPI_ROPE, positions=positions, rope_table=tab, rope_cols=2 * H)
+            norm_a = a if keep_ln else None
         lse = torch.empty((heads, T), device=dev, dtype=F32)
         o = ops.attn_varlen_fwd(qkv, cu_seqlens, max_seqlen, heads, -1 if is_global else cfg.window_half, lse=lse)
         ug = torch.empty((T, 2 * I), device=dev, dtype=BF16)
@@ -94,11 +111,14 @@ def encoder_forward(enc, x0: torch.Tensor, cu_seqlens, max_seqlen: int, position
                           stats_out=stats[2 * i + 1] if i + 1 < n_layers else None)
         else:
             x1 = ops.gemm(o, w["wo"], epilogue=ops.EPI_RESIDUAL, aux=x)
+            if keep_ln:
+                a = torch.empty_like(x0)
             ops.layernorm(x1, w["mlp_norm"], eps, out=a)
             h = ops.gemm(a, w["wi"], epilogue=ops.EPI_GEGLU_SAVE, c2=ug)
             x2 = ops.gemm(h, w["wo2"], epilogue=ops.EPI_RESIDUAL, aux=x1)
+            norm_m = a if keep_ln else None
         layers.append(dict(x_in=x, qkv=qkv, o=o, lse=lse, x1=x1, ug=ug, window=-1 if is_global else cfg.window_half,
-                           tab=tab))
+                           tab=tab, norm_a=norm_a, norm_m=norm_m))
         x = x2
     last = ops.layernorm(x, pk["final_norm"], cfg.norm_eps)
     saved = dict(layers=layers, x_final=x, cu=cu_seqlens, max_seqlen=max_seqlen, positions=positions)
@@ -133,9 +153,11 @@ def encoder_backward(enc, saved, dlast: torch.Tensor, g: GradStore) -> torch.Ten
         _dgrad(dx, w["wo2"], out=dh)
         ops.geglu_bwd(s["ug"], dh, dug=dug, h=h)
         _wgrad(dx, h, g(layer.mlp.Wo.weight))
-        ops.layernorm(s["x1"], w["mlp_norm"], eps, out=norm)
+        norm_m = s["norm_m"]
+        if norm_m is None:
+            norm_m = ops.layernorm(s["x1"], w["mlp_norm"], eps, out=norm)
         g_wi_il.zero_()
-        _wgrad(dug, norm, g_wi_il)
+        _wgrad(dug, norm_m, g_wi_il)
         g(layer.mlp.Wi.weight).add_(ops.deinterleave_wi(g_wi_il))
         _dgrad(dug, w["wi"], out=dtmp)
         ops.layernorm_bwd(s["x1"], dtmp, w["mlp_norm"], eps, dres=dx, dx=dx, dgamma=g(layer.mlp_norm.weight))
@@ -148,8 +170,10 @@ def encoder_backward(enc, saved, dlast: torch.Tensor, g: GradStore) -> torch.Ten
             _wgrad(dqkv, s["x_in"], g(layer.attn.Wqkv.weight))
             _dgrad(dqkv, w["wqkv"], out=dx, epilogue=ops.EPI_RESIDUAL, aux=dx)
         else:
-            ops.layernorm(s["x_in"], w["attn_norm"], eps, out=norm)
-            _wgrad(dqkv, norm, g(layer.attn.Wqkv.weight))
+            norm_a = s["norm_a"]
+            if norm_a is None:
+                norm_a = ops.layernorm(s["x_in"], w["attn_norm"], eps, out=norm)
+            _wgrad(dqkv, norm_a, g(layer.attn.Wqkv.weight))
             _dgrad(dqkv, w["wqkv"], out=dtmp)
             ops.layernorm_bwd(s["x_in"], dtmp, w["attn_norm"], eps, dres=dx, dx=dx,
                               dgamma=g(layer.attn_norm.weight))

@@ -121,6 +121,18 @@ def bench_ln(T, H):
 
 if __name__ == "__main__":
     if "attn" in sys.argv[1:]:
+        B = int(os.environ.get("CM3P_BENCH_B", "64"))  # 256 = the train step's windows per GPU
+        if B != 64:
+            bench_attn(B, 2000, 12, -1)
+            bench_attn(B, 2000, 12, 64)
+            bench_attn(B, 800, 8, -1)
+            bench_attn(B, 800, 8, 64)
+            if "bwd" in sys.argv[1:]:
+                bench_attn_bwd(B, 2000, 12, -1)
+                bench_attn_bwd(B, 2000, 12, 64)
+                bench_attn_bwd(B, 800, 8, -1)
+                bench_attn_bwd(B, 800, 8, 64)
+            sys.exit(0)
         bench_attn(64, 2000, 12, -1)
         bench_attn(64, 2000, 12, 64)
         bench_attn(64, 800, 8, -1)
