@@ -286,27 +286,32 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params 
 
 // ================================================================================================
 // v2: one CTA per SM streams `blocks_per_cta` consecutive 256-query blocks of one (sequence, head); a block
-// is two 128-row Q tiles A and B.  12 warps:
-//   warps 0-3 softmax group A, warps 4-7 softmax group B (thread <-> query row <-> TMEM lane),
-//   warp 8 TMA producer (+ TMEM alloc), warps 9 / 10 MMA issuers of tile A / B, warp 11 idle.
+// is two 128-row Q tiles A and B.  20 warps:
+//   warps 0-7 softmax group A, warps 8-15 softmax group B: TMEM lane quadrant (warp & 3) x 64-key column half,
+//   so a query row is shared by two threads that exchange their row maximum through shared memory once per
+//   tile (four light warps per scheduler hide exp / FMA latency that two heavy ones could not);
+//   warp 16 TMA producer (+ TMEM alloc), warps 17 / 18 MMA issuers of tile A / B, warp 19 idle.
 // K/V tiles (128 rows) stream through a 3-stage ring shared by both Q tiles; Q and the O accumulators are
 // double-buffered across blocks, so the next block's loads and first S GEMM run under the current block's
 // epilogue.  Per Q tile the pipeline is decoupled in both directions: S_x(t+1) is issued as soon as group x
-// has copied S_x(t) into registers (s_free), and PV_x(t) is issued per 64-key half of P as soon as that half
-// is written (p_full / pv_done per half), so neither the group nor the tensor pipe waits for the other in
-// steady state (measured with the CM3P_ATTN_PROF clock64 counters: the exp phase is 75 % of a tile).
+// has copied S_x(t) into registers (s_free), and PV_x(t) is issued per 64-key half of P as soon as the four
+// warps of that half have written it (p_full / pv_done per half), so neither the group nor the tensor pipe
+// waits for the other in steady state.
 // O_A / O_B stay in TMEM for the whole KV loop (tcgen05.mma accumulate); the running maximum is only raised
-// when it grows by more than 2^8 (then the owning warp rescales its 32 O rows in TMEM with tcgen05.ld/st),
-// so the common iteration is: one TMEM read of the 128 scores, max (3-input), exp2 (packed f32x2 arithmetic,
-// a quarter of the exponentials as a polynomial on the FMA pipe), bf16 pack into swizzled smem, mbarrier
-// arrives.  Masking (-inf) is only applied on tiles that need it (sequence tail, window band).
+// when it grows by more than 2^8 (then each warp rescales its 32 rows x 32 columns of O in TMEM with
+// tcgen05.ld/st), so the common iteration is: one TMEM read of 64 scores, max (3-input), exchange, exp2
+// (packed f32x2 arithmetic, a quarter of the exponentials as a polynomial on the FMA pipe), bf16 pack into
+// swizzled smem, mbarrier arrive.  Masking (-inf) is only applied on tiles that need it (tail, window band).
 // TMEM columns: S_A [0,128)  S_B [128,256)  O_A / O_B of even blocks [256,384), of odd blocks [384,512).
 namespace v2 {
 
 constexpr int KV_STAGES2 = 3;
-constexpr int THREADS2 = 384;  // 3 warpgroups: softmax A, softmax B, {TMA, MMA issuer A, MMA issuer B, idle}
+constexpr int THREADS2 = 640;  // 5 warpgroups: softmax A (2), softmax B (2), {TMA, MMA issuer A, MMA issuer B, idle}
+constexpr int SM_WARPS = 16;    // softmax warps: 8 per Q tile = 4 TMEM lane quadrants x 2 column halves
+constexpr int REG_SM = 104, REG_AUX2 = 64;
 constexpr int SMEM_TILES2 = 2 * 2 * Q_BYTES + KV_STAGES2 * 2 * KV_TILE_BYTES + 2 * P_BYTES;  // 64 + 96 + 64 = 224 KB
-constexpr int SMEM_BYTES2 = SMEM_TILES2 + 512;
+constexpr int SMEM_XCHG = 2 * 2 * BQ * 4;  // row maxima / row sums exchanged between the two warps of a row
+constexpr int SMEM_BYTES2 = SMEM_TILES2 + 512 + SMEM_XCHG;
 constexpr uint32_t TM_S = 0, TM_O = 256;  // S: + 128 x;  O: + 128 (block parity) + 64 x
 constexpr float RESCALE_LOG2 = 8.0f;
 constexpr int MAX_BLOCKS_PER_CTA = 16;
@@ -357,21 +362,22 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
   uint64_t* kv_full = q_empty + 2;         // [3]
   uint64_t* kv_empty = kv_full + KV_STAGES2;  // [3] 2 arrivals (both issuers)
   uint64_t* s_full = kv_empty + KV_STAGES2;   // [2]
-  uint64_t* s_free = s_full + 2;           // [2] 4 arrivals (one per warp): S_x is in registers
+  uint64_t* s_free = s_full + 2;           // [2] 8 arrivals (one per warp): S_x is in registers
   uint64_t* p_full = s_free + 2;           // [2][2] per 64-key half of P_x, 128 arrivals each
   uint64_t* pv_done = p_full + 4;          // [2][2] PV_x(u, half) retired: that half of the P_x buffer is reusable
   uint64_t* o_full = pv_done + 4;          // [2][2] (x, block parity)
-  uint64_t* o_free = o_full + 4;           // [2][2] 4 arrivals: O_x of the block is in registers
+  uint64_t* o_free = o_full + 4;           // [2][2] 8 arrivals: O_x of the block is in registers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 4);
+  float* smem_xchg = reinterpret_cast<float*>(smem + SMEM_TILES2 + 512);  // [2 Q tiles][2 halves][128 rows]
 
   if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
 
-  if (warp == 9 && lane == 0) {
+  if (warp == SM_WARPS + 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&q_full[i], 1);
       ptx::mbar_init(&q_empty[i], 2);
       ptx::mbar_init(&s_full[i], 1);
-      ptx::mbar_init(&s_free[i], 4);
+      ptx::mbar_init(&s_free[i], 8);
     }
     for (int s = 0; s < KV_STAGES2; ++s) {
       ptx::mbar_init(&kv_full[s], 1);
@@ -381,11 +387,11 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
       ptx::mbar_init(&p_full[i], 128);
       ptx::mbar_init(&pv_done[i], 1);
       ptx::mbar_init(&o_full[i], 1);
-      ptx::mbar_init(&o_free[i], 4);
+      ptx::mbar_init(&o_free[i], 8);
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 8) {
+  if (warp == SM_WARPS) {
     if (lane == 0) ptx::prefetch_tmap(&tma_qkv);
     ptx::tmem_alloc(tmem_slot, 512);
     ptx::tmem_relinquish();
@@ -395,10 +401,10 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // 12 warps x 168 registers at launch; the data-movement warpgroup hands registers to the softmax ones
-  if (warp >= 8) {
-    ptx::setmaxnreg_dec<96>();
-    if (warp == 8 && lane == 0) {
+  // the data-movement warpgroup hands registers to the softmax ones
+  if (warp >= SM_WARPS) {
+    ptx::setmaxnreg_dec<REG_AUX2>();
+    if (warp == SM_WARPS && lane == 0) {
       // ---------------------------------------------------------------- TMA producer
       const int col_q = head * D, col_k = p.hidden + head * D, col_v = 2 * p.hidden + head * D;
       int ring = 0;
@@ -419,7 +425,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
           ptx::tma_load_2d(smem_v + s * KV_TILE_BYTES, &tma_qkv, &kv_full[s], col_v, row);
         }
       }
-    } else if (warp == 9 || warp == 10) {
+    } else if (warp == SM_WARPS + 1 || warp == SM_WARPS + 2) {
       // ---------------------------------------------------------------- MMA issuers (one per Q tile)
       // Each Q tile has its own issuing warp, so its MMAs follow the order in which its softmax group
       // produces the events: "S_x buffer drained into registers" -> S_x(t+1) (runs on the tensor pipe WHILE
@@ -429,7 +435,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
       // control flow keeps the descriptor arithmetic in the uniform datapath: back-to-back UTCHMMA instead
       // of ~10 address-move instructions per MMA); one elected lane issues.
       const bool leader = ptx::elect_one();
-      const int x = warp - 9;
+      const int x = warp - (SM_WARPS + 1);
       const uint32_t idesc_s = ptx::umma_idesc_bf16(BQ, BKV, 0, 0);
       const uint32_t idesc_o = ptx::umma_idesc_bf16(BQ, D, 0, 1);  // V is MN-major
       const uint32_t p_base = ptx::smem_u32(smem_p + x * P_BYTES);
@@ -508,54 +514,54 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
     }
   } else {
     // ------------------------------------------------------------------ softmax groups
-    ptx::setmaxnreg_inc<200>();
-    const int x = warp >> 2;            // 0 = A, 1 = B
-    const int r = threadIdx.x & 127;    // query row inside the tile == TMEM lane
+    // 8 warps per Q tile: TMEM lane quadrant (warp & 3) x 64-key column half ((warp >> 2) & 1).  A query row
+    // is shared by two threads (one per half); they exchange their partial row maximum through shared memory
+    // once per tile (named barrier of the two warps) and their partial row sums once per block.  Four light
+    // warps per scheduler instead of two heavy ones: the exp / FMA latencies of one warp are covered by the
+    // others (the exp phase of the 2-warp version reached 62 % of the MUFU rate).
+    ptx::setmaxnreg_inc<REG_SM>();
+    const int x = warp >> 3;            // 0 = A, 1 = B
+    const int hc = (warp >> 2) & 1;     // column half of the 128-key tile
+    const int r = (warp & 3) * 32 + lane;  // query row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t t_s = tmem_base + TM_S + x * 128 + lane_off;
-    uint8_t* my_p = smem_p + x * P_BYTES;
+    const uint32_t t_s = tmem_base + TM_S + x * 128 + lane_off + hc * 64;
+    uint8_t* my_p = smem_p + x * P_BYTES + hc * (BQ * 128);  // this half's 64-key K block of P_x
+    float* my_x = smem_xchg + (x * 2 + hc) * BQ + r;
+    const float* peer_x = smem_xchg + (x * 2 + (hc ^ 1)) * BQ + r;
+    const int pair_bar = 1 + x * 4 + (warp & 3);  // named barrier of the two warps that share these 32 rows
     const float c = p.scale_log2;
     const float2 c2 = make_float2(c, c);
     int it = 0;  // tiles consumed so far by this group (phase of its barriers)
-#ifdef CM3P_ATTN_PROF
-    long long pf_s = 0, pf_ld = 0, pf_max = 0, pf_pv = 0, pf_exp = 0, pf_epi = 0, pf_t0 = clock64(), pf_a = pf_t0, pf_b;
-#define PF_B(acc) do { pf_b = clock64(); acc += pf_b - pf_a; pf_a = pf_b; } while (0)
-#else
-#define PF_B(acc)
-#endif
     for (int bi = 0; bi < n_b; ++bi) {
       const int q0 = (b_begin + bi) * 2 * BQ;
       const BlockRange br = block_range(q0, len, p.window);
       const int qi = q0 + x * BQ + r;
       const bool valid = qi < len;
-      const uint32_t t_o = tmem_base + TM_O + (bi & 1) * 128 + x * 64 + lane_off;
+      const uint32_t t_o = tmem_base + TM_O + (bi & 1) * 128 + x * 64 + lane_off + hc * 32;  // this thread's 32 of the 64 O columns
       float m_run = -INFINITY, l = 0.f;
       const int lo_x = br.lo[x];
       const int n_iter = br.hi[x] - lo_x;
 
       for (int jj = 0; jj < n_iter; ++jj, ++it) {
         const int kv0 = br.kv_base + (lo_x + jj) * BKV;
-        PF_B(pf_epi);
         ptx::mbar_wait(&s_full[x], it & 1);
-        PF_B(pf_s);
         ptx::tc_fence_after();
-        uint32_t sr[4][32];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) ptx::tmem_ld_32x32b_x32(t_s + q * 32, sr[q]);
+        uint32_t sr[2][32];
+        ptx::tmem_ld_32x32b_x32(t_s, sr[0]);
+        ptx::tmem_ld_32x32b_x32(t_s + 32, sr[1]);
         ptx::tmem_ld_wait();
         // the scores are in registers: hand the S buffer back so S_x(jj+1) overlaps this tile's softmax
         ptx::tc_fence_before();
         if (lane == 0) ptx::mbar_arrive(&s_free[x]);
-        PF_B(pf_ld);
         // Masking state per 32-column chunk and per warp (32 consecutive query rows): 0 = no allowed key
         // for any row of the warp (skip: no exp, P = 0), 1 = some rows partially masked, 2 = fully allowed.
         // Interior tiles of global layers take the branch-free path (every chunk fully allowed).
         const bool masked_tile = (p.window >= 0) || (kv0 + BKV > len);  // CTA-uniform
-        int state[4] = {2, 2, 2, 2};
-        float mxq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        int state[2] = {2, 2};
+        float mxq[2] = {-INFINITY, -INFINITY};
         if (!masked_tile) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < 2; ++q) {
             float ma = -INFINITY, mb = -INFINITY;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -578,13 +584,13 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
             ib = min(ib, qw + p.window + 1 - kv0);
           }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int c0 = q * 32, c1 = q * 32 + 32;
+          for (int q = 0; q < 2; ++q) {
+            const int c0 = hc * 64 + q * 32, c1 = c0 + 32;
             state[q] = (c1 <= wa || c0 >= wb) ? 0 : ((c0 >= ia && c1 <= ib) ? 2 : 1);
             if (state[q] == 1) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                const int kj = q * 32 + i;
+                const int kj = c0 + i;
                 if (kj < a || kj >= b) sr[q][i] = 0xff800000u;  // -inf
               }
             }
@@ -599,20 +605,23 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
             }
           }
         }
-        const float m_new = ptx::max3(m_run, fmaxf(mxq[0], mxq[1]), fmaxf(mxq[2], mxq[3]));
-        PF_B(pf_max);
+        // row maximum over all 128 keys: exchange the two halves (the peer reads this slot right after the
+        // barrier; it is rewritten a whole tile later)
+        *my_x = fmaxf(mxq[0], mxq[1]);
+        ptx::named_bar_sync(pair_bar, 64);
+        const float m_new = ptx::max3(m_run, fmaxf(mxq[0], mxq[1]), *peer_x);
         if (jj == 0) {
           m_run = m_new;
         } else {
           const bool grow = (m_new - m_run) * c > RESCALE_LOG2;  // also true for -inf -> finite
-          if (__any_sync(0xffffffffu, grow)) {
+          if (__any_sync(0xffffffffu, grow)) {  // same vote in both warps of the pair: same rows, same maxima
             // both halves of PV(jj-1) must have retired before O is rescaled
             ptx::mbar_wait(&pv_done[2 * x], (it - 1) & 1);
             ptx::mbar_wait(&pv_done[2 * x + 1], (it - 1) & 1);
             ptx::tc_fence_after();
             const float alpha = grow ? ptx::ex2_approx((m_run - m_new) * c) : 1.f;
 #pragma unroll 1
-            for (int h = 0; h < D; h += 16) {
+            for (int h = 0; h < 32; h += 16) {
               uint32_t o[16];
               ptx::tmem_ld_32x32b_x16(t_o + h, o);
               ptx::tmem_ld_wait();
@@ -628,9 +637,17 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
         const float mc = (m_run == -INFINITY) ? 0.f : m_run * c;
         const float2 nmc2 = make_float2(-mc, -mc);
         float2 rs[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};  // independent partial row sums (ILP)
-        auto exp_chunk = [&](int q, bool on) {
+        // this half of the P buffer is still being read by the PV of the previous tile until pv_done fires;
+        // that MMA was issued a whole exp phase ago, so this wait is normally already satisfied
+        if (it > 0) ptx::mbar_wait(&pv_done[2 * x + hc], (it - 1) & 1);
+        uint8_t* prow = my_p + r * 128;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
           uint32_t packed[16];
-          if (on) {
+          if (masked_tile && state[q] == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) packed[i] = 0u;
+          } else {
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
               const float2 t = ptx::fma2(make_float2(__uint_as_float(sr[q][i]), __uint_as_float(sr[q][i + 1])), c2, nmc2);
@@ -638,85 +655,60 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
               rs[(i >> 1) & 3] = ptx::add2(rs[(i >> 1) & 3], e);
               packed[i >> 1] = ptx::pack_bf16x2(e.x, e.y);
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) packed[i] = 0u;
           }
-          // half (q >> 1) of the P buffer is still being read by the PV of the previous tile until pv_done fires;
-          // that MMA was issued half a tile ago, so this wait is normally already satisfied
-          if ((q & 1) == 0 && it > 0) {
-            PF_B(pf_exp);
-            ptx::mbar_wait(&pv_done[2 * x + (q >> 1)], (it - 1) & 1);
-            PF_B(pf_pv);
-          }
-          uint8_t* prow = my_p + (q >> 1) * (BQ * 128) + r * 128;
-          const int u0 = (q & 1) ? 4 : 0;
 #pragma unroll
           for (int uu = 0; uu < 4; ++uu) {
-            const int unit = (u0 + uu) ^ (r & 7);
+            const int unit = (q * 4 + uu) ^ (r & 7);
             *reinterpret_cast<uint4*>(prow + unit * 16) =
                 make_uint4(packed[uu * 4], packed[uu * 4 + 1], packed[uu * 4 + 2], packed[uu * 4 + 3]);
           }
-          if (q & 1) {  // a 64-key half of P is complete: PV on it can start while the other half is computed
-            ptx::tc_fence_before();
-            ptx::fence_proxy_async_smem();
-            ptx::mbar_arrive(&p_full[2 * x + (q >> 1)]);
-          }
-        };
-        if (!masked_tile) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) exp_chunk(q, true);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) exp_chunk(q, state[q] != 0);
         }
+        // this 64-key half of P is complete: its PV can start while the other half is still being computed
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&p_full[2 * x + hc]);
         const float2 rsum = ptx::add2(ptx::add2(rs[0], rs[1]), ptx::add2(rs[2], rs[3]));
         l += rsum.x + rsum.y;
-        PF_B(pf_exp);
       }
       if (n_iter > 0) {
-        // epilogue of the block; meanwhile the issuer already runs S of the next block's first tile
+        // epilogue of the block; meanwhile the issuer already runs S of the next block's first tile.
+        // Row sum over both halves: second use of the exchange slots (the peer has read the last maximum:
+        // the extra barrier orders that read before this write).
+        ptx::named_bar_sync(pair_bar, 64);
+        *my_x = l;
+        ptx::named_bar_sync(pair_bar, 64);
+        l += *peer_x;
+        ptx::named_bar_sync(pair_bar, 64);  // both sums are read before the next block's first maximum lands
         ptx::mbar_wait(&o_full[2 * x + (bi & 1)], (bi >> 1) & 1);
         ptx::tc_fence_after();
-        float o[D];
-#pragma unroll
-        for (int h = 0; h < D; h += 32) {
-          uint32_t rr[32];
-          ptx::tmem_ld_32x32b_x32(t_o + h, rr);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[h + i] = __uint_as_float(rr[i]);
-        }
+        uint32_t rr[32];
+        ptx::tmem_ld_32x32b_x32(t_o, rr);
+        ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&o_free[2 * x + (bi & 1)]);
         if (valid) {
           const float inv = 1.f / l;
           const int64_t row = static_cast<int64_t>(seq_start) + qi;
-          __nv_bfloat16* dst = p.out + row * p.hidden + head * D;
+          __nv_bfloat16* dst = p.out + row * p.hidden + head * D + hc * 32;
 #pragma unroll
-          for (int i = 0; i < D; i += 8) {
+          for (int i = 0; i < 32; i += 8) {
             uint4 uo;
-            uo.x = ptx::pack_bf16x2(o[i] * inv, o[i + 1] * inv);
-            uo.y = ptx::pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv);
-            uo.z = ptx::pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv);
-            uo.w = ptx::pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv);
+            uo.x = ptx::pack_bf16x2(__uint_as_float(rr[i]) * inv, __uint_as_float(rr[i + 1]) * inv);
+            uo.y = ptx::pack_bf16x2(__uint_as_float(rr[i + 2]) * inv, __uint_as_float(rr[i + 3]) * inv);
+            uo.z = ptx::pack_bf16x2(__uint_as_float(rr[i + 4]) * inv, __uint_as_float(rr[i + 5]) * inv);
+            uo.w = ptx::pack_bf16x2(__uint_as_float(rr[i + 6]) * inv, __uint_as_float(rr[i + 7]) * inv);
             *reinterpret_cast<uint4*>(dst + i) = uo;
           }
-          if (p.lse) p.lse[static_cast<int64_t>(head) * p.total_tokens + row] = m_run * c + log2f(l);
+          if (p.lse && hc == 0) p.lse[static_cast<int64_t>(head) * p.total_tokens + row] = m_run * c + log2f(l);
         }
       }
     }
-#ifdef CM3P_ATTN_PROF
-    if (r == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
-      printf("attn prof x=%d blocks=%d tiles=%d total=%lld wait_s=%lld ld=%lld max=%lld wait_pv=%lld exp=%lld epilogue=%lld\n", x,
-             n_b, it, clock64() - pf_t0, pf_s, pf_ld, pf_max, pf_pv, pf_exp, pf_epi);
-#endif
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == SM_WARPS) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
   }
