@@ -313,9 +313,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, u
 // 17 instructions (two of them MUFU) instead of the 32 of the erff() form: the GeGLU GEMM epilogue evaluates
 // 256 of these per thread and tile and was issue-bound on them.  Max abs error of the GELU vs the erff() form
 // 2e-7 (relative 2e-4 where |gelu| > 1e-3), far below the bf16 rounding of its consumers.
-__device__ __forceinline__ float gelu_erf(float u) {
+// Phi(u) (the standard normal CDF) and exp(-u^2 / 2) from one evaluation
+__device__ __forceinline__ void normal_cdf_exp(float u, float& cdf, float& e) {
   const float x = fabsf(u) * 0.70710678118654752f;
-  float t, e;
+  float t;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, x, 1.0f)));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -1.4426950408889634f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
@@ -323,7 +324,19 @@ __device__ __forceinline__ float gelu_erf(float u) {
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
   const float hq = 0.5f * (p * t * e);  // (1 - erf(|x|)) / 2
-  return u * (u >= 0.f ? 1.0f - hq : hq);
+  cdf = u >= 0.f ? 1.0f - hq : hq;
+}
+__device__ __forceinline__ float gelu_erf(float u) {
+  float cdf, e;
+  normal_cdf_exp(u, cdf, e);
+  return u * cdf;
+}
+// gelu(u) and d/du gelu(u) = Phi(u) + u phi(u)
+__device__ __forceinline__ void gelu_erf_and_grad(float u, float& y, float& dy) {
+  float cdf, e;
+  normal_cdf_exp(u, cdf, e);
+  y = u * cdf;
+  dy = fmaf(u * 0.3989422804014327f, e, cdf);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -42,9 +42,9 @@ __device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, flo
 }
 // d/dx gelu_erf(x) = Phi(x) + x * phi(x)
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float y, dy;
+  ptx::gelu_erf_and_grad(x, y, dy);
+  return dy;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -225,9 +225,10 @@ geglu_bwd_kernel(const __nv_bfloat16* __restrict__ ug, const __nv_bfloat16* __re
     unpack8(*reinterpret_cast<const uint4*>(dh + r * I + c), d);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float ge = ptx::gelu_erf(u[k]);
+      float ge, gd;
+      ptx::gelu_erf_and_grad(u[k], ge, gd);
       hh[k] = ge * g[k];
-      du[k] = d[k] * g[k] * gelu_erf_grad(u[k]);
+      du[k] = d[k] * g[k] * gd;
       dgt[k] = d[k] * ge;
     }
     *reinterpret_cast<uint4*>(dug + r * 2 * I + ucol) = pack8(du);

@@ -119,7 +119,20 @@ def bench_ln(T, H):
                           gbs=round(2.0 * T * H * 2 / t / 1e9, 1))), flush=True)
 
 
+def bench_geglu_bwd(T, I):
+    ug = torch.randn(T, 2 * I, device=DEV).bfloat16()
+    dh = torch.randn(T, I, device=DEV).bfloat16()
+    dug, h = torch.empty_like(ug), torch.empty_like(dh)
+    t = timeit(lambda: ops.geglu_bwd(ug, dh, dug=dug, h=h))
+    print(json.dumps(dict(kernel="geglu_bwd", T=T, I=I, ms=round(t * 1e3, 4),
+                          gbs=round(6.0 * T * I * 2 / t / 1e9, 1))), flush=True)
+
+
 if __name__ == "__main__":
+    if "rowwise" in sys.argv[1:]:
+        bench_geglu_bwd(343608, 1152)
+        bench_ln(343608, 768)
+        sys.exit(0)
     if "attn" in sys.argv[1:]:
         B = int(os.environ.get("CM3P_BENCH_B", "64"))  # 256 = the train step's windows per GPU
         if B != 64:
