@@ -244,13 +244,44 @@ def _bench_workload(workload, args, dist, dev, world, rank, local_rank) -> dict 
         return {"quick": True, "workload": workload, "ms_per_step": round(ms_step, 3),
                 "gpu_launches": int(launches)} if rank == 0 else None
 
-    # ---- end-to-end through the public API with pinned host inputs and a D2H read of the result
+    # ---- end-to-end through the public API with pinned host inputs and a D2H read of the result.
+    # Every step copies ITS inputs host -> device and its result device -> host inside the timed region; as
+    # in any serving / training input pipeline the copies are double-buffered: the inputs of step i+1 travel on
+    # a copy stream while step i computes, and the host reads the result of step i (from pinned memory, after
+    # its copy event) once step i+1 has been enqueued, so the host never idles the GPU.
+    copy_stream = torch.cuda.Stream(device=dev)
+    result_shape = () if train else (B, cfg.projection_dim)
+    result_host = [torch.empty(result_shape, dtype=torch.float32).pin_memory() for _ in range(2)]
+    pipe = {"i": 0, "pending": None, "last": None}
+
+    def upload():
+        with torch.cuda.stream(copy_stream):
+            feed = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return feed, ev
+
+    pipe["next"] = upload()
+
     def e2e_step():
-        feed = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        feed, ev = pipe["next"]
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        for v in feed.values():
+            v.record_stream(cur)
+        pipe["next"] = upload()  # inputs of the following step, under this step's compute
         out = step(feed)
-        if train:
-            return out.loss.detach().float().cpu()
-        return out.beatmap_embeds.float().cpu()
+        res = out.loss.detach().float() if train else out.beatmap_embeds.float()
+        slot = pipe["i"] & 1
+        result_host[slot].copy_(res, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(cur)
+        if pipe["pending"] is not None:  # read the previous step's result on the host
+            prev_slot, prev_done = pipe["pending"]
+            prev_done.synchronize()
+            pipe["last"] = float(result_host[prev_slot].flatten()[0])
+        pipe["pending"] = (slot, done)
+        pipe["i"] += 1
 
     for _ in range(2):
         e2e_step()
