@@ -291,28 +291,30 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params 
 //   so a query row is shared by two threads that exchange their row maximum through shared memory once per
 //   tile (four light warps per scheduler hide exp / FMA latency that two heavy ones could not);
 //   warp 16 TMA producer (+ TMEM alloc), warps 17 / 18 MMA issuers of tile A / B, warp 19 idle.
-// K/V tiles (128 rows) stream through a 3-stage ring shared by both Q tiles; Q and the O accumulators are
-// double-buffered across blocks, so the next block's loads and first S GEMM run under the current block's
-// epilogue.  Per Q tile the pipeline is decoupled in both directions: S_x(t+1) is issued as soon as group x
-// has copied S_x(t) into registers (s_free), and PV_x(t) is issued per 64-key half of P as soon as the four
-// warps of that half have written it (p_full / pv_done per half), so neither the group nor the tensor pipe
-// waits for the other in steady state.
+// K/V tiles (128 rows) stream through a 4-stage ring shared by both Q tiles; Q is double-buffered across
+// blocks, so the next block's loads and first S GEMM run under the current block's epilogue.  Per Q tile the
+// pipeline is decoupled in both directions: S_x(t+1) is issued as soon as group x has copied S_x(t) into
+// registers (s_free), and PV_x(t) is issued per 64-key half of P as soon as the four warps of that half have
+// written it (p_full / pv_done per half), so neither the group nor the tensor pipe waits for the other in
+// steady state.  P never touches shared memory: the softmax threads write it to TMEM as packed bf16
+// (tcgen05.st, thread = row = lane) and PV reads its A operand from TMEM; with P in shared memory a K tile
+// moved 256 KB through the SM's 128 B/clk (S and PV operand reads, P writes, TMA): 2048 of ~3000 clk.
 // O_A / O_B stay in TMEM for the whole KV loop (tcgen05.mma accumulate); the running maximum is only raised
 // when it grows by more than 2^8 (then each warp rescales its 32 rows x 32 columns of O in TMEM with
 // tcgen05.ld/st), so the common iteration is: one TMEM read of 64 scores, max (3-input), exchange, exp2
-// (packed f32x2 arithmetic, a quarter of the exponentials as a polynomial on the FMA pipe), bf16 pack into
-// swizzled smem, mbarrier arrive.  Masking (-inf) is only applied on tiles that need it (tail, window band).
-// TMEM columns: S_A [0,128)  S_B [128,256)  O_A / O_B of even blocks [256,384), of odd blocks [384,512).
+// (packed f32x2 arithmetic, a quarter of the exponentials as a polynomial on the FMA pipe), bf16 pack,
+// tcgen05.st, mbarrier arrive.  Masking (-inf) is only applied on tiles that need it (tail, window band).
+// TMEM columns: S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)  P_A [384,448)  P_B [448,512).
 namespace v2 {
 
-constexpr int KV_STAGES2 = 3;
+constexpr int KV_STAGES2 = 4;
 constexpr int THREADS2 = 640;  // 5 warpgroups: softmax A (2), softmax B (2), {TMA, MMA issuer A, MMA issuer B, idle}
 constexpr int SM_WARPS = 16;    // softmax warps: 8 per Q tile = 4 TMEM lane quadrants x 2 column halves
 constexpr int REG_SM = 104, REG_AUX2 = 64;
-constexpr int SMEM_TILES2 = 2 * 2 * Q_BYTES + KV_STAGES2 * 2 * KV_TILE_BYTES + 2 * P_BYTES;  // 64 + 96 + 64 = 224 KB
+constexpr int SMEM_TILES2 = 2 * 2 * Q_BYTES + KV_STAGES2 * 2 * KV_TILE_BYTES;  // 64 + 128 = 192 KB
 constexpr int SMEM_XCHG = 2 * 2 * BQ * 4;  // row maxima / row sums exchanged between the two warps of a row
 constexpr int SMEM_BYTES2 = SMEM_TILES2 + 512 + SMEM_XCHG;
-constexpr uint32_t TM_S = 0, TM_O = 256;  // S: + 128 x;  O: + 128 (block parity) + 64 x
+constexpr uint32_t TM_S = 0, TM_O = 256, TM_P = 384;  // S: + 128 x;  O: + 64 x;  P (bf16 pairs): + 64 x
 constexpr float RESCALE_LOG2 = 8.0f;
 constexpr int MAX_BLOCKS_PER_CTA = 16;
 
@@ -353,21 +355,20 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
   if (n_b <= 0) return;
 
   uint8_t* smem_q = smem;                                   // [2 blocks][2 tiles][16 KB]
-  uint8_t* smem_k = smem + 4 * Q_BYTES;                     // [3][16 KB]
-  uint8_t* smem_v = smem_k + KV_STAGES2 * KV_TILE_BYTES;    // [3][16 KB]
-  uint8_t* smem_p = smem_v + KV_STAGES2 * KV_TILE_BYTES;    // [2][32 KB]
+  uint8_t* smem_k = smem + 4 * Q_BYTES;                     // [4][16 KB]
+  uint8_t* smem_v = smem_k + KV_STAGES2 * KV_TILE_BYTES;    // [4][16 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_TILES2);
   uint64_t* q_full = bars;                 // [2]
   uint64_t* q_empty = q_full + 2;          // [2] 2 arrivals: both issuers have retired their S MMAs of the block
-  uint64_t* kv_full = q_empty + 2;         // [3]
-  uint64_t* kv_empty = kv_full + KV_STAGES2;  // [3] 2 arrivals (both issuers)
+  uint64_t* kv_full = q_empty + 2;         // [4]
+  uint64_t* kv_empty = kv_full + KV_STAGES2;  // [4] 2 arrivals (both issuers)
   uint64_t* s_full = kv_empty + KV_STAGES2;   // [2]
   uint64_t* s_free = s_full + 2;           // [2] 8 arrivals (one per warp): S_x is in registers
-  uint64_t* p_full = s_free + 2;           // [2][2] per 64-key half of P_x, 128 arrivals each
+  uint64_t* p_full = s_free + 2;           // [2][2] per 64-key half of P_x (in TMEM), 128 arrivals each
   uint64_t* pv_done = p_full + 4;          // [2][2] PV_x(u, half) retired: that half of the P_x buffer is reusable
-  uint64_t* o_full = pv_done + 4;          // [2][2] (x, block parity)
-  uint64_t* o_free = o_full + 4;           // [2][2] 8 arrivals: O_x of the block is in registers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 4);
+  uint64_t* o_full = pv_done + 4;          // [2] per Q tile
+  uint64_t* o_free = o_full + 2;           // [2] 8 arrivals: O_x of the block is in registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
   float* smem_xchg = reinterpret_cast<float*>(smem + SMEM_TILES2 + 512);  // [2 Q tiles][2 halves][128 rows]
 
   if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
@@ -386,6 +387,8 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
     for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(&p_full[i], 128);
       ptx::mbar_init(&pv_done[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&o_full[i], 1);
       ptx::mbar_init(&o_free[i], 8);
     }
@@ -438,7 +441,9 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
       const int x = warp - (SM_WARPS + 1);
       const uint32_t idesc_s = ptx::umma_idesc_bf16(BQ, BKV, 0, 0);
       const uint32_t idesc_o = ptx::umma_idesc_bf16(BQ, D, 0, 1);  // V is MN-major
-      const uint32_t p_base = ptx::smem_u32(smem_p + x * P_BYTES);
+      const uint32_t t_p = tmem_base + TM_P + x * 64;
+      constexpr uint32_t HI = ptx::umma_desc_hi_sw128(1024);
+      int blk = 0;  // blocks of this Q tile that had work so far (phase of its o_full / o_free)
       const uint32_t t_s = tmem_base + TM_S + x * 128;
       int ring_base = 0;  // ring position of tile 0 of the current block
       int it = 0;         // tiles this Q-tile stream has consumed so far (phase of its s / p barriers)
@@ -448,7 +453,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
         const int lo_x = br.lo[x], hi_x = br.hi[x];
         const int qb = bi & 1;
         const uint32_t q_addr = ptx::smem_u32(smem_q + qb * 2 * Q_BYTES + x * Q_BYTES);
-        const uint32_t t_o = tmem_base + TM_O + qb * 128 + x * 64;
+        const uint32_t t_o = tmem_base + TM_O + x * 64;
         auto issue_s = [&](int t) {
           const int r = ring_base + t;
           const int s = r % KV_STAGES2;
@@ -474,10 +479,11 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
         for (int u = 0; u < lo_x; ++u) ack(u);
         if (hi_x > lo_x) {
           // the S buffer was drained when the group loaded the last tile of the previous block (s_free of tile
-          // it-1 has completed long ago); O_x of two blocks ago must have been copied out
-          ptx::mbar_wait(&o_free[2 * x + qb], ((bi >> 1) & 1) ^ 1);
-          ptx::tc_fence_after();
+          // it-1 has completed long ago)
           issue_s(lo_x);
+          // O_x of the previous block must have been copied out before the first PV overwrites it
+          if (blk > 0) ptx::mbar_wait(&o_free[x], (blk - 1) & 1);
+          ptx::tc_fence_after();
         } else if (leader) {
           ptx::umma_commit(&q_empty[qb]);
         }
@@ -488,28 +494,27 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
             ptx::mbar_wait(&s_free[x], it & 1);
             issue_s(t + 1);
           }
-          const uint32_t v_base = ptx::smem_u32(smem_v + ((ring_base + t) % KV_STAGES2) * KV_TILE_BYTES);
+          // V tile as the MN-major B operand (LBO = 8192: distance of 64-element MN chunks, unused)
+          const uint32_t v_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_v + ((ring_base + t) % KV_STAGES2) * KV_TILE_BYTES), 8192);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            ptx::mbar_wait(&p_full[2 * x + h], it & 1);  // this half of P_x(t) is in smem (O_x rescaled if needed)
+            ptx::mbar_wait(&p_full[2 * x + h], it & 1);  // this half of P_x(t) is in TMEM (O_x rescaled if needed)
             ptx::tc_fence_after();
-            const uint32_t p_addr = p_base + h * (BQ * 128);
-            const uint32_t v_addr = v_base + h * (64 * 128);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int k = 0; k < 4; ++k)  // 16-key steps: 8 TMEM columns of P (A operand), 16 rows of V
               if (leader)
-                ptx::umma_bf16(t_o, ptx::umma_smem_desc_sw128(p_addr + k * 32, 16, 1024),
-                               ptx::umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_o,
-                               (j | h | k) != 0 ? 1u : 0u);
+                ptx::umma_bf16_ts(t_o, t_p + (4 * h + k) * 8, v_lo + (((4 * h + k) * 2048) >> 4), HI, idesc_o,
+                                  (j | h | k) != 0 ? 1u : 0u);
             if (leader) {
               ptx::umma_commit(&pv_done[2 * x + h]);
-              if (h == 1 && t + 1 == hi_x) ptx::umma_commit(&o_full[2 * x + qb]);
+              if (h == 1 && t + 1 == hi_x) ptx::umma_commit(&o_full[x]);
             }
           }
           if (leader) ptx::umma_commit(&kv_empty[(ring_base + t) % KV_STAGES2]);
         }
         for (int u = max(hi_x, lo_x); u < br.U; ++u) ack(u);
         ring_base += br.U;
+        if (hi_x > lo_x) ++blk;
       }
     }
   } else {
@@ -525,7 +530,8 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
     const int r = (warp & 3) * 32 + lane;  // query row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t t_s = tmem_base + TM_S + x * 128 + lane_off + hc * 64;
-    uint8_t* my_p = smem_p + x * P_BYTES + hc * (BQ * 128);  // this half's 64-key K block of P_x
+    const uint32_t t_p = tmem_base + TM_P + x * 64 + lane_off + hc * 32;  // this thread's 64 keys of P_x as bf16 pairs
+    int blk = 0;  // blocks with work so far (phase of o_full / o_free)
     float* my_x = smem_xchg + (x * 2 + hc) * BQ + r;
     const float* peer_x = smem_xchg + (x * 2 + (hc ^ 1)) * BQ + r;
     const int pair_bar = 1 + x * 4 + (warp & 3);  // named barrier of the two warps that share these 32 rows
@@ -537,7 +543,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
       const BlockRange br = block_range(q0, len, p.window);
       const int qi = q0 + x * BQ + r;
       const bool valid = qi < len;
-      const uint32_t t_o = tmem_base + TM_O + (bi & 1) * 128 + x * 64 + lane_off + hc * 32;  // this thread's 32 of the 64 O columns
+      const uint32_t t_o = tmem_base + TM_O + x * 64 + lane_off + hc * 32;  // this thread's 32 of the 64 O columns
       float m_run = -INFINITY, l = 0.f;
       const int lo_x = br.lo[x];
       const int n_iter = br.hi[x] - lo_x;
@@ -637,10 +643,10 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
         const float mc = (m_run == -INFINITY) ? 0.f : m_run * c;
         const float2 nmc2 = make_float2(-mc, -mc);
         float2 rs[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};  // independent partial row sums (ILP)
-        // this half of the P buffer is still being read by the PV of the previous tile until pv_done fires;
-        // that MMA was issued a whole exp phase ago, so this wait is normally already satisfied
+        // this half of P_x in TMEM is still being read by the PV of the previous tile until pv_done fires; that
+        // MMA was issued a whole exp phase ago, so this wait is normally already satisfied
         if (it > 0) ptx::mbar_wait(&pv_done[2 * x + hc], (it - 1) & 1);
-        uint8_t* prow = my_p + r * 128;
+        ptx::tc_fence_after();
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           uint32_t packed[16];
@@ -656,16 +662,11 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
               packed[i >> 1] = ptx::pack_bf16x2(e.x, e.y);
             }
           }
-#pragma unroll
-          for (int uu = 0; uu < 4; ++uu) {
-            const int unit = (q * 4 + uu) ^ (r & 7);
-            *reinterpret_cast<uint4*>(prow + unit * 16) =
-                make_uint4(packed[uu * 4], packed[uu * 4 + 1], packed[uu * 4 + 2], packed[uu * 4 + 3]);
-          }
+          ptx::tmem_st_32x32b_x16(t_p + q * 16, packed);
         }
+        ptx::tmem_st_wait();
         // this 64-key half of P is complete: its PV can start while the other half is still being computed
         ptx::tc_fence_before();
-        ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&p_full[2 * x + hc]);
         const float2 rsum = ptx::add2(ptx::add2(rs[0], rs[1]), ptx::add2(rs[2], rs[3]));
         l += rsum.x + rsum.y;
@@ -679,14 +680,15 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
         ptx::named_bar_sync(pair_bar, 64);
         l += *peer_x;
         ptx::named_bar_sync(pair_bar, 64);  // both sums are read before the next block's first maximum lands
-        ptx::mbar_wait(&o_full[2 * x + (bi & 1)], (bi >> 1) & 1);
+        ptx::mbar_wait(&o_full[x], blk & 1);
         ptx::tc_fence_after();
         uint32_t rr[32];
         ptx::tmem_ld_32x32b_x32(t_o, rr);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&o_free[2 * x + (bi & 1)]);
+        if (lane == 0) ptx::mbar_arrive(&o_free[x]);
+        ++blk;
         if (valid) {
           const float inv = 1.f / l;
           const int64_t row = static_cast<int64_t>(seq_start) + qi;

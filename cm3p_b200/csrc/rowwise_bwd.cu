@@ -55,7 +55,7 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 // GATHER variant = embedding layer: the row is re-gathered exactly as in embed_gather_ln_kernel and
 // dx is scattered: audio rows -> d_audio[slot] (unique), token rows -> atomic add into d_tok[id].
 template <bool GATHER, int NV>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                      const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dres,
                      __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, int64_t rows, int H, float eps,
@@ -81,37 +81,57 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
     *reinterpret_cast<float4*>(my_dg + (lane + i * 32) * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float invH = 1.f / H;
-  for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp; row < rows; row += static_cast<int64_t>(gridDim.x) * 8) {
+  // Software pipeline: the loads of the warp's NEXT row are issued before the current row is reduced, so a warp
+  // always has a row of loads in flight (one row at a time left the memory system idle during the two shuffle
+  // rounds and the dgamma update: 4.0 TB/s).
+  const int64_t row_step = static_cast<int64_t>(gridDim.x) * 8;
+  uint4 nx[NV], ng[NV], nr[NV];
+  int nslot = -1;
+  int64_t nid = 0;
+  auto load_row = [&](int64_t row) {
     const __nv_bfloat16* src;
-    int slot = -1;
-    int64_t id = 0;
+    nslot = -1;
+    nid = 0;
     if constexpr (GATHER) {
       const int64_t flat = src_index ? src_index[row] : row;
-      slot = audio_slot ? audio_slot[row] : -1;
-      if (slot >= 0 && audio_embeds) {
-        src = audio_embeds + static_cast<int64_t>(slot) * H;
+      nslot = audio_slot ? audio_slot[row] : -1;
+      if (nslot >= 0 && audio_embeds) {
+        src = audio_embeds + static_cast<int64_t>(nslot) * H;
       } else {
-        slot = -1;
-        id = ids[flat];
-        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
-        src = tok_emb + id * H;
+        nslot = -1;
+        nid = ids[flat];
+        nid = nid < 0 ? 0 : (nid >= vocab ? vocab - 1 : nid);
+        src = tok_emb + nid * H;
       }
     } else {
       src = x + row * H;
     }
-    uint4 px[NV], pg[NV], pr[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + i * 32;
-      px[i] = pg[i] = pr[i] = make_uint4(0, 0, 0, 0);
+      nx[i] = ng[i] = nr[i] = make_uint4(0, 0, 0, 0);
       if (vi < nvec) {
-        px[i] = *reinterpret_cast<const uint4*>(src + vi * 8);
-        pg[i] = *reinterpret_cast<const uint4*>(dy + row * H + vi * 8);
+        nx[i] = *reinterpret_cast<const uint4*>(src + vi * 8);
+        ng[i] = *reinterpret_cast<const uint4*>(dy + row * H + vi * 8);
         if constexpr (!GATHER) {
-          if (dres) pr[i] = *reinterpret_cast<const uint4*>(dres + row * H + vi * 8);
+          if (dres) nr[i] = *reinterpret_cast<const uint4*>(dres + row * H + vi * 8);
         }
       }
     }
+  };
+  const int64_t first_row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  if (first_row < rows) load_row(first_row);
+  for (int64_t row = first_row; row < rows; row += row_step) {
+    uint4 px[NV], pg[NV], pr[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      px[i] = nx[i];
+      pg[i] = ng[i];
+      pr[i] = nr[i];
+    }
+    const int slot = nslot;
+    const int64_t id = nid;
+    if (row + row_step < rows) load_row(row + row_step);
     float s = 0.f, q = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -517,7 +537,7 @@ int layernorm_bwd(const void* x, const void* dy, const float* gamma, const void*
                MAXV * 256);
   if (rows == 0) return kOk;
   const int64_t want = (rows + 7) / 8;
-  const int grid = static_cast<int>(want < 6LL * num_sms() ? want : 6LL * num_sms());
+  const int grid = static_cast<int>(want < 4LL * num_sms() ? want : 4LL * num_sms());  // 2 waves of 2 CTAs per SM
 #define CM3P_LN_BWD(NV)                                                                                             \
   layernorm_bwd_kernel<false, NV><<<grid, 256, 0, stream>>>(                                                        \
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), gamma,                 \
@@ -540,7 +560,7 @@ int embed_gather_ln_bwd(const int64_t* ids, const int32_t* src_index, const int3
                MAXV * 256);
   if (rows == 0) return kOk;
   const int64_t want = (rows + 7) / 8;
-  const int grid = static_cast<int>(want < 6LL * num_sms() ? want : 6LL * num_sms());
+  const int grid = static_cast<int>(want < 4LL * num_sms() ? want : 4LL * num_sms());  // 2 waves of 2 CTAs per SM
 #define CM3P_LN_BWD(NV)                                                                                            \
   layernorm_bwd_kernel<true, NV><<<grid, 256, 0, stream>>>(                                                        \
       nullptr, reinterpret_cast<const __nv_bfloat16*>(dy), gamma, nullptr, nullptr, dgamma, rows, H, eps, ids,     \

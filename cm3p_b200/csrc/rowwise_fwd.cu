@@ -82,14 +82,91 @@ __device__ __forceinline__ void ln_row(const __nv_bfloat16* __restrict__ src, co
   }
 }
 
-__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+// NR rows per warp with every load issued before the first use: at 6.4 TB/s the memory system needs ~80 KB in
+// flight per SM, which one 1.5 KB row per warp (plus its dependent shuffle reductions) does not sustain
+// (measured 4.6 TB/s with one row per warp).
+#ifndef CM3P_LN_NR
+#define CM3P_LN_NR 2    // rows per warp
+#define CM3P_LN_MINB 3  // CTAs per SM the register budget is sized for (measured best: 2 rows, 3 CTAs -> 5.8 TB/s)
+#endif
+template <int NR>
+__global__ void __launch_bounds__(256, CM3P_LN_MINB) layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
                                                             const float* __restrict__ gamma,
                                                             __nv_bfloat16* __restrict__ y, float2* __restrict__ stats,
                                                             int64_t rows, int H, float eps) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  ln_row(x + row * H, gamma, y + row * H, stats ? stats + row : nullptr, H, eps, lane);
+  const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * NR;
+  if (row0 >= rows) return;
+  const int nvec = H >> 3;
+  uint4 raw[NR][MAXV];
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = lane + i * 32;
+      raw[r][i] = make_uint4(0, 0, 0, 0);
+      if (vi < nvec && row0 + r < rows) raw[r][i] = *reinterpret_cast<const uint4*>(x + (row0 + r) * H + vi * 8);
+    }
+  float s[NR], q[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    s[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      float f[8];
+      unpack8(raw[r][i], f);  // zero beyond the row
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s[r] += f[k];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < NR; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const float mean = s[r] / H;
+    s[r] = mean;
+    q[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      if (lane + i * 32 < nvec) {
+        float f[8];
+        unpack8(raw[r][i], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float d = f[k] - mean;
+          q[r] += d * d;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < NR; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    if (row0 + r >= rows) break;
+    const float mean = s[r];
+    const float rstd = rsqrtf(q[r] / H + eps);
+    if (stats && lane == 0) stats[row0 + r] = make_float2(mean, rstd);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        const float4 g0 = *reinterpret_cast<const float4*>(gamma + vi * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(gamma + vi * 8 + 4);
+        float f[8], o[8];
+        unpack8(raw[r][i], f);
+        o[0] = (f[0] - mean) * rstd * g0.x; o[1] = (f[1] - mean) * rstd * g0.y;
+        o[2] = (f[2] - mean) * rstd * g0.z; o[3] = (f[3] - mean) * rstd * g0.w;
+        o[4] = (f[4] - mean) * rstd * g1.x; o[5] = (f[5] - mean) * rstd * g1.y;
+        o[6] = (f[6] - mean) * rstd * g1.z; o[7] = (f[7] - mean) * rstd * g1.w;
+        *reinterpret_cast<uint4*>(y + (row0 + r) * H + vi * 8) = pack8(o);
+      }
+    }
+  }
 }
 
 // x0[t] = LN( is_audio(t) ? audio_embeds[audio_slot[t]] : tok_emb[ids[src_index[t]]] )
@@ -345,7 +422,8 @@ int layernorm_fwd(const void* x, const float* gamma, void* y, float* stats, int6
   CM3P_REQUIRE(H % 8 == 0 && H <= MAXV * 256, kBadShape, "layernorm: hidden size %d must be a multiple of 8 and <= %d",
                H, MAXV * 256);
   if (rows == 0) return kOk;
-  layernorm_fwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
+  constexpr int NR = CM3P_LN_NR;
+  layernorm_fwd_kernel<NR><<<static_cast<unsigned>((rows + 8 * NR - 1) / (8 * NR)), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), gamma, reinterpret_cast<__nv_bfloat16*>(y),
       reinterpret_cast<float2*>(stats), rows, H, eps);
   CM3P_CUDA_TRY(cudaGetLastError());

@@ -119,6 +119,18 @@ def bench_ln(T, H):
                           gbs=round(2.0 * T * H * 2 / t / 1e9, 1))), flush=True)
 
 
+def bench_ln_bwd(T, H):
+    x = torch.randn(T, H, device=DEV).bfloat16()
+    dy = torch.randn(T, H, device=DEV).bfloat16()
+    dres = torch.randn(T, H, device=DEV).bfloat16()
+    g = torch.ones(H, device=DEV)
+    dx = torch.empty_like(x)
+    dgamma = torch.zeros(H, device=DEV)
+    t = timeit(lambda: ops.layernorm_bwd(x, dy, g, 1e-5, dres=dres, dx=dx, dgamma=dgamma))
+    print(json.dumps(dict(kernel="layernorm_bwd", T=T, H=H, ms=round(t * 1e3, 4),
+                          gbs=round(4.0 * T * H * 2 / t / 1e9, 1))), flush=True)
+
+
 def bench_geglu_bwd(T, I):
     ug = torch.randn(T, 2 * I, device=DEV).bfloat16()
     dh = torch.randn(T, I, device=DEV).bfloat16()
@@ -132,6 +144,7 @@ if __name__ == "__main__":
     if "rowwise" in sys.argv[1:]:
         bench_geglu_bwd(343608, 1152)
         bench_ln(343608, 768)
+        bench_ln_bwd(343608, 768)
         sys.exit(0)
     if "attn" in sys.argv[1:]:
         B = int(os.environ.get("CM3P_BENCH_B", "64"))  # 256 = the train step's windows per GPU
