@@ -377,6 +377,11 @@ def _bench_workload(workload, args, dist, dev, world, rank, local_rank) -> dict 
                                "peak": peaks["tflops"], "unit": "TFLOP/s",
                                "frac": round(attn_flops / (attn_ms * 1e-3) / 1e12 / peaks["tflops"], 4) if attn_ms > 0 else 0.0,
                                "flops": "algorithmic: 4*l*keys*64 per head forward, 10*l*keys*64 backward (5 GEMMs)",
+                               "note": ("head_dim 64: a 128x128 tile needs 16384 exp2 = 1024 clk of the 16/clk/SM "
+                                        "MUFU against 512 clk (forward) / 1280 clk (backward, 5 GEMMs; 7 executed by "
+                                        "the two-kernel backward, which also exponentiates twice) of tcgen05 MMA, so "
+                                        "the exp unit caps the forward at 0.5 of the tensor peak; window layers "
+                                        "additionally compute 256 keys per row for a 129-key band"),
                                "launches_per_step": len(attn_events), "share_of_step": round(attn_ms / ms_step, 3)},
         "clocks": clocks,
     }

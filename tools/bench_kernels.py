@@ -119,6 +119,24 @@ def bench_ln(T, H):
                           gbs=round(2.0 * T * H * 2 / t / 1e9, 1))), flush=True)
 
 
+def bench_gemm_bwd(T, N, K, name=""):
+    """The two backward GEMMs of a Linear [N, K] over T tokens: dgrad dx = dy.W and wgrad dW += dy^T.x (split-K)."""
+    dy = torch.randn(T, N, device=DEV).bfloat16()
+    x = torch.randn(T, K, device=DEV).bfloat16()
+    w = (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
+    dx = torch.empty(T, K, device=DEV, dtype=torch.bfloat16)
+    dw = torch.zeros(N, K, device=DEV)
+    flops = 2.0 * T * N * K
+    t = timeit(lambda: ops.gemm(dy, w, trans_b=True, out=dx))
+    t_ref = timeit(lambda: torch.matmul(dy, w))
+    print(json.dumps(dict(kernel=f"dgrad{name}", T=T, N=N, K=K, ms=round(t * 1e3, 4), tflops=round(flops / t / 1e12, 1),
+                          cublas_tflops=round(flops / t_ref / 1e12, 1))), flush=True)
+    t = timeit(lambda: ops.gemm(dy, x, trans_a=True, trans_b=True, epilogue=ops.EPI_SCALE_F32, accumulate=True, out=dw))
+    t_ref = timeit(lambda: torch.matmul(dy.t(), x))
+    print(json.dumps(dict(kernel=f"wgrad{name}", T=T, N=N, K=K, ms=round(t * 1e3, 4), tflops=round(flops / t / 1e12, 1),
+                          cublas_tflops=round(flops / t_ref / 1e12, 1))), flush=True)
+
+
 def bench_ln_bwd(T, H):
     x = torch.randn(T, H, device=DEV).bfloat16()
     dy = torch.randn(T, H, device=DEV).bfloat16()
@@ -141,6 +159,13 @@ def bench_geglu_bwd(T, I):
 
 
 if __name__ == "__main__":
+    if "gemmbwd" in sys.argv[1:]:
+        T = 343608
+        bench_gemm_bwd(T, 2304, 768, "_wqkv")
+        bench_gemm_bwd(T, 768, 768, "_wo")
+        bench_gemm_bwd(T, 2304, 768, "_wi")
+        bench_gemm_bwd(T, 768, 1152, "_wo2")
+        sys.exit(0)
     if "rowwise" in sys.argv[1:]:
         bench_geglu_bwd(343608, 1152)
         bench_ln(343608, 768)
