@@ -73,36 +73,6 @@ __device__ __forceinline__ void unpack8f(const uint4& u, float* f) {
   t = ptx::unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
   t = ptx::unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
 }
-// accumulator row (64 fp32 columns, already in registers) -> optional inverse RoPE -> bf16 -> global
-__device__ __forceinline__ void store_grad_regs(const uint32_t (&r1)[32], const uint32_t (&r2)[32], __nv_bfloat16* dst,
-                                                const float2* cs) {
-  float o1[32], o2[32];
-  if (cs) {
-    const float4* tab = reinterpret_cast<const float4*>(cs);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const float4 f = __ldg(tab + k);
-      const float a0 = __uint_as_float(r1[2 * k]), b0 = __uint_as_float(r2[2 * k]);
-      const float a1 = __uint_as_float(r1[2 * k + 1]), b1 = __uint_as_float(r2[2 * k + 1]);
-      o1[2 * k] = a0 * f.x + b0 * f.y;
-      o2[2 * k] = b0 * f.x - a0 * f.y;
-      o1[2 * k + 1] = a1 * f.z + b1 * f.w;
-      o2[2 * k + 1] = b1 * f.z - a1 * f.w;
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      o1[k] = __uint_as_float(r1[k]);
-      o2[k] = __uint_as_float(r2[k]);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    *reinterpret_cast<uint4*>(dst + i * 8) = pack8f(o1 + i * 8);
-    *reinterpret_cast<uint4*>(dst + 32 + i * 8) = pack8f(o2 + i * 8);
-  }
-}
-
 // Allowed columns [a,b) of one row inside a 32-column slice whose column 0 sits at sequence position t0,
 // and the state of the slice for the row's warp (0 skip, 1 mask per element, 2 no mask).
 struct Band {
@@ -219,7 +189,7 @@ attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
   uint64_t* dz_full = s_free + 1;          // [slice] 128 arrivals: a 32-column slice of dZ is in TMEM
   uint64_t* dz_free = dz_full + 4;         // [slice] the dQ MMAs that read the slice have retired
   uint64_t* acc_full = dz_free + 4;        // [2]
-  uint64_t* acc_free = acc_full + 2;       // [2] 8 arrivals: the accumulator has been copied out
+  uint64_t* acc_free = acc_full + 2;       // [2] 16 arrivals: the accumulator has been copied out
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
 
   if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
@@ -229,7 +199,7 @@ attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
       ptx::mbar_init(&q_full[i], 33);
       ptx::mbar_init(&q_empty[i], 1);
       ptx::mbar_init(&acc_full[i], 1);
-      ptx::mbar_init(&acc_free[i], 8);
+      ptx::mbar_init(&acc_free[i], EW_WARPS);
     }
     for (int s = 0; s < NS; ++s) {
       ptx::mbar_init(&kv_full[s], 1);
@@ -382,16 +352,16 @@ attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
     const uint32_t t_dz = tmem_base + TM_DZ + lane_off + c * (HC / 2);
     const uint32_t t_s = tmem_base + TM_S + lane_off + c * HC;
     const uint32_t t_dp = tmem_base + TM_DP + lane_off + c * HC;
-    // dQ of outer tile `po`: slices 0 / 1 each take 16 + 16 columns (a RoPE pair is columns k and k + 32)
+    // dQ of outer tile `po`: every slice takes 8 + 8 columns (a RoPE pair is columns k and k + 32), so the
+    // write-out costs all 16 warps the same short detour
     auto write_out = [&](int po) {
-      if (c >= 2) return;
       const int ab = po & 1;
       ptx::mbar_wait(&acc_full[ab], (po >> 1) & 1);
       ptx::tc_fence_after();
-      uint32_t r1[16], r2[16];
-      const uint32_t t_acc = tmem_base + TM_DQ + ab * 64 + lane_off + c * 16;
-      ptx::tmem_ld_32x32b_x16(t_acc, r1);
-      ptx::tmem_ld_32x32b_x16(t_acc + 32, r2);
+      uint32_t r1[8], r2[8];
+      const uint32_t t_acc = tmem_base + TM_DQ + ab * 64 + lane_off + c * 8;
+      ptx::tmem_ld_32x32b_x8(t_acc, r1);
+      ptx::tmem_ld_32x32b_x8(t_acc + 32, r2);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
@@ -399,11 +369,11 @@ attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
       const int qi = (o_begin + po) * BT + t;
       if (qi >= len) return;
       const int64_t row = static_cast<int64_t>(seq_start) + qi;
-      float o1[16], o2[16];
+      float o1[8], o2[8];
       if (p.rope_table && p.positions) {
-        const float4* tab = reinterpret_cast<const float4*>(p.rope_table + static_cast<int64_t>(p.positions[row]) * 32) + c * 8;
+        const float4* tab = reinterpret_cast<const float4*>(p.rope_table + static_cast<int64_t>(p.positions[row]) * 32) + c * 4;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 4; ++k) {
           const float4 f = __ldg(tab + k);
           const float a0 = __uint_as_float(r1[2 * k]), b0 = __uint_as_float(r2[2 * k]);
           const float a1 = __uint_as_float(r1[2 * k + 1]), b1 = __uint_as_float(r2[2 * k + 1]);
@@ -414,16 +384,14 @@ attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
         }
       } else {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < 8; ++k) {
           o1[k] = __uint_as_float(r1[k]);
           o2[k] = __uint_as_float(r2[k]);
         }
       }
-      __nv_bfloat16* dst = p.dqkv + row * 3 * p.hidden + head * D + c * 16;
+      __nv_bfloat16* dst = p.dqkv + row * 3 * p.hidden + head * D + c * 8;
       *reinterpret_cast<uint4*>(dst) = pack8f(o1);
-      *reinterpret_cast<uint4*>(dst + 8) = pack8f(o1 + 8);
       *reinterpret_cast<uint4*>(dst + 32) = pack8f(o2);
-      *reinterpret_cast<uint4*>(dst + 40) = pack8f(o2 + 8);
     };
     int it = 0;
 #ifdef CM3P_ATTN_PROF
@@ -540,7 +508,7 @@ attn_bwd_dkv_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __g
   uint64_t* pz_full = s_free + 1;         // [slice] 128 arrivals: 32-column slices of P^T and dZ^T are in TMEM
   uint64_t* pz_free = pz_full + 4;        // [slice]
   uint64_t* acc_full = pz_free + 4;
-  uint64_t* acc_free = acc_full + 1;      // 8 arrivals: dK and dV have been copied out
+  uint64_t* acc_free = acc_full + 1;      // 16 arrivals: dK and dV have been copied out
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1);
 
   if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
@@ -561,7 +529,7 @@ attn_bwd_dkv_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __g
       ptx::mbar_init(&pz_free[i], 1);
     }
     ptx::mbar_init(acc_full, 1);
-    ptx::mbar_init(acc_free, 8);
+    ptx::mbar_init(acc_free, EW_WARPS);
     ptx::fence_barrier_init();
   }
   if (warp == EW_WARPS) {
@@ -774,15 +742,16 @@ attn_bwd_dkv_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __g
         ptx::tc_fence_before();
         ptx::mbar_arrive(&pz_full[c]);
       }
-      // dK (slice-0 warps, inverse RoPE) and dV (slice-1 warps) of this outer tile; the accumulators are
-      // released as soon as they are in registers
-      if (c < 2) {
+      // dK (slices 0 / 1: 16 + 16 columns each, a RoPE pair is columns k and k + 32) and dV (slices 2 / 3: 32
+      // columns each) of this outer tile, spread over all 16 warps so that no warp falls behind the others;
+      // the accumulators are released as soon as they are in registers
+      {
         ptx::mbar_wait(acc_full, oi & 1);
         ptx::tc_fence_after();
-        uint32_t r1[32], r2[32];
-        const uint32_t t_acc = tmem_base + (c == 0 ? TM_DK : TM_DV) + lane_off;
-        ptx::tmem_ld_32x32b_x32(t_acc, r1);
-        ptx::tmem_ld_32x32b_x32(t_acc + 32, r2);
+        uint32_t r1[16], r2[16];
+        const uint32_t t_acc = tmem_base + lane_off + (c < 2 ? TM_DK + c * 16 : TM_DV + (c - 2) * 32);
+        ptx::tmem_ld_32x32b_x16(t_acc, r1);
+        ptx::tmem_ld_32x32b_x16(t_acc + (c < 2 ? 32 : 16), r2);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
@@ -790,9 +759,34 @@ attn_bwd_dkv_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __g
         if (valid) {
           const int64_t row = static_cast<int64_t>(seq_start) + kj;
           __nv_bfloat16* base = p.dqkv + row * 3 * p.hidden + head * D;
-          const float2* cs = nullptr;
-          if (c == 0 && p.rope_table && p.positions) cs = p.rope_table + static_cast<int64_t>(p.positions[row]) * 32;
-          store_grad_regs(r1, r2, base + (c == 0 ? p.hidden : 2 * p.hidden), cs);
+          float o1[16], o2[16];
+          if (c < 2 && p.rope_table && p.positions) {
+            const float4* tab =
+                reinterpret_cast<const float4*>(p.rope_table + static_cast<int64_t>(p.positions[row]) * 32) + c * 8;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float4 f = __ldg(tab + k);
+              const float a0 = __uint_as_float(r1[2 * k]), b0 = __uint_as_float(r2[2 * k]);
+              const float a1 = __uint_as_float(r1[2 * k + 1]), b1 = __uint_as_float(r2[2 * k + 1]);
+              o1[2 * k] = a0 * f.x + b0 * f.y;
+              o2[2 * k] = b0 * f.x - a0 * f.y;
+              o1[2 * k + 1] = a1 * f.z + b1 * f.w;
+              o2[2 * k + 1] = b1 * f.z - a1 * f.w;
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              o1[k] = __uint_as_float(r1[k]);
+              o2[k] = __uint_as_float(r2[k]);
+            }
+          }
+          // dK: columns c*16.. and 32 + c*16..; dV: columns (c-2)*32.. and (c-2)*32 + 16..
+          __nv_bfloat16* d1 = base + (c < 2 ? p.hidden + c * 16 : 2 * p.hidden + (c - 2) * 32);
+          __nv_bfloat16* d2 = d1 + (c < 2 ? 32 : 16);
+          *reinterpret_cast<uint4*>(d1) = pack8f(o1);
+          *reinterpret_cast<uint4*>(d1 + 8) = pack8f(o1 + 8);
+          *reinterpret_cast<uint4*>(d2) = pack8f(o2);
+          *reinterpret_cast<uint4*>(d2 + 8) = pack8f(o2 + 8);
         }
       }
     }

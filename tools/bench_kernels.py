@@ -90,7 +90,11 @@ def bench_attn_bwd(B, L, heads, window):
     lse = torch.empty(heads, T, device=DEV)
     out = ops.attn_varlen_fwd(qkv, cu_t, L, heads, window, lse=lse)
     dqkv, delta = torch.empty_like(qkv), torch.empty_like(lse)
-    t = timeit(lambda: ops.attn_varlen_bwd(qkv, out, dout, lse, cu_t, L, heads, window, dqkv=dqkv, delta=delta))
+    # positions + RoPE table as in the train step (the dQ / dK epilogues undo the forward's rotation)
+    pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens]).to(DEV)
+    tab = ops.rope_table(160000.0, 2048, DEV)
+    t = timeit(lambda: ops.attn_varlen_bwd(qkv, out, dout, lse, cu_t, L, heads, window, positions=pos, rope_table=tab,
+                                           dqkv=dqkv, delta=delta))
     if window < 0:
         flops = sum(10.0 * n * n * 64 * heads for n in lens)
     else:
