@@ -836,11 +836,9 @@ int attn_varlen_bwd_v3(const AttnBwdArgs& a, cudaStream_t stream) {
   attn_bwd_delta_kernel<<<static_cast<unsigned>((vec_units + 255) / 256), 256, 0, stream>>>(p.out, p.dout, p.delta,
                                                                                        a.total_tokens, a.heads);
   CM3P_CUDA_TRY(cudaGetLastError());
-  static int forced_opc = -1;
-  if (forced_opc < 0) {
-    const char* e = getenv("CM3P_BWD_OUTER_PER_CTA");
-    forced_opc = e ? atoi(e) : 0;
-  }
+  // read on every call (not cached): the tests sweep it
+  const char* opc_env = getenv("CM3P_BWD_OUTER_PER_CTA");
+  const int forced_opc = opc_env ? atoi(opc_env) : 0;
   const int64_t units = (a.total_tokens / BT + a.batch / 2 + 1) * a.heads;  // ~ (sequence, head, outer tile) triples
   const int64_t target_ctas = static_cast<int64_t>(num_sms()) * (a.window >= 0 ? 4 : 16);
   int opc = static_cast<int>((units + target_ctas - 1) / target_ctas);

@@ -763,11 +763,9 @@ int attn_varlen_fwd(const AttnFwdArgs& a, cudaStream_t stream) {
       configured2 = true;
     }
     // blocks per CTA: enough CTAs for ~16 (global) / ~4 (window) waves of uneven work
-    static int forced_bpc = -1;
-    if (forced_bpc < 0) {
-      const char* e = getenv("CM3P_FWD_BLOCKS_PER_CTA");
-      forced_bpc = e ? atoi(e) : 0;
-    }
+    // read on every call (not cached): the tests sweep it
+    const char* bpc_env = getenv("CM3P_FWD_BLOCKS_PER_CTA");
+    const int forced_bpc = bpc_env ? atoi(bpc_env) : 0;
     const int64_t units = (a.total_tokens / (2 * BQ) + a.batch / 2 + 1) * a.heads;
     const int64_t target_ctas = static_cast<int64_t>(num_sms()) * (a.window >= 0 ? 4 : 16);
     int bpc = static_cast<int>((units + target_ctas - 1) / target_ctas);

@@ -116,6 +116,38 @@ def test_attention_bwd(lens, heads, window, rope):
         _close(f"{tag} d{n}", got[:, i], want[:, i], 0.03 * float(want[:, i].abs().max()) + 1e-3, 5e-2)
 
 
+@pytest.mark.parametrize("outer_per_cta", [1, 2, 3, 16])
+@pytest.mark.parametrize("window", [-1, 64])
+def test_attention_bwd_streaming(outer_per_cta, window, monkeypatch):
+    """Several outer tiles per CTA (double-buffered 128-row operands and dQ accumulator, write-out one tile
+    late, single-tile outer tiles at sequence ends): same gradients whatever the split."""
+    monkeypatch.setenv("CM3P_BWD_OUTER_PER_CTA", str(outer_per_cta))  # re-read by the launcher on every call
+    ops = _ops()
+    lens, heads = [1100, 257, 1, 640, 129, 385], 2
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    T, H = cu[-1], heads * 64
+    raw = _rand((T, 3 * H), 1.0, seed=7)
+    dout = _rand((T, H), 1.0, seed=8)
+    cu_t = torch.tensor(cu, dtype=torch.int32, device=DEV)
+    pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens]).to(DEV)
+    tab = ops.rope_table(10000.0, 2048, DEV)
+    rotated, _, want_dqkv = _attn_ref_autograd(raw, dout, cu, heads, window, pos, tab)
+    qkv = rotated.to(torch.bfloat16).contiguous()
+    lse = torch.empty((heads, T), device=DEV, dtype=torch.float32)
+    out = ops.attn_varlen_fwd(qkv, cu_t, max(lens), heads, window, lse=lse)
+    dqkv = ops.attn_varlen_bwd(qkv, out, dout, lse, cu_t, max(lens), heads, window, positions=pos, rope_table=tab)
+    torch.cuda.synchronize()
+    assert torch.isfinite(dqkv.float()).all()
+    want = want_dqkv.view(T, 3, H)
+    got = dqkv.float().view(T, 3, H)
+    for i, n in enumerate("qkv"):
+        tag = f"attn_bwd streaming opc={outer_per_cta} w={window} d{n}"
+        _relerr(tag, got[:, i], want[:, i], 2e-2)
+        _close(tag, got[:, i], want[:, i], 0.03 * float(want[:, i].abs().max()) + 1e-3, 5e-2)
+
+
 # --------------------------------------------------------------------------------- row-wise kernels
 @pytest.mark.parametrize("H,with_res", [(768, True), (512, False), (256, True), (64, True), (1024, False)])
 def test_layernorm_bwd(H, with_res):

@@ -133,6 +133,13 @@ def test_gemm_transposed_operands():
 
 
 # ------------------------------------------------------------------------------------- attention
+@pytest.fixture
+def blocks_per_cta(request, monkeypatch):
+    """Force how many 256-query blocks one forward CTA streams (the launcher re-reads the variable per call)."""
+    monkeypatch.setenv("CM3P_FWD_BLOCKS_PER_CTA", str(request.param))
+    return request.param
+
+
 def _attn_ref(qkv, cu, heads, window):
     T = qkv.shape[0]
     out = torch.empty((T, heads * 64), device=qkv.device, dtype=torch.float32)
@@ -172,6 +179,26 @@ def test_attention_fwd(lens, heads, window):
         idx = torch.arange(L, device=DEV)
         sc = sc.masked_fill((idx[:, None] - idx[None, :]).abs() > window, float("-inf"))
     _report("attn lse", lse[0, :L], torch.logsumexp(sc, -1) / math.log(2.0), 2e-2, 1e-3)
+
+
+@pytest.mark.parametrize("blocks_per_cta", [1, 2, 3, 16], indirect=True)
+@pytest.mark.parametrize("window", [-1, 64])
+def test_attention_fwd_streaming(blocks_per_cta, window):
+    """Several 256-query blocks per CTA (double-buffered Q, O reuse across blocks, inactive second Q tile in the
+    last block, block counts that do not divide the sequence): same result whatever the split."""
+    ops = _ops()
+    lens, heads = [2000, 257, 1, 640, 1153, 129, 512], 2
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    T = cu[-1]
+    qkv = _rand((T, 3 * heads * 64), 1.0, seed=11)
+    cu_t = torch.tensor(cu, dtype=torch.int32, device=DEV)
+    lse = torch.empty((heads, T), device=DEV, dtype=torch.float32)
+    out = ops.attn_varlen_fwd(qkv, cu_t, max(lens), heads, window, lse=lse)
+    torch.cuda.synchronize()
+    _report(f"attn streaming bpc={blocks_per_cta} w={window}", out, _attn_ref(qkv, cu, heads, window), 2e-2, 2e-2)
+    assert bool(torch.isfinite(lse).all())
 
 
 # --------------------------------------------------------------------------------- row-wise kernels
