@@ -538,6 +538,13 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
     const float c = p.scale_log2;
     const float2 c2 = make_float2(c, c);
     int it = 0;  // tiles consumed so far by this group (phase of its barriers)
+    // -DCM3P_ATTN_PROF: clock64 spent per phase by one thread of CTA (0,0,0), printed at the end (tools/attn_one.py)
+#ifdef CM3P_ATTN_PROF
+    long long pf_s = 0, pf_ld = 0, pf_max = 0, pf_exp = 0, pf_epi = 0, pf_t0 = clock64(), pf_a = pf_t0, pf_b;
+#define PF_B(acc) do { pf_b = clock64(); acc += pf_b - pf_a; pf_a = pf_b; } while (0)
+#else
+#define PF_B(acc)
+#endif
     for (int bi = 0; bi < n_b; ++bi) {
       const int q0 = (b_begin + bi) * 2 * BQ;
       const BlockRange br = block_range(q0, len, p.window);
@@ -550,7 +557,9 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
 
       for (int jj = 0; jj < n_iter; ++jj, ++it) {
         const int kv0 = br.kv_base + (lo_x + jj) * BKV;
+        PF_B(pf_epi);
         ptx::mbar_wait(&s_full[x], it & 1);
+        PF_B(pf_s);
         ptx::tc_fence_after();
         uint32_t sr[2][32];
         ptx::tmem_ld_32x32b_x32(t_s, sr[0]);
@@ -559,6 +568,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
         // the scores are in registers: hand the S buffer back so S_x(jj+1) overlaps this tile's softmax
         ptx::tc_fence_before();
         if (lane == 0) ptx::mbar_arrive(&s_free[x]);
+        PF_B(pf_ld);
         // Masking state per 32-column chunk and per warp (32 consecutive query rows): 0 = no allowed key
         // for any row of the warp (skip: no exp, P = 0), 1 = some rows partially masked, 2 = fully allowed.
         // Interior tiles of global layers take the branch-free path (every chunk fully allowed).
@@ -616,6 +626,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
         *my_x = fmaxf(mxq[0], mxq[1]);
         ptx::named_bar_sync(pair_bar, 64);
         const float m_new = ptx::max3(m_run, fmaxf(mxq[0], mxq[1]), *peer_x);
+        PF_B(pf_max);
         if (jj == 0) {
           m_run = m_new;
         } else {
@@ -670,6 +681,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
         ptx::mbar_arrive(&p_full[2 * x + hc]);
         const float2 rsum = ptx::add2(ptx::add2(rs[0], rs[1]), ptx::add2(rs[2], rs[3]));
         l += rsum.x + rsum.y;
+        PF_B(pf_exp);
       }
       if (n_iter > 0) {
         // epilogue of the block; meanwhile the issuer already runs S of the next block's first tile.
@@ -706,6 +718,12 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
         }
       }
     }
+#ifdef CM3P_ATTN_PROF
+    PF_B(pf_epi);
+    if (lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+      printf("attn fwd warp %2d: blocks=%d tiles=%d total=%lld wait_s=%lld ld=%lld max+exchange=%lld exp+store=%lld "
+             "epilogue=%lld\n", warp, n_b, it, clock64() - pf_t0, pf_s, pf_ld, pf_max, pf_exp, pf_epi);
+#endif
   }
 
   ptx::tc_fence_before();
