@@ -17,8 +17,10 @@
 //     shared memory per tile (2048 clk at the SM's 128 B/clk).  They are handed over in the 32-column
 //     slices, each with its own mbarrier pair: the GEMM on a slice is issued as soon as it is written,
 //     and the slice is reusable by the time its warps get to it in the next tile.
-//   * all issuer / producer waits are blocking mbarrier waits (a polling issuer steals issue slots from
-//     the element-wise warps on its scheduler); packed f32x2 arithmetic in the element-wise loops.
+//   * two issuer warps on different schedulers (S / dP of the next tile; the accumulating GEMMs on the
+//     slices), each running its loop warp-uniformly with one elected lane issuing; all issuer / producer
+//     waits are blocking mbarrier waits (a polling issuer steals issue slots from the element-wise warps
+//     on its scheduler); packed f32x2 arithmetic in the element-wise loops.
 //
 // Two deterministic kernels as before (no atomics): dQ (outer = 128 queries, streams K/V) and dK/dV on
 // the transposed problem (outer = 128 keys as TMEM lanes, streams Q/dO with their lse / delta rows).
@@ -203,7 +205,7 @@ attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
     }
     for (int s = 0; s < NS; ++s) {
       ptx::mbar_init(&kv_full[s], 1);
-      ptx::mbar_init(&kv_empty[s], 1);
+      ptx::mbar_init(&kv_empty[s], 2);  // S / dP issuer + dQ issuer
     }
     ptx::mbar_init(s_full, 1);
     ptx::mbar_init(s_free, EW_WARPS);
@@ -273,7 +275,6 @@ attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
       // address moves and the issuer, not the tensor pipe, set the pace (measured).
       const bool leader = ptx::elect_one();
       const uint32_t idesc_s = ptx::umma_idesc_bf16(BT, BI, 0, 0);
-      const uint32_t idesc_dq = ptx::umma_idesc_bf16(BT, D, 0, 1);  // K as MN-major B operand
       constexpr uint32_t HI = ptx::umma_desc_hi_sw128(1024);
       // S / dP of global tile t (stage t % NS) from the Q / dO buffer qb; `last` = last inner tile of its outer tile
       auto issue_s_dp = [&](int t, int qb, bool last) {
@@ -292,6 +293,7 @@ attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
           if (leader) ptx::umma_bf16_split(tmem_base + TM_DP, do_lo + k * 2, v_lo + k * 2, HI, idesc_s, k != 0 ? 1u : 0u);
         if (leader) {
           ptx::umma_commit(s_full);
+          ptx::umma_commit(&kv_empty[s]);            // one of the two releases of the K / V stage (the dQ issuer: the other)
           if (last) ptx::umma_commit(&q_empty[qb]);  // Q / dO of this outer tile are not read again
         }
       };
@@ -302,10 +304,8 @@ attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
       for (int oi = 0; oi < n_o; ++oi) {
         const int n = tile_range((o_begin + oi) * BT, len, p.window).n;
         const int qb = oi & 1;
-        const uint32_t t_acc = tmem_base + TM_DQ + qb * 64;
 #pragma unroll 1
         for (int j = 0; j < n; ++j, ++it) {
-          const int s = it % NS;
           // chain the S / dP GEMM of the next tile of the stream (same outer tile, or the next one's first)
           if (j + 1 < n) {
             ptx::mbar_wait(s_free, it & 1);  // S / dP of tile `it` are in registers
@@ -315,10 +315,30 @@ attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
             ptx::mbar_wait(s_free, it & 1);
             issue_s_dp(it + 1, qb ^ 1, tile_range((o_begin + oi + 1) * BT, len, p.window).n == 1);
           }
-          if (j == 0) {  // the accumulator buffer was last used two outer tiles ago: wait until it is copied out
-            ptx::mbar_wait(&acc_free[qb], ((oi >> 1) & 1) ^ 1);
-            ptx::tc_fence_after();
-          }
+        }
+      }
+    } else if (warp == EW_WARPS + 2) {
+      // ---------------------------------------------------------------- second issuer: dQ += dZ K
+      // A warp of its own (on another scheduler than the S / dP issuer): the S / dP GEMM of the next tile is
+      // never queued behind the wait for this tile's dZ slices, and the issuing work is spread over two
+      // schedulers (with one issuer the four element-wise warps sharing its scheduler ran 20 % behind the
+      // other twelve and paced every slice hand-over).  The two issuers write disjoint TMEM regions.
+      const bool leader = ptx::elect_one();
+      const uint32_t idesc_dq = ptx::umma_idesc_bf16(BT, D, 0, 1);  // K as MN-major B operand
+      constexpr uint32_t HI = ptx::umma_desc_hi_sw128(1024);
+      int it = 0;
+#pragma unroll 1
+      for (int oi = 0; oi < n_o; ++oi) {
+        const int n = tile_range((o_begin + oi) * BT, len, p.window).n;
+        const int qb = oi & 1;
+        const uint32_t t_acc = tmem_base + TM_DQ + qb * 64;
+        // the accumulator buffer was last used two outer tiles ago: wait until it is copied out
+        ptx::mbar_wait(&acc_free[qb], ((oi >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int j = 0; j < n; ++j, ++it) {
+          const int s = it % NS;
+          ptx::mbar_wait(&kv_full[s], (it / NS) & 1);  // already complete (S of this tile was computed from it)
           // K tile as the MN-major B operand of dQ += dZ K (LBO = 8192: distance of 64-element MN chunks, unused)
           const uint32_t kmn_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_k + s * TILE_BYTES), 8192);
 #pragma unroll
@@ -520,7 +540,7 @@ attn_bwd_dkv_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __g
     }
     for (int s = 0; s < NS; ++s) {
       ptx::mbar_init(&qdo_full[s], 33);
-      ptx::mbar_init(&qdo_empty[s], 1);
+      ptx::mbar_init(&qdo_empty[s], 2);  // S^T / dP^T issuer + dK / dV issuer
     }
     ptx::mbar_init(s_full, 1);
     ptx::mbar_init(s_free, EW_WARPS);
@@ -588,7 +608,6 @@ attn_bwd_dkv_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __g
       // ------------------------------------------------------------------ MMA issuer (see the dQ kernel)
       const bool leader = ptx::elect_one();
       const uint32_t idesc_s = ptx::umma_idesc_bf16(BT, BI, 0, 0);
-      const uint32_t idesc_acc = ptx::umma_idesc_bf16(BT, D, 0, 1);
       constexpr uint32_t HI = ptx::umma_desc_hi_sw128(1024);
       auto issue_s_dp = [&](int t, int kb, bool last) {
         const int s = t % NS;
@@ -606,6 +625,7 @@ attn_bwd_dkv_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __g
           if (leader) ptx::umma_bf16_split(tmem_base + TM_DPT, v_lo + k * 2, do_lo + k * 2, HI, idesc_s, k != 0 ? 1u : 0u);
         if (leader) {
           ptx::umma_commit(s_full);
+          ptx::umma_commit(&qdo_empty[s]);            // one of the two releases of the Q / dO stage
           if (last) ptx::umma_commit(&kv_empty[kb]);  // K / V of this outer tile are not read again
         }
       };
@@ -618,7 +638,6 @@ attn_bwd_dkv_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __g
         const int kb = oi & 1;
 #pragma unroll 1
         for (int i = 0; i < n; ++i, ++it) {
-          const int s = it % NS;
           if (i + 1 < n) {
             ptx::mbar_wait(s_free, it & 1);
             issue_s_dp(it + 1, kb, i + 2 == n);
@@ -627,10 +646,26 @@ attn_bwd_dkv_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __g
             ptx::mbar_wait(s_free, it & 1);
             issue_s_dp(it + 1, kb ^ 1, tile_range((o_begin + oi + 1) * BT, len, p.window).n == 1);
           }
-          if (i == 0 && oi > 0) {  // dK / dV of the previous outer tile must have been copied out
-            ptx::mbar_wait(acc_free, (oi - 1) & 1);
-            ptx::tc_fence_after();
-          }
+        }
+      }
+    } else if (warp == EW_WARPS + 2) {
+      // ------------------------------------------------------------------ second issuer: dV += P^T dO, dK += dZ^T Q
+      // (see the dQ kernel: own warp on another scheduler, disjoint TMEM regions)
+      const bool leader = ptx::elect_one();
+      const uint32_t idesc_acc = ptx::umma_idesc_bf16(BT, D, 0, 1);
+      constexpr uint32_t HI = ptx::umma_desc_hi_sw128(1024);
+      int it = 0;
+#pragma unroll 1
+      for (int oi = 0; oi < n_o; ++oi) {
+        const int n = tile_range((o_begin + oi) * BT, len, p.window).n;
+        if (oi > 0) {  // dK / dV of the previous outer tile must have been copied out
+          ptx::mbar_wait(acc_free, (oi - 1) & 1);
+          ptx::tc_fence_after();
+        }
+#pragma unroll 1
+        for (int i = 0; i < n; ++i, ++it) {
+          const int s = it % NS;
+          ptx::mbar_wait(&qdo_full[s], (it / NS) & 1);  // already complete (S^T of this tile was computed from it)
           const uint32_t qmn_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_q + s * TILE_BYTES), 8192);
           const uint32_t domn_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_do + s * TILE_BYTES), 8192);
 #pragma unroll
