@@ -183,7 +183,7 @@ attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
   float* smem_vec = reinterpret_cast<float*>(smem + DQ_TILES);  // [2][-lse 128 | -delta*scale 128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_TILES + DQ_VEC);
   uint64_t* q_full = bars;                 // [2] TMA bytes + 32 staging-lane arrivals
-  uint64_t* q_empty = q_full + 2;          // [2] the S / dP MMAs of the outer tile have retired
+  uint64_t* q_empty = q_full + 2;          // [2] the S / dP MMAs of the outer tile have retired and its row constants are read
   uint64_t* kv_full = q_empty + 2;         // [NS]
   uint64_t* kv_empty = kv_full + NS;       // [NS]
   uint64_t* s_full = kv_empty + NS;        // S and dP of a tile are in TMEM
@@ -199,7 +199,7 @@ attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
   if (warp == EW_WARPS + 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&q_full[i], 33);
-      ptx::mbar_init(&q_empty[i], 1);
+      ptx::mbar_init(&q_empty[i], 1 + EW_WARPS);  // issuer commit (Q / dO) + every element-wise warp (row constants)
       ptx::mbar_init(&acc_full[i], 1);
       ptx::mbar_init(&acc_free[i], EW_WARPS);
     }
@@ -430,6 +430,10 @@ attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
       ptx::mbar_wait(&q_full[oi & 1], (oi >> 1) & 1);
       const float nlse = smem_vec[(oi & 1) * 2 * BT + t];
       const float ndsc = smem_vec[(oi & 1) * 2 * BT + BT + t];
+      // the producer may refill this buffer two outer tiles ahead: with a single inner tile per outer tile
+      // (tiny windows) the S / dP GEMM alone could release it before these reads
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&q_empty[oi & 1]);
       const float2 nlse2 = make_float2(nlse, nlse), ndsc2 = make_float2(ndsc, ndsc);
       for (int j = 0; j < tr.n; ++j, ++it) {
         const int kv0 = tr.base + j * BI + c * HC;

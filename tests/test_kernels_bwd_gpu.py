@@ -117,7 +117,7 @@ def test_attention_bwd(lens, heads, window, rope):
 
 
 @pytest.mark.parametrize("outer_per_cta", [1, 2, 3, 16])
-@pytest.mark.parametrize("window", [-1, 64])
+@pytest.mark.parametrize("window", [-1, 64, 0, 200])
 def test_attention_bwd_streaming(outer_per_cta, window, monkeypatch):
     """Several outer tiles per CTA (double-buffered 128-row operands and dQ accumulator, write-out one tile
     late, single-tile outer tiles at sequence ends): same gradients whatever the split."""
@@ -142,8 +142,15 @@ def test_attention_bwd_streaming(outer_per_cta, window, monkeypatch):
     assert torch.isfinite(dqkv.float()).all()
     want = want_dqkv.view(T, 3, H)
     got = dqkv.float().view(T, 3, H)
+    scale = float(want.abs().max())
     for i, n in enumerate("qkv"):
         tag = f"attn_bwd streaming opc={outer_per_cta} w={window} d{n}"
+        if window == 0 and n != "v":
+            # a single key per query: dq = dk = 0 exactly; the kernel's P (dP - delta) only cancels up to the
+            # bf16 rounding of the forward output, so compare on the scale of dv (window 0 is here for the
+            # one-inner-tile-per-outer-tile path of the streaming kernels)
+            _close(tag, got[:, i], want[:, i], 0.03 * scale, 5e-2)
+            continue
         _relerr(tag, got[:, i], want[:, i], 2e-2)
         _close(tag, got[:, i], want[:, i], 0.03 * float(want[:, i].abs().max()) + 1e-3, 5e-2)
 

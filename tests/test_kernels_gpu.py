@@ -182,7 +182,7 @@ def test_attention_fwd(lens, heads, window):
 
 
 @pytest.mark.parametrize("blocks_per_cta", [1, 2, 3, 16], indirect=True)
-@pytest.mark.parametrize("window", [-1, 64])
+@pytest.mark.parametrize("window", [-1, 64, 0, 200])
 def test_attention_fwd_streaming(blocks_per_cta, window):
     """Several 256-query blocks per CTA (double-buffered Q, O reuse across blocks, inactive second Q tile in the
     last block, block counts that do not divide the sequence): same result whatever the split."""
