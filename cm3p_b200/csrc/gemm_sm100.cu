@@ -56,8 +56,8 @@ struct Params {
   int splits;        // split-K factor (>1 only with the atomic F32 epilogue: weight gradients, K = tokens)
   int kb_per_split;  // k-blocks per split
   int cluster;       // 1, or 2: CTA pairs on adjacent M tiles share every B tile through TMA multicast
-  float* stats_out;        // RESIDUAL: per-row (sum, sum^2) of the written rows, or null
-  const float* row_stats;  // ROPE / GEGLU(_SAVE): per-row (sum, sum^2) of the A rows -> LayerNorm folded in, or null
+  float* stats_out;        // RESIDUAL: [ceil(N/256)][M] (sum, sum^2) partials of the written rows, one per N tile, or null
+  const float* row_stats;  // ROPE / GEGLU(_SAVE): [ceil(K/256)][M] partials of the A rows -> LayerNorm folded in, or null
   const float* col_corr;   // [N] column sums of B (= W . diag(gamma))
   float ln_eps;
 };
@@ -276,7 +276,14 @@ __device__ __forceinline__ void epilogue_tile_staged(const Params& p, const CUte
   if constexpr (EPI == EPI_ROPE || EPI == EPI_GEGLU || EPI == EPI_GEGLU_SAVE) {
     ln = p.row_stats != nullptr;
     if (ln && row < p.M) {
-      const float2 sq = *reinterpret_cast<const float2*>(p.row_stats + row * 2);
+      // the producer wrote one (sum, sum^2) partial per 256-column tile of this row; summed in tile order, so the
+      // statistics (and everything downstream) do not depend on which CTA finished first
+      float2 sq = make_float2(0.f, 0.f);
+      for (int64_t part = 0; part < (p.K + BN - 1) / BN; ++part) {
+        const float2 t = *reinterpret_cast<const float2*>(p.row_stats + (part * p.M + row) * 2);
+        sq.x += t.x;
+        sq.y += t.y;
+      }
       const float inv_w = 1.f / static_cast<float>(p.K);
       ln_mean = sq.x * inv_w;
       ln_rstd = rsqrtf(fmaxf(sq.y * inv_w - ln_mean * ln_mean, 0.f) + p.ln_eps);
@@ -446,10 +453,8 @@ __device__ __forceinline__ void epilogue_tile_staged(const Params& p, const CUte
     ++st.g;
   }
   if constexpr (EPI == EPI_RESIDUAL) {
-    if (p.stats_out && row < p.M) {
-      atomicAdd(p.stats_out + row * 2, st_sum);
-      atomicAdd(p.stats_out + row * 2 + 1, st_sq);
-    }
+    if (p.stats_out && row < p.M)  // this tile's partial: slot [n0 / BN][row]
+      *reinterpret_cast<float2*>(p.stats_out + ((n0 / BN) * p.M + row) * 2) = make_float2(st_sum, st_sq);
   }
 }
 

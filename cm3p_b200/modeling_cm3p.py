@@ -203,7 +203,7 @@ class ModernBertEncoder(nn.Module):
         if ops.FUSE_LAYERNORM:
             # The two pre-norm LayerNorms of every block are folded into the GEMMs around them: the residual
             # GEMM that writes x also accumulates its row statistics, the consuming GEMM applies them.
-            stats = torch.zeros((2 * n_layers, T, 2), device=dev, dtype=torch.float32)
+            stats = torch.empty((2 * n_layers, (H + 255) // 256, T, 2), device=dev, dtype=torch.float32)
         for i, w in enumerate(pk["layers"]):
             is_global = cfg.layer_is_global(i)
             tab = tab_g if is_global else tab_l

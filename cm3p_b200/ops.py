@@ -59,7 +59,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, epilogue: int = EPI_STORE, out: to
          ln_eps: float = 1e-5) -> torch.Tensor:
     """out[M,N] = epilogue(A @ B^T).  A: [M,K] (or [K,M] if trans_a); B: [N,K] (or [K,N] if trans_b).
 
-    LayerNorm folding (cm3p_gemm_bf16_ln): `stats_out` [M,2] fp32 (+= row sum / sum of squares of the rows an
+    LayerNorm folding (cm3p_gemm_bf16_ln): `stats_out` [ceil(N/256),M,2] fp32 (per-tile row sum / sum of squares of the rows an
     EPI_RESIDUAL GEMM writes); `row_stats` + `col_corr` on an EPI_ROPE / EPI_GEGLU(_SAVE) GEMM whose B is
     W.diag(gamma) apply the normalisation of the A rows in the epilogue."""
     _req(a, torch.bfloat16, "a")

@@ -82,7 +82,7 @@ def encoder_forward(enc, x0: torch.Tensor, cu_seqlens, max_seqlen: int, position
     eps, n_layers = cfg.norm_eps, len(pk["layers"])
     fuse = ops.FUSE_LAYERNORM  # LayerNorms folded into the neighbouring GEMMs (the backward recomputes them from x)
     if fuse:
-        stats = torch.zeros((2 * n_layers, T, 2), device=dev, dtype=F32)
+        stats = torch.empty((2 * n_layers, (H + 255) // 256, T, 2), device=dev, dtype=F32)
     # keep the LayerNorm outputs for the weight-gradient GEMMs instead of recomputing them in the backward
     keep_ln = (not fuse) and _keep_layernorm_outputs(2 * n_layers * T * H * 2, dev)
     for i, w in enumerate(pk["layers"]):

@@ -63,10 +63,13 @@ int cm3p_gemm_bf16(const void* a, int64_t lda, int trans_a, const void* b, int64
 
 /* The same GEMM with a LayerNorm folded into the GEMMs on both sides of it, so that the pre-norm blocks of
  * ModernBERT (MB:313-342: `attn(attn_norm(x))`, `mlp(mlp_norm(x))`) need no LayerNorm pass at all:
- *   producer, epilogue CM3P_EPI_RESIDUAL: stats_out [M][2] fp32 += (sum, sum of squares) of the bf16 rows written
+ *   producer, epilogue CM3P_EPI_RESIDUAL: stats_out [ceil(N/256)][M][2] fp32 = (sum, sum of squares) of the bf16
+ *     values each 256-column tile wrote to a row (one partial per tile: no atomics, no zero-fill, results do not
+ *     depend on the order in which CTAs finish)
  *   consumer, epilogue CM3P_EPI_ROPE / CM3P_EPI_GEGLU(_SAVE), with b = W . diag(gamma) (bf16) and
  *     col_corr [N] = row sums of b:   acc <- rstd_m * (acc - mean_m * col_corr[n])
- *     where mean / rstd come from row_stats [M][2] (the producer's stats_out; width = K, eps = ln_eps).
+ *     where mean / rstd come from row_stats [ceil(K/256)][M][2] (the producer's stats_out, partials summed in
+ *     tile order; width = K, eps = ln_eps).
  * Operands K-major only; outputs must be 16-byte aligned bf16 rows. */
 int cm3p_gemm_bf16_ln(const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t M, int64_t N,
                       int64_t K, int epilogue, const void* aux, int64_t ld_aux, void* c2, int64_t ldc2,

@@ -297,12 +297,12 @@ def test_gemm_layernorm_folding():
     a, wo = _rand((T, H), seed=1), _rand((H, H), 0.03, seed=2)
     x0 = _rand((T, H), 2.0, seed=3) + 0.7  # non-zero mean rows
     gamma = _rand((H,), 0.2, seed=4, dtype=torch.float32) + 1.0
-    stats = torch.zeros((T, 2), device=DEV)
+    stats = torch.full(((H + 255) // 256, T, 2), float("nan"), device=DEV)  # one partial per 256-column tile
     x = ops.gemm(a, wo, epilogue=ops.EPI_RESIDUAL, aux=x0, stats_out=stats)
     torch.cuda.synchronize()
     xf = x.float()
-    _report("stats sum", stats[:, 0], xf.sum(-1), 5e-2, 1e-3)
-    _report("stats sumsq", stats[:, 1], (xf * xf).sum(-1), 5e-1, 1e-3)
+    _report("stats sum", stats[..., 0].sum(0), xf.sum(-1), 5e-2, 1e-3)
+    _report("stats sumsq", stats[..., 1].sum(0), (xf * xf).sum(-1), 5e-1, 1e-3)
     ln = F.layer_norm(xf, (H,), gamma, None, 1e-5)
     # --- GeGLU consumer
     wi = _rand((2 * I, H), 0.05, seed=5)
