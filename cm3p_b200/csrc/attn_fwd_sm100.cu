@@ -312,7 +312,7 @@ constexpr int THREADS2 = 640;  // 5 warpgroups: softmax A (2), softmax B (2), {T
 constexpr int SM_WARPS = 16;    // softmax warps: 8 per Q tile = 4 TMEM lane quadrants x 2 column halves
 constexpr int REG_SM = 104, REG_AUX2 = 64;
 constexpr int SMEM_TILES2 = 2 * 2 * Q_BYTES + KV_STAGES2 * 2 * KV_TILE_BYTES;  // 64 + 128 = 192 KB
-constexpr int SMEM_XCHG = 2 * 2 * BQ * 4;  // row maxima / row sums exchanged between the two warps of a row
+constexpr int SMEM_XCHG = 3 * 2 * 2 * BQ * 4;  // row maxima (one plane per tile parity) and row sums exchanged between the two warps of a row
 constexpr int SMEM_BYTES2 = SMEM_TILES2 + 512 + SMEM_XCHG;
 constexpr uint32_t TM_S = 0, TM_O = 256, TM_P = 384;  // S: + 128 x;  O: + 64 x;  P (bf16 pairs): + 64 x
 constexpr float RESCALE_LOG2 = 8.0f;
@@ -369,7 +369,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
   uint64_t* o_full = pv_done + 4;          // [2] per Q tile
   uint64_t* o_free = o_full + 2;           // [2] 8 arrivals: O_x of the block is in registers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
-  float* smem_xchg = reinterpret_cast<float*>(smem + SMEM_TILES2 + 512);  // [2 Q tiles][2 halves][128 rows]
+  float* smem_xchg = reinterpret_cast<float*>(smem + SMEM_TILES2 + 512);  // [max even tiles | max odd tiles | sums][2 Q tiles][2 halves][128 rows]
 
   if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
 
@@ -532,6 +532,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
     const uint32_t t_s = tmem_base + TM_S + x * 128 + lane_off + hc * 64;
     const uint32_t t_p = tmem_base + TM_P + x * 64 + lane_off + hc * 32;  // this thread's 64 keys of P_x as bf16 pairs
     int blk = 0;  // blocks with work so far (phase of o_full / o_free)
+    constexpr int XS = 2 * 2 * BQ;  // floats per exchange plane
     float* my_x = smem_xchg + (x * 2 + hc) * BQ + r;
     const float* peer_x = smem_xchg + (x * 2 + (hc ^ 1)) * BQ + r;
     const int pair_bar = 1 + x * 4 + (warp & 3);  // named barrier of the two warps that share these 32 rows
@@ -621,11 +622,12 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
             }
           }
         }
-        // row maximum over all 128 keys: exchange the two halves (the peer reads this slot right after the
-        // barrier; it is rewritten a whole tile later)
-        *my_x = fmaxf(mxq[0], mxq[1]);
+        // row maximum over all 128 keys: exchange the two halves.  One plane per tile parity: the peer may still
+        // be reading this tile's slot when the next tile's maximum is written; the slot of tile t is rewritten at
+        // tile t + 2, after both warps have passed the barrier of tile t + 1 (and so have read tile t's value)
+        my_x[(it & 1) * XS] = fmaxf(mxq[0], mxq[1]);
         ptx::named_bar_sync(pair_bar, 64);
-        const float m_new = ptx::max3(m_run, fmaxf(mxq[0], mxq[1]), *peer_x);
+        const float m_new = ptx::max3(m_run, fmaxf(mxq[0], mxq[1]), peer_x[(it & 1) * XS]);
         PF_B(pf_max);
         if (jj == 0) {
           m_run = m_new;
@@ -685,13 +687,11 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
       }
       if (n_iter > 0) {
         // epilogue of the block; meanwhile the issuer already runs S of the next block's first tile.
-        // Row sum over both halves: second use of the exchange slots (the peer has read the last maximum:
-        // the extra barrier orders that read before this write).
+        // Row sum over both halves (third plane of the exchange area).
+        my_x[2 * XS] = l;
         ptx::named_bar_sync(pair_bar, 64);
-        *my_x = l;
-        ptx::named_bar_sync(pair_bar, 64);
-        l += *peer_x;
-        ptx::named_bar_sync(pair_bar, 64);  // both sums are read before the next block's first maximum lands
+        l += peer_x[2 * XS];
+        ptx::named_bar_sync(pair_bar, 64);  // both sums are read before the next block's are written
         ptx::mbar_wait(&o_full[x], blk & 1);
         ptx::tc_fence_after();
         uint32_t rr[32];
