@@ -651,6 +651,11 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
             ptx::tmem_st_wait();
             l *= alpha;
             if (grow) m_run = m_new;
+            // PV of this tile accumulates into all 64 columns of O as soon as EITHER half of P is complete: the
+            // peer warp (same vote, same branch) must not get there before this warp's 32 columns are rescaled
+            ptx::tc_fence_before();
+            ptx::named_bar_sync(pair_bar, 64);
+            ptx::tc_fence_after();
           }
         }
         const float mc = (m_run == -INFINITY) ? 0.f : m_run * c;
