@@ -1,25 +1,27 @@
 """bench.py — headline benchmark of the CM3P hot path on B200 (contract: see the build brief).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload all|infer|train]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload all|train|infer|mlm] [--variations V] [--train-batch B] [--global-negatives]
 
 One "step" = one pass of the hot path over one batch of synthetic input per GPU.
 
-  workload infer (BASELINE.json configs[1], the headline line): base CM3P, bf16, batch 64 windows/GPU
-      of 16 s (L = 2000 padded, real lengths U{600..2000}, 200 audio tokens + 80x1600 log-mel per
-      window), beatmap tower + audio encoder + metadata tower (V = 1) + projections + logits,
-      `return_loss=False`  ->  beatmap embeds/s.
-  workload train (BASELINE.json configs[2]): the contrastive train step, fp32 master weights / bf16
-      compute, batch 256 windows/GPU, V = 8 metadata variations, forward + explicit backward + ONE
-      gradient all-reduce (NCCL) when N > 1; optimizer step excluded -> pairs/s.
-      `--global-negatives` switches to configs[3] semantics (embedding all-gather, global loss).
-  workload mlm (BASELINE.json configs[4], not part of the default run): CM3PForMaskedLM train step on
-      8192-token windows, 8 windows/GPU, 15 % masked -> real tokens/s.
-  workload all (default): the infer line with the train result attached under the key "train".
+  workload train (BASELINE.json configs[2], THE HEADLINE LINE): the contrastive train step, fp32 master
+      weights / bf16 compute, batch 256 windows/GPU of 16 s (L = 2000 padded, real lengths U{600..2000},
+      200 audio tokens + 80x1600 log-mel per window), V = 8 metadata variations (`--variations 256` = the value
+      the reference trains with, configs/train/v7.yaml:40), forward + explicit backward + bucketed gradient
+      all-reduce (NCCL, overlapped with the backward pass) when N > 1 -> pairs/s.  The optimizer step is
+      excluded from the step and reported separately as `optimizer_step_ms` (Muon + AdamW).
+      `--global-negatives --train-batch 512 --variations 1` = configs[3] (embedding all-gather, global loss).
+  workload infer (configs[1]): base CM3P bf16, batch 64 windows/GPU, beatmap tower + audio encoder +
+      metadata tower (V = 1) + projections + logits, `return_loss=False` -> beatmap embeds/s.
+  workload mlm (configs[4]): CM3PForMaskedLM train step on 8192-token windows, 8 windows/GPU, 15 % masked
+      -> real tokens/s.
+  workload all (default): the train line with the inference result attached under the key "infer".
 
-Prints ONE JSON line on rank 0.  `value` is measured with inputs resident in HBM; `e2e` goes through
-the public `CM3PModel.__call__` with pinned host inputs (H2D inside the timed region) and a D2H
-read of the result.  `--impl reference` times the CPU oracle (the reference's algorithm on the host
-cores) on a bounded sample of the same workload.
+Prints ONE JSON line on rank 0.  `value` is measured with inputs resident in HBM; `e2e` goes through the
+public `CM3PModel.__call__` with pinned host inputs (H2D inside the timed region) and a D2H read of the
+result.  `--impl reference` times the reference's own CPU path (the unmodified reference model from
+oracle/_ref when present, else the oracle port) on the host cores, on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
@@ -43,7 +45,6 @@ from cm3p_b200.configuration_cm3p import CM3PConfig, base_config_dict  # noqa: E
 from cm3p_b200.synthetic import synthetic_batch, synthetic_state_dict  # noqa: E402
 
 BATCH_PER_GPU = {"infer": 64, "train": 256}
-TRAIN_STEPS_CAP = 5  # a train step is ~0.6 s of device time; keep the default run short
 SEQ_LEN = 2000
 MIN_LEN = 600
 TRAIN_VARIATIONS = 8
@@ -54,7 +55,7 @@ MLM_SEQ_LEN, MLM_BATCH = 8192, 8
 # the ncu launch lists committed under profiles/ (it cannot be measured from inside this script)
 GEMM_TRAFFIC = {
     "infer": (263.5e6, "profiles/r1_infer_launch_summary_v2.txt (ncu, batch 64)"),
-    "train": (1254.0e6, "profiles/r1_train256_launch_summary.txt (ncu, batch 256)"),
+    "train": (1254.0e6, "profiles/r1_train256_launch_summary.txt (ncu, batch 256, V=8)"),
 }
 
 
@@ -141,19 +142,21 @@ def _algorithmic_flops_infer(cfg: CM3PConfig, batch: dict) -> float:
     total += B * (2 * frames * ac.hidden_size * 3 * ac.n_mels + 2 * t2 * ac.hidden_size * 3 * ac.hidden_size)
     total += B * (t2 * tower_linear(ac) + attn(ac, t2))
     total += B * (t2 // 4) * 2 * (ac.projector_intermediate_size * ac.projector_dim + ac.projector_dim ** 2)
-    mlens = batch["metadata_attention_mask"].reshape(-1, batch["metadata_attention_mask"].shape[-1]).sum(-1).tolist()
-    total += sum(mlens) * tower_linear(mc) + sum(attn(mc, n) for n in mlens)
+    mlens = batch["metadata_attention_mask"].reshape(-1, batch["metadata_attention_mask"].shape[-1]).sum(-1)
+    mg = sum(1 for i in range(mc.num_hidden_layers) if mc.layer_is_global(i))
+    total += float(mlens.sum()) * tower_linear(mc)
+    total += float((mlens.double() ** 2).sum()) * 4 * mc.hidden_size * mg  # all metadata layers are global in the base config
     total += B * 2 * bc.hidden_size * cfg.projection_dim + len(mlens) * 2 * mc.hidden_size * cfg.projection_dim
     total += 2 * len(mlens) * B * cfg.projection_dim
     return float(total)
 
 
-def _make_batch(cfg, workload, rank, batch):
+def _make_batch(cfg, workload, rank, batch, variations):
     if workload == "mlm":
         b = synthetic_batch(cfg, batch=batch, seq_len=MLM_SEQ_LEN, seed=1 + rank, min_len=MLM_SEQ_LEN // 2,
                             with_labels=True)
         return {k: b[k] for k in ("input_ids", "attention_mask", "input_features", "labels")}
-    V = 1 if workload == "infer" else TRAIN_VARIATIONS
+    V = 1 if workload == "infer" else variations
     return synthetic_batch(cfg, batch=batch, seq_len=SEQ_LEN, variations=V, seed=1 + rank, min_len=MIN_LEN)
 
 
@@ -161,10 +164,10 @@ WORKLOAD_TEXT = {
     "infer": "BASELINE.json configs[1]: CM3P base inference, beatmap tower + audio encoder + metadata tower (V=1) "
              "bf16, batch {B} synthetic 16 s windows per GPU (L=2000 padded, real lengths U{{600..2000}}), "
              "return_loss=False",
-    "train": "BASELINE.json configs[2]: CM3P base contrastive train step (audio fusion + V=8 metadata variations), "
-             "fp32 master weights / bf16 compute, batch {B} synthetic 16 s windows per GPU (L=2000 padded, real "
-             "lengths U{{600..2000}}), forward + backward + gradient all-reduce, {neg} negatives; optimizer step "
-             "excluded",
+    "train": "BASELINE.json configs[{cfgno}]: CM3P base contrastive train step (audio fusion + V={V} metadata "
+             "variations), fp32 master weights / bf16 compute, batch {B} synthetic 16 s windows per GPU (L=2000 "
+             "padded, real lengths U{{600..2000}}), forward + backward + bucketed overlapped gradient all-reduce, "
+             "{neg} negatives; optimizer step excluded (reported as optimizer_step_ms)",
     "mlm": "BASELINE.json configs[4]: CM3PForMaskedLM train step (beatmap tower + audio encoder + MLM head), fp32 "
            "master weights / bf16 compute, {B} windows of L=8192 per GPU (real lengths U{{4096..8192}}), 15 % masked, "
            "forward + backward + gradient all-reduce ({neg}); value = real tokens/s; optimizer step excluded",
@@ -178,6 +181,7 @@ def _bench_workload(workload, args, dist, dev, world, rank, local_rank) -> dict 
     from cm3p_b200.modeling_cm3p import CM3PModel
 
     train = workload in ("train", "mlm")
+    V = args.variations if workload == "train" else 1
     B = MLM_BATCH if workload == "mlm" else (args.train_batch if train else BATCH_PER_GPU["infer"])
     cfg = CM3PConfig(attn_implementation="flash_attention_2",
                      **copy.deepcopy(base_config_dict(has_decoder_head=(workload == "mlm"))))
@@ -190,14 +194,15 @@ def _bench_workload(workload, args, dist, dev, world, rank, local_rank) -> dict 
         model = CM3PModel(cfg)
         model.load_state_dict(synthetic_state_dict(cfg, seed=0), strict=True)
     model = model.to(dev)
+    dp = None
     if train:
         model.train()
         if world > 1:
-            dp_utils.enable_data_parallel(model, global_negatives=args.global_negatives)
+            dp = dp_utils.enable_data_parallel(model, global_negatives=args.global_negatives)
     else:
         model = model.to(torch.bfloat16).eval()
 
-    host = _make_batch(cfg, workload, rank, B)
+    host = _make_batch(cfg, workload, rank, B, V)
     pinned = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
 
@@ -228,7 +233,7 @@ def _bench_workload(workload, args, dist, dev, world, rank, local_rank) -> dict 
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) / steps
 
-    steps = min(args.steps, TRAIN_STEPS_CAP) if (train and args.workload == "all") else args.steps
+    steps = args.steps
     n_warm = args.warmup if args.quick else max(args.warmup, 3)
     torch.cuda.reset_peak_memory_stats()
     for _ in range(n_warm):
@@ -289,6 +294,51 @@ def _bench_workload(workload, args, dist, dev, world, rank, local_rank) -> dict 
     h2d = sum(v.numel() * v.element_size() for v in pinned.values())
     d2h = 4 if train else B * cfg.projection_dim * 4
 
+    # ---- communication (N > 1, train): the gradient all-reduce alone, and how much of it the step still shows
+    comm = None
+    if train and dp is not None:
+        n_params = sum((p.numel() + 3) // 4 * 4 for p in model.parameters())
+        flat = torch.zeros(n_params, device=dev, dtype=torch.float32)
+        for _ in range(2):
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        ar_ms = timed(lambda: dist.all_reduce(flat, op=dist.ReduceOp.AVG), 5)
+        del flat
+        model._dp = None  # same per-rank work, no collective
+        step(resident)
+        ms_nocomm = timed(lambda: step(resident), min(steps, 5))
+        model._dp = dp
+        ms_comm = timed(lambda: step(resident), min(steps, 5))  # back to back with the no-collective run
+        exposed = max(0.0, ms_comm - ms_nocomm)
+        comm = {"all_reduce_ms": round(ar_ms, 3), "all_reduce_bytes": int(n_params * 4),
+                "all_reduce_busbw_gbs": round(2 * (world - 1) / world * n_params * 4 / (ar_ms * 1e-3) / 1e9, 1),
+                "step_ms_without_collectives": round(ms_nocomm, 3), "step_ms_with_collectives": round(ms_comm, 3),
+                "exposed_ms": round(exposed, 3),
+                "overlap": round(min(1.0, max(0.0, 1.0 - exposed / ar_ms)), 3) if ar_ms > 0 else None,
+                "how": "all_reduce_ms = the whole fp32 gradient buffer reduced alone (CUDA events, max over ranks, "
+                       "5 reps); exposed_ms = step time with minus without the collectives, 5 steps each, back to "
+                       "back; overlap = 1 - exposed / all_reduce"}
+
+    # ---- optimizer step (Muon for the matrices, its internal AdamW for embeddings / vectors), reported separately
+    opt_ms = None
+    if workload == "train":
+        from cm3p_b200.muon import Muon, split_muon_adamw
+        muon_params, adamw_params = split_muon_adamw(model)
+        opt = Muon(muon_params, lr=4e-4, adamw_params=adamw_params)
+        step(resident)  # fresh gradients
+        # lr = 0 steps would still do all the work, but keep the weights finite and realistic: tiny lr
+        for group in opt.param_groups:
+            group["lr"] = 1e-6
+        opt.step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            opt.step()
+        e1.record()
+        torch.cuda.synchronize()
+        opt_ms = e0.elapsed_time(e1) / 3
+        del opt
+
     # ---- roofline of the dominant kernel family (the tcgen05 GEMM), timed live with CUDA events around
     #      every GEMM launch of one extra step on the launching stream
     gemm_events = []
@@ -347,15 +397,21 @@ def _bench_workload(workload, args, dist, dev, world, rank, local_rank) -> dict 
     units = float(host["attention_mask"].sum()) if workload == "mlm" else float(B)  # tokens or windows per step
     total_flops = 0.0 if workload == "mlm" else _algorithmic_flops_infer(cfg, host) * (3.0 if train else 1.0)
     metric, unit = METRIC[workload]
-    neg = "global (embedding all-gather)" if (train and args.global_negatives and world > 1) else "local (per-rank)"
+    glob = bool(train and args.global_negatives and world > 1)
+    neg = "global (embedding all-gather)" if glob else "local (per-rank)"
+    default_cfg = workload != "train" or (V == TRAIN_VARIATIONS and B == BATCH_PER_GPU["train"])
     result = {
         "metric": metric, "value": round(world * units / (ms_step * 1e-3), 2), "unit": unit, "n_gpus": world,
         "steps": steps, "warmup": n_warm, "ms_per_step": round(ms_step, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "impl": "ours",
         "config": {
-            "workload": WORKLOAD_TEXT[workload].format(B=B, neg=neg),
-            "batch_per_gpu": B, "seq_len": MLM_SEQ_LEN if workload == "mlm" else SEQ_LEN, "real_tokens_per_step": int(host["attention_mask"].sum()),
+            "workload": WORKLOAD_TEXT[workload].format(B=B, neg=neg, V=V, cfgno=3 if args.global_negatives else 2),
+            "batch_per_gpu": B, "variations": V, "global_batch": B * world,
+            "seq_len": MLM_SEQ_LEN if workload == "mlm" else SEQ_LEN,
+            "real_tokens_per_step": int(host["attention_mask"].sum()),
+            "metadata_sequences_per_step": int(host["metadata_attention_mask"].numel() // host["metadata_attention_mask"].shape[-1]) if "metadata_attention_mask" in host else 0,
+            "parallelism": f"dp{world}",
             "weights": "random init (seeded), 136.9 M params",
             "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2; no explicit flush",
         },
@@ -363,30 +419,39 @@ def _bench_workload(workload, args, dist, dev, world, rank, local_rank) -> dict 
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "model_tflops": round(total_flops / (ms_step * 1e-3) / 1e12, 1),
+        "mfu": round(total_flops / (ms_step * 1e-3) / 1e12 / peaks["tflops"], 4),
         "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
         "roofline": {"kernel": "gemm_bf16_sm100_kernel (all epilogues)", "bound": "tensor",
                      "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
                      "frac": round(achieved / peaks["tflops"], 4),
-                     "traffic": GEMM_TRAFFIC[workload][0] if (workload in GEMM_TRAFFIC and B == BATCH_PER_GPU.get(workload)) else None,
+                     "traffic": GEMM_TRAFFIC[workload][0] if (workload in GEMM_TRAFFIC and default_cfg) else None,
                      "traffic_source": GEMM_TRAFFIC[workload][1] if workload in GEMM_TRAFFIC else None,
                      "algorithmic_bytes_per_launch": round(gemm_bytes / max(1, len(gemm_events))),
                      "launches_per_step": len(gemm_events), "share_of_step": round(gemm_ms / ms_step, 3),
                      "peak_source": peaks["source"]},
-        "roofline_attention": {"kernel": "attn_fwd_v2 / attn_bwd_dq + attn_bwd_dkv (varlen, D=64)", "bound": "tensor",
+        "roofline_attention": {"kernel": "attn_fwd_v2 / attn_bwd_dq + attn_bwd_dkv (varlen, D=64); packed short-sequence "
+                                         "kernels for the metadata tower", "bound": "tensor",
                                "achieved": round(attn_flops / (attn_ms * 1e-3) / 1e12, 1) if attn_ms > 0 else 0.0,
                                "peak": peaks["tflops"], "unit": "TFLOP/s",
                                "frac": round(attn_flops / (attn_ms * 1e-3) / 1e12 / peaks["tflops"], 4) if attn_ms > 0 else 0.0,
                                "flops": "algorithmic: 4*l*keys*64 per head forward, 10*l*keys*64 backward (5 GEMMs)",
                                "note": ("head_dim 64: a 128x128 tile needs 16384 exp2 = 1024 clk of the 16/clk/SM "
-                                        "MUFU against 512 clk (forward) / 1280 clk (backward, 5 GEMMs; 7 executed by "
-                                        "the two-kernel backward, which also exponentiates twice) of tcgen05 MMA, so "
-                                        "the exp unit caps the forward at 0.5 of the tensor peak; window layers "
-                                        "additionally compute 256 keys per row for a 129-key band"),
+                                        "MUFU against 512 clk (forward) / 1280 clk (backward, 5 GEMMs) of tcgen05 "
+                                        "MMA, so the exp unit caps the forward at 0.5 of the tensor peak; window "
+                                        "layers additionally compute 256 keys per row for a 129-key band"),
                                "launches_per_step": len(attn_events), "share_of_step": round(attn_ms / ms_step, 3)},
         "clocks": clocks,
     }
+    if comm is not None:
+        result.update(all_reduce_ms=comm["all_reduce_ms"], overlap=comm["overlap"], comm=comm)
+    elif train:
+        result.update(all_reduce_ms=0.0, overlap=None)
+    if opt_ms is not None:
+        result["optimizer_step_ms"] = round(opt_ms, 3)
+        result["optimizer"] = ("Muon (Newton-Schulz-5 x6, grouped over same-shape matrices) + internal AdamW; 3 timed "
+                               "steps, CUDA events; not part of ms_per_step")
     if rank == 0 and world == 1 and not args.no_cpu_baseline and workload != "mlm":
-        result["cpu_baseline"] = cpu_baseline(cfg, workload, sample_batch=2, reps=1)
+        result["cpu_baseline"] = cpu_baseline(cfg, workload, sample_batch=2, reps=1, variations=V)
     del model, resident, pinned
     torch.cuda.empty_cache()
     return result if rank == 0 else None
@@ -405,7 +470,7 @@ def run_ours(args) -> dict | None:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     try:
-        order = ["infer", "train"] if args.workload == "all" else [args.workload]
+        order = ["train", "infer"] if args.workload == "all" else [args.workload]
         results = {w: _bench_workload(w, args, dist, dev, world, rank, local_rank) for w in order}
     finally:
         if world > 1:
@@ -414,43 +479,77 @@ def run_ours(args) -> dict | None:
         return None
     head = results[order[0]]
     if len(order) > 1:
-        head["train"] = results["train"]
+        head["infer"] = results["infer"]
     return head
 
 
 # ------------------------------------------------------------------------------------------------
-def _cpu_run(cfg, workload, sample_batch, sd):
-    """One pass of the reference's algorithm (CPU oracle) over `sample_batch` windows; returns seconds."""
+# CPU arm: the reference's own implementation of the path on the host cores
+
+_REF = {}
+
+
+def _reference_model(cfg_dict):
+    """The UNMODIFIED reference CM3PModel (oracle/_ref, vendored by oracle/build_ref.py; /root/reference in the
+    build container) with the benchmark's seeded weights, or None when it is not available on this box."""
+    if "model" in _REF:
+        return _REF["model"]
+    model = None
+    try:
+        from oracle.ref_shim import build_reference_model, reference_available
+        if reference_available():
+            model, rcfg = build_reference_model(cfg_dict, attn_implementation="sdpa")
+            cfg = CM3PConfig(**copy.deepcopy(cfg_dict))
+            missing, unexpected = model.load_state_dict(synthetic_state_dict(cfg, seed=0), strict=False)
+            bad = [k for k in missing if "tok_embeddings" not in k or "audio_encoder" not in k]
+            if bad or unexpected:
+                raise RuntimeError(f"reference state dict mismatch: missing {bad[:4]} unexpected {list(unexpected)[:4]}")
+    except Exception as exc:  # noqa: BLE001  (no reference on this box: fall back to the oracle port, say so)
+        print(f"[bench] reference model unavailable ({type(exc).__name__}: {exc}); timing the oracle port", file=sys.stderr)
+        model = None
+    _REF["model"] = model
+    return model
+
+
+def _cpu_run(cfg, workload, sample_batch, sd, variations):
+    """One pass of the reference's CPU path over `sample_batch` windows; returns (seconds, kind)."""
     from oracle import cm3p_oracle as O
 
-    V = 1 if workload == "infer" else TRAIN_VARIATIONS
+    V = 1 if workload == "infer" else variations
     batch = synthetic_batch(cfg, batch=sample_batch, seq_len=SEQ_LEN, variations=V, seed=1, min_len=MIN_LEN)
+    ref = _reference_model(base_config_dict())
     t0 = time.perf_counter()
+    if ref is not None:
+        if workload == "infer":
+            with torch.no_grad():
+                ref(**{k: v.clone() for k, v in batch.items()}, return_loss=False)
+        else:
+            ref.zero_grad(set_to_none=True)
+            out = ref(**{k: v.clone() for k, v in batch.items()})
+            out.loss.backward()
+        return time.perf_counter() - t0, "reference"
     if workload == "infer":
         with torch.no_grad():
             O.model_forward(sd, cfg, **batch, return_loss=False)
     else:
         O.forward_backward(sd, cfg, batch)
-    return time.perf_counter() - t0
+    return time.perf_counter() - t0, "port"
 
 
-def cpu_baseline(cfg, workload, sample_batch, reps):
-    """The reference's algorithm (CPU oracle, fp32, torch SDPA like the reference's `sdpa` path) on
-    the host cores, on a bounded sample of the same workload."""
-    from oracle import cm3p_oracle as O
-
+def cpu_baseline(cfg, workload, sample_batch, reps, variations=TRAIN_VARIATIONS):
+    """The reference's CPU `sdpa` path (fp32) on the host cores, on a bounded sample of the same workload."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = synthetic_state_dict(cfg, seed=0)
-    with torch.no_grad():
-        warm = synthetic_batch(cfg, batch=1, seq_len=256, variations=1, seed=5, min_len=220)
-        O.model_forward(sd, cfg, **warm, return_loss=False)
-    best = min(_cpu_run(cfg, workload, sample_batch, sd) for _ in range(reps))
+    runs = [_cpu_run(cfg, workload, sample_batch, sd, variations) for _ in range(reps + 1)]  # first = warm-up
+    best = min(t for t, _ in runs[1:])
+    kind = runs[-1][1]
     metric, unit = METRIC[workload]
     what = "forward" if workload == "infer" else "forward + autograd backward"
-    return {"value": round(sample_batch / best, 4), "unit": unit, "cores": cores, "kind": "port",
-            "sample": f"{sample_batch} windows of the same workload (L={SEQ_LEN}), {what}, fp32, torch CPU SDPA, "
-                      f"{cores} threads, best of {reps}; {best:.2f} s"}
+    impl = "unmodified reference CM3PModel (oracle/_ref), sdpa" if kind == "reference" else "oracle port, torch CPU SDPA"
+    return {"value": round(sample_batch / best, 4), "unit": unit, "cores": cores, "kind": kind,
+            "sample": f"{sample_batch} windows of the same workload (L={SEQ_LEN}), {what}, fp32, {impl}, "
+                      f"{cores} threads, best of {reps} after a warm-up pass; {best:.2f} s"}
 
 
 def _reference_workload(workload, args) -> dict:
@@ -458,40 +557,46 @@ def _reference_workload(workload, args) -> dict:
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = synthetic_state_dict(cfg, seed=0)
-    sample = 2
+    V = args.variations if workload == "train" else 1
+    # bounded sample: 2 windows per step unless a probe pass says the whole run would exceed ~3 minutes
+    probe, kind = _cpu_run(cfg, workload, 1, sd, V)   # also the lazy-initialisation pass
+    probe, kind = _cpu_run(cfg, workload, 1, sd, V)
+    sample = 2 if 2 * probe * (args.warmup + args.steps) <= 180.0 else 1
     times = []
     for i in range(args.warmup + args.steps):
-        dt = _cpu_run(cfg, workload, sample, sd)
+        dt, kind = _cpu_run(cfg, workload, sample, sd, V)
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
     metric, unit = METRIC[workload]
     value = round(sample / (ms * 1e-3), 4)
     what = "forward" if workload == "infer" else "forward + autograd backward"
+    impl = "unmodified reference CM3PModel (oracle/_ref), sdpa" if kind == "reference" else "oracle port, torch CPU SDPA"
     return {
         "impl": "reference", "metric": metric, "value": value, "unit": unit,
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD_TEXT[workload].format(B=sample, neg="local (per-rank)")
-                   + f" -- CPU arm: each step = a bounded sample of {sample} windows, {what}", "seq_len": SEQ_LEN},
-        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port",
-                         "sample": f"{sample} windows/step (L={SEQ_LEN}), {what}, fp32, torch CPU SDPA, "
-                                   f"{cores} threads"},
+        "config": {"workload": WORKLOAD_TEXT[workload].format(B=sample, neg="local (per-rank)", V=V, cfgno=2)
+                   + f" -- CPU arm: each step = a bounded sample of {sample} windows, {what}", "seq_len": SEQ_LEN,
+                   "variations": V},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind,
+                         "sample": f"{sample} windows/step (L={SEQ_LEN}), {what}, fp32, {impl}, {cores} threads"},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
 
 
 def run_reference(args) -> dict | None:
-    """The reference's own CPU implementation of the path (oracle port: the reference is Python and does
-    not travel to the GPU box) on the host cores.  Rank 0 only."""
+    """The reference's own CPU implementation of the path on the host cores.  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return None
-    order = ["infer", "train"] if args.workload == "all" else [args.workload]
+    order = ["train", "infer"] if args.workload == "all" else [args.workload]
+    if "mlm" in order:
+        return {"impl": "reference", "unavailable": "the CPU arm covers the train and infer workloads only"}
     res = {w: _reference_workload(w, args) for w in order}
     head = res[order[0]]
     if len(order) > 1:
-        head["train"] = res["train"]
+        head["infer"] = res["infer"]
     return head
 
 
@@ -503,8 +608,11 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=["all", "infer", "train", "mlm"], default="all")
     ap.add_argument("--train-batch", type=int, default=BATCH_PER_GPU["train"], help="train windows per GPU")
+    ap.add_argument("--variations", type=int, default=TRAIN_VARIATIONS,
+                    help="metadata variations per beatmap in the train step (reference v7: 256)")
     ap.add_argument("--global-negatives", action="store_true",
-                    help="train: all-gather embeddings and use the global loss (BASELINE.json configs[3])")
+                    help="train: all-gather embeddings and use the global loss (BASELINE.json configs[3]: "
+                         "--train-batch 512 --variations 1 on 8 GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true",
                     help="profiling aid: only the device-resident timed loop (no e2e / roofline / CPU legs)")

@@ -18,12 +18,16 @@ extern "C" {
 const char* cm3p_last_error(void) { return last_error(); }
 int cm3p_version(void) { return CM3P_B200_VERSION; }
 int cm3p_num_sms(void) { return num_sms(); }
+int cm3p_set_option(int option, int value) { return set_option(option, value); }
+int cm3p_get_option(int option) { return get_option(option); }
 
 int cm3p_gemm_bf16(const void* a, int64_t lda, int trans_a, const void* b, int64_t ldb, int trans_b, void* c,
                    int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue, const void* aux, int64_t ld_aux,
                    void* c2, int64_t ldc2, float scale, int accumulate, const int32_t* positions,
-                   const float* rope_table, int64_t rope_cols, void* stream) {
+                   const float* rope_table, int64_t rope_cols, int32_t* tile_sem, int64_t tile_sem_count,
+                   int64_t group_m, void* stream) {
   GemmArgs g;
+  g.tile_sem = tile_sem; g.tile_sem_count = tile_sem_count; g.group_m = group_m;
   g.a = a; g.lda = lda; g.trans_a = trans_a;
   g.b = b; g.ldb = ldb; g.trans_b = trans_b;
   g.c = c; g.ldc = ldc;
@@ -53,9 +57,16 @@ int cm3p_gemm_bf16_ln(const void* a, int64_t lda, const void* b, int64_t ldb, vo
   return gemm_bf16(g, as_stream(stream));
 }
 
+int cm3p_attn_pack_groups(const int32_t* cu_seqlens, int batch, int32_t* groups, int32_t* n_groups, int max_groups,
+                          void* stream) {
+  return attn_pack_groups(cu_seqlens, batch, groups, n_groups, max_groups, as_stream(stream));
+}
+
 int cm3p_attn_varlen_fwd(const void* qkv, void* out, float* lse, const int32_t* cu_seqlens, int64_t total_tokens,
-                         int batch, int heads, int head_dim, int max_seqlen, int window, void* stream) {
+                         int batch, int heads, int head_dim, int max_seqlen, int window, const int32_t* groups,
+                         const int32_t* n_groups, int max_groups, void* stream) {
   AttnFwdArgs a;
+  a.groups = groups; a.n_groups = n_groups; a.max_groups = max_groups;
   a.qkv = qkv; a.out = out; a.lse = lse; a.cu_seqlens = cu_seqlens;
   a.total_tokens = total_tokens; a.batch = batch; a.heads = heads; a.head_dim = head_dim;
   a.max_seqlen = max_seqlen; a.window = window;
@@ -158,8 +169,9 @@ int cm3p_clip_loss_fwd(const float* S, const int32_t* true_idx, float* row_lse, 
 int cm3p_attn_varlen_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
                          const int32_t* cu_seqlens, const int32_t* positions, const float* rope_table,
                          int64_t total_tokens, int batch, int heads, int head_dim, int max_seqlen, int window,
-                         void* stream) {
+                         const int32_t* groups, const int32_t* n_groups, int max_groups, void* stream) {
   AttnBwdArgs a;
+  a.groups = groups; a.n_groups = n_groups; a.max_groups = max_groups;
   a.qkv = qkv; a.out = out; a.dout = dout; a.lse = lse; a.delta = delta; a.dqkv = dqkv;
   a.cu_seqlens = cu_seqlens; a.positions = positions; a.rope_table = rope_table;
   a.total_tokens = total_tokens; a.batch = batch; a.heads = heads; a.head_dim = head_dim;

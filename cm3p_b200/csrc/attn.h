@@ -16,7 +16,17 @@ struct AttnFwdArgs {
   int head_dim = 64;
   int max_seqlen = 0;
   int window = -1;  // < 0: global attention; otherwise attend iff |i-j| <= window
+  // packed short sequences (all three or none): group table from attn_pack_groups, needs max_seqlen <= 128
+  const int32_t* groups = nullptr;    // [max_groups][2] (first sequence, end sequence)
+  const int32_t* n_groups = nullptr;  // device scalar
+  int max_groups = 0;
 };
+
+// Packs consecutive sequences into groups of <= 128 tokens (the unit of work of the packed attention kernels).
+// groups: [max_groups][2] int32, n_groups: device scalar (zeroed here).  max_groups must be at least
+// min(batch, 2 * (total_tokens / 128) + ceil(batch / 64) + 1).
+int attn_pack_groups(const int32_t* cu_seqlens, int batch, int32_t* groups, int32_t* n_groups, int max_groups,
+                     cudaStream_t stream);
 
 int attn_varlen_fwd(const AttnFwdArgs& args, cudaStream_t stream);
 
@@ -36,10 +46,12 @@ struct AttnBwdArgs {
   int head_dim = 64;
   int max_seqlen = 0;
   int window = -1;
+  const int32_t* groups = nullptr;  // packed short sequences, as in AttnFwdArgs
+  const int32_t* n_groups = nullptr;
+  int max_groups = 0;
 };
 
 int attn_varlen_bwd(const AttnBwdArgs& args, cudaStream_t stream);
-int attn_varlen_bwd_v2(const AttnBwdArgs& args, cudaStream_t stream);  // 1 CTA/SM ping-pong kernels (CM3P_ATTN_BWD=v2)
 int attn_varlen_bwd_v3(const AttnBwdArgs& args, cudaStream_t stream);  // 128x128 tiles, early S/dP issue (long sequences)
 
 }  // namespace cm3p

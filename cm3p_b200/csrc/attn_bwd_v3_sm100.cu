@@ -62,6 +62,7 @@ struct BwdParams {
   float scale_log2;
   float scale;
   int outer_per_cta;
+  int ctas_per_seq;  // grid.x = batch * ctas_per_seq (grid.z stops at 65535 sequences)
 };
 
 __device__ __forceinline__ uint4 pack8f(const float* v) {
@@ -169,10 +170,10 @@ attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int seq = blockIdx.z, head = blockIdx.y;
+  const int seq = blockIdx.x / p.ctas_per_seq, head = blockIdx.y;
   const int seq_start = p.cu_seqlens[seq];
   const int len = p.cu_seqlens[seq + 1] - seq_start;
-  const int o_begin = blockIdx.x * p.outer_per_cta;
+  const int o_begin = (blockIdx.x % p.ctas_per_seq) * p.outer_per_cta;
   const int n_o = min(p.outer_per_cta, (len + BT - 1) / BT - o_begin);  // outer tiles of this CTA
   if (n_o <= 0) return;
 
@@ -481,7 +482,7 @@ attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __gr
     }
     write_out(n_o - 1);
 #ifdef CM3P_ATTN_PROF
-    if (threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    if (threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < p.ctas_per_seq) {
       const long long pf1 = clock64();
       for (int oi = 0; oi < n_o; ++oi) printf("dq cta %d outer %d start +%lld\n", blockIdx.x, oi, pf_ev[oi] - pf0);
       printf("dq cta %d end +%lld tiles=%d\n", blockIdx.x, pf1 - pf0, it);
@@ -510,10 +511,10 @@ attn_bwd_dkv_v3_kernel(const __grid_constant__ CUtensorMap tma_qkv128, const __g
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int seq = blockIdx.z, head = blockIdx.y;
+  const int seq = blockIdx.x / p.ctas_per_seq, head = blockIdx.y;
   const int seq_start = p.cu_seqlens[seq];
   const int len = p.cu_seqlens[seq + 1] - seq_start;
-  const int o_begin = blockIdx.x * p.outer_per_cta;
+  const int o_begin = (blockIdx.x % p.ctas_per_seq) * p.outer_per_cta;
   const int n_o = min(p.outer_per_cta, (len + BT - 1) / BT - o_begin);
   if (n_o <= 0) return;
 
@@ -850,12 +851,8 @@ int attn_varlen_bwd_v3(const AttnBwdArgs& a, cudaStream_t stream) {
   int rc;
   if ((rc = encode_tmap_2d_bf16(&qkv128, a.qkv, 3 * H, T, 3 * H * 2, 64, BT)) != kOk) return rc;
   if ((rc = encode_tmap_2d_bf16(&do128, a.dout, H, T, H * 2, 64, BT)) != kOk) return rc;
-  static bool configured = false;
-  if (!configured) {
-    CM3P_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dq_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
-    CM3P_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dkv_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
-    configured = true;
-  }
+  CM3P_ENSURE_DYN_SMEM(attn_bwd_dq_v3_kernel, DQ_SMEM);
+  CM3P_ENSURE_DYN_SMEM(attn_bwd_dkv_v3_kernel, DKV_SMEM);
   BwdParams p;
   p.cu_seqlens = a.cu_seqlens;
   p.out = reinterpret_cast<const __nv_bfloat16*>(a.out);
@@ -875,16 +872,17 @@ int attn_varlen_bwd_v3(const AttnBwdArgs& a, cudaStream_t stream) {
   attn_bwd_delta_kernel<<<static_cast<unsigned>((vec_units + 255) / 256), 256, 0, stream>>>(p.out, p.dout, p.delta,
                                                                                        a.total_tokens, a.heads);
   CM3P_CUDA_TRY(cudaGetLastError());
-  // read on every call (not cached): the tests sweep it
-  const char* opc_env = getenv("CM3P_BWD_OUTER_PER_CTA");
-  const int forced_opc = opc_env ? atoi(opc_env) : 0;
+  const int forced_opc = get_option(kOptBwdOuterPerCta);  // 0 = heuristic (the tests sweep it)
   const int64_t units = (a.total_tokens / BT + a.batch / 2 + 1) * a.heads;  // ~ (sequence, head, outer tile) triples
   const int64_t target_ctas = static_cast<int64_t>(num_sms()) * (a.window >= 0 ? 4 : 16);
   int opc = static_cast<int>((units + target_ctas - 1) / target_ctas);
   opc = opc < 2 ? 2 : (opc > MAX_OUTER_PER_CTA ? MAX_OUTER_PER_CTA : opc);
   if (forced_opc > 0) opc = forced_opc > MAX_OUTER_PER_CTA ? MAX_OUTER_PER_CTA : forced_opc;
   p.outer_per_cta = opc;
-  dim3 grid((a.max_seqlen + BT * opc - 1) / (BT * opc), a.heads, a.batch);
+  p.ctas_per_seq = (a.max_seqlen + BT * opc - 1) / (BT * opc);
+  CM3P_REQUIRE(static_cast<int64_t>(p.ctas_per_seq) * a.batch <= 0x7fffffffLL && a.heads <= 65535, kBadShape,
+               "attn_bwd: grid too large (batch=%d max_seqlen=%d heads=%d)", a.batch, a.max_seqlen, a.heads);
+  dim3 grid(static_cast<unsigned>(p.ctas_per_seq) * a.batch, a.heads, 1);
   attn_bwd_dq_v3_kernel<<<grid, THREADS, DQ_SMEM, stream>>>(qkv128, do128, p);
   CM3P_CUDA_TRY(cudaGetLastError());
   attn_bwd_dkv_v3_kernel<<<grid, THREADS, DKV_SMEM, stream>>>(qkv128, do128, p);

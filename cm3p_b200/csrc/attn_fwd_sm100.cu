@@ -51,6 +51,7 @@ struct Params {
   int window;  // < 0: global
   float scale_log2;  // (1/sqrt(64)) * log2(e)
   int blocks_per_cta;  // v2: consecutive 256-query blocks streamed by one CTA
+  int ctas_per_seq;    // grid.x = batch * ctas_per_seq (the sequence index lives in grid.x: grid.z stops at 65535)
 };
 
 __global__ void __launch_bounds__(THREADS, 2)
@@ -59,11 +60,11 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int seq = blockIdx.z;
+  const int seq = blockIdx.x / p.ctas_per_seq;
   const int head = blockIdx.y;
   const int seq_start = p.cu_seqlens[seq];
   const int len = p.cu_seqlens[seq + 1] - seq_start;
-  const int q0 = blockIdx.x * BQ;
+  const int q0 = (blockIdx.x % p.ctas_per_seq) * BQ;
   if (q0 >= len) return;  // whole CTA exits together, before any barrier / TMEM use
 
   uint8_t* smem_q = smem;
@@ -285,6 +286,248 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params 
 
 
 // ================================================================================================
+// Packed short sequences (metadata tower: ~17-25 real tokens per sequence, B*V up to 65 536 sequences).
+// One 128-row tile per SEQUENCE wastes >80 % of every MMA and exp pass and pays a CTA's fixed cost per 21
+// tokens.  Here consecutive sequences are packed into groups of <= 128 tokens (attn_pack_groups_kernel:
+// greedy inside chunks of 64 sequences, one warp per chunk, group order irrelevant), and one CTA handles one
+// (group, head): Q = K = V rows are the same 128-row slab of the token matrix, S = Q K^T is ONE 128x128 MMA
+// whose mask is block diagonal (row i attends to the columns of its own sequence), O = P V one more.
+// 80 KB smem, 256 TMEM columns: two CTAs per SM.
+namespace packed {
+
+constexpr int CHUNK_SEQS = 64;       // sequences walked by one warp of the group builder
+constexpr int SB_INTS = CHUNK_SEQS + 4;
+
+__global__ void __launch_bounds__(256)
+attn_pack_groups_kernel(const int32_t* __restrict__ cu, int batch, int2* __restrict__ groups,
+                        int32_t* __restrict__ n_groups, int max_groups) {
+  __shared__ int32_t s_cu[8][CHUNK_SEQS + 1];
+  __shared__ int2 s_grp[8][CHUNK_SEQS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int base = (blockIdx.x * 8 + warp) * CHUNK_SEQS;
+  if (base >= batch) return;  // warp-uniform
+  const int n = min(CHUNK_SEQS, batch - base);
+  for (int i = lane; i <= n; i += 32) s_cu[warp][i] = cu[base + i];
+  __syncwarp();
+  int s = 0, k = 0;
+  while (s < n) {
+    const int c0 = s_cu[warp][s];
+    // largest e in (s, n] with cu[e] - cu[s] <= 128 (monotone in e); at least s + 1
+    const int e1 = lane + 1, e2 = lane + 33;
+    const bool ok1 = e1 > s && e1 <= n && s_cu[warp][e1] - c0 <= BQ;
+    const bool ok2 = e2 > s && e2 <= n && s_cu[warp][e2] - c0 <= BQ;
+    const unsigned m1 = __ballot_sync(0xffffffffu, ok1), m2 = __ballot_sync(0xffffffffu, ok2);
+    int e = s + 1;
+    if (m2) e = 33 + (31 - __clz(m2));
+    else if (m1) e = 1 + (31 - __clz(m1));
+    if (s_cu[warp][e] - c0 > 0) {  // groups without tokens (empty sequences only) are dropped
+      if (lane == 0) s_grp[warp][k] = make_int2(base + s, base + e);
+      ++k;
+    }
+    s = e;
+  }
+  __syncwarp();
+  int off = 0;
+  if (lane == 0 && k > 0) off = atomicAdd(n_groups, k);
+  off = __shfl_sync(0xffffffffu, off, 0);
+  for (int i = lane; i < k; i += 32)
+    if (off + i < max_groups) groups[off + i] = s_grp[warp][i];
+}
+
+constexpr int P_SMEM_TILES = 3 * Q_BYTES + P_BYTES;  // Q, K, V (16 KB each) + P (32 KB) = 80 KB
+constexpr int P_SMEM_BYTES = P_SMEM_TILES + SB_INTS * 4 + 128;
+
+struct PackedParams {
+  const int32_t* cu_seqlens;
+  const int2* groups;
+  const int32_t* n_groups;
+  __nv_bfloat16* out;
+  float* lse;
+  int64_t total_tokens;
+  int hidden;
+  float scale_log2;
+};
+
+// bounds [lo, hi) (rows relative to the group's first token) of the sequence that holds row t
+__device__ __forceinline__ void row_bounds(const int* sb, int nseq, int t, int& lo, int& hi) {
+  int a = 0, b = nseq;  // sb[a] <= t < sb[b]
+  while (b - a > 1) {
+    const int m = (a + b) >> 1;
+    if (sb[m] <= t) a = m; else b = m;
+  }
+  lo = sb[a];
+  hi = sb[b];
+}
+
+__global__ void __launch_bounds__(THREADS, 2)
+attn_fwd_packed_kernel(const __grid_constant__ CUtensorMap tma_qkv, const PackedParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x, head = blockIdx.y;
+  if (g >= *p.n_groups) return;  // the grid is sized for the worst case
+  const int2 grp = p.groups[g];
+  const int tok0 = p.cu_seqlens[grp.x];
+  const int rows = p.cu_seqlens[grp.y] - tok0;  // 1..128
+  const int nseq = grp.y - grp.x;
+  if (rows <= 0) return;
+
+  uint8_t* smem_q = smem;
+  uint8_t* smem_k = smem + Q_BYTES;
+  uint8_t* smem_v = smem + 2 * Q_BYTES;
+  uint8_t* smem_p = smem + 3 * Q_BYTES;
+  int* sb = reinterpret_cast<int*>(smem + P_SMEM_TILES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_SMEM_TILES + SB_INTS * 4);
+  uint64_t* ld_full = bars;
+  uint64_t* s_full = bars + 1;
+  uint64_t* p_full = bars + 2;
+  uint64_t* o_full = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
+  for (int i = threadIdx.x; i <= nseq; i += THREADS) sb[i] = p.cu_seqlens[grp.x + i] - tok0;
+  if (warp == 5 && lane == 0) {
+    ptx::mbar_init(ld_full, 1);
+    ptx::mbar_init(s_full, 1);
+    ptx::mbar_init(p_full, 128);
+    ptx::mbar_init(o_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 4) {
+    if (lane == 0) ptx::prefetch_tmap(&tma_qkv);
+    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int ksteps = (rows + 15) >> 4;  // 16-key steps of P.V that can hold a non-zero probability
+
+  if (warp == 4) {
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(ld_full, 3 * Q_BYTES);
+      ptx::tma_load_2d(smem_q, &tma_qkv, ld_full, head * D, tok0);
+      ptx::tma_load_2d(smem_k, &tma_qkv, ld_full, p.hidden + head * D, tok0);
+      ptx::tma_load_2d(smem_v, &tma_qkv, ld_full, 2 * p.hidden + head * D, tok0);
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc_s = ptx::umma_idesc_bf16(BQ, BKV, 0, 0);
+      const uint32_t idesc_o = ptx::umma_idesc_bf16(BQ, D, 0, 1);  // V is MN-major
+      const uint32_t q_addr = ptx::smem_u32(smem_q), k_addr = ptx::smem_u32(smem_k);
+      const uint32_t v_addr = ptx::smem_u32(smem_v), p_addr = ptx::smem_u32(smem_p);
+      ptx::mbar_wait(ld_full, 0);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k)
+        ptx::umma_bf16(tmem_base + TMEM_S, ptx::umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                       ptx::umma_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+      ptx::umma_commit(s_full);
+      ptx::mbar_wait(p_full, 0);
+      ptx::tc_fence_after();
+      for (int k = 0; k < ksteps; ++k)
+        ptx::umma_bf16(tmem_base + TMEM_O,
+                       ptx::umma_smem_desc_sw128(p_addr + (k >> 2) * (BQ * 128) + (k & 3) * 32, 16, 1024),
+                       ptx::umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_o, k != 0 ? 1u : 0u);
+      ptx::umma_commit(o_full);
+    }
+  } else {
+    const int t = threadIdx.x;  // row inside the group == TMEM lane
+    const bool valid = t < rows;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const float c = p.scale_log2;
+    int lo = 0, hi = 0;
+    if (valid) row_bounds(sb, nseq, t, lo, hi);
+    // columns any row of this warp may attend to: chunks outside are skipped (zeros, no TMEM read, no exp)
+    const int wa = __reduce_min_sync(0xffffffffu, valid ? lo : BKV);
+    const int wb = __reduce_max_sync(0xffffffffu, valid ? hi : 0);
+    ptx::mbar_wait(s_full, 0);
+    ptx::tc_fence_after();
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BKV; c0 += 32) {
+      if (c0 + 32 <= wa || c0 >= wb) continue;  // warp-uniform
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(tmem_base + TMEM_S + lane_off + c0, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int kj = c0 + i;
+        mx = fmaxf(mx, (kj >= lo && kj < hi) ? __uint_as_float(r[i]) : -INFINITY);
+      }
+    }
+    const float mc = (mx == -INFINITY) ? 0.f : mx * c;
+    float rs = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BKV; c0 += 32) {
+      uint8_t* prow = smem_p + (c0 >> 6) * (BQ * 128) + t * 128;
+      const int u0 = (c0 & 32) ? 4 : 0;
+      if (c0 + 32 <= wa || c0 >= wb) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(prow + (((u0 + u) ^ (t & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+        continue;
+      }
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(tmem_base + TMEM_S + lane_off + c0, r);
+      ptx::tmem_ld_wait();
+      uint32_t packed[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const int kj = c0 + i;
+        const float p0 = (kj >= lo && kj < hi) ? ptx::ex2_approx(__uint_as_float(r[i]) * c - mc) : 0.f;
+        const float p1 = (kj + 1 >= lo && kj + 1 < hi) ? ptx::ex2_approx(__uint_as_float(r[i + 1]) * c - mc) : 0.f;
+        packed[i >> 1] = ptx::pack_bf16x2(p0, p1);
+        const float2 pr = ptx::unpack_bf16x2(packed[i >> 1]);  // sum what the tensor core multiplies
+        rs += pr.x + pr.y;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        *reinterpret_cast<uint4*>(prow + (((u0 + u) ^ (t & 7)) << 4)) =
+            make_uint4(packed[u * 4], packed[u * 4 + 1], packed[u * 4 + 2], packed[u * 4 + 3]);
+    }
+    ptx::tc_fence_before();
+    ptx::fence_proxy_async_smem();
+    ptx::mbar_arrive(p_full);
+    ptx::mbar_wait(o_full, 0);
+    ptx::tc_fence_after();
+    uint32_t o[64];
+    {
+      uint32_t r1[32], r2[32];
+      ptx::tmem_ld_32x32b_x32(tmem_base + TMEM_O + lane_off, r1);
+      ptx::tmem_ld_32x32b_x32(tmem_base + TMEM_O + lane_off + 32, r2);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { o[i] = r1[i]; o[32 + i] = r2[i]; }
+    }
+    if (valid) {
+      const float inv = 1.f / rs;
+      const int64_t row = static_cast<int64_t>(tok0) + t;
+      __nv_bfloat16* dst = p.out + row * p.hidden + head * D;
+#pragma unroll
+      for (int i = 0; i < D; i += 8) {
+        uint4 u;
+        u.x = ptx::pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+        u.y = ptx::pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+        u.z = ptx::pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+        u.w = ptx::pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+        *reinterpret_cast<uint4*>(dst + i) = u;
+      }
+      if (p.lse) p.lse[static_cast<int64_t>(head) * p.total_tokens + row] = mc + log2f(rs);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace packed
+
+// ================================================================================================
 // v2: one CTA per SM streams `blocks_per_cta` consecutive 256-query blocks of one (sequence, head); a block
 // is two 128-row Q tiles A and B.  20 warps:
 //   warps 0-7 softmax group A, warps 8-15 softmax group B: TMEM lane quadrant (warp & 3) x 64-key column half,
@@ -347,10 +590,10 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int seq = blockIdx.z, head = blockIdx.y;
+  const int seq = blockIdx.x / p.ctas_per_seq, head = blockIdx.y;
   const int seq_start = p.cu_seqlens[seq];
   const int len = p.cu_seqlens[seq + 1] - seq_start;
-  const int b_begin = blockIdx.x * p.blocks_per_cta;
+  const int b_begin = (blockIdx.x % p.ctas_per_seq) * p.blocks_per_cta;
   const int n_b = min(p.blocks_per_cta, (len + 2 * BQ - 1) / (2 * BQ) - b_begin);  // 256-query blocks of this CTA
   if (n_b <= 0) return;
 
@@ -725,7 +968,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
     }
 #ifdef CM3P_ATTN_PROF
     PF_B(pf_epi);
-    if (lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+    if (lane == 0 && blockIdx.x == 0 && blockIdx.y == 0)
       printf("attn fwd warp %2d: blocks=%d tiles=%d total=%lld wait_s=%lld ld=%lld max+exchange=%lld exp+store=%lld "
              "epilogue=%lld\n", warp, n_b, it, clock64() - pf_t0, pf_s, pf_ld, pf_max, pf_exp, pf_epi);
 #endif
@@ -742,6 +985,21 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
 }  // namespace v2
 }  // namespace
 
+int attn_pack_groups(const int32_t* cu_seqlens, int batch, int32_t* groups, int32_t* n_groups, int max_groups,
+                     cudaStream_t stream) {
+  int rc = check_arch();
+  if (rc != kOk) return rc;
+  CM3P_REQUIRE(cu_seqlens && groups && n_groups && batch > 0 && max_groups > 0, kBadShape,
+               "attn_pack_groups: null pointer or empty batch");
+  CM3P_REQUIRE((reinterpret_cast<uintptr_t>(groups) & 7) == 0, kBadAlignment, "attn_pack_groups: groups must be 8-byte aligned");
+  CM3P_CUDA_TRY(cudaMemsetAsync(n_groups, 0, sizeof(int32_t), stream));
+  const int chunks = (batch + packed::CHUNK_SEQS - 1) / packed::CHUNK_SEQS;
+  packed::attn_pack_groups_kernel<<<(chunks + 7) / 8, 256, 0, stream>>>(cu_seqlens, batch, reinterpret_cast<int2*>(groups),
+                                                                      n_groups, max_groups);
+  CM3P_CUDA_TRY(cudaGetLastError());
+  return kOk;
+}
+
 int attn_varlen_fwd(const AttnFwdArgs& a, cudaStream_t stream) {
   int rc = check_arch();
   if (rc != kOk) return rc;
@@ -750,14 +1008,30 @@ int attn_varlen_fwd(const AttnFwdArgs& a, cudaStream_t stream) {
                "attn: empty problem (batch=%d heads=%d tokens=%lld max_seqlen=%d)", a.batch, a.heads,
                (long long)a.total_tokens, a.max_seqlen);
   CM3P_REQUIRE(a.qkv && a.out && a.cu_seqlens, kBadShape, "attn: null pointer");
+  CM3P_REQUIRE(a.heads <= 65535, kBadShape, "attn: heads=%d exceeds the grid limit", a.heads);
   const int H = a.heads * 64;
   CUtensorMap tmap;
   rc = encode_tmap_2d_bf16(&tmap, a.qkv, 3 * (uint64_t)H, (uint64_t)a.total_tokens, 3 * (uint64_t)H * 2, 64, BKV);
   if (rc != kOk) return rc;
-  static bool configured = false;
-  if (!configured) {
-    CM3P_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
+  if (a.groups) {
+    // packed short sequences: one CTA per (group of sequences with <= 128 tokens in total, head)
+    CM3P_REQUIRE(a.n_groups && a.max_groups > 0, kBadShape, "attn(packed): n_groups / max_groups missing");
+    CM3P_REQUIRE(a.max_seqlen <= BQ && a.window < 0, kBadShape,
+                 "attn(packed): needs max_seqlen <= 128 (got %d) and a global layer (window %d)", a.max_seqlen, a.window);
+    CM3P_ENSURE_DYN_SMEM(packed::attn_fwd_packed_kernel, packed::P_SMEM_BYTES);
+    packed::PackedParams pp;
+    pp.cu_seqlens = a.cu_seqlens;
+    pp.groups = reinterpret_cast<const int2*>(a.groups);
+    pp.n_groups = a.n_groups;
+    pp.out = reinterpret_cast<__nv_bfloat16*>(a.out);
+    pp.lse = a.lse;
+    pp.total_tokens = a.total_tokens;
+    pp.hidden = H;
+    pp.scale_log2 = 0.125f * 1.4426950408889634f;
+    dim3 grid(a.max_groups, a.heads, 1);
+    packed::attn_fwd_packed_kernel<<<grid, THREADS, packed::P_SMEM_BYTES, stream>>>(tmap, pp);
+    CM3P_CUDA_TRY(cudaGetLastError());
+    return kOk;
   }
   Params p;
   p.cu_seqlens = a.cu_seqlens;
@@ -769,33 +1043,26 @@ int attn_varlen_fwd(const AttnFwdArgs& a, cudaStream_t stream) {
   p.window = a.window;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   p.blocks_per_cta = 1;
-  static int use_v1 = -1;
-  if (use_v1 < 0) {
-    const char* e = getenv("CM3P_ATTN_FWD_V1");
-    use_v1 = (e && e[0] == '1') ? 1 : 0;
-  }
-  // short sequences (metadata tower: ~20 tokens) fit one 128-row tile: the light 2-CTA/SM kernel wins there
-  if (use_v1 || a.max_seqlen <= BQ) {
-    dim3 grid((a.max_seqlen + BQ - 1) / BQ, a.heads, a.batch);
+  // short sequences fit one 128-row tile: the light 2-CTA/SM kernel wins there
+  if (get_option(kOptAttnForceTileKernels) || a.max_seqlen <= BQ) {
+    CM3P_ENSURE_DYN_SMEM(attn_fwd_sm100_kernel, SMEM_BYTES);
+    p.ctas_per_seq = (a.max_seqlen + BQ - 1) / BQ;
+    CM3P_REQUIRE(static_cast<int64_t>(p.ctas_per_seq) * a.batch <= 0x7fffffffLL, kBadShape, "attn: grid too large");
+    dim3 grid(static_cast<unsigned>(p.ctas_per_seq) * a.batch, a.heads, 1);
     attn_fwd_sm100_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmap, p);
   } else {
-    static bool configured2 = false;
-    if (!configured2) {
-      CM3P_CUDA_TRY(cudaFuncSetAttribute(v2::attn_fwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         v2::SMEM_BYTES2));
-      configured2 = true;
-    }
+    CM3P_ENSURE_DYN_SMEM(v2::attn_fwd_v2_kernel, v2::SMEM_BYTES2);
     // blocks per CTA: enough CTAs for ~16 (global) / ~4 (window) waves of uneven work
-    // read on every call (not cached): the tests sweep it
-    const char* bpc_env = getenv("CM3P_FWD_BLOCKS_PER_CTA");
-    const int forced_bpc = bpc_env ? atoi(bpc_env) : 0;
+    const int forced_bpc = get_option(kOptFwdBlocksPerCta);
     const int64_t units = (a.total_tokens / (2 * BQ) + a.batch / 2 + 1) * a.heads;
     const int64_t target_ctas = static_cast<int64_t>(num_sms()) * (a.window >= 0 ? 4 : 16);
     int bpc = static_cast<int>((units + target_ctas - 1) / target_ctas);
     bpc = bpc < 1 ? 1 : (bpc > v2::MAX_BLOCKS_PER_CTA ? v2::MAX_BLOCKS_PER_CTA : bpc);
     if (forced_bpc > 0) bpc = forced_bpc > v2::MAX_BLOCKS_PER_CTA ? v2::MAX_BLOCKS_PER_CTA : forced_bpc;
     p.blocks_per_cta = bpc;
-    dim3 grid((a.max_seqlen + 2 * BQ * bpc - 1) / (2 * BQ * bpc), a.heads, a.batch);
+    p.ctas_per_seq = (a.max_seqlen + 2 * BQ * bpc - 1) / (2 * BQ * bpc);
+    CM3P_REQUIRE(static_cast<int64_t>(p.ctas_per_seq) * a.batch <= 0x7fffffffLL, kBadShape, "attn: grid too large");
+    dim3 grid(static_cast<unsigned>(p.ctas_per_seq) * a.batch, a.heads, 1);
     v2::attn_fwd_v2_kernel<<<grid, v2::THREADS2, v2::SMEM_BYTES2, stream>>>(tmap, p);
   }
   CM3P_CUDA_TRY(cudaGetLastError());

@@ -19,9 +19,39 @@ enum Status : int {
 int set_error(int code, const char* fmt, ...);
 const char* last_error();
 
-// device properties cached per process
+// device properties of the CURRENT device (cached per device ordinal)
 int num_sms();
 int check_arch();  // kOk on sm_100, error otherwise (no fallback)
+
+// One-time-per-device marker for per-device state such as cudaFuncSetAttribute opt-ins (a `static bool` would
+// configure only the first GPU a process touches).
+struct DeviceOnce {
+  unsigned long long mask[2] = {0ull, 0ull};  // device ordinals 0..127
+  bool done() const;
+  void mark();
+};
+#define CM3P_ENSURE_DYN_SMEM(kernel, bytes)                                                                   \
+  do {                                                                                                        \
+    static ::cm3p::DeviceOnce _once;                                                                          \
+    if (!_once.done()) {                                                                                      \
+      CM3P_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));        \
+      _once.mark();                                                                                           \
+    }                                                                                                         \
+  } while (0)
+
+// Run-time tuning knobs (cm3p_set_option in the C ABI; values are part of the ABI, see include/cm3p_b200.h).
+// They exist for the tests (sweeps of the streaming depth) and for A/B measurements; the defaults are the product.
+enum Option : int {
+  kOptFwdBlocksPerCta = 0,   // attention forward: 256-query blocks streamed per CTA (0 = heuristic)
+  kOptBwdOuterPerCta = 1,    // attention backward: outer tiles streamed per CTA (0 = heuristic)
+  kOptGemmCluster = 2,       // 1 = no clusters, 2 = CTA pairs sharing B tiles by TMA multicast (default)
+  kOptAttnForceTileKernels = 3,  // 1 = one-tile-per-CTA attention kernels for every sequence length
+  kOptWgradDeterministic = 4,    // 1 = split-K partials through a workspace + ordered reduction (default), 0 = atomics
+  kOptTmapCache = 5,             // 1 = cache encoded CUtensorMaps by (pointer, shape, pitch, box) (default)
+  kOptCount = 6,
+};
+int get_option(int opt);
+int set_option(int opt, int value);
 
 // 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows, row pitch in BYTES,
 // 128-byte swizzle, zero fill out of bounds.  box_inner * 2 bytes must be <= 128.

@@ -46,6 +46,15 @@ struct GemmArgs {
   const float* row_stats = nullptr;
   const float* col_corr = nullptr;
   float ln_eps = 1e-5f;
+  // Ordered split-K accumulation (EPI_SCALE_F32 with accumulate): `tile_sem` points to `tile_sem_count` zeroed
+  // int32 counters that the kernel uses as per-output-tile turnstiles and leaves zeroed; the K splits of a tile then
+  // add their partial sums in split order and the result is bit-reproducible.  null: fp32 atomics (red.global.add).
+  int32_t* tile_sem = nullptr;
+  int64_t tile_sem_count = 0;
+  // Grouped GEMM: M / group_m independent problems (group_m x N x K each) in one launch.  Operands are stacked
+  // along their outer dimension: A [M, K] (trans_a: [groups*K, group_m]), B [groups*N, K] (trans_b: [groups*K, N]),
+  // C / aux [M, N].  group_m % 256 == 0, K % 64 == 0.  0 = one problem.
+  int64_t group_m = 0;
 };
 
 int gemm_bf16(const GemmArgs& args, cudaStream_t stream);

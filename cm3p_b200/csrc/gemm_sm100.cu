@@ -60,6 +60,9 @@ struct Params {
   const float* row_stats;  // ROPE / GEGLU(_SAVE): [ceil(K/256)][M] partials of the A rows -> LayerNorm folded in, or null
   const float* col_corr;   // [N] column sums of B (= W . diag(gamma))
   float ln_eps;
+  int32_t* tile_sem;  // split-K turnstile, one counter per output tile (zero between launches), or null = fp32 atomics
+  int64_t mn_tiles;   // output tiles (per split) as the kernel counts them
+  int64_t group_m;    // > 0: grouped GEMM, see GemmArgs::group_m
 };
 
 __device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
@@ -139,6 +142,11 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc
     return;
   }
 
+  float sc = p.scale;
+  if constexpr (EPI == EPI_SCALE_F32) {
+    // optional device-side factor exp(*aux): the logits' `* logit_scale.exp()` without a host read of the parameter
+    if (p.aux) sc *= expf(__ldg(reinterpret_cast<const float*>(p.aux)));
+  }
 #pragma unroll 1
   for (int c = 0; c < BN; c += 32) {
     const int64_t col = n0 + c;
@@ -207,20 +215,27 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           if (p.vec_c && col + i * 4 + 4 <= p.N) {
-            if (p.accumulate) {
-              red_add_f32x4(dst + i * 4, v[i * 4] * p.scale, v[i * 4 + 1] * p.scale, v[i * 4 + 2] * p.scale,
-                            v[i * 4 + 3] * p.scale);
+            if (p.accumulate == 2) {  // ordered accumulation: this CTA owns the tile until it passes the turnstile on
+              float4 cur = __ldcg(reinterpret_cast<const float4*>(dst + i * 4));
+              cur.x += v[i * 4] * sc; cur.y += v[i * 4 + 1] * sc;
+              cur.z += v[i * 4 + 2] * sc; cur.w += v[i * 4 + 3] * sc;
+              __stcg(reinterpret_cast<float4*>(dst + i * 4), cur);
+            } else if (p.accumulate) {
+              red_add_f32x4(dst + i * 4, v[i * 4] * sc, v[i * 4 + 1] * sc, v[i * 4 + 2] * sc,
+                            v[i * 4 + 3] * sc);
             } else {
-              *reinterpret_cast<float4*>(dst + i * 4) = make_float4(v[i * 4] * p.scale, v[i * 4 + 1] * p.scale,
-                                                                    v[i * 4 + 2] * p.scale, v[i * 4 + 3] * p.scale);
+              *reinterpret_cast<float4*>(dst + i * 4) = make_float4(v[i * 4] * sc, v[i * 4 + 1] * sc,
+                                                                    v[i * 4 + 2] * sc, v[i * 4 + 3] * sc);
             }
           } else {
             for (int j = 0; j < 4; ++j)
               if (col + i * 4 + j < p.N) {
-                if (p.accumulate)
-                  atomicAdd(dst + i * 4 + j, v[i * 4 + j] * p.scale);
+                if (p.accumulate == 2)
+                  __stcg(dst + i * 4 + j, __ldcg(dst + i * 4 + j) + v[i * 4 + j] * sc);
+                else if (p.accumulate)
+                  atomicAdd(dst + i * 4 + j, v[i * 4 + j] * sc);
                 else
-                  dst[i * 4 + j] = v[i * 4 + j] * p.scale;
+                  dst[i * 4 + j] = v[i * 4 + j] * sc;
               }
           }
         }
@@ -229,6 +244,19 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc
   }
 }
 
+// Split-K turnstile: the splits of one output tile add their partial sums into C in split order, so weight
+// gradients are bit-reproducible from run to run (fp32 atomics are not: the order in which CTAs arrive changes the
+// rounding).  Work units are numbered split-major and every CTA takes its units in increasing order, so split s of
+// a tile starts after split s-1 has started: the wait is short and cannot deadlock (the lowest unfinished unit
+// never waits for an unfinished one).
+__device__ __forceinline__ int32_t ld_acquire_gpu(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int32_t* p, int32_t v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------------
 // Staged epilogue (bf16 outputs with 16-byte aligned rows): per 128x64 output slab
@@ -513,7 +541,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
   const int64_t tiles_n = (p.N + BN - 1) / BN;
   // work units: (group of `cluster` adjacent M tiles, N tile, K split); CTA `crank` of the cluster takes M tile
   // group*cluster + crank (possibly past the end of M: it then only serves its half of the B loads)
-  const int64_t mn_tiles = ((tiles_m + p.cluster - 1) / p.cluster) * tiles_n;
+  const int64_t mn_tiles = ((tiles_m + p.cluster - 1) / p.cluster) * tiles_n;  // counted in cluster units
   const int64_t num_tiles = mn_tiles * p.splits;
   const int64_t unit0 = blockIdx.x / p.cluster, unit_step = gridDim.x / p.cluster;
   const int num_kb_total = static_cast<int>((p.K + BK - 1) / BK);
@@ -531,6 +559,14 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       const int32_t n0 = static_cast<int32_t>(tile_n0(t));
       const int kb0 = static_cast<int>(t / mn_tiles) * p.kb_per_split;
       const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+      // grouped GEMM: operands of group g = m0 / group_m are stacked along their outer dimension
+      int32_t a_m = m0, a_koff = 0, b_noff = 0, b_koff = 0;
+      if (p.group_m > 0) {
+        const int32_t grp = static_cast<int32_t>(m0 / p.group_m);
+        if (p.trans_a) { a_m = m0 - grp * static_cast<int32_t>(p.group_m); a_koff = grp * static_cast<int32_t>(p.K); }
+        if (p.trans_b) b_koff = grp * static_cast<int32_t>(p.K);
+        else b_noff = grp * static_cast<int32_t>(p.N);
+      }
       for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&empty[s], ph ^ 1);
         ptx::mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
@@ -541,26 +577,26 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         } else {
 #pragma unroll
           for (int i = 0; i < BM / 64; ++i)  // box {64 m, 64 k} per 64-wide M chunk
-            ptx::tma_load_2d(sa + i * (BK * 128), &tma_a, &full[s], m0 + i * 64, kb * BK);
+            ptx::tma_load_2d(sa + i * (BK * 128), &tma_a, &full[s], a_m + i * 64, kb * BK + a_koff);
         }
         if (p.cluster == 1) {
           if (!p.trans_b) {
-            ptx::tma_load_2d(sb, &tma_b, &full[s], kb * BK, n0);  // box {64 k, 256 n}
+            ptx::tma_load_2d(sb, &tma_b, &full[s], kb * BK, n0 + b_noff);  // box {64 k, 256 n}
           } else {
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i)  // box {64 n, 64 k}
-              ptx::tma_load_2d(sb + i * (BK * 128), &tma_b, &full[s], n0 + i * 64, kb * BK);
+              ptx::tma_load_2d(sb + i * (BK * 128), &tma_b, &full[s], n0 + i * 64, kb * BK + b_koff);
           }
         } else {
           // this CTA's half of the B tile, delivered to both CTAs of the pair
           if (!p.trans_b) {
             ptx::tma_load_2d_multicast(sb + crank * (B_STAGE_BYTES / 2), &tma_bh, &full[s], kb * BK,
-                                       n0 + static_cast<int32_t>(crank) * (BN / 2), 0x3);  // box {64 k, 128 n}
+                                       n0 + b_noff + static_cast<int32_t>(crank) * (BN / 2), 0x3);  // box {64 k, 128 n}
           } else {
 #pragma unroll
             for (int i = 0; i < BN / 128; ++i) {
               const int j = static_cast<int>(crank) * (BN / 128) + i;
-              ptx::tma_load_2d_multicast(sb + j * (BK * 128), &tma_b, &full[s], n0 + j * 64, kb * BK, 0x3);
+              ptx::tma_load_2d_multicast(sb + j * (BK * 128), &tma_b, &full[s], n0 + j * 64, kb * BK + b_koff, 0x3);
             }
           }
         }
@@ -632,7 +668,32 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         epilogue_tile_staged<EPI>(p, &tma_c, &tma_c2, &tma_aux, slabs, res_full, st, tmem_base + as * BN, quad, m0,
                                   n0, tile_m0(tn), tile_n0(tn), tn < num_tiles);
       } else {
-        epilogue_tile<EPI>(p, tmem_base + as * BN, quad, m0, n0);
+        if constexpr (EPI == EPI_SCALE_F32) {
+          if (p.accumulate == 2) {
+            // wait until the previous split of this CTA's output tile has added its partial sums
+            int32_t* sem = p.tile_sem + (t % mn_tiles) * p.cluster + crank;
+            const int32_t split = static_cast<int32_t>(t / mn_tiles);
+            if (quad == 0 && lane == 0) {
+              const long long t_wait = clock64();
+              while (ld_acquire_gpu(sem) != split) {
+                __nanosleep(64);
+                if (clock64() - t_wait > CM3P_MBAR_TIMEOUT_CYCLES) {  // stale counters: never hang the GPU
+                  printf("cm3p_b200: split-K turnstile timed out (tile %lld split %d)\n", (long long)(t % mn_tiles), split);
+                  __trap();
+                }
+              }
+            }
+            ptx::named_bar_sync(1, 128);
+            epilogue_tile<EPI>(p, tmem_base + as * BN, quad, m0, n0);
+            __threadfence();
+            ptx::named_bar_sync(2, 128);
+            if (quad == 0 && lane == 0) st_release_gpu(sem, split + 1 == p.splits ? 0 : split + 1);
+          } else {
+            epilogue_tile<EPI>(p, tmem_base + as * BN, quad, m0, n0);
+          }
+        } else {
+          epilogue_tile<EPI>(p, tmem_base + as * BN, quad, m0, n0);
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -656,12 +717,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
 template <int EPI, bool STAGED>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2,
            const CUtensorMap& taux, const CUtensorMap& tbh, const Params& p, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    CM3P_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_sm100_kernel<EPI, STAGED>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
-  }
+  CM3P_ENSURE_DYN_SMEM((gemm_bf16_sm100_kernel<EPI, STAGED>), SMEM_BYTES);
   const int64_t tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
   const int64_t units = ((tiles_m + p.cluster - 1) / p.cluster) * tiles_n * p.splits;
   const int64_t max_clusters = num_sms() / p.cluster;
@@ -721,16 +777,27 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   if (g.epilogue == EPI_GEGLU || g.epilogue == EPI_GEGLU_SAVE)
     CM3P_REQUIRE(vec, kBadAlignment, "gemm(geglu): outputs must be 16-byte aligned with ld %% 8 == 0");
 
+  // grouped GEMM: `groups` independent problems of group_m x N x K whose operands are stacked along their outer
+  // dimension (A: M rows, or K rows when transposed; B: N rows, or K rows when transposed; C/aux: M rows)
+  int64_t groups = 1;
+  if (g.group_m > 0) {
+    CM3P_REQUIRE(g.M % g.group_m == 0 && g.group_m % (2 * BM) == 0 && g.K % BK == 0, kBadShape,
+                 "gemm(grouped): M=%lld must be a multiple of group_m=%lld, group_m of %d and K=%lld of %d",
+                 (long long)g.M, (long long)g.group_m, 2 * BM, (long long)g.K, BK);
+    CM3P_REQUIRE(!(g.epilogue == EPI_SCALE_F32 && g.accumulate) && !g.stats_out && !g.row_stats, kBadShape,
+                 "gemm(grouped): split-K accumulation and LayerNorm folding are not supported");
+    groups = g.M / g.group_m;
+  }
   CUtensorMap ta, tb;
   if (!g.trans_a)
     rc = encode_tmap_2d_bf16(&ta, g.a, g.K, g.M, g.lda * 2, BK, BM);
   else
-    rc = encode_tmap_2d_bf16(&ta, g.a, g.M, g.K, g.lda * 2, 64, BK);
+    rc = encode_tmap_2d_bf16(&ta, g.a, g.group_m > 0 ? g.group_m : g.M, g.K * groups, g.lda * 2, 64, BK);
   if (rc != kOk) return rc;
   if (!g.trans_b)
-    rc = encode_tmap_2d_bf16(&tb, g.b, g.K, g.N, g.ldb * 2, BK, BN);
+    rc = encode_tmap_2d_bf16(&tb, g.b, g.K, g.N * groups, g.ldb * 2, BK, BN);
   else
-    rc = encode_tmap_2d_bf16(&tb, g.b, g.N, g.K, g.ldb * 2, 64, BK);
+    rc = encode_tmap_2d_bf16(&tb, g.b, g.N, g.K * groups, g.ldb * 2, 64, BK);
   if (rc != kOk) return rc;
 
   // staged epilogue: output (and residual / raw) rows must allow TMA (16-byte aligned base and pitch)
@@ -766,6 +833,9 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   p.row_stats = g.row_stats;
   p.col_corr = g.col_corr;
   p.ln_eps = g.ln_eps;
+  p.tile_sem = nullptr;
+  p.mn_tiles = 0;
+  p.group_m = g.group_m;
   if (g.stats_out)
     CM3P_REQUIRE(g.epilogue == EPI_RESIDUAL && vec, kBadShape,
                  "gemm: stats_out needs the staged EPI_RESIDUAL epilogue (16-byte aligned bf16 rows)");
@@ -804,18 +874,21 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
 
   // CTA pairs (2-CTA clusters) on adjacent M tiles share each B tile through TMA multicast: a third less
   // L2 -> SM traffic per CTA (ncu: the MMA thread waited ~30% of the time for operands without it).
-  static int cluster_mode = -1;
-  if (cluster_mode < 0) {
-    const char* e = getenv("CM3P_GEMM_CLUSTER");
-    cluster_mode = e ? atoi(e) : 2;
-    if (cluster_mode != 1 && cluster_mode != 2) cluster_mode = 2;
-  }
+  const int cluster_mode = get_option(kOptGemmCluster) == 1 ? 1 : 2;
   const int64_t tiles_m_total = (g.M + BM - 1) / BM;
   p.cluster = (cluster_mode == 2 && tiles_m_total >= 2 && g.N > BN / 2) ? 2 : 1;
   CUtensorMap tbh = tb;
   if (p.cluster == 2 && !g.trans_b) {
-    rc = encode_tmap_2d_bf16(&tbh, g.b, g.K, g.N, g.ldb * 2, BK, BN / 2);
+    rc = encode_tmap_2d_bf16(&tbh, g.b, g.K, g.N * groups, g.ldb * 2, BK, BN / 2);
     if (rc != kOk) return rc;
+  }
+  if (g.epilogue == EPI_SCALE_F32 && g.accumulate && g.tile_sem && get_option(kOptWgradDeterministic)) {
+    // ordered split-K accumulation through one turnstile counter per output tile
+    const int64_t sems = ((tiles_m_total + p.cluster - 1) / p.cluster) * ((g.N + BN - 1) / BN) * p.cluster;
+    CM3P_REQUIRE(sems <= g.tile_sem_count, kBadShape, "gemm: %lld output tiles exceed the %lld turnstile counters",
+                 (long long)sems, (long long)g.tile_sem_count);
+    p.tile_sem = g.tile_sem;
+    p.accumulate = 2;
   }
 
   switch (g.epilogue) {

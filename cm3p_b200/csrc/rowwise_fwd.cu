@@ -259,8 +259,8 @@ __global__ void __launch_bounds__(256)
 mean_pool_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ cu, __nv_bfloat16* __restrict__ out,
                  int H) {
   __shared__ float red[32][64 + 1];
-  const int b = blockIdx.y;
-  const int c0 = blockIdx.x * 64;
+  const int b = blockIdx.x;  // sequences in grid.x: B*V can exceed the 65535 limit of grid.y
+  const int c0 = blockIdx.y * 64;
   const int start = cu[b], len = cu[b + 1] - start;
   const int v = threadIdx.x & 7;   // 8 vectors of 8 columns
   const int rl = threadIdx.x >> 3;  // 32 row lanes
@@ -476,7 +476,7 @@ int gather_rows(const void* x, const int32_t* index, void* out, int rows, int H,
 int mean_pool(const void* x, const int32_t* cu_seqlens, void* out, int batch, int H, cudaStream_t stream) {
   CM3P_REQUIRE(H % 8 == 0, kBadShape, "mean_pool: H %% 8 required");
   if (batch == 0) return kOk;
-  dim3 grid((H + 63) / 64, batch);
+  dim3 grid(batch, (H + 63) / 64);
   mean_pool_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), cu_seqlens,
                                              reinterpret_cast<__nv_bfloat16*>(out), H);
   CM3P_CUDA_TRY(cudaGetLastError());

@@ -6,9 +6,9 @@ contrastive loss over its own batch and gradients are mean-all-reduced (SURVEY.m
 /root/reference/train.py:360-375).  Two modes are provided here:
 
 * local negatives (reference semantics): no data-path collective; the fp32 gradients of all
-  parameters live in ONE flat buffer (training.GradStore) which is all-reduced with a single NCCL
-  call and divided by the world size.  (Wrapping the model in torch DDP also works — the explicit
-  backward is attached to autograd — but costs one bucketed all-reduce per 25 MB instead of one.)
+  parameters live in ONE flat buffer (training.GradStore) laid out in backward order and all-reduced
+  (mean) in ~64 MB buckets, each enqueued on NCCL's stream as soon as the backward pass has moved past
+  it, so the transfer overlaps the rest of the backward pass.
 * global negatives (BASELINE.json configs[3]): the L2-normalised embeddings (bf16, B x 512 per
   tower and rank — a few MB in total) are all-gathered, every rank evaluates the full
   (B_global*V) x B_global logits and loss redundantly on the tensor cores (17 GFLOP at 4096 x 4096 —
@@ -74,6 +74,32 @@ def reduce_gradients(flat: torch.Tensor, dp: DataParallel) -> torch.Tensor:
         if not dp.global_negatives:
             flat.div_(dp.world_size)
     return flat
+
+
+class _Done:
+    def wait(self):
+        return None
+
+
+def reduce_gradients_async(flat: torch.Tensor, dp: DataParallel, sum_reduce: bool):
+    """Enqueue the all-reduce of one gradient bucket and return a handle with `.wait()`.  NCCL: the collective
+    runs on the process group's own stream, ordered after everything already enqueued on the current stream, and
+    overlaps with what the caller enqueues next; the mean is taken by the collective itself (ReduceOp.AVG)."""
+    if dp.world_size == 1:
+        return _Done()
+    backend = dist.get_backend(dp.group)
+    if sum_reduce:
+        return dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=dp.group, async_op=True)
+    if backend == "nccl":
+        return dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=dp.group, async_op=True)
+    work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=dp.group, async_op=True)  # gloo has no AVG
+
+    class _Mean:
+        def wait(self_inner):
+            work.wait()
+            flat.div_(dp.world_size)
+
+    return _Mean()
 
 
 def broadcast_parameters(model, dp: DataParallel, src: int = 0) -> None:

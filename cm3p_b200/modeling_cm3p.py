@@ -174,20 +174,21 @@ class ModernBertEncoder(nn.Module):
                         "wi": ops.interleave_wi(layer.mlp.Wi.weight.detach().to(bf)).contiguous(),
                         "wo2": layer.mlp.Wo.weight.detach().to(bf).contiguous(),
                     }
-                    # LayerNorm folded into the GEMM that consumes it (cm3p_gemm_bf16_ln): W' = W.diag(gamma)
-                    # in bf16 and its row sums (of the rounded W', which is what the tensor core multiplies)
-                    if i > 0:
-                        wq = (layer.attn.Wqkv.weight.detach().float() * e["attn_norm"][None, :]).to(bf).contiguous()
-                        e["wqkv_ln"], e["cqkv"] = wq, wq.float().sum(dim=1).contiguous()
-                    wi = (layer.mlp.Wi.weight.detach().float() * e["mlp_norm"][None, :]).to(bf)
-                    wi = ops.interleave_wi(wi).contiguous()
-                    e["wi_ln"], e["ci"] = wi, wi.float().sum(dim=1).contiguous()
+                    if ops.FUSE_LAYERNORM:
+                        # LayerNorm folded into the GEMM that consumes it (cm3p_gemm_bf16_ln): W' = W.diag(gamma)
+                        # in bf16 and its row sums (of the rounded W', which is what the tensor core multiplies)
+                        if i > 0:
+                            wq = (layer.attn.Wqkv.weight.detach().float() * e["attn_norm"][None, :]).to(bf).contiguous()
+                            e["wqkv_ln"], e["cqkv"] = wq, wq.float().sum(dim=1).contiguous()
+                        wi = (layer.mlp.Wi.weight.detach().float() * e["mlp_norm"][None, :]).to(bf)
+                        wi = ops.interleave_wi(wi).contiguous()
+                        e["wi_ln"], e["ci"] = wi, wi.float().sum(dim=1).contiguous()
                     pk["layers"].append(e)
             self._packed, self._packed_key = pk, key
         return self._packed
 
     def run_layers(self, x: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int,
-                   positions: torch.Tensor) -> torch.Tensor:
+                   positions: torch.Tensor, groups=None) -> torch.Tensor:
         """x [T,H] bf16 = already-normalised embeddings (updated in place) -> final-normed [T,H]."""
         cfg, pk = self.config, self.packed()
         T, H = x.shape
@@ -217,7 +218,8 @@ class ModernBertEncoder(nn.Module):
                 ops.layernorm(x, w["attn_norm"], eps, out=a)
                 ops.gemm(a, w["wqkv"], epilogue=ops.EPI_ROPE, out=qkv, positions=positions, rope_table=tab,
                          rope_cols=2 * H)
-            ops.attn_varlen_fwd(qkv, cu_seqlens, max_seqlen, heads, -1 if is_global else cfg.window_half, out=a)
+            ops.attn_varlen_fwd(qkv, cu_seqlens, max_seqlen, heads, -1 if is_global else cfg.window_half, out=a,
+                                groups=groups)
             if ops.FUSE_LAYERNORM:
                 ops.gemm(a, w["wo"], epilogue=ops.EPI_RESIDUAL, out=x, aux=x, stats_out=stats[2 * i])
                 ops.gemm(x, w["wi_ln"], epilogue=ops.EPI_GEGLU, out=h, row_stats=stats[2 * i], col_corr=w["ci"],
@@ -245,9 +247,10 @@ class _Unpadded:
     max_len: int
     batch: int
     seq_len: int
+    groups: Any = None        # ops.PackedGroups when the batch is made of many short sequences (metadata tower)
 
 
-def _unpad(attention_mask: Optional[torch.Tensor], batch: int, seq_len: int, device) -> _Unpadded:
+def _unpad(attention_mask: Optional[torch.Tensor], batch: int, seq_len: int, device, pack: bool = False) -> _Unpadded:
     """Same information as `_unpad_cm3p_input` (modeling_cm3p.py:65-103): one small D2H copy of the
     B sequence lengths is the only host sync of a forward pass."""
     if attention_mask is None:
@@ -266,7 +269,11 @@ def _unpad(attention_mask: Optional[torch.Tensor], batch: int, seq_len: int, dev
         cu[1:] = torch.cumsum(lens, dim=0, dtype=torch.int32)
         src = torch.nonzero_static(m.reshape(-1), size=total).reshape(-1).to(torch.int32)
     pos = torch.remainder(src, seq_len).to(torch.int32)
-    return _Unpadded(src, cu, pos, lens_cpu, total, max(lens_cpu) if lens_cpu else 0, batch, seq_len)
+    up = _Unpadded(src, cu, pos, lens_cpu, total, max(lens_cpu) if lens_cpu else 0, batch, seq_len)
+    if pack and seq_len <= 128 and batch >= 4 and 0 < total <= 64 * batch:
+        # many short sequences (metadata: ~21 real tokens of 128): several of them share one 128-row attention tile
+        up.groups = ops.attn_pack_groups(cu, total)
+    return up
 
 
 def _repad(x: torch.Tensor, up: _Unpadded) -> torch.Tensor:
@@ -344,11 +351,11 @@ class CM3PMetadataTransformer(nn.Module):
         _require_cuda(input_ids, "metadata input_ids")
         S = input_ids.shape[-1]
         ids = input_ids.reshape(-1, S).contiguous()
-        up = _unpad(attention_mask, ids.shape[0], S, ids.device)
+        up = _unpad(attention_mask, ids.shape[0], S, ids.device, pack=True)
         pk = self.encoder.packed()
         x = ops.embed_gather_ln(ids.reshape(-1), up.src_index, None, pk["tok_emb"], None, pk["emb_norm"],
                                 self.config.norm_eps, rows=up.total)
-        last = self.encoder.run_layers(x, up.cu_seqlens, up.max_len, up.positions)
+        last = self.encoder.run_layers(x, up.cu_seqlens, up.max_len, up.positions, groups=up.groups)
         return last, up
 
     def forward(self, input_ids=None, attention_mask=None, indices=None, cu_seqlens=None, max_seqlen=None,
@@ -607,7 +614,7 @@ class CM3PModel(CM3PPreTrainedModel):
         beatmap_embeds = metadata_embeds = logits_per_beatmap = logits_per_metadata = logits = None
         beatmap_outputs = metadata_outputs = None
         loss = 0 if return_loss else None
-        be16 = me16 = None
+        be16 = me16 = mlm_loss = None
 
         if input_ids is not None:
             last, up, audio_out = self.beatmap_model.encode(input_ids, input_features, attention_mask)
@@ -619,8 +626,16 @@ class CM3PModel(CM3PPreTrainedModel):
             beatmap_outputs = CM3PBeatmapModelOutput(last_hidden_state=hidden, pooler_output=pooled.to(odt),
                                                      audio_model_output=audio_out)
             if output_logits:
-                logits = self._mlm_logits(last)
-                logits = (_repad(logits, up) if True else logits).to(odt)
+                logits_u = self._mlm_logits(last)
+                if labels is not None and return_loss:
+                    # loss += 0.5 * MLM cross-entropy (:994-996), also on the evaluation path
+                    _, loss_sum, count = ops.vocab_ce_fwd(logits_u, logits_u.shape[1], labels.reshape(-1).contiguous(),
+                                                          up.src_index)
+                    n_items = kwargs.get("num_items_in_batch")
+                    denom = count if n_items is None else torch.as_tensor(n_items, device=count.device,
+                                                                          dtype=torch.float32).reshape(1)
+                    mlm_loss = (loss_sum / denom).reshape(())
+                logits = _repad(logits_u, up).to(odt)
 
         if metadata_ids is not None:
             mlast, mup = self.metadata_model.encode(metadata_ids, metadata_attention_mask)
@@ -634,9 +649,9 @@ class CM3PModel(CM3PPreTrainedModel):
                                                           pooler_output=mpooled.view(*lead, -1).to(odt))
 
         if be16 is not None and me16 is not None:
-            # S = M . B^T * exp(logit_scale), scale fused in the GEMM epilogue (:976-977)
-            scale = float(self.logit_scale.detach().float().exp())
-            S = ops.gemm(me16, be16, epilogue=ops.EPI_SCALE_F32, scale=scale)  # [Bm*V, Bb] fp32
+            # S = M . B^T * exp(logit_scale), the factor read on the device in the GEMM epilogue (:976-977)
+            S = ops.gemm(me16, be16, epilogue=ops.EPI_SCALE_F32,
+                         aux=self.logit_scale.detach().float().reshape(1))  # [Bm*V, Bb] fp32
             Bb = be16.shape[0]
             if metadata_ids.dim() == 3:
                 Bm, V = metadata_ids.shape[:2]
@@ -654,6 +669,9 @@ class CM3PModel(CM3PPreTrainedModel):
                 else:
                     true_idx = torch.zeros(Bm, device=S.device, dtype=torch.int32)
                 loss = ops.clip_loss_fwd(S, true_idx.contiguous(), V)[0].reshape(())
+
+        if mlm_loss is not None:
+            loss = loss + 0.5 * mlm_loss
 
         return CM3POutput(loss=loss, logits_per_beatmap=logits_per_beatmap, logits_per_metadata=logits_per_metadata,
                           metadata_embeds=metadata_embeds, beatmap_embeds=beatmap_embeds, logits=logits,

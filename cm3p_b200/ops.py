@@ -40,6 +40,35 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# run-time knobs of the library (include/cm3p_b200.h CM3P_OPT_*)
+OPT_FWD_BLOCKS_PER_CTA, OPT_BWD_OUTER_PER_CTA, OPT_GEMM_CLUSTER = 0, 1, 2
+OPT_ATTN_FORCE_TILE_KERNELS, OPT_WGRAD_DETERMINISTIC, OPT_TMAP_CACHE = 3, 4, 5
+
+
+def set_option(option: int, value: int) -> None:
+    _lib.check(_lib.load().cm3p_set_option(int(option), int(value)), "cm3p_set_option")
+
+
+def get_option(option: int) -> int:
+    return int(_lib.load().cm3p_get_option(int(option)))
+
+
+# zeroed int32 counters the split-K weight-gradient GEMMs use as per-tile turnstiles (ordered, bit-reproducible
+# accumulation); one buffer per (device, stream): launches on one stream are serialised, and the kernel leaves the
+# counters zeroed
+_SEM_COUNT = 16384
+_SEM_CACHE: dict = {}
+
+
+def _tile_sem(device) -> torch.Tensor:
+    key = (device.index, _stream())
+    t = _SEM_CACHE.get(key)
+    if t is None:
+        t = torch.zeros(_SEM_COUNT, device=device, dtype=torch.int32)
+        _SEM_CACHE[key] = t
+    return t
+
+
 def _ptr(t) -> int | None:
     return None if t is None else t.data_ptr()
 
@@ -56,8 +85,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, epilogue: int = EPI_STORE, out: to
          accumulate: bool = False, positions: torch.Tensor | None = None, rope_table: torch.Tensor | None = None,
          rope_cols: int = 0, trans_a: bool = False, trans_b: bool = False, stats_out: torch.Tensor | None = None,
          row_stats: torch.Tensor | None = None, col_corr: torch.Tensor | None = None,
-         ln_eps: float = 1e-5) -> torch.Tensor:
+         ln_eps: float = 1e-5, groups: int = 1) -> torch.Tensor:
     """out[M,N] = epilogue(A @ B^T).  A: [M,K] (or [K,M] if trans_a); B: [N,K] (or [K,N] if trans_b).
+
+    groups > 1: `groups` independent problems in one launch, operands stacked along their outer dimension
+    (A [groups*m, K] or transposed [groups*K, m]; B [groups*N, K] or [groups*K, N]; out / aux [groups*m, N]).
 
     LayerNorm folding (cm3p_gemm_bf16_ln): `stats_out` [ceil(N/256),M,2] fp32 (per-tile row sum / sum of squares of the rows an
     EPI_RESIDUAL GEMM writes); `row_stats` + `col_corr` on an EPI_ROPE / EPI_GEGLU(_SAVE) GEMM whose B is
@@ -67,6 +99,16 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, epilogue: int = EPI_STORE, out: to
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
     M, K = (a.shape[1], a.shape[0]) if trans_a else a.shape
     N, Kb = (b.shape[1], b.shape[0]) if trans_b else b.shape
+    group_m = 0
+    if groups > 1:
+        if trans_a:
+            group_m, M, K = M, M * groups, K // groups
+        else:
+            group_m = M // groups
+        if trans_b:
+            Kb //= groups
+        else:
+            N //= groups
     if K != Kb:
         raise ValueError(f"gemm: inner dimensions differ ({K} vs {Kb})")
     n_out = N // 2 if epilogue in (EPI_GEGLU, EPI_GEGLU_SAVE) else N
@@ -89,19 +131,43 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, epilogue: int = EPI_STORE, out: to
         _lib.check(rc, "cm3p_gemm_bf16_ln")
         _count("gemm")
         return out
+    sem = _tile_sem(a.device) if (accumulate and epilogue == EPI_SCALE_F32) else None
     rc = lib.cm3p_gemm_bf16(
         a.data_ptr(), a.stride(0), int(trans_a), b.data_ptr(), b.stride(0), int(trans_b), out.data_ptr(),
         out.stride(0), M, N, K, epilogue, _ptr(aux), (aux.stride(0) if aux is not None and aux.dim() == 2 else 0),
         _ptr(c2), (c2.stride(0) if c2 is not None else 0), float(scale), int(accumulate), _ptr(positions),
-        _ptr(rope_table), rope_cols, _stream())
+        _ptr(rope_table), rope_cols, _ptr(sem), (_SEM_COUNT if sem is not None else 0), group_m, _stream())
     _lib.check(rc, "cm3p_gemm_bf16")
     _count("gemm")
     return out
 
 
+class PackedGroups:
+    """Group table of the packed short-sequence attention kernels (cm3p_attn_pack_groups)."""
+
+    def __init__(self, table: torch.Tensor, count: torch.Tensor, max_groups: int):
+        self.table, self.count, self.max_groups = table, count, max_groups
+
+
+def attn_pack_groups(cu_seqlens: torch.Tensor, total_tokens: int) -> PackedGroups:
+    """Packs consecutive sequences (each <= 128 tokens) into groups of <= 128 tokens; device-side, no host sync."""
+    _req(cu_seqlens, torch.int32, "cu_seqlens")
+    batch = cu_seqlens.numel() - 1
+    max_groups = max(1, min(batch, 2 * (int(total_tokens) // 128) + (batch + 63) // 64 + 1))
+    table = torch.empty((max_groups, 2), device=cu_seqlens.device, dtype=torch.int32)
+    count = torch.empty((1,), device=cu_seqlens.device, dtype=torch.int32)
+    rc = _lib.load().cm3p_attn_pack_groups(cu_seqlens.data_ptr(), batch, table.data_ptr(), count.data_ptr(), max_groups,
+                                           _stream())
+    _lib.check(rc, "cm3p_attn_pack_groups")
+    _count("rowwise")
+    return PackedGroups(table, count, max_groups)
+
+
 def attn_varlen_fwd(qkv: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int, heads: int, window: int = -1,
-                    out: torch.Tensor | None = None, lse: torch.Tensor | None = None) -> torch.Tensor:
-    """qkv [T, 3*heads*64] bf16 (rotated) -> out [T, heads*64] bf16.  window < 0 = global."""
+                    out: torch.Tensor | None = None, lse: torch.Tensor | None = None,
+                    groups: PackedGroups | None = None) -> torch.Tensor:
+    """qkv [T, 3*heads*64] bf16 (rotated) -> out [T, heads*64] bf16.  window < 0 = global.
+    groups: packed short sequences (attn_pack_groups; every sequence <= 128 tokens)."""
     _req(qkv, torch.bfloat16, "qkv")
     _req(cu_seqlens, torch.int32, "cu_seqlens")
     T = qkv.shape[0]
@@ -109,8 +175,12 @@ def attn_varlen_fwd(qkv: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int
     assert qkv.shape[1] == 3 * H and qkv.is_contiguous()
     if out is None:
         out = torch.empty((T, H), device=qkv.device, dtype=torch.bfloat16)
+    g = groups if (groups is not None and window < 0) else None
     rc = _lib.load().cm3p_attn_varlen_fwd(qkv.data_ptr(), out.data_ptr(), _ptr(lse), cu_seqlens.data_ptr(), T,
-                                          cu_seqlens.numel() - 1, heads, 64, int(max_seqlen), int(window), _stream())
+                                          cu_seqlens.numel() - 1, heads, 64, int(max_seqlen), int(window),
+                                          None if g is None else g.table.data_ptr(),
+                                          None if g is None else g.count.data_ptr(),
+                                          0 if g is None else g.max_groups, _stream())
     _lib.check(rc, "cm3p_attn_varlen_fwd")
     _count("attn")
     return out
@@ -221,7 +291,8 @@ def clip_loss_fwd(S: torch.Tensor, true_idx: torch.Tensor, V: int):
 def attn_varlen_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, lse: torch.Tensor,
                     cu_seqlens: torch.Tensor, max_seqlen: int, heads: int, window: int = -1,
                     positions: torch.Tensor | None = None, rope_table: torch.Tensor | None = None,
-                    dqkv: torch.Tensor | None = None, delta: torch.Tensor | None = None) -> torch.Tensor:
+                    dqkv: torch.Tensor | None = None, delta: torch.Tensor | None = None,
+                    groups: PackedGroups | None = None) -> torch.Tensor:
     """-> dqkv [T, 3*heads*64] bf16, gradient w.r.t. the un-rotated Wqkv output when positions/rope_table
     are given (otherwise w.r.t. the qkv passed in)."""
     for t, n in ((qkv, "qkv"), (out, "out"), (dout, "dout")):
@@ -235,12 +306,15 @@ def attn_varlen_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, ls
         dqkv = torch.empty_like(qkv)
     if delta is None:
         delta = torch.empty_like(lse)
+    g = groups if (groups is not None and window < 0) else None
     rc = _lib.load().cm3p_attn_varlen_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
                                           delta.data_ptr(), dqkv.data_ptr(), cu_seqlens.data_ptr(), _ptr(positions),
                                           _ptr(rope_table), T, cu_seqlens.numel() - 1, heads, 64, int(max_seqlen),
-                                          int(window), _stream())
+                                          int(window), None if g is None else g.table.data_ptr(),
+                                          None if g is None else g.count.data_ptr(),
+                                          0 if g is None else g.max_groups, _stream())
     _lib.check(rc, "cm3p_attn_varlen_bwd")
-    _count("attn_bwd")
+    _count("attn_bwd" if g is None else "attn")
     return dqkv
 
 

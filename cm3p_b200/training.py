@@ -30,20 +30,87 @@ BF16, F32 = torch.bfloat16, torch.float32
 
 
 class GradStore:
-    """fp32 gradient buffers, one per parameter, carved out of a single zero-filled allocation."""
+    """fp32 gradient buffers, one per parameter, carved out of a single zero-filled allocation.
 
-    def __init__(self, params):
+    Data parallel: the buffer is laid out in the order in which the backward pass first touches the parameters
+    (recorded on the first step: every parameter gradient is written by exactly one launch, so a prefix of that
+    order is final as soon as a later parameter is touched).  It is cut into buckets of ~`BUCKET_BYTES`; a bucket's
+    NCCL all-reduce is enqueued (async, on NCCL's own stream, ordered after the launches already on the compute
+    stream) the moment the backward pass moves past it, so the reduction of the metadata tower / MLM head / upper
+    beatmap layers travels over NVLink while the lower layers are still being differentiated.
+    """
+
+    BUCKET_BYTES = 64 << 20
+
+    def __init__(self, params, order=None, dp=None, sum_reduce=False):
         self.params = list(params)
+        self.dp = dp if (dp is not None and dp.world_size > 1) else None
+        self.sum_reduce = sum_reduce
+        laid = self.params if order is None else [self.params[i] for i in order]
         offs, total = [], 0
-        for p in self.params:
+        for p in laid:
             offs.append(total)
             total += (p.numel() + 3) // 4 * 4  # keep every view 16-byte aligned
         dev = self.params[0].device
         self.flat = torch.zeros(total, device=dev, dtype=F32)
-        self.views = {id(p): self.flat[o:o + p.numel()].view(p.shape) for p, o in zip(self.params, offs)}
+        self.views = {id(p): self.flat[o:o + p.numel()].view(p.shape) for p, o in zip(laid, offs)}
+        self.touched: list[int] = []       # first-touch order (indices into self.params), recorded when order is None
+        self._index = {id(p): i for i, p in enumerate(self.params)}
+        self._seen: set[int] = set()
+        self._works = []
+        self._hold = 0  # > 0: a section of the backward pass revisits parameters (chunked recompute): nothing is final
+        # buckets over the laid-out order: (first position, end position, flat start, flat end)
+        self._pos = {id(p): k for k, p in enumerate(laid)} if (order is not None and self.dp is not None) else None
+        self._buckets, self._next = [], 0
+        if self._pos is not None:
+            start_k, start_o = 0, 0
+            for k, (p, o) in enumerate(zip(laid, offs)):
+                end_o = o + (p.numel() + 3) // 4 * 4
+                if (end_o - start_o) * 4 >= self.BUCKET_BYTES or k == len(laid) - 1:
+                    self._buckets.append((start_k, k + 1, start_o, end_o))
+                    start_k, start_o = k + 1, end_o
 
     def __call__(self, p: torch.Tensor) -> torch.Tensor:
-        return self.views[id(p)]
+        pid = id(p)
+        if pid not in self._seen:
+            self._seen.add(pid)
+            self.touched.append(self._index[pid])
+            if self._pos is not None and self._hold == 0:
+                # every bucket that lies entirely before this parameter is final: send it off
+                k = self._pos[pid]
+                while self._next < len(self._buckets) and self._buckets[self._next][1] <= k:
+                    self._launch(self._buckets[self._next])
+                    self._next += 1
+        return self.views[pid]
+
+    def hold(self) -> None:
+        self._hold += 1
+
+    def release(self) -> None:
+        self._hold -= 1
+
+    def _launch(self, bucket) -> None:
+        _, _, o0, o1 = bucket
+        self._works.append(dp_utils.reduce_gradients_async(self.flat[o0:o1], self.dp, self.sum_reduce))
+
+    def finish(self) -> None:
+        """Reduce whatever has not been sent yet and make the compute stream wait for all reductions."""
+        if self.dp is None:
+            return
+        if self._pos is None:
+            self._works.append(dp_utils.reduce_gradients_async(self.flat, self.dp, self.sum_reduce))
+        else:
+            while self._next < len(self._buckets):
+                self._launch(self._buckets[self._next])
+                self._next += 1
+        for w in self._works:
+            w.wait()
+        self._works = []
+
+    def order(self) -> list[int]:
+        """Parameter indices in first-touch order, untouched (frozen / unused) parameters last."""
+        rest = [i for i in range(len(self.params)) if i not in set(self.touched)]
+        return self.touched + rest
 
 
 def _wgrad(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor) -> None:
@@ -68,7 +135,7 @@ def _keep_layernorm_outputs(nbytes: int, dev) -> bool:
     return nbytes < free // 4
 
 
-def encoder_forward(enc, x0: torch.Tensor, cu_seqlens, max_seqlen: int, positions):
+def encoder_forward(enc, x0: torch.Tensor, cu_seqlens, max_seqlen: int, positions, groups=None):
     """x0 [T,H] = normalised embeddings.  -> (final-normed hidden [T,H], saved activations)."""
     cfg, pk = enc.config, enc.packed()
     T, H = x0.shape
@@ -101,7 +168,8 @@ def encoder_forward(enc, x0: torch.Tensor, cu_seqlens, max_seqlen: int, position
             qkv = ops.gemm(a, w["wqkv"], epilogue=ops.EPI_ROPE, positions=positions, rope_table=tab, rope_cols=2 * H)
             norm_a = a if keep_ln else None
         lse = torch.empty((heads, T), device=dev, dtype=F32)
-        o = ops.attn_varlen_fwd(qkv, cu_seqlens, max_seqlen, heads, -1 if is_global else cfg.window_half, lse=lse)
+        o = ops.attn_varlen_fwd(qkv, cu_seqlens, max_seqlen, heads, -1 if is_global else cfg.window_half, lse=lse,
+                                groups=groups)
         ug = torch.empty((T, 2 * I), device=dev, dtype=BF16)
         if fuse:
             x1 = ops.gemm(o, w["wo"], epilogue=ops.EPI_RESIDUAL, aux=x, stats_out=stats[2 * i])
@@ -121,7 +189,7 @@ def encoder_forward(enc, x0: torch.Tensor, cu_seqlens, max_seqlen: int, position
                            tab=tab, norm_a=norm_a, norm_m=norm_m))
         x = x2
     last = ops.layernorm(x, pk["final_norm"], cfg.norm_eps)
-    saved = dict(layers=layers, x_final=x, cu=cu_seqlens, max_seqlen=max_seqlen, positions=positions)
+    saved = dict(layers=layers, x_final=x, cu=cu_seqlens, max_seqlen=max_seqlen, positions=positions, groups=groups)
     return last, saved
 
 
@@ -165,7 +233,8 @@ def encoder_backward(enc, saved, dlast: torch.Tensor, g: GradStore) -> torch.Ten
         _dgrad(dx, w["wo"], out=dtmp)  # d(attention output)
         _wgrad(dx, s["o"], g(layer.attn.Wo.weight))
         ops.attn_varlen_bwd(s["qkv"], s["o"], dtmp, s["lse"], cu, max_seqlen, heads, s["window"],
-                            positions=positions, rope_table=s["tab"], dqkv=dqkv, delta=delta)
+                            positions=positions, rope_table=s["tab"], dqkv=dqkv, delta=delta,
+                            groups=saved["groups"])
         if i == 0:
             _wgrad(dqkv, s["x_in"], g(layer.attn.Wqkv.weight))
             _dgrad(dqkv, w["wqkv"], out=dx, epilogue=ops.EPI_RESIDUAL, aux=dx)
@@ -272,26 +341,77 @@ def beatmap_backward(tower, saved, dlast, g: GradStore) -> None:
         audio_backward(tower.audio_encoder, saved["audio"], d_audio, g)
 
 
+# Saved activations of the metadata tower above which its backward pass re-runs the forward in chunks of sequences
+# instead of keeping every layer's activations alive next to the beatmap tower's.  At the reference's 256 metadata
+# variations per beatmap (configs/train/v7.yaml:40) the tower sees 65 536 sequences = 1.4 M tokens per GPU: 42 GB
+# of saved activations, on top of the ~145 GB of the beatmap tower.
+METADATA_SAVE_BUDGET = 6 << 30
+
+
+def _encoder_saved_bytes_per_token(cfg) -> int:
+    H, I = cfg.hidden_size, int(cfg.intermediate_size)
+    return cfg.num_hidden_layers * 2 * (8 * H + 2 * I)  # x_in, qkv, o, x1, ug + the two LayerNorm outputs
+
+
 def metadata_forward(tower, metadata_ids, attention_mask):
     from .modeling_cm3p import _unpad
     S = metadata_ids.shape[-1]
     ids = metadata_ids.reshape(-1, S).contiguous()
-    up = _unpad(attention_mask, ids.shape[0], S, ids.device)
+    up = _unpad(attention_mask, ids.shape[0], S, ids.device, pack=True)
     pk = tower.encoder.packed()
     ids_flat = ids.reshape(-1)
     x0 = ops.embed_gather_ln(ids_flat, up.src_index, None, pk["tok_emb"], None, pk["emb_norm"], tower.config.norm_eps,
                              rows=up.total)
-    last, enc_saved = encoder_forward(tower.encoder, x0, up.cu_seqlens, up.max_len, up.positions)
+    if up.total * _encoder_saved_bytes_per_token(tower.config) > METADATA_SAVE_BUDGET:
+        # too large to keep: forward without saving anything; metadata_backward re-runs it chunk by chunk
+        last = tower.encoder.run_layers(x0, up.cu_seqlens, up.max_len, up.positions, groups=up.groups)
+        return last, up, dict(ids=ids_flat, up=up, enc=None)
+    last, enc_saved = encoder_forward(tower.encoder, x0, up.cu_seqlens, up.max_len, up.positions, groups=up.groups)
     return last, up, dict(ids=ids_flat, up=up, enc=enc_saved)
 
 
 def metadata_backward(tower, saved, dlast, g: GradStore) -> None:
     enc, up = tower.encoder, saved["up"]
     pk = enc.packed()
-    dx0 = encoder_backward(enc, saved["enc"], dlast, g)
-    ops.embed_gather_ln_bwd(saved["ids"], up.src_index, None, pk["tok_emb"], None, pk["emb_norm"], dx0,
-                            tower.config.norm_eps, d_tok_emb=g(enc.embeddings.tok_embeddings.weight),
-                            d_audio_embeds=None, dgamma=g(enc.embeddings.norm.weight))
+    cfg = tower.config
+    if saved["enc"] is not None:
+        dx0 = encoder_backward(enc, saved["enc"], dlast, g)
+        ops.embed_gather_ln_bwd(saved["ids"], up.src_index, None, pk["tok_emb"], None, pk["emb_norm"], dx0,
+                                cfg.norm_eps, d_tok_emb=g(enc.embeddings.tok_embeddings.weight),
+                                d_audio_embeds=None, dgamma=g(enc.embeddings.norm.weight))
+        return
+    # chunked recompute (the sequences are independent): forward + backward of `n_seq` sequences at a time; the
+    # weight gradients of all chunks accumulate into the same buffers, so no gradient bucket may leave before the end
+    per_tok = _encoder_saved_bytes_per_token(cfg)
+    tok_budget = max(1, METADATA_SAVE_BUDGET // per_tok)
+    import numpy as np
+    cum = np.concatenate(([0], np.cumsum(np.asarray(up.lens_cpu, dtype=np.int64))))
+    n_seq = len(up.lens_cpu)
+    g.hold()
+    try:
+        s0 = 0
+        while s0 < n_seq:
+            # as many whole sequences as fit the token budget (at least one)
+            s1 = int(np.searchsorted(cum, cum[s0] + tok_budget, side="right")) - 1
+            s1 = min(max(s1, s0 + 1), n_seq)
+            t0, t1 = int(cum[s0]), int(cum[s1])
+            if t1 > t0:
+                cu = (up.cu_seqlens[s0:s1 + 1] - t0).contiguous()
+                src = up.src_index[t0:t1].contiguous()
+                pos = up.positions[t0:t1].contiguous()
+                groups = ops.attn_pack_groups(cu, t1 - t0) if up.groups is not None else None
+                x0 = ops.embed_gather_ln(saved["ids"], src, None, pk["tok_emb"], None, pk["emb_norm"], cfg.norm_eps,
+                                         rows=t1 - t0)
+                max_len = int(np.max(cum[s0 + 1:s1 + 1] - cum[s0:s1]))
+                _, enc_saved = encoder_forward(enc, x0, cu, max_len, pos, groups=groups)
+                dx0 = encoder_backward(enc, enc_saved, dlast[t0:t1], g)
+                ops.embed_gather_ln_bwd(saved["ids"], src, None, pk["tok_emb"], None, pk["emb_norm"], dx0, cfg.norm_eps,
+                                        d_tok_emb=g(enc.embeddings.tok_embeddings.weight), d_audio_embeds=None,
+                                        dgamma=g(enc.embeddings.norm.weight))
+                del enc_saved, dx0, x0
+            s0 = s1
+    finally:
+        g.release()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -408,26 +528,33 @@ class _StepState:
         self.saved = None
         if sv is None:
             raise RuntimeError("cm3p_b200: backward called twice on the same training step")
-        g = GradStore(self.params)
+        dp = getattr(model, "_dp", None)
+        # global negatives: every rank differentiates the SAME global contrastive loss, so parameter gradients are
+        # summed; every other objective (local negatives, MLM, classification) is a per-rank mean -> averaged
+        sum_reduce = bool(dp is not None and dp.global_negatives and self.backward_fn is _contrastive_backward)
+        key = (tuple(id(p) for p in self.params), self.backward_fn)
+        cached = getattr(model, "_grad_order", None)
+        order = cached[1] if (cached is not None and cached[0] == key) else None
+        g = GradStore(self.params, order=order, dp=dp, sum_reduce=sum_reduce)
         gout = grad_out.detach().to(device=self.params[0].device, dtype=F32).reshape(1).contiguous()
         self.backward_fn(model, sv, gout, g)
-        dp = getattr(model, "_dp", None)
-        if dp is not None:
-            if dp.global_negatives and hasattr(model, "logit_scale"):
-                # every rank evaluated the full loss, so d(logit_scale) is already complete on each rank
-                g(model.logit_scale).div_(dp.world_size)
-            dp_utils.reduce_gradients(g.flat, dp)  # ONE all-reduce for every parameter gradient
+        g.finish()
+        if order is None:
+            model._grad_order = (key, g.order())
         return [g(p).to(p.dtype) if p.requires_grad else None for p in self.params]
 
 
 def _contrastive_backward(model, sv, gout, g: GradStore) -> None:
+    dp = sv["dp"]
+    world = dp.world_size if (dp is not None and dp.global_negatives) else 1
     dls = g(model.logit_scale).view(1)
     dS = ops.clip_loss_bwd(sv["S"], sv["true_idx"], sv["row_lse"], sv["col_lse"], sv["V"], gout, dls)
-    scale = sv["scale"]
-    dme = ops.gemm(dS, sv["be16"], trans_b=True, epilogue=ops.EPI_SCALE_F32, scale=scale)
-    dbe = ops.gemm(dS, sv["me16"], trans_a=True, trans_b=True, epilogue=ops.EPI_SCALE_F32, scale=scale)
+    if world > 1:
+        # every rank evaluated the full loss, so d(logit_scale) is already complete on each rank (gradients are summed)
+        dls.div_(world)
+    dme = ops.gemm(dS, sv["be16"], trans_b=True, epilogue=ops.EPI_SCALE_F32, aux=sv["ls"])
+    dbe = ops.gemm(dS, sv["me16"], trans_a=True, trans_b=True, epilogue=ops.EPI_SCALE_F32, aux=sv["ls"])
     del dS
-    dp = sv["dp"]
     if dp is not None and dp.global_negatives:
         # every rank holds d(global loss)/d(all embeddings); its own rows are its row block
         dme = dp_utils.local_rows(dme, dp).contiguous()
@@ -440,8 +567,9 @@ def _contrastive_backward(model, sv, gout, g: GradStore) -> None:
     if sv.get("mlm") is not None:
         # auxiliary masked-LM loss: loss += 0.5 * CE  (modeling_cm3p.py:994-996)
         ce = sv["mlm_ce"]
+        # (a per-rank mean: pre-divided by the world size where the gradients of this step are summed over ranks)
         ops.vocab_ce_bwd(sv["mlm"]["buf"], ce["vocab"], ce["labels"], ce["src_index"], ce["row_lse"],
-                         (gout * 0.5 / ce["denom"]).contiguous())
+                         (gout * (0.5 / world) / ce["denom"]).contiguous())
         dlast_b = mlm_head_backward(model.head, model.decoder, sv["mlm"], g)
         sv["mlm"] = None
     dlast_b = head_backward(sv["bhead"], dbe, sv["w_bp"], g(model.beatmap_projection.weight), dlast=dlast_b)
@@ -474,7 +602,7 @@ def forward_with_grad(model, *, input_ids=None, input_features=None, metadata_id
     sv["w_mp"] = _pack_linear(model.metadata_projection, model._wcache, "mp")
     me32, me16, sv["mhead"] = head_forward(last_m, up_m.cu_seqlens, not cfg.metadata_config.cls_embed, sv["w_mp"])
 
-    scale = float(model.logit_scale.detach().float().exp())
+    ls = model.logit_scale.detach().float().reshape(1)  # exp() is taken on the device, in the GEMM epilogues
     if metadata_ids.dim() == 3:
         Bm, V = metadata_ids.shape[:2]
         if metadata_variation_classes is None:
@@ -493,7 +621,7 @@ def forward_with_grad(model, *, input_ids=None, input_features=None, metadata_id
         be16, me16 = dp_utils.all_gather_rows(be16, dp), dp_utils.all_gather_rows(me16, dp)
         true_idx = dp_utils.all_gather_rows(true_idx, dp)
         Bm = Bm * dp.world_size
-    S = ops.gemm(me16, be16, epilogue=ops.EPI_SCALE_F32, scale=scale)
+    S = ops.gemm(me16, be16, epilogue=ops.EPI_SCALE_F32, aux=ls)
     Bb = be16.shape[0]
     if metadata_ids.dim() == 3:
         logits_per_metadata = S.view(Bm, V, Bb)
@@ -501,11 +629,12 @@ def forward_with_grad(model, *, input_ids=None, input_features=None, metadata_id
     else:
         logits_per_metadata, logits_per_beatmap = S, S.t()
     loss_val, row_lse, col_lse = ops.clip_loss_fwd(S, true_idx, V)
-    sv.update(S=S, true_idx=true_idx, row_lse=row_lse, col_lse=col_lse, V=V, scale=scale, be16=be16, me16=me16)
+    sv.update(S=S, true_idx=true_idx, row_lse=row_lse, col_lse=col_lse, V=V, ls=ls, be16=be16, me16=me16)
 
     logits_out = None
-    if cfg.has_decoder_head and (output_logits or labels is not None):
-        # decoder(head(last_hidden)) on every real token (:987-993); bf16 like the reference under autocast
+    if cfg.has_decoder_head and output_logits:
+        # decoder(head(last_hidden)) on every real token (:987-993), only when logits are requested (the reference
+        # gates the MLM term on output_logits, :987, :994); bf16 like the reference under autocast
         bc = cfg.beatmap_config
         logits_u, mlm_saved = mlm_head_forward(model.head, model.decoder, bc.norm_eps, last_b, model._wcache)
         if labels is not None:

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CM3P_B200_VERSION 100 /* 0.1.0 */
+#define CM3P_B200_VERSION 200 /* 0.2.0 */
 
 #define CM3P_OK 0
 #define CM3P_ERR_SHAPE (-1)
@@ -42,12 +42,25 @@ extern "C" {
 #define CM3P_EPI_GEGLU 5      /* C[M,N/2] = gelu_erf(u)*g; B rows interleaved in groups of 16 (u,g) */
 #define CM3P_EPI_GEGLU_SAVE 6 /* as GEGLU, and C2[M,N] = acc (pre-activation kept for backward) */
 #define CM3P_EPI_ROPE 7       /* rotate-half RoPE on columns [0, rope_cols) per 64-wide head */
-#define CM3P_EPI_SCALE_F32 8  /* C(fp32) = scale*acc; accumulate != 0: C += scale*acc with fp32 atomics, K split
-                                 across CTAs (weight gradients: K = number of tokens) */
+#define CM3P_EPI_SCALE_F32 8  /* C(fp32) = scale*acc (aux != NULL: scale *= exp(*aux), aux a device fp32 scalar such as
+                                 logit_scale); accumulate != 0: C += scale*acc with fp32 atomics, K split
+                                 across CTAs (weight gradients: K = number of tokens); with tile_sem the splits of a
+                                 tile add in split order instead (bit-reproducible) */
 
 const char* cm3p_last_error(void);
 int cm3p_version(void);
 int cm3p_num_sms(void); /* host query; 0 if no CUDA device */
+
+/* Run-time knobs (process-wide, thread-safe).  The defaults are the product; the tests sweep the streaming depths
+ * and the benchmarks use the others for A/B measurements.  Nothing is read from the environment. */
+#define CM3P_OPT_FWD_BLOCKS_PER_CTA 0      /* attention forward: 256-query blocks streamed per CTA; 0 = heuristic */
+#define CM3P_OPT_BWD_OUTER_PER_CTA 1       /* attention backward: outer tiles streamed per CTA; 0 = heuristic */
+#define CM3P_OPT_GEMM_CLUSTER 2            /* 2 = CTA pairs share B tiles through TMA multicast (default), 1 = off */
+#define CM3P_OPT_ATTN_FORCE_TILE_KERNELS 3 /* 1 = one-tile-per-CTA attention kernels for every sequence length */
+#define CM3P_OPT_WGRAD_DETERMINISTIC 4     /* 1 = ordered split-K accumulation when turnstile counters are given (default) */
+#define CM3P_OPT_TMAP_CACHE 5              /* 1 = cache encoded CUtensorMaps by (pointer, shape, pitch, box) (default) */
+int cm3p_set_option(int option, int value);
+int cm3p_get_option(int option);
 
 /* C[M,N] = epilogue(A . B^T) on tcgen05 tensor cores, fp32 accumulation in TMEM.
  * Replaces nn.Linear everywhere on the path: MB:74-91 (Wi/Wo), MB:232-310 (Wqkv/Wo),
@@ -55,11 +68,17 @@ int cm3p_num_sms(void); /* host query; 0 if no CUDA device */
  * logit-scale multiply), :1229-1238 (MLM head); with CM3P_EPI_ROPE also MB:197-228.
  *   a: trans_a == 0 -> [M,K] K-contiguous, else [K,M] M-contiguous; lda = row pitch in elements
  *   b: trans_b == 0 -> [N,K] K-contiguous (nn.Linear.weight layout), else [K,N]
- *   positions [M] int32 + rope_table [max_pos][32][2] fp32 (cos,sin) only for CM3P_EPI_ROPE */
+ *   positions [M] int32 + rope_table [max_pos][32][2] fp32 (cos,sin) only for CM3P_EPI_ROPE
+ *   tile_sem: tile_sem_count zeroed int32 counters (left zeroed) for ordered split-K accumulation, or NULL
+ *   group_m > 0: grouped GEMM, M / group_m independent (group_m x N x K) problems in one launch whose operands are
+ *     stacked along their outer dimension (A [M,K] or, transposed, [groups*K, group_m]; B [groups*N, K] or
+ *     [groups*K, N]; C / aux [M, N]); group_m % 256 == 0 and K % 64 == 0.  Used for the Newton-Schulz iterations of
+ *     Muon over all same-shaped weight matrices at once (utils/muon_utils.py:35-57). */
 int cm3p_gemm_bf16(const void* a, int64_t lda, int trans_a, const void* b, int64_t ldb, int trans_b, void* c,
                    int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue, const void* aux, int64_t ld_aux,
                    void* c2, int64_t ldc2, float scale, int accumulate, const int32_t* positions,
-                   const float* rope_table, int64_t rope_cols, void* stream);
+                   const float* rope_table, int64_t rope_cols, int32_t* tile_sem, int64_t tile_sem_count,
+                   int64_t group_m, void* stream);
 
 /* The same GEMM with a LayerNorm folded into the GEMMs on both sides of it, so that the pre-norm blocks of
  * ModernBERT (MB:313-342: `attn(attn_norm(x))`, `mlp(mlp_norm(x))`) need no LayerNorm pass at all:
@@ -81,9 +100,20 @@ int cm3p_gemm_bf16_ln(const void* a, int64_t lda, const void* b, int64_t ldb, vo
  * with the padding + sliding-window masks (transformers/masking_utils.py:121-131) and the
  * unpad/repad helpers cm3p/modeling_cm3p.py:65-134.
  *   qkv [T,3,heads,64] bf16 (q,k already rotated), out [T,heads*64] bf16, lse [heads,T] fp32 or NULL
- *   window < 0: global layer; window = w: attend iff |i-j| <= w (ModernBERT: local_attention/2) */
+ *   window < 0: global layer; window = w: attend iff |i-j| <= w (ModernBERT: local_attention/2)
+ *   groups / n_groups / max_groups (all or none): packed short sequences.  When every sequence has <= 128 tokens
+ *     (the metadata tower: B*V sequences of ~21 tokens, cm3p/modeling_cm3p.py:351-380, tokenization_cm3p.py:632-654)
+ *     consecutive sequences are packed into groups of <= 128 tokens by cm3p_attn_pack_groups and one CTA serves a
+ *     whole group with a block-diagonal mask, instead of one 128-row tile per sequence. */
 int cm3p_attn_varlen_fwd(const void* qkv, void* out, float* lse, const int32_t* cu_seqlens, int64_t total_tokens,
-                         int batch, int heads, int head_dim, int max_seqlen, int window, void* stream);
+                         int batch, int heads, int head_dim, int max_seqlen, int window, const int32_t* groups,
+                         const int32_t* n_groups, int max_groups, void* stream);
+
+/* Group table for the packed attention kernels: groups [max_groups][2] int32 = (first sequence, end sequence) of
+ * consecutive sequences holding <= 128 tokens together, in no particular order; *n_groups (device) = their number.
+ * max_groups >= min(batch, 2 * (total_tokens / 128) + (batch + 63) / 64 + 1).  Integer work only. */
+int cm3p_attn_pack_groups(const int32_t* cu_seqlens, int batch, int32_t* groups, int32_t* n_groups, int max_groups,
+                          void* stream);
 
 /* y = LayerNorm(x) * gamma (no bias), rows of H bf16; stats [rows][2] = (mean, rstd) or NULL.
  * Replaces nn.LayerNorm at MB:63 (embeddings.norm), MB:318-323 (attn_norm / mlp_norm), final_norm. */
@@ -137,11 +167,12 @@ int cm3p_im2col_k3(const void* x, int x_layout, void* ws, int64_t ld_ws, int bat
 
 /* Gradient of cm3p_attn_varlen_fwd w.r.t. the un-rotated Wqkv output: dqkv [T,3,heads,64] bf16.
  *   out/dout [T,heads*64] bf16; lse [heads,T] from the forward; delta [heads,T] fp32 workspace;
- *   positions + rope_table (both or neither): dq/dk are rotated back (inverse of CM3P_EPI_ROPE). */
+ *   positions + rope_table (both or neither): dq/dk are rotated back (inverse of CM3P_EPI_ROPE).
+ *   groups / n_groups / max_groups: packed short sequences as in the forward (one kernel, 5 GEMMs per group). */
 int cm3p_attn_varlen_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
                          const int32_t* cu_seqlens, const int32_t* positions, const float* rope_table,
                          int64_t total_tokens, int batch, int heads, int head_dim, int max_seqlen, int window,
-                         void* stream);
+                         const int32_t* groups, const int32_t* n_groups, int max_groups, void* stream);
 
 /* dx = LayerNorm'(x; gamma) . dy (+ dres, the gradient arriving through the residual connection);
  * dgamma[H] fp32 += sum_rows dy * xhat (NULL to skip).  Statistics are recomputed from x. */

@@ -1,8 +1,9 @@
-"""Build the UNMODIFIED reference model from /root/reference.  TEST INFRASTRUCTURE ONLY.
+"""Build the UNMODIFIED reference model.  TEST INFRASTRUCTURE ONLY.
 
-Only usable in the build container (the GPU box has no /root/reference): it is what
-`oracle/make_golden.py` uses to pin `oracle/cm3p_oracle.py`.  No reference source is copied; the
-reference package is imported from where it lies.
+In the build container the reference package is imported from where it lies (/root/reference): that is what
+`oracle/make_golden.py` uses to pin `oracle/cm3p_oracle.py`.  On the GPU box, where /root/reference does not
+exist, the untouched copies that `oracle/build_ref.py` placed under the git-ignored `oracle/_ref/` are imported
+instead (CPU baseline of bench.py, tools/bench_reference_gpu.py).
 
 The installed transformers (5.5.0) ModernBERT reads `layer_types`, `rope_parameters` and
 `sliding_window` from its config, which the reference's configs (written for 4.55.0) do not have,
@@ -14,7 +15,10 @@ from __future__ import annotations
 import os
 import sys
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_ROOT = os.environ.get("CM3P_REFERENCE_ROOT", "/root/reference")
+if not os.path.isfile(os.path.join(REFERENCE_ROOT, "cm3p", "modeling_cm3p.py")):
+    REFERENCE_ROOT = os.path.join(_HERE, "_ref")
 
 
 def reference_available() -> bool:

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/cm3p_b200.h but not exported"
     assert set(declared) == set(_lib.SIGNATURES), set(declared) ^ set(_lib.SIGNATURES)
-    assert lib.cm3p_version() == 100
+    assert lib.cm3p_version() == 200
 
 
 def test_compute_entry_fails_loudly_without_gpu():

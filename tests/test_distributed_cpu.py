@@ -114,3 +114,53 @@ def test_gather_and_slice_roundtrip_single_process():
     assert torch.equal(D.local_rows(x, dp), x)
     dp4 = D.DataParallel(group=None, world_size=4, rank=2)
     assert torch.equal(D.local_rows(x, dp4), x[2:3])
+
+
+# ------------------------------------------------------------------------------------------------
+# bucketed, overlapped gradient reduction (training.GradStore): layout in backward order, a bucket is sent the
+# moment the backward pass touches a parameter behind it, mean for per-rank objectives / sum for the global loss
+
+def _gradstore_worker(rank, world, port, sum_reduce, out_dir):
+    from cm3p_b200 import training as T
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        params = [torch.zeros(n) for n in (1000, 7, 4096, 300, 1, 2048, 513)]
+        touch = [4, 0, 2, 6, 1, 5]  # backward order; parameter 3 is never touched (frozen)
+        dp = D.DataParallel(group=None, world_size=world, rank=rank, global_negatives=sum_reduce)
+        T.GradStore.BUCKET_BYTES = 8192  # several buckets for these sizes
+
+        def backward(order):
+            g = T.GradStore(params, order=order, dp=dp, sum_reduce=sum_reduce)
+            sent = []
+            for i in touch:
+                g(params[i]).add_(float(rank + 1) * (i + 1))
+                sent.append(len(g._works))
+            g.finish()
+            return g, sent
+
+        g1, sent1 = backward(None)           # first step: records the order, one reduction at the end
+        order = g1.order()
+        g2, sent2 = backward(order)          # steady state: buckets leave during the backward pass
+        torch.save({"order": order, "sent1": sent1, "sent2": sent2, "buckets": len(g2._buckets),
+                    "vals1": [float(g1(p).flatten()[0]) for p in params],
+                    "vals2": [float(g2(p).flatten()[0]) for p in params]},
+                   os.path.join(out_dir, f"gs_{int(sum_reduce)}_{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("sum_reduce", [False, True])
+def test_gradstore_bucketed_reduction_gloo(tmp_path, sum_reduce):
+    mp.spawn(_gradstore_worker, args=(WORLD, _free_port(), sum_reduce, str(tmp_path)), nprocs=WORLD, join=True)
+    res = [torch.load(os.path.join(tmp_path, f"gs_{int(sum_reduce)}_{r}.pt")) for r in range(WORLD)]
+    touch = [4, 0, 2, 6, 1, 5]
+    assert res[0]["order"] == touch + [3]
+    assert res[0]["sent1"] == [0] * len(touch)          # nothing leaves early on the recording step
+    assert res[0]["buckets"] >= 3
+    assert res[0]["sent2"][-1] >= 1 and res[0]["sent2"] == sorted(res[0]["sent2"])  # buckets left during backward
+    ranks_total = sum(r + 1 for r in range(WORLD))
+    for i in range(7):
+        want = 0.0 if i == 3 else (i + 1) * ranks_total / (1 if sum_reduce else WORLD)
+        for r in range(WORLD):
+            assert abs(res[r]["vals1"][i] - want) < 1e-6 and abs(res[r]["vals2"][i] - want) < 1e-6, (i, res[r])

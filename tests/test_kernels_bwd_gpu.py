@@ -55,6 +55,31 @@ def test_gemm_wgrad_split_k_atomic(T, Nout, Kin):
     _relerr("wgrad split-K x1.5", out - 1.0, want * 1.5, 2e-3)
 
 
+def test_gemm_wgrad_bit_reproducible():
+    """Ordered split-K accumulation (per-tile turnstile): the weight gradient is bit-identical from run to run and
+    across different amounts of concurrent work; the atomic path agrees with it to rounding."""
+    ops = _ops()
+    T, Nout, Kin = 60000, 768, 768
+    dy, x = _rand((T, Nout), 0.5, seed=1), _rand((T, Kin), 0.5, seed=2)
+    outs = []
+    for _ in range(4):
+        out = torch.zeros((Nout, Kin), device=DEV, dtype=torch.float32)
+        ops.gemm(dy, x, trans_a=True, trans_b=True, epilogue=ops.EPI_SCALE_F32, accumulate=True, out=out)
+        outs.append(out)
+    torch.cuda.synchronize()
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0]), "ordered split-K accumulation is not bit-reproducible"
+    ops.set_option(ops.OPT_WGRAD_DETERMINISTIC, 0)
+    try:
+        atomic = torch.zeros((Nout, Kin), device=DEV, dtype=torch.float32)
+        ops.gemm(dy, x, trans_a=True, trans_b=True, epilogue=ops.EPI_SCALE_F32, accumulate=True, out=atomic)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(ops.OPT_WGRAD_DETERMINISTIC, 1)
+    _relerr("atomic vs ordered split-K", atomic, outs[0], 1e-5)
+    _relerr("ordered split-K vs fp32", outs[0], dy.float().t() @ x.float(), 2e-3)
+
+
 # ------------------------------------------------------------------------------------- attention
 def _attn_ref_autograd(qkv, dout, cu, heads, window, positions=None, table=None):
     """fp32 autograd reference; if a rope table is given, `qkv` is the un-rotated projection."""
@@ -116,13 +141,63 @@ def test_attention_bwd(lens, heads, window, rope):
         _close(f"{tag} d{n}", got[:, i], want[:, i], 0.03 * float(want[:, i].abs().max()) + 1e-3, 5e-2)
 
 
+@pytest.mark.parametrize("name", ["mixed", "metadata", "ones", "full"])
+@pytest.mark.parametrize("rope", [False, True])
+def test_attention_bwd_packed(name, rope):
+    """Packed short-sequence backward (one kernel, 5 GEMMs per group of sequences) vs fp32 autograd and vs the
+    one-tile-per-sequence kernels."""
+    from test_kernels_gpu import _packed_lens
+    ops = _ops()
+    lens, heads = _packed_lens(name), 4
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    T, H = cu[-1], heads * 64
+    raw = _rand((T, 3 * H), 1.0, seed=5)
+    dout = _rand((T, H), 1.0, seed=6)
+    cu_t = torch.tensor(cu, dtype=torch.int32, device=DEV)
+    pos = tab = None
+    if rope:
+        pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens]).to(DEV)
+        tab = ops.rope_table(10000.0, 128, DEV)
+    rotated, _, want_dqkv = _attn_ref_autograd(raw, dout, cu, heads, -1, pos, tab)
+    qkv = rotated.to(torch.bfloat16).contiguous() if rope else raw
+    groups = ops.attn_pack_groups(cu_t, T)
+    lse = torch.empty((heads, T), device=DEV, dtype=torch.float32)
+    out = ops.attn_varlen_fwd(qkv, cu_t, max(lens), heads, -1, lse=lse, groups=groups)
+    dqkv = ops.attn_varlen_bwd(qkv, out, dout, lse, cu_t, max(lens), heads, -1, positions=pos, rope_table=tab,
+                               groups=groups)
+    dqkv_tile = ops.attn_varlen_bwd(qkv, out, dout, lse, cu_t, max(lens), heads, -1, positions=pos, rope_table=tab)
+    torch.cuda.synchronize()
+    assert torch.isfinite(dqkv.float()).all()
+    want = want_dqkv.view(T, 3, H)
+    got = dqkv.float().view(T, 3, H)
+    ref2 = dqkv_tile.float().view(T, 3, H)
+    for i, n in enumerate("qkv"):
+        tag = f"attn_bwd packed {name} rope={rope} d{n}"
+        if name == "ones" and n != "v":
+            # one key per query: dq = dk = 0 exactly; P (dP - delta) only cancels up to fp32 summation order
+            _close(tag, got[:, i], want[:, i], 1e-3 * float(want.abs().max()), 0.0)
+            continue
+        _relerr(tag, got[:, i], want[:, i], 2e-2)
+        _close(tag, got[:, i], want[:, i], 0.03 * float(want[:, i].abs().max()) + 1e-3, 5e-2)
+        _relerr(tag + " vs tile kernels", got[:, i], ref2[:, i], 1e-2)
+
+
 @pytest.mark.parametrize("outer_per_cta", [1, 2, 3, 16])
 @pytest.mark.parametrize("window", [-1, 64, 0, 200])
-def test_attention_bwd_streaming(outer_per_cta, window, monkeypatch):
+def test_attention_bwd_streaming(outer_per_cta, window):
     """Several outer tiles per CTA (double-buffered 128-row operands and dQ accumulator, write-out one tile
     late, single-tile outer tiles at sequence ends): same gradients whatever the split."""
-    monkeypatch.setenv("CM3P_BWD_OUTER_PER_CTA", str(outer_per_cta))  # re-read by the launcher on every call
     ops = _ops()
+    ops.set_option(ops.OPT_BWD_OUTER_PER_CTA, outer_per_cta)
+    try:
+        _attention_bwd_streaming_case(ops, outer_per_cta, window)
+    finally:
+        ops.set_option(ops.OPT_BWD_OUTER_PER_CTA, 0)
+
+
+def _attention_bwd_streaming_case(ops, outer_per_cta, window):
     lens, heads = [1100, 257, 1, 640, 129, 385], 2
     cu = [0]
     for n in lens:

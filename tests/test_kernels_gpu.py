@@ -134,10 +134,12 @@ def test_gemm_transposed_operands():
 
 # ------------------------------------------------------------------------------------- attention
 @pytest.fixture
-def blocks_per_cta(request, monkeypatch):
-    """Force how many 256-query blocks one forward CTA streams (the launcher re-reads the variable per call)."""
-    monkeypatch.setenv("CM3P_FWD_BLOCKS_PER_CTA", str(request.param))
-    return request.param
+def blocks_per_cta(request):
+    """Force how many 256-query blocks one forward CTA streams (cm3p_set_option, restored afterwards)."""
+    ops = _ops()
+    ops.set_option(ops.OPT_FWD_BLOCKS_PER_CTA, request.param)
+    yield request.param
+    ops.set_option(ops.OPT_FWD_BLOCKS_PER_CTA, 0)
 
 
 def _attn_ref(qkv, cu, heads, window):
@@ -199,6 +201,98 @@ def test_attention_fwd_streaming(blocks_per_cta, window):
     torch.cuda.synchronize()
     _report(f"attn streaming bpc={blocks_per_cta} w={window}", out, _attn_ref(qkv, cu, heads, window), 2e-2, 2e-2)
     assert bool(torch.isfinite(lse).all())
+
+
+def _packed_lens(name):
+    g = torch.Generator().manual_seed(3)
+    if name == "mixed":
+        return [1, 17, 25, 128, 25, 17, 1, 1, 64, 64, 21, 128, 127, 2]
+    if name == "metadata":  # the metadata tower: many sequences of 17..25 tokens (more than one 64-sequence chunk)
+        return torch.randint(17, 26, (300,), generator=g).tolist()
+    if name == "ones":
+        return [1] * 200
+    if name == "full":
+        return [128] * 5
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["mixed", "metadata", "ones", "full"])
+@pytest.mark.parametrize("heads", [1, 4])
+def test_attention_fwd_packed(name, heads):
+    """Packed short sequences (several sequences per 128-row tile, block-diagonal mask) == one tile per sequence
+    == the fp32 reference; the group table covers every sequence exactly once."""
+    ops = _ops()
+    lens = _packed_lens(name)
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    T = cu[-1]
+    qkv = _rand((T, 3 * heads * 64), 1.0, seed=5)
+    cu_t = torch.tensor(cu, dtype=torch.int32, device=DEV)
+    groups = ops.attn_pack_groups(cu_t, T)
+    n_groups = int(groups.count.item())
+    assert 0 < n_groups <= groups.max_groups
+    tab = groups.table[:n_groups].cpu()
+    tab = tab[tab[:, 0].argsort()]
+    assert int(tab[0, 0]) == 0 and int(tab[-1, 1]) == len(lens)
+    assert bool((tab[1:, 0] == tab[:-1, 1]).all())
+    tok = torch.tensor(cu)[tab[:, 1].long()] - torch.tensor(cu)[tab[:, 0].long()]
+    assert int(tok.max()) <= 128 and int(tok.min()) >= 1
+    lse = torch.empty((heads, T), device=DEV, dtype=torch.float32)
+    lse_p = torch.empty_like(lse)
+    out = ops.attn_varlen_fwd(qkv, cu_t, max(lens), heads, -1, lse=lse)
+    out_p = ops.attn_varlen_fwd(qkv, cu_t, max(lens), heads, -1, lse=lse_p, groups=groups)
+    torch.cuda.synchronize()
+    want = _attn_ref(qkv, cu, heads, -1)
+    _report(f"attn packed {name} h={heads}", out_p, want, 2e-2, 2e-2)
+    _report(f"attn packed vs tile kernel {name} h={heads}", out_p, out, 1e-2, 1e-2)
+    _report(f"attn packed lse {name} h={heads}", lse_p, lse, 1e-3, 1e-4)
+
+
+def test_attention_more_than_65535_sequences():
+    """B*V = 256*256 + 1 metadata sequences: the sequence index lives in grid.x (grid.z stops at 65535)."""
+    ops = _ops()
+    n, heads = 65537, 1
+    g = torch.Generator().manual_seed(0)
+    lens = torch.randint(1, 4, (n,), generator=g)
+    cu = torch.zeros(n + 1, dtype=torch.int32)
+    cu[1:] = lens.cumsum(0)
+    T = int(cu[-1])
+    qkv = _rand((T, 3 * heads * 64), 1.0, seed=9)
+    cu_t = cu.to(DEV)
+    out = ops.attn_varlen_fwd(qkv, cu_t, 3, heads, -1)                      # one tile per sequence
+    out_p = ops.attn_varlen_fwd(qkv, cu_t, 3, heads, -1, groups=ops.attn_pack_groups(cu_t, T))
+    torch.cuda.synchronize()
+    # last sequence against the reference, and the two kernels against each other everywhere
+    s, e = int(cu[-2]), int(cu[-1])
+    q3 = qkv.float().view(T, 3, 64)
+    want = ((q3[s:e, 0] @ q3[s:e, 1].t()) / 8.0).softmax(-1) @ q3[s:e, 2]
+    _report("attn >65535 sequences (tail)", out[s:e], want, 2e-2, 2e-2)
+    _report("attn >65535 sequences packed vs tile", out_p, out, 1e-2, 1e-2)
+
+
+@pytest.mark.parametrize("trans", [False, True])
+def test_gemm_grouped(trans):
+    """Grouped GEMM (operands stacked along their outer dimension) == a loop over the groups; the shapes are the
+    Newton-Schulz products of Muon over all layers at once."""
+    ops = _ops()
+    G, m, K = 5, 256, 320
+    if not trans:
+        x = _rand((G * m, K), 0.3, seed=1)                                # A_g = X_g X_g^T
+        got = ops.gemm(x, x, groups=G)
+        want = torch.cat([x[g * m:(g + 1) * m].float() @ x[g * m:(g + 1) * m].float().t() for g in range(G)])
+        _report("gemm grouped X X^T", got, want, 5e-2, 2e-2)
+        bmat = _rand((G * m, m), 0.1, seed=2)                             # X_g <- B_g X_g + aux  (B operand [K, N])
+        aux = _rand((G * m, K), 1.0, seed=3)
+        got = ops.gemm(bmat, x, trans_b=True, epilogue=ops.EPI_RESIDUAL, aux=aux, groups=G)
+        want = torch.cat([bmat[g * m:(g + 1) * m].float() @ x[g * m:(g + 1) * m].float() for g in range(G)]) + aux.float()
+        _report("gemm grouped B X + aux", got, want, 5e-2, 2e-2)
+    else:
+        R = 640                                                           # tall matrices: A_g = G_g^T G_g
+        x = _rand((G * R, m), 0.3, seed=4)
+        got = ops.gemm(x, x, trans_a=True, trans_b=True, groups=G)
+        want = torch.cat([x[g * R:(g + 1) * R].float().t() @ x[g * R:(g + 1) * R].float() for g in range(G)])
+        _report("gemm grouped G^T G", got, want, 5e-2, 2e-2)
 
 
 # --------------------------------------------------------------------------------- row-wise kernels

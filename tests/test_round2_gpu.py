@@ -1,0 +1,260 @@
+"""Round-2 parity cases on a B200: the wrappers around the two towers, the evaluation-path MLM loss, the chunked
+recompute of the metadata tower, bit-reproducibility of the whole train step, the production architecture at the
+benchmark's full sequence length against the CPU oracle, and run-to-run determinism of the streaming attention
+kernels across streaming depths (formerly tools/stress_attn.py)."""
+import copy
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from cm3p_b200.configuration_cm3p import CM3PConfig, base_config_dict, small_config_dict
+from cm3p_b200.synthetic import synthetic_batch, synthetic_state_dict
+from oracle.make_golden import CASES
+
+DEV = "cuda"
+
+
+def _cos(a, b):
+    a, b = torch.as_tensor(a).double().flatten(0, -2), torch.as_tensor(b).double().flatten(0, -2)
+    return torch.nn.functional.cosine_similarity(a, b, dim=-1)
+
+
+def _sub_state(sd, prefix_map):
+    out = {}
+    for k, v in sd.items():
+        for src, dst in prefix_map.items():
+            if k.startswith(src):
+                out[dst + k[len(src):]] = v
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# wrappers (reference modeling_cm3p.py:411-467, :658-725, :1016-1128, :773-841)
+
+def test_tower_wrappers_and_feature_helpers_match_oracle():
+    from cm3p_b200.modeling_cm3p import (CM3PBeatmapModel, CM3PBeatmapModelWithProjection, CM3PMetadataModel,
+                                         CM3PMetadataModelWithProjection, CM3PModel)
+    from oracle import cm3p_oracle as O
+    case = CASES["small_b4_l400_v3_grads"]
+    cfg = CM3PConfig(**copy.deepcopy(case["cfg"]))
+    sd = synthetic_state_dict(cfg, seed=case["wseed"], gain=case["gain"])
+    batch = synthetic_batch(cfg, **case["batch"])
+    feed = {k: v.cuda() for k, v in batch.items()}
+    want = O.model_forward(sd, cfg, **batch)
+    mask = batch["attention_mask"].bool()
+    mmask = batch["metadata_attention_mask"].bool()
+
+    with torch.no_grad():
+        # bare towers
+        bm = CM3PBeatmapModel(cfg.beatmap_config)
+        bm.load_state_dict(_sub_state(sd, {"beatmap_model.": "beatmap_model."}), strict=True)
+        out = bm.cuda().eval()(input_ids=feed["input_ids"], input_features=feed["input_features"],
+                               attention_mask=feed["attention_mask"])
+        assert out.last_hidden_state.shape == (*mask.shape, cfg.beatmap_config.hidden_size)
+        assert float(_cos(out.last_hidden_state.float().cpu()[mask], want["beatmap_last_hidden"][mask]).min()) >= 0.995
+        assert out.pooler_output.shape == (mask.shape[0], cfg.beatmap_config.hidden_size)
+
+        mm = CM3PMetadataModel(cfg.metadata_config)
+        mm.load_state_dict(_sub_state(sd, {"metadata_model.": "metadata_model."}), strict=True)
+        mout = mm.cuda().eval()(input_ids=feed["metadata_ids"], attention_mask=feed["metadata_attention_mask"])
+        assert mout.last_hidden_state.shape == (*mmask.shape, cfg.metadata_config.hidden_size)
+        got = mout.last_hidden_state.float().cpu()[mmask]
+        assert float(_cos(got, want["metadata_last_hidden"].reshape(*mmask.shape, -1)[mmask]).min()) >= 0.995
+
+        # towers with projection: projection WITHOUT the L2 normalisation (:1016-1128)
+        bcfg = copy.deepcopy(cfg.beatmap_config)
+        bcfg.projection_dim = cfg.projection_dim
+        bp = CM3PBeatmapModelWithProjection(bcfg)
+        bp.load_state_dict(_sub_state(sd, {"beatmap_model.": "beatmap_model.",
+                                           "beatmap_projection.": "beatmap_projection."}), strict=True)
+        pout = bp.cuda().eval()(input_ids=feed["input_ids"], input_features=feed["input_features"],
+                                attention_mask=feed["attention_mask"])
+        e = pout.beatmap_embeds.float().cpu()
+        assert float(_cos(e, want["beatmap_embeds"]).min()) >= 0.999          # same direction as the normalised embeds
+        assert float((e.norm(dim=-1) - 1).abs().min()) > 1e-3                   # ... but not normalised
+
+        mcfg = copy.deepcopy(cfg.metadata_config)
+        mcfg.projection_dim = cfg.projection_dim
+        mp = CM3PMetadataModelWithProjection(mcfg)
+        mp.load_state_dict(_sub_state(sd, {"metadata_model.": "metadata_model.",
+                                           "metadata_projection.": "metadata_projection."}), strict=True)
+        mpo = mp.cuda().eval()(input_ids=feed["metadata_ids"], attention_mask=feed["metadata_attention_mask"])
+        assert mpo.metadata_embeds.shape == (*batch["metadata_ids"].shape[:-1], cfg.projection_dim)
+        assert float(_cos(mpo.metadata_embeds.float().cpu(), want["metadata_embeds"]).min()) >= 0.999
+
+        # feature helpers of the dual-tower model (:773-841)
+        model = CM3PModel(cfg)
+        model.load_state_dict(sd, strict=True)
+        model = model.cuda().eval()
+        bf = model.get_beatmap_features(input_ids=feed["input_ids"], input_features=feed["input_features"],
+                                        attention_mask=feed["attention_mask"])
+        assert float(_cos(bf.float().cpu(), want["beatmap_embeds"]).min()) >= 0.999
+        torch.testing.assert_close(bf.float(), pout.beatmap_embeds.float(), rtol=1e-2, atol=1e-2)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_eval_loss_includes_mlm_term(golden_dir):
+    """no-grad forward with labels: loss = contrastive + 0.5 * MLM like the reference (:994-996); the golden's loss
+    was produced by the unmodified reference with the decoder head on."""
+    from cm3p_b200.modeling_cm3p import CM3PModel
+    case = CASES["small_b3_l320_mlm"]
+    gold = np.load(os.path.join(golden_dir, "small_b3_l320_mlm.npz"))
+    cfg = CM3PConfig(**copy.deepcopy(case["cfg"]))
+    model = CM3PModel(cfg)
+    model.load_state_dict(synthetic_state_dict(cfg, seed=case["wseed"], gain=case["gain"]), strict=True)
+    model = model.cuda().eval()
+    batch = synthetic_batch(cfg, **case["batch"])
+    assert "labels" in batch
+    with torch.no_grad():
+        out = model(**{k: v.cuda() for k, v in batch.items()})
+        no_labels = model(**{k: v.cuda() for k, v in batch.items() if k != "labels"})
+    assert abs(float(out.loss) - float(gold["loss"])) <= 1e-2 * abs(float(gold["loss"]))
+    assert float(out.loss) > float(no_labels.loss) + 0.1   # the MLM term is really there (~0.5 * ln(vocab))
+    # the train path computes the same loss
+    tmodel = model.float().train()
+    tout = tmodel(**{k: v.cuda() for k, v in batch.items()})
+    assert abs(float(tout.loss.detach()) - float(out.loss)) <= 5e-3 * abs(float(out.loss))
+
+
+# ------------------------------------------------------------------------------------------------
+def _train_grads(cfg, sd, batch):
+    from cm3p_b200.modeling_cm3p import CM3PModel
+    model = CM3PModel(cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    out = model(**{k: v.cuda() for k, v in batch.items()})
+    out.loss.backward()
+    torch.cuda.synchronize()
+    return float(out.loss.detach()), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+
+
+def test_metadata_chunked_recompute_matches_single_pass(monkeypatch):
+    """V = 256-scale batches re-run the metadata tower chunk by chunk in the backward pass (training.
+    METADATA_SAVE_BUDGET); the gradients must be those of the single-pass backward."""
+    from cm3p_b200 import training
+    cfg = CM3PConfig(**copy.deepcopy(small_config_dict()))
+    sd = synthetic_state_dict(cfg, seed=3, gain=1.0)
+    batch = synthetic_batch(cfg, batch=6, seq_len=320, variations=40, seed=2, pad_variations=2)  # 240 metadata sequences
+    loss_a, ga = _train_grads(cfg, sd, batch)
+    per_tok = training._encoder_saved_bytes_per_token(cfg.metadata_config)
+    monkeypatch.setattr(training, "METADATA_SAVE_BUDGET", per_tok * 700)  # ~8 chunks of <= 700 tokens
+    loss_b, gb = _train_grads(cfg, sd, batch)
+    assert abs(loss_a - loss_b) <= 1e-3 * abs(loss_a)
+    assert set(ga) == set(gb)
+    for k in ga:
+        a, b = ga[k].double(), gb[k].double()
+        if float(a.norm()) < 1e-9:
+            continue
+        rel = float((a - b).norm() / a.norm())
+        # beatmap side: identical inputs; metadata side: the recomputed forward is the same arithmetic
+        assert rel <= 2e-2, (k, rel)
+
+
+def test_train_step_is_bit_reproducible():
+    """Same weights, same batch, two independent runs: identical loss and identical gradients, bit for bit
+    (ordered split-K weight gradients, no-atomics attention backward).  The token-embedding gradient is a
+    scatter-add with fp32 atomics and is only required to agree to rounding."""
+    case = CASES["small_b4_l400_v3_grads"]
+    cfg = CM3PConfig(**copy.deepcopy(case["cfg"]))
+    sd = synthetic_state_dict(cfg, seed=case["wseed"], gain=case["gain"])
+    batch = synthetic_batch(cfg, **case["batch"])
+    loss_a, ga = _train_grads(cfg, sd, batch)
+    loss_b, gb = _train_grads(cfg, sd, batch)
+    assert loss_a == loss_b
+    loose = ("tok_embeddings.weight", "norm.weight", "bias", "logit_scale")
+    for k in ga:
+        if k.endswith(loose):
+            torch.testing.assert_close(ga[k], gb[k], rtol=1e-4, atol=1e-6 * float(ga[k].abs().max()) + 1e-12)
+        else:
+            assert torch.equal(ga[k], gb[k]), f"{k}: gradient differs between two identical runs"
+
+
+# ------------------------------------------------------------------------------------------------
+def test_base_config_full_length_forward_and_gradients_vs_oracle():
+    """The production architecture at the benchmark's sequence length: 2 windows padded to L = 2000 (one full, one
+    ragged), V = 3, forward embeddings / loss and the gradients against the CPU oracle (itself pinned to the
+    reference's goldens).  North-star tolerances."""
+    from oracle import cm3p_oracle as O
+    cfg = CM3PConfig(**copy.deepcopy(base_config_dict()))
+    sd = synthetic_state_dict(cfg, seed=11, gain=None)
+    batch = synthetic_batch(cfg, batch=2, seq_len=2000, variations=3, seed=12, min_len=600)
+    torch.set_num_threads(os.cpu_count() or 1)
+    wout, want = O.forward_backward(sd, cfg, batch)
+    loss, got = _train_grads(cfg, sd, batch)
+    assert abs(loss - float(wout["loss"])) <= 1e-2 * abs(float(wout["loss"]))
+    gn_got = float(torch.sqrt(sum(v.double().pow(2).sum() for k, v in got.items() if k in want)))
+    gn_want = O.global_grad_norm(want)
+    assert abs(gn_got - gn_want) <= 1e-2 * gn_want, (gn_got, gn_want)
+    bad = []
+    for k, w in want.items():
+        if float(w.norm()) < 1e-4 * gn_want:
+            continue
+        g = got[k].double().cpu().flatten()
+        c = float((g @ w.double().flatten()) / (g.norm() * w.norm()).clamp_min(1e-300))
+        if c < 0.98:
+            bad.append((round(c, 4), k))
+    assert not bad, sorted(bad)[:12]
+    # forward (inference regime, bf16 weights) on the same windows
+    from cm3p_b200.modeling_cm3p import CM3PModel
+    model = CM3PModel(cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().to(torch.bfloat16).eval()
+    with torch.no_grad():
+        out = model(**{k: v.cuda() for k, v in batch.items()})
+    assert float(_cos(out.beatmap_embeds.float().cpu(), wout["beatmap_embeds"].detach()).min()) >= 0.999
+    assert float(_cos(out.metadata_embeds.float().cpu(), wout["metadata_embeds"].detach()).min()) >= 0.999
+
+
+# ------------------------------------------------------------------------------------------------
+def _attn_run(ops, qkv, dout, cu_t, L, heads, window, pos, tab, split):
+    ops.set_option(ops.OPT_FWD_BLOCKS_PER_CTA, split or 0)
+    ops.set_option(ops.OPT_BWD_OUTER_PER_CTA, split or 0)
+    T = qkv.shape[0]
+    lse = torch.empty((heads, T), device=DEV, dtype=torch.float32)
+    out = ops.attn_varlen_fwd(qkv, cu_t, L, heads, window, lse=lse)
+    dqkv = ops.attn_varlen_bwd(qkv, out, dout, lse, cu_t, L, heads, window, positions=pos, rope_table=tab)
+    torch.cuda.synchronize()
+    return out, lse, dqkv
+
+
+def test_streaming_attention_is_bitwise_independent_of_the_streaming_depth():
+    """Race hunt: random ragged batches, forward + backward; every 128- / 256-row tile is computed independently of
+    how many tiles one CTA streams, so outputs and gradients must be bit-identical for every depth and from run to
+    run.  A data race in the double-buffered pipelines shows up here as a flipped bit."""
+    from cm3p_b200 import ops
+    rng = random.Random(0)
+    tab = ops.rope_table(160000.0, 2048, DEV)
+    bad = []
+    try:
+        for it in range(24):
+            B = rng.choice([1, 2, 3, 7, 16, 40])
+            top = rng.choice([130, 300, 700, 1300, 2000])
+            lens = [rng.randint(1, top) for _ in range(B)]
+            lens[rng.randrange(B)] = top
+            heads = rng.choice([1, 2, 4, 8, 12])
+            window = rng.choice([-1, -1, 64, 64, 8])
+            cu = [0]
+            for n in lens:
+                cu.append(cu[-1] + n)
+            T = cu[-1]
+            g = torch.Generator(device=DEV).manual_seed(it)
+            qkv = torch.randn((T, 3 * heads * 64), device=DEV, generator=g).bfloat16()
+            dout = torch.randn((T, heads * 64), device=DEV, generator=g).bfloat16()
+            cu_t = torch.tensor(cu, dtype=torch.int32, device=DEV)
+            pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens]).to(DEV)
+            ref = _attn_run(ops, qkv, dout, cu_t, max(lens), heads, window, pos, tab, 1)
+            for split in (None, rng.choice([2, 3, 5, 16]), None):
+                got = _attn_run(ops, qkv, dout, cu_t, max(lens), heads, window, pos, tab, split)
+                for name, a, b in zip(("out", "lse", "dqkv"), ref, got):
+                    if not torch.isfinite(b.float()).all() or not torch.equal(a, b):
+                        bad.append((it, name, split, B, top, heads, window,
+                                    float((a.float() - b.float()).abs().max())))
+    finally:
+        ops.set_option(ops.OPT_FWD_BLOCKS_PER_CTA, 0)
+        ops.set_option(ops.OPT_BWD_OUTER_PER_CTA, 0)
+    assert not bad, bad[:8]
