@@ -614,9 +614,16 @@ def main():
                     help="train: all-gather embeddings and use the global loss (BASELINE.json configs[3]: "
                          "--train-batch 512 --variations 1 on 8 GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[],
+                    help="library option KEY=VALUE (cm3p_set_option, include/cm3p_b200.h CM3P_OPT_*), for A/B runs")
     ap.add_argument("--quick", action="store_true",
                     help="profiling aid: only the device-resident timed loop (no e2e / roofline / CPU legs)")
     args = ap.parse_args()
+    if args.opt and args.impl == "ours":
+        from cm3p_b200 import ops
+        for kv in args.opt:
+            k, v = kv.split("=")
+            ops.set_option(int(k), int(v))
     res = run_reference(args) if args.impl == "reference" else run_ours(args)
     if res is not None:
         print(json.dumps(res), flush=True)

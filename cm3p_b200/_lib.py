@@ -33,10 +33,11 @@ SIGNATURES = {
     "cm3p_attn_varlen_fwd": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     "cm3p_layernorm_fwd": (_I, [_P, _P, _P, _P, _L, _I, _F, _P]),
     "cm3p_embed_gather_ln": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _F, _P]),
-    "cm3p_conv1d_k3_gelu_fwd": (_I, [_P, _I, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P]),
+    "cm3p_conv1d_k3_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "cm3p_conv1d_k3_wgrad": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
+    "cm3p_transpose_cast_bf16": (_I, [_P, _P, _I, _I, _I, _P]),
     "cm3p_pool_project_normalize": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "cm3p_clip_loss_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
-    "cm3p_im2col_k3": (_I, [_P, _I, _P, _L, _I, _I, _I, _I, _P]),
     "cm3p_attn_varlen_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     "cm3p_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _F, _P]),
     "cm3p_embed_gather_ln_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _F, _P]),

@@ -89,48 +89,38 @@ int cm3p_embed_gather_ln(const int64_t* ids, const int32_t* src_index, const int
                          as_stream(stream));
 }
 
-int cm3p_conv1d_k3_gelu_fwd(const void* x, int x_layout, const void* weight, const float* bias, void* ws,
-                            int64_t ld_ws, void* out, int batch, int c_in, int frames, int c_out, int stride,
-                            void* stream) {
+int cm3p_transpose_cast_bf16(const float* x, void* out, int batch, int channels, int frames, void* stream) {
   int rc = check_arch();
   if (rc != kOk) return rc;
-  CM3P_REQUIRE((x_layout == 0 && stride == 1) || (x_layout == 1 && stride == 2), kBadShape,
-               "conv1d_k3_gelu: supported forms are (fp32 channels-first, stride 1) and (bf16 channels-last, stride 2)");
-  CM3P_REQUIRE(ld_ws >= 3 * c_in && ld_ws % 8 == 0, kBadShape, "conv1d_k3_gelu: ld_ws=%lld must be >= 3*c_in and %% 8",
-               (long long)ld_ws);
-  cudaStream_t s = as_stream(stream);
-  if (x_layout == 0) {
-    rc = im2col_conv1(reinterpret_cast<const float*>(x), ws, batch, c_in, frames, static_cast<int>(ld_ws), s);
-  } else {
-    CM3P_REQUIRE(ld_ws == 3 * c_in, kBadShape, "conv1d_k3_gelu: channels-last form needs ld_ws == 3*c_in");
-    rc = im2col_conv2(x, ws, batch, frames, c_in, s);
-  }
-  if (rc != kOk) return rc;
-  GemmArgs g;
-  g.a = ws; g.lda = ld_ws;
-  g.b = weight; g.ldb = 3 * c_in;
-  g.c = out; g.ldc = c_out;
-  g.M = static_cast<int64_t>(batch) * (frames / stride);
-  g.N = c_out;
-  g.K = 3 * c_in;
-  g.epilogue = EPI_BIAS_GELU;
-  g.aux = bias;
-  return gemm_bf16(g, s);
+  return transpose_cast(x, out, batch, channels, frames, as_stream(stream));
 }
 
-int cm3p_im2col_k3(const void* x, int x_layout, void* ws, int64_t ld_ws, int batch, int c_in, int frames, int stride,
-                   void* stream) {
-  int rc = check_arch();
-  if (rc != kOk) return rc;
-  CM3P_REQUIRE((x_layout == 0 && stride == 1) || (x_layout == 1 && stride == 2), kBadShape,
-               "im2col_k3: supported forms are (fp32 channels-first, stride 1) and (bf16 channels-last, stride 2)");
-  CM3P_REQUIRE(ld_ws >= 3 * c_in && ld_ws % 8 == 0, kBadShape, "im2col_k3: ld_ws=%lld must be >= 3*c_in and %% 8",
-               (long long)ld_ws);
-  if (x_layout == 0)
-    return im2col_conv1(reinterpret_cast<const float*>(x), ws, batch, c_in, frames, static_cast<int>(ld_ws),
-                        as_stream(stream));
-  CM3P_REQUIRE(ld_ws == 3 * c_in, kBadShape, "im2col_k3: channels-last form needs ld_ws == 3*c_in");
-  return im2col_conv2(x, ws, batch, frames, c_in, as_stream(stream));
+int cm3p_conv1d_k3_fwd(const void* x, const void* weight, const float* bias, void* out, int batch, int c_in, int c_pad,
+                       int frames, int c_out, int stride, int gelu, void* stream) {
+  GemmArgs g;
+  g.conv_mode = 1; g.conv_stride = stride; g.conv_batch = batch; g.conv_frames = frames; g.conv_cin = c_in;
+  g.conv_cpad = c_pad;
+  g.a = x; g.b = weight; g.c = out;
+  g.N = c_out;
+  g.M = 1; g.K = 1;  // derived by the launcher
+  g.epilogue = gelu ? EPI_BIAS_GELU : EPI_BIAS;
+  g.aux = bias;
+  return gemm_bf16(g, as_stream(stream));
+}
+
+int cm3p_conv1d_k3_wgrad(const void* dz, const void* x, float* dw, int batch, int c_in, int c_pad, int frames, int c_out,
+                         int stride, int32_t* tile_sem, int64_t tile_sem_count, void* stream) {
+  GemmArgs g;
+  g.conv_mode = 2; g.conv_stride = stride; g.conv_batch = batch; g.conv_frames = frames; g.conv_cin = c_in;
+  g.conv_cpad = c_pad;
+  g.a = dz; g.b = x; g.c = dw;
+  g.M = c_out;
+  g.N = 1; g.K = 1;  // derived by the launcher
+  g.epilogue = EPI_SCALE_F32;
+  g.accumulate = 1;
+  g.scale = 1.f;
+  g.tile_sem = tile_sem; g.tile_sem_count = tile_sem_count;
+  return gemm_bf16(g, as_stream(stream));
 }
 
 int cm3p_pool_project_normalize(const void* hidden_states, const int32_t* cu_seqlens, int mode, const void* proj_w,

@@ -175,4 +175,23 @@ int encode_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint
   return kOk;
 }
 
+int encode_tmap_4d_bf16(CUtensorMap* map, const void* base, const uint64_t dims[4], const uint64_t pitches_bytes[3],
+                        const uint32_t box[4]) {
+  EncodeTiledFn fn = get_encode_fn();
+  CM3P_REQUIRE(fn != nullptr, kDriverError, "cuTensorMapEncodeTiled entry point not available");
+  CM3P_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, kBadAlignment, "TMA base %p not 16-byte aligned", base);
+  for (int i = 0; i < 3; ++i)
+    CM3P_REQUIRE((pitches_bytes[i] & 15) == 0, kBadAlignment, "TMA pitch %llu B not a multiple of 16",
+                 (unsigned long long)pitches_bytes[i]);
+  cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t st[3] = {pitches_bytes[0], pitches_bytes[1], pitches_bytes[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), d, st, bx, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CM3P_REQUIRE(r == CUDA_SUCCESS, kDriverError, "cuTensorMapEncodeTiled(4d) failed with %d", (int)r);
+  return kOk;
+}
+
 }  // namespace cm3p

@@ -62,6 +62,10 @@ int encode_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint
                         uint64_t pitch_mid_bytes, uint64_t pitch_outer_bytes, uint32_t box_inner, uint32_t box_mid,
                         uint32_t box_outer);
 
+// 4-D variant (d0 contiguous; byte pitches for d1..d3); boxes of {box0, box1, box2, 1}.
+int encode_tmap_4d_bf16(CUtensorMap* map, const void* base, const uint64_t dims[4], const uint64_t pitches_bytes[3],
+                        const uint32_t box[4]);
+
 #define CM3P_CUDA_TRY(expr)                                                                        \
   do {                                                                                             \
     cudaError_t _e = (expr);                                                                       \

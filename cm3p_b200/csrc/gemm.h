@@ -55,6 +55,16 @@ struct GemmArgs {
   // along their outer dimension: A [M, K] (trans_a: [groups*K, group_m]), B [groups*N, K] (trans_b: [groups*K, N]),
   // C / aux [M, N].  group_m % 256 == 0, K % 64 == 0.  0 = one problem.
   int64_t group_m = 0;
+  // Implicit-GEMM conv1d, kernel 3, padding 1 (cm3p/modeling_cm3p.py:488-489, :501-502).  x = channels-last bf16
+  // input [conv_batch, conv_frames, conv_cin]; conv_cpad = conv_cin rounded up to 64 = channels per tap in the
+  // packed weight [C_out, 3 * conv_cpad] (k index = tap * conv_cpad + c, zero columns for c >= conv_cin).
+  //   conv_mode 1 (forward):  a = x, b = packed weight, c = out [conv_batch, conv_frames / stride, N] bf16,
+  //                           epilogue EPI_BIAS / EPI_BIAS_GELU (aux = bias); M, K are derived.
+  //   conv_mode 2 (weight gradient): a = dz [conv_batch, conv_frames / stride, M] bf16, b = x,
+  //                           c = dW [M, 3 * conv_cpad] fp32 (+=), epilogue EPI_SCALE_F32 with accumulate; N, K derived.
+  int conv_mode = 0;
+  int conv_stride = 1;
+  int conv_batch = 0, conv_frames = 0, conv_cin = 0, conv_cpad = 0;
 };
 
 int gemm_bf16(const GemmArgs& args, cudaStream_t stream);

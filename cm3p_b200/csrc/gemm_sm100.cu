@@ -63,7 +63,27 @@ struct Params {
   int32_t* tile_sem;  // split-K turnstile, one counter per output tile (zero between launches), or null = fp32 atomics
   int64_t mn_tiles;   // output tiles (per split) as the kernel counts them
   int64_t group_m;    // > 0: grouped GEMM, see GemmArgs::group_m
+  // Implicit-GEMM conv1d (k = 3, pad 1): the A (forward) / B (weight gradient) operand is never materialised; its
+  // 64-channel x 128-frame boxes are fetched straight from the channels-last input [B, F, C] through a 4-D tensor
+  // map (c, frame parity, frame / stride, window), one shifted box per tap; out-of-range frames (the zero padding)
+  // are the tensor map's out-of-bounds fill.
+  int conv_mode;      // 0 plain GEMM, 1 conv forward, 2 conv weight gradient
+  int conv_stride;    // 1 or 2
+  int conv_per_win;   // forward: M tiles per window; weight gradient: 64-row K blocks per window
+  int conv_kb_per_tap;  // forward: 64-channel K blocks per tap
+  int conv_cpad;      // weight gradient: padded input channels per tap (N = 3 * conv_cpad)
 };
+
+// input frame (parity r, index u) read by output frame t' for tap j: stride * t' + j - 1
+__device__ __forceinline__ void conv_tap_coord(int stride, int tap, int t0, int& r, int& u0) {
+  if (stride == 1) {
+    r = 0;
+    u0 = t0 + tap - 1;
+  } else {  // stride 2: frame 2 t' + tap - 1 = 2 (t' - 1) + 1 | 2 t' | 2 t' + 1
+    r = (tap == 1) ? 0 : 1;
+    u0 = (tap == 0) ? t0 - 1 : t0;
+  }
+}
 
 __device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
@@ -212,31 +232,45 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc
     } else if constexpr (EPI == EPI_SCALE_F32) {
       if (row_ok) {
         float* dst = reinterpret_cast<float*>(p.c) + row * p.ldc + col;
+        if (p.accumulate == 2 && p.vec_c && col + 32 <= p.N) {
+          // ordered accumulation (this CTA owns the tile until it passes the turnstile on): all eight 16-byte loads
+          // of the row chunk are in flight together, ONE memory round trip per chunk instead of eight dependent ones
+          float4 cur[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (p.vec_c && col + i * 4 + 4 <= p.N) {
-            if (p.accumulate == 2) {  // ordered accumulation: this CTA owns the tile until it passes the turnstile on
-              float4 cur = __ldcg(reinterpret_cast<const float4*>(dst + i * 4));
-              cur.x += v[i * 4] * sc; cur.y += v[i * 4 + 1] * sc;
-              cur.z += v[i * 4 + 2] * sc; cur.w += v[i * 4 + 3] * sc;
-              __stcg(reinterpret_cast<float4*>(dst + i * 4), cur);
-            } else if (p.accumulate) {
-              red_add_f32x4(dst + i * 4, v[i * 4] * sc, v[i * 4 + 1] * sc, v[i * 4 + 2] * sc,
-                            v[i * 4 + 3] * sc);
-            } else {
-              *reinterpret_cast<float4*>(dst + i * 4) = make_float4(v[i * 4] * sc, v[i * 4 + 1] * sc,
-                                                                    v[i * 4 + 2] * sc, v[i * 4 + 3] * sc);
-            }
-          } else {
-            for (int j = 0; j < 4; ++j)
-              if (col + i * 4 + j < p.N) {
-                if (p.accumulate == 2)
-                  __stcg(dst + i * 4 + j, __ldcg(dst + i * 4 + j) + v[i * 4 + j] * sc);
-                else if (p.accumulate)
-                  atomicAdd(dst + i * 4 + j, v[i * 4 + j] * sc);
-                else
-                  dst[i * 4 + j] = v[i * 4 + j] * sc;
+          for (int i = 0; i < 8; ++i) cur[i] = __ldcg(reinterpret_cast<const float4*>(dst + i * 4));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            cur[i].x += v[i * 4] * sc; cur[i].y += v[i * 4 + 1] * sc;
+            cur[i].z += v[i * 4 + 2] * sc; cur[i].w += v[i * 4 + 3] * sc;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) __stcg(reinterpret_cast<float4*>(dst + i * 4), cur[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (p.vec_c && col + i * 4 + 4 <= p.N) {
+              if (p.accumulate == 2) {
+                float4 cur = __ldcg(reinterpret_cast<const float4*>(dst + i * 4));
+                cur.x += v[i * 4] * sc; cur.y += v[i * 4 + 1] * sc;
+                cur.z += v[i * 4 + 2] * sc; cur.w += v[i * 4 + 3] * sc;
+                __stcg(reinterpret_cast<float4*>(dst + i * 4), cur);
+              } else if (p.accumulate) {
+                red_add_f32x4(dst + i * 4, v[i * 4] * sc, v[i * 4 + 1] * sc, v[i * 4 + 2] * sc, v[i * 4 + 3] * sc);
+              } else {
+                *reinterpret_cast<float4*>(dst + i * 4) = make_float4(v[i * 4] * sc, v[i * 4 + 1] * sc,
+                                                                      v[i * 4 + 2] * sc, v[i * 4 + 3] * sc);
               }
+            } else {
+              for (int j = 0; j < 4; ++j)
+                if (col + i * 4 + j < p.N) {
+                  if (p.accumulate == 2)
+                    __stcg(dst + i * 4 + j, __ldcg(dst + i * 4 + j) + v[i * 4 + j] * sc);
+                  else if (p.accumulate)
+                    atomicAdd(dst + i * 4 + j, v[i * 4 + j] * sc);
+                  else
+                    dst[i * 4 + j] = v[i * 4 + j] * sc;
+                }
+            }
           }
         }
       }
@@ -474,8 +508,14 @@ __device__ __forceinline__ void epilogue_tile_staged(const Params& p, const CUte
     ptx::fence_proxy_async_smem();
     ptx::named_bar_sync(2, 128);
     if (leader) {
-      ptx::tma_store_2d((EPI == EPI_GEGLU_SAVE) ? tma_c2 : tma_c, slab, static_cast<int32_t>(out_col),
-                        static_cast<int32_t>(m0));
+      if (p.conv_mode == 1) {  // output [B, frames / stride, C_out] through a 3-D map: rows past the window are clipped
+        const int32_t tile_idx = static_cast<int32_t>(m0 / BM);
+        ptx::tma_store_3d(tma_c, slab, static_cast<int32_t>(out_col), (tile_idx % p.conv_per_win) * BM,
+                          tile_idx / p.conv_per_win);
+      } else {
+        ptx::tma_store_2d((EPI == EPI_GEGLU_SAVE) ? tma_c2 : tma_c, slab, static_cast<int32_t>(out_col),
+                          static_cast<int32_t>(m0));
+      }
       ptx::tma_store_commit();
     }
     ++st.g;
@@ -572,14 +612,37 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         ptx::mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
         uint8_t* sa = smem_a + s * A_STAGE_BYTES;
         uint8_t* sb = smem_b + s * B_STAGE_BYTES;
-        if (!p.trans_a) {
+        if (p.conv_mode == 1) {
+          // A rows = output frames t0 .. t0+127 of window b; K block = 64 input channels of one tap
+          const int tile_idx = m0 / BM, b = tile_idx / p.conv_per_win, t0 = (tile_idx % p.conv_per_win) * BM;
+          const int tap = kb / p.conv_kb_per_tap, c0 = (kb % p.conv_kb_per_tap) * BK;
+          int r, u0;
+          conv_tap_coord(p.conv_stride, tap, t0, r, u0);
+          ptx::tma_load_4d(sa, &tma_a, &full[s], c0, r, u0, b);  // box {64 c, 1, 128 frames, 1}
+        } else if (p.conv_mode == 2) {
+          // K block = 64 output frames of window b; A = dz^T (3-D map: rows past the window are zero-filled)
+          const int b = kb / p.conv_per_win, kq = (kb % p.conv_per_win) * BK;
+#pragma unroll
+          for (int i = 0; i < BM / 64; ++i)
+            ptx::tma_load_3d(sa + i * (BK * 128), &tma_a, &full[s], m0 + i * 64, kq, b);
+#pragma unroll
+          for (int i = 0; i < BN / 64; ++i) {  // B = the input shifted by the tap this 64-column chunk belongs to
+            const int col = n0 + i * 64;
+            const int tap = min(col / p.conv_cpad, 2), c0 = col - tap * p.conv_cpad;  // c0 >= C: zero fill
+            int r, u0;
+            conv_tap_coord(p.conv_stride, tap, kq, r, u0);
+            ptx::tma_load_4d(sb + i * (BK * 128), &tma_b, &full[s], c0, r, u0, b);  // box {64 c, 1, 64 frames, 1}
+          }
+        } else if (!p.trans_a) {
           ptx::tma_load_2d(sa, &tma_a, &full[s], kb * BK, m0);  // box {64 k, 128 m}
         } else {
 #pragma unroll
           for (int i = 0; i < BM / 64; ++i)  // box {64 m, 64 k} per 64-wide M chunk
             ptx::tma_load_2d(sa + i * (BK * 128), &tma_a, &full[s], a_m + i * 64, kb * BK + a_koff);
         }
-        if (p.cluster == 1) {
+        if (p.conv_mode == 2) {
+          // B already loaded above
+        } else if (p.cluster == 1) {
           if (!p.trans_b) {
             ptx::tma_load_2d(sb, &tma_b, &full[s], kb * BK, n0 + b_noff);  // box {64 k, 256 n}
           } else {
@@ -752,9 +815,37 @@ int launch_any(bool staged, const CUtensorMap& ta, const CUtensorMap& tb, const 
 
 }  // namespace
 
-int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
+int gemm_bf16(const GemmArgs& g_in, cudaStream_t stream) {
   int rc = check_arch();
   if (rc != kOk) return rc;
+  GemmArgs g = g_in;
+  int conv_rows = 0, conv_per_win = 0;  // output frames per window; M tiles (fwd) / K blocks (wgrad) per window
+  if (g.conv_mode != 0) {
+    CM3P_REQUIRE(g.conv_mode == 1 || g.conv_mode == 2, kBadShape, "conv: unknown mode %d", g.conv_mode);
+    CM3P_REQUIRE((g.conv_stride == 1 || g.conv_stride == 2) && g.conv_batch > 0 && g.conv_frames > 0 &&
+                     g.conv_frames % g.conv_stride == 0 && g.conv_cin > 0 && g.conv_cin % 8 == 0 &&
+                     g.conv_cpad % BK == 0 && g.conv_cpad >= g.conv_cin,
+                 kBadShape, "conv: stride %d batch %d frames %d c_in %d c_pad %d unsupported", g.conv_stride,
+                 g.conv_batch, g.conv_frames, g.conv_cin, g.conv_cpad);
+    CM3P_REQUIRE(g.group_m == 0 && !g.stats_out && !g.row_stats, kBadShape, "conv: not combinable with grouping / LN folding");
+    conv_rows = g.conv_frames / g.conv_stride;
+    if (g.conv_mode == 1) {
+      CM3P_REQUIRE(g.epilogue == EPI_BIAS || g.epilogue == EPI_BIAS_GELU, kBadShape, "conv forward: epilogue must be BIAS(_GELU)");
+      conv_per_win = (conv_rows + BM - 1) / BM;
+      g.M = static_cast<int64_t>(g.conv_batch) * conv_per_win * BM;  // virtual rows: tiles never straddle windows
+      g.K = 3LL * g.conv_cpad;
+      g.trans_a = 0; g.trans_b = 0;
+      g.ldb = 3LL * g.conv_cpad;
+      g.ldc = g.N;
+    } else {
+      CM3P_REQUIRE(g.epilogue == EPI_SCALE_F32 && g.accumulate, kBadShape, "conv wgrad: needs EPI_SCALE_F32 with accumulate");
+      conv_per_win = (conv_rows + BK - 1) / BK;
+      g.N = 3LL * g.conv_cpad;
+      g.K = static_cast<int64_t>(g.conv_batch) * conv_per_win * BK;  // virtual K: blocks never straddle windows
+      g.trans_a = 1; g.trans_b = 1;
+      if (g.ldc == 0) g.ldc = g.N;
+    }
+  }
   CM3P_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, kBadShape, "gemm: empty problem M=%lld N=%lld K=%lld", (long long)g.M,
                (long long)g.N, (long long)g.K);
   CM3P_REQUIRE(g.epilogue >= 0 && g.epilogue < EPI_COUNT, kBadShape, "gemm: unknown epilogue %d", g.epilogue);
@@ -789,6 +880,23 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
     groups = g.M / g.group_m;
   }
   CUtensorMap ta, tb;
+  if (g.conv_mode != 0) {
+    // x [B, F, C] seen as (c, frame parity, frame / stride, window)
+    const void* x = g.conv_mode == 1 ? g.a : g.b;
+    const uint64_t C = g.conv_cin, S = g.conv_stride, F = g.conv_frames;
+    const uint64_t dims[4] = {C, S, F / S, static_cast<uint64_t>(g.conv_batch)};
+    const uint64_t pitches[3] = {C * 2, S * C * 2, F * C * 2};
+    const uint32_t box[4] = {BK, 1, static_cast<uint32_t>(g.conv_mode == 1 ? BM : BK), 1};
+    rc = encode_tmap_4d_bf16(g.conv_mode == 1 ? &ta : &tb, x, dims, pitches, box);
+    if (rc != kOk) return rc;
+    if (g.conv_mode == 1) {
+      rc = encode_tmap_2d_bf16(&tb, g.b, g.K, g.N, g.ldb * 2, BK, BN);
+    } else {  // dz [B, rows, M] as (m, frame, window): frames past the window are zero-filled
+      rc = encode_tmap_3d_bf16(&ta, g.a, g.M, conv_rows, g.conv_batch, static_cast<uint64_t>(g.M) * 2,
+                               static_cast<uint64_t>(conv_rows) * g.M * 2, 64, BK, 1);
+    }
+    if (rc != kOk) return rc;
+  } else {
   if (!g.trans_a)
     rc = encode_tmap_2d_bf16(&ta, g.a, g.K, g.M, g.lda * 2, BK, BM);
   else
@@ -799,6 +907,7 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   else
     rc = encode_tmap_2d_bf16(&tb, g.b, g.N, g.K * groups, g.ldb * 2, 64, BK);
   if (rc != kOk) return rc;
+  }
 
   // staged epilogue: output (and residual / raw) rows must allow TMA (16-byte aligned base and pitch)
   const bool staged = vec && g.epilogue != EPI_SCALE_F32;
@@ -807,6 +916,9 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
     const int64_t n_out = (g.epilogue == EPI_GEGLU) ? g.N / 2 : g.N;
     if (g.epilogue == EPI_GEGLU_SAVE) {
       rc = encode_tmap_2d_bf16(&tc2, g.c2, g.N, g.M, g.ldc2 * 2, 64, BM);
+    } else if (g.conv_mode == 1) {
+      rc = encode_tmap_3d_bf16(&tc, g.c, g.N, conv_rows, g.conv_batch, static_cast<uint64_t>(g.N) * 2,
+                               static_cast<uint64_t>(conv_rows) * g.N * 2, 64, BM, 1);
     } else {
       rc = encode_tmap_2d_bf16(&tc, g.c, n_out, g.M, g.ldc * 2, 64, BM);
     }
@@ -836,6 +948,13 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   p.tile_sem = nullptr;
   p.mn_tiles = 0;
   p.group_m = g.group_m;
+  p.conv_mode = g.conv_mode;
+  p.conv_stride = g.conv_stride;
+  p.conv_per_win = conv_per_win;
+  p.conv_kb_per_tap = g.conv_cpad / BK;
+  p.conv_cpad = g.conv_cpad;
+  if (g.conv_mode == 1)
+    CM3P_REQUIRE(vec && g.N % 8 == 0, kBadAlignment, "conv forward: output must be 16-byte aligned with C_out %% 8 == 0");
   if (g.stats_out)
     CM3P_REQUIRE(g.epilogue == EPI_RESIDUAL && vec, kBadShape,
                  "gemm: stats_out needs the staged EPI_RESIDUAL epilogue (16-byte aligned bf16 rows)");
@@ -876,7 +995,7 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   // L2 -> SM traffic per CTA (ncu: the MMA thread waited ~30% of the time for operands without it).
   const int cluster_mode = get_option(kOptGemmCluster) == 1 ? 1 : 2;
   const int64_t tiles_m_total = (g.M + BM - 1) / BM;
-  p.cluster = (cluster_mode == 2 && tiles_m_total >= 2 && g.N > BN / 2) ? 2 : 1;
+  p.cluster = (cluster_mode == 2 && tiles_m_total >= 2 && g.N > BN / 2 && g.conv_mode != 2) ? 2 : 1;
   CUtensorMap tbh = tb;
   if (p.cluster == 2 && !g.trans_b) {
     rc = encode_tmap_2d_bf16(&tbh, g.b, g.K, g.N * groups, g.ldb * 2, BK, BN / 2);

@@ -10,8 +10,7 @@ int layernorm_fwd(const void* x, const float* gamma, void* y, float* stats, int6
 int embed_gather_ln(const int64_t* ids, const int32_t* src_index, const int32_t* audio_slot, const void* tok_emb,
                     const void* audio_embeds, const float* gamma, void* y, float* stats, int64_t rows, int H,
                     int vocab, float eps, cudaStream_t stream);
-int im2col_conv1(const float* x, void* a, int B, int C, int F, int lda, cudaStream_t stream);
-int im2col_conv2(const void* y1, void* a, int B, int F, int C, cudaStream_t stream);
+int transpose_cast(const float* x, void* out, int B, int C, int F, cudaStream_t stream);  // [B,C,F] fp32 -> [B,F,C] bf16
 int gather_rows(const void* x, const int32_t* index, void* out, int rows, int H, cudaStream_t stream);
 int mean_pool(const void* x, const int32_t* cu_seqlens, void* out, int batch, int H, cudaStream_t stream);
 int l2norm_rows(const float* e, float* out_f32, void* out_bf16, float* inv_norm, int rows, int P,

@@ -1,5 +1,5 @@
 // HBM-bound forward kernels: LayerNorm, token-embedding gather (+ audio-slot select) + LayerNorm,
-// conv im2col row builders, pooling, L2 normalisation and the CLIP-style loss.  All are
+// the conv input transpose, pooling, L2 normalisation and the CLIP-style loss.  All are
 // vectorised (16-byte accesses), coalesced, and use warp-shuffle reductions; rows are bf16, all
 // statistics are fp32.
 #include <cuda_bf16.h>
@@ -194,50 +194,27 @@ embed_gather_ln_kernel(const int64_t* __restrict__ ids, const int32_t* __restric
   ln_row(src, gamma, y + row * H, stats ? stats + row : nullptr, H, eps, lane);
 }
 
-// conv1 (k=3, pad 1, stride 1) as a GEMM: A1[(b, t), c*3 + j] = x[b, c, t + j - 1]  (fp32 -> bf16).
-// Column order matches conv1.weight.view(C_out, C_in*3), so the weight needs no re-layout.
-// Tiled through shared memory so both the read (along t) and the write (along K) are coalesced.
+// Log-mel input [B, C, F] fp32 (channels-first, as the processor produces it) -> [B, F, C] bf16 channels-last, the
+// layout the implicit-GEMM conv reads through its tensor map.  32 x 32 tiles through shared memory: both the read
+// (along F) and the write (along C) are coalesced.
 __global__ void __launch_bounds__(256)
-im2col_conv1_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int B, int C, int F, int lda) {
-  extern __shared__ float tile[];  // [C][34]
-  const int b = blockIdx.y;
-  const int t0 = blockIdx.x * 32;
+transpose_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int C, int F) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int f0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const float* xb = x + static_cast<int64_t>(b) * C * F;
-  for (int i = threadIdx.x; i < C * 34; i += blockDim.x) {
-    const int c = i / 34, dt = i % 34;
-    const int t = t0 + dt - 1;
-    tile[i] = (t >= 0 && t < F) ? xb[static_cast<int64_t>(c) * F + t] : 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int c = c0 + ty + k, f = f0 + tx;
+    tile[ty + k][tx] = (c < C && f < F) ? xb[static_cast<int64_t>(c) * F + f] : 0.f;
   }
   __syncthreads();
-  const int K = C * 3;
-  for (int i = threadIdx.x; i < 32 * K; i += blockDim.x) {
-    const int r = i / K, col = i % K;
-    const int t = t0 + r;
-    if (t < F) {
-      const int c = col / 3, j = col % 3;
-      a[(static_cast<int64_t>(b) * F + t) * lda + col] = __float2bfloat16(tile[c * 34 + r + j]);
-    }
-  }
-}
-
-// conv2 (k=3, pad 1, stride 2) as a GEMM over channels-last rows:
-// A2[(b, t), j*C + c] = y1[b, 2t + j - 1, c]; weight re-laid out once on the host to (C_out, 3, C_in).
-__global__ void __launch_bounds__(256)
-im2col_conv2_kernel(const __nv_bfloat16* __restrict__ y1, __nv_bfloat16* __restrict__ a, int B, int F, int C) {
-  const int Fo = F / 2;
-  const int vec_per_row = 3 * C / 8;
-  const int64_t total = static_cast<int64_t>(B) * Fo * vec_per_row;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int v = static_cast<int>(i % vec_per_row);
-    const int64_t r = i / vec_per_row;
-    const int t = static_cast<int>(r % Fo);
-    const int b = static_cast<int>(r / Fo);
-    const int j = (v * 8) / C, c = (v * 8) % C;
-    const int ts = 2 * t + j - 1;
-    uint4 u = make_uint4(0, 0, 0, 0);
-    if (ts >= 0 && ts < F) u = *reinterpret_cast<const uint4*>(y1 + (static_cast<int64_t>(b) * F + ts) * C + c);
-    *reinterpret_cast<uint4*>(a + r * (3 * C) + v * 8) = u;
+  __nv_bfloat16* ob = out + static_cast<int64_t>(b) * F * C;
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int f = f0 + ty + k, c = c0 + tx;
+    if (f < F && c < C) ob[static_cast<int64_t>(f) * C + c] = __float2bfloat16(tile[tx][ty + k]);
   }
 }
 
@@ -444,21 +421,10 @@ int embed_gather_ln(const int64_t* ids, const int32_t* src_index, const int32_t*
   return kOk;
 }
 
-int im2col_conv1(const float* x, void* a, int B, int C, int F, int lda, cudaStream_t stream) {
-  CM3P_REQUIRE(lda >= 3 * C, kBadShape, "im2col_conv1: lda %d < 3*C", lda);
-  dim3 grid((F + 31) / 32, B);
-  im2col_conv1_kernel<<<grid, 256, C * 34 * sizeof(float), stream>>>(x, reinterpret_cast<__nv_bfloat16*>(a), B, C, F,
-                                                                     lda);
-  CM3P_CUDA_TRY(cudaGetLastError());
-  return kOk;
-}
-
-int im2col_conv2(const void* y1, void* a, int B, int F, int C, cudaStream_t stream) {
-  CM3P_REQUIRE(C % 8 == 0 && F % 2 == 0, kBadShape, "im2col_conv2: C %% 8 and F %% 2 required (C=%d F=%d)", C, F);
-  const int64_t total = static_cast<int64_t>(B) * (F / 2) * (3 * C / 8);
-  const int grid = static_cast<int>(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
-  im2col_conv2_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(y1),
-                                                reinterpret_cast<__nv_bfloat16*>(a), B, F, C);
+int transpose_cast(const float* x, void* out, int B, int C, int F, cudaStream_t stream) {
+  CM3P_REQUIRE(B > 0 && B <= 65535 && C > 0 && F > 0, kBadShape, "transpose_cast: B=%d C=%d F=%d", B, C, F);
+  dim3 grid((F + 31) / 32, (C + 31) / 32, B);
+  transpose_cast_kernel<<<grid, 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), C, F);
   CM3P_CUDA_TRY(cudaGetLastError());
   return kOk;
 }

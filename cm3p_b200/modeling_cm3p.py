@@ -382,7 +382,7 @@ class CM3PMultiModalProjector(nn.Module):
 
 
 class CM3PAudioEncoder(nn.Module):
-    """reference: modeling_cm3p.py:484-528 — conv1d x2 (+GELU) -> ModernBERT(audio) -> 4:1 projector."""
+    """reference: modeling_cm3p.py:484-528 — conv1d x2 (+GELU, implicit GEMM) -> ModernBERT(audio) -> 4:1 projector."""
 
     def __init__(self, config: CM3PAudioConfig):
         super().__init__()
@@ -403,10 +403,10 @@ class CM3PAudioEncoder(nn.Module):
                 bf, f32 = torch.bfloat16, torch.float32
                 c = self.config
                 self._packed = {
-                    # conv1: K index = c_in*3 + tap (weight as stored); conv2: K index = tap*C + c_in
-                    "w1": self.conv1.weight.detach().to(bf).reshape(c.hidden_size, -1).contiguous(),
+                    # implicit-GEMM conv weights: K index = tap * c_pad + c_in (c_pad = c_in rounded up to 64)
+                    "w1": ops.pack_conv_weight(self.conv1.weight),
                     "b1": self.conv1.bias.detach().to(f32).contiguous(),
-                    "w2": self.conv2.weight.detach().to(bf).permute(0, 2, 1).reshape(c.hidden_size, -1).contiguous(),
+                    "w2": ops.pack_conv_weight(self.conv2.weight),
                     "b2": self.conv2.bias.detach().to(f32).contiguous(),
                     "p1": self.multi_modal_projector.linear_1.weight.detach().to(bf).contiguous(),
                     "p2": self.multi_modal_projector.linear_2.weight.detach().to(bf).contiguous(),
@@ -419,9 +419,9 @@ class CM3PAudioEncoder(nn.Module):
         _require_cuda(input_features, "input_features")
         cfg, pk = self.config, self.packed()
         B, _, Fr = input_features.shape
-        feats = input_features.float().contiguous()
-        y1 = ops.conv1d_k3_gelu(feats, pk["w1"], pk["b1"], stride=1)      # [B, F, H_a] channels-last
-        y2 = ops.conv1d_k3_gelu(y1, pk["w2"], pk["b2"], stride=2)         # [B, F/2, H_a]
+        feats = ops.transpose_cast(input_features.float().contiguous())   # [B, F, n_mels] bf16 channels-last
+        y1 = ops.conv1d_k3(feats, pk["w1"], pk["b1"], stride=1, gelu=True)  # [B, F, H_a] channels-last
+        y2 = ops.conv1d_k3(y1, pk["w2"], pk["b2"], stride=2, gelu=True)     # [B, F/2, H_a]
         T2 = Fr // 2
         dev = feats.device
         x = ops.layernorm(y2.view(B * T2, cfg.hidden_size), self.encoder.packed()["emb_norm"], cfg.norm_eps)

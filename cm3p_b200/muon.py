@@ -38,39 +38,49 @@ def _axpy(out, a, x, y=None):
     return out
 
 
-def newton_schulz5(x: torch.Tensor, steps: int) -> torch.Tensor:
-    """x: bf16 [R, C] (already normalised) -> orthogonalised bf16 [R, C] (a fresh or the same buffer).
+def newton_schulz5(x: torch.Tensor, steps: int, groups: int = 1) -> torch.Tensor:
+    """x: bf16 [groups*R, C] (already normalised, `groups` same-shape matrices stacked along the rows) ->
+    orthogonalised bf16 of the same shape (a fresh or the same buffer).
 
     Reference iteration on X = G (wide) or G^T (tall): A = X X^T; B = b A + (c A) A; X = a X + B X.
     Here G keeps its layout: wide  (R <= C): A = G G^T, G <- a G + B G;
                              tall  (R >  C): A = G^T G, G <- a G + G B   (B symmetric).
+    With groups > 1 every product is ONE grouped tcgen05 GEMM launch over all matrices (the 22 layers' Wqkv / Wi /
+    Wo / Wo2 have four shapes between them): a single 768x768 Gram matrix is 18 output tiles on 148 SMs.
     """
     a, b, c = NS_COEFFS
-    R, C = x.shape
+    RG, C = x.shape
+    R = RG // groups
     tall = R > C
     n = C if tall else R
     dev = x.device
     ld = _pad8(n)
-    A = torch.empty((n, ld), device=dev, dtype=torch.bfloat16)[:, :n]
-    cA = torch.empty((n, ld), device=dev, dtype=torch.bfloat16)[:, :n]
-    B = torch.empty((n, ld), device=dev, dtype=torch.bfloat16)[:, :n]
-    ax = torch.empty((R, _pad8(C)), device=dev, dtype=torch.bfloat16)[:, :C]
-    nxt = torch.empty((R, _pad8(C)), device=dev, dtype=torch.bfloat16)[:, :C]  # ping-pong: X is also a GEMM operand
+    A = torch.empty((groups * n, ld), device=dev, dtype=torch.bfloat16)[:, :n]
+    cA = torch.empty((groups * n, ld), device=dev, dtype=torch.bfloat16)[:, :n]
+    B = torch.empty((groups * n, ld), device=dev, dtype=torch.bfloat16)[:, :n]
+    ax = torch.empty((RG, _pad8(C)), device=dev, dtype=torch.bfloat16)[:, :C]
+    nxt = torch.empty((RG, _pad8(C)), device=dev, dtype=torch.bfloat16)[:, :C]  # ping-pong: X is also a GEMM operand
     for _ in range(steps):
         if tall:
-            ops.gemm(x, x, trans_a=True, trans_b=True, out=A)     # G^T G
+            ops.gemm(x, x, trans_a=True, trans_b=True, out=A, groups=groups)     # G^T G
         else:
-            ops.gemm(x, x, out=A)                                 # G G^T
+            ops.gemm(x, x, out=A, groups=groups)                                 # G G^T
         _axpy(cA, c, A)                                           # bf16(c * A)
-        ops.gemm(cA, A, out=B)                                    # (c A) A   (A symmetric: A . A^T == A . A)
+        ops.gemm(cA, A, out=B, groups=groups)                     # (c A) A   (A symmetric: A . A^T == A . A)
         _axpy(B, b, A, B)                                         # bf16(bf16(b A) + (cA)A)
         _axpy(ax, a, x)                                           # bf16(a X)
         if tall:
-            ops.gemm(x, B, epilogue=ops.EPI_RESIDUAL, aux=ax, out=nxt)               # G B + a G
+            ops.gemm(x, B, epilogue=ops.EPI_RESIDUAL, aux=ax, out=nxt, groups=groups)               # G B + a G
         else:
-            ops.gemm(B, x, trans_b=True, epilogue=ops.EPI_RESIDUAL, aux=ax, out=nxt)  # B G + a G
+            ops.gemm(B, x, trans_b=True, epilogue=ops.EPI_RESIDUAL, aux=ax, out=nxt, groups=groups)  # B G + a G
         x, nxt = nxt, x
     return x
+
+
+def _groupable(R: int, C: int) -> bool:
+    """Shapes the grouped GEMM takes (group rows % 256, K % 64) for all three products of an iteration."""
+    n = min(R, C)
+    return n % 256 == 0 and R % 64 == 0 and C % 64 == 0 and (R <= C or R % 256 == 0)
 
 
 class Muon(torch.optim.Optimizer):
@@ -108,6 +118,7 @@ class Muon(torch.optim.Optimizer):
         for group in self.param_groups:
             lr, momentum = group["lr"], group["momentum"]
             b1, b2 = group["adamw_betas"]
+            muon_by_shape: dict = {}
             for p in group["params"]:
                 g = p.grad
                 if g is None:
@@ -118,35 +129,7 @@ class Muon(torch.optim.Optimizer):
                 state = self.state[p]
                 if state["use_muon"] == 1:
                     R = p.shape[0]
-                    C = p.numel() // R
-                    if "momentum_buffer" not in state:
-                        state["momentum_buffer"] = torch.zeros((R, C), device=p.device, dtype=torch.float32)
-                    buf = state["momentum_buffer"]
-                    xbuf = torch.empty((R, _pad8(C)), device=p.device, dtype=torch.bfloat16)
-                    contiguous_x = xbuf.shape[1] == C
-                    x = xbuf[:, :C]
-                    sumsq = torch.zeros((1,), device=p.device, dtype=torch.float32)
-                    if contiguous_x:
-                        _lib.check(lib.cm3p_muon_momentum(g.data_ptr(), buf.data_ptr(), x.data_ptr(), R * C,
-                                                          float(momentum), int(group["nesterov"]), sumsq.data_ptr(),
-                                                          _stream()), "cm3p_muon_momentum")
-                        _lib.check(lib.cm3p_bf16_normalize(x.data_ptr(), R * C, sumsq.data_ptr(), 1e-7, _stream()),
-                                   "cm3p_bf16_normalize")
-                    else:  # row pitch padded to 16 bytes for TMA: go through a dense staging copy
-                        dense = torch.empty((R, C), device=p.device, dtype=torch.bfloat16)
-                        _lib.check(lib.cm3p_muon_momentum(g.data_ptr(), buf.data_ptr(), dense.data_ptr(), R * C,
-                                                          float(momentum), int(group["nesterov"]), sumsq.data_ptr(),
-                                                          _stream()), "cm3p_muon_momentum")
-                        _lib.check(lib.cm3p_bf16_normalize(dense.data_ptr(), R * C, sumsq.data_ptr(), 1e-7,
-                                                           _stream()), "cm3p_bf16_normalize")
-                        x.copy_(dense)
-                    x = newton_schulz5(x, group["ns_steps"])
-                    upd = x if x.is_contiguous() else x.contiguous()
-                    post = max(1.0, R / C) ** 0.5
-                    _lib.check(lib.cm3p_muon_apply(p.data_ptr(), upd.data_ptr(), R * C, float(post), float(-lr),
-                                                   _stream()), "cm3p_muon_apply")
-                    # the kernels write through raw pointers: tell autograd / the bf16 weight-pack caches
-                    torch.autograd.graph.increment_version(p)
+                    muon_by_shape.setdefault((R, p.numel() // R, p.device), []).append((p, g))
                 else:
                     if "step" not in state:
                         state["step"] = 0
@@ -161,6 +144,40 @@ class Muon(torch.optim.Optimizer):
                                                    float(group["adamw_eps"]), float(1 - adamw_lr * group["adamw_wd"]),
                                                    float(lr / scale), _stream()), "cm3p_adamw_step")
                     torch.autograd.graph.increment_version(p)
+            # Muon parameters, all matrices of one shape at a time: momentum + normalisation per matrix into one
+            # stacked bf16 buffer, Newton-Schulz on the stack (grouped GEMMs), update per matrix
+            for (R, C, dev), items in muon_by_shape.items():
+                chunk = len(items) if (_groupable(R, C) and ops.GROUPED_MUON) else 1
+                for i0 in range(0, len(items), chunk):
+                    part = items[i0:i0 + chunk]
+                    G = len(part)
+                    dense = _pad8(C) == C
+                    xs = torch.empty((G * R, C), device=dev, dtype=torch.bfloat16)
+                    sumsq = torch.zeros((G,), device=dev, dtype=torch.float32)
+                    for i, (p, g) in enumerate(part):
+                        state = self.state[p]
+                        if "momentum_buffer" not in state:
+                            state["momentum_buffer"] = torch.zeros((R, C), device=dev, dtype=torch.float32)
+                        xi = xs[i * R:(i + 1) * R]
+                        _lib.check(lib.cm3p_muon_momentum(g.data_ptr(), state["momentum_buffer"].data_ptr(),
+                                                          xi.data_ptr(), R * C, float(momentum),
+                                                          int(group["nesterov"]), sumsq[i:i + 1].data_ptr(), _stream()),
+                                   "cm3p_muon_momentum")
+                        _lib.check(lib.cm3p_bf16_normalize(xi.data_ptr(), R * C, sumsq[i:i + 1].data_ptr(), 1e-7,
+                                                           _stream()), "cm3p_bf16_normalize")
+                    if dense:
+                        x = xs
+                    else:  # row pitch padded to 16 bytes for TMA (only ungrouped shapes get here)
+                        x = torch.empty((G * R, _pad8(C)), device=dev, dtype=torch.bfloat16)[:, :C]
+                        x.copy_(xs)
+                    x = newton_schulz5(x, group["ns_steps"], groups=G)
+                    upd = x if x.is_contiguous() else x.contiguous()
+                    post = max(1.0, R / C) ** 0.5
+                    for i, (p, _) in enumerate(part):
+                        _lib.check(lib.cm3p_muon_apply(p.data_ptr(), upd[i * R:(i + 1) * R].data_ptr(), R * C,
+                                                       float(post), float(-lr), _stream()), "cm3p_muon_apply")
+                        # the kernels write through raw pointers: tell autograd / the bf16 weight-pack caches
+                        torch.autograd.graph.increment_version(p)
         return loss
 
 

@@ -23,10 +23,13 @@ FUSE_LAYERNORM = _os.environ.get("CM3P_FUSE_LN", "0") == "1"
 # training: keep LayerNorm outputs for the backward ("1"), recompute them ("0"), or decide by free memory ("auto")
 SAVE_LAYERNORM = _os.environ.get("CM3P_SAVE_LN", "auto")
 
+# Muon: orthogonalise all same-shape weight matrices with grouped GEMM launches (off = one matrix at a time)
+GROUPED_MUON = True
+
 # kernel launches issued through this module (bench.py reports it as `gpu_launches`)
 LAUNCH_COUNT = 0
 _LAUNCHES_PER_CALL = {
-    "gemm": 1, "attn": 1, "layernorm": 1, "embed": 1, "conv": 2, "pool_project": 3, "pool": 1, "clip_loss": 2,
+    "gemm": 1, "attn": 1, "layernorm": 1, "embed": 1, "pool_project": 3, "pool": 1, "clip_loss": 2,
     "attn_bwd": 2, "rowwise": 1,
 }
 
@@ -218,28 +221,70 @@ def embed_gather_ln(ids: torch.Tensor, src_index: torch.Tensor | None, audio_slo
     return out
 
 
-def conv1d_k3_gelu(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride: int,
-                   out: torch.Tensor | None = None, ws: torch.Tensor | None = None) -> torch.Tensor:
-    """x fp32 [B,C,F] (stride 1) or bf16 [B,F,C] channels-last (stride 2) -> bf16 [B, F/stride, C_out]."""
+def transpose_cast(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """fp32 [B, C, F] (the processor's log-mel layout) -> bf16 [B, F, C] channels-last."""
+    _req(x, torch.float32, "x")
+    assert x.dim() == 3 and x.is_contiguous()
+    B, C, F = x.shape
+    if out is None:
+        out = torch.empty((B, F, C), device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().cm3p_transpose_cast_bf16(x.data_ptr(), out.data_ptr(), B, C, F, _stream()),
+               "cm3p_transpose_cast_bf16")
+    _count("rowwise")
+    return out
+
+
+def pack_conv_weight(weight: torch.Tensor) -> torch.Tensor:
+    """conv.weight [C_out, C_in, 3] -> bf16 [C_out, 3 * c_pad], column tap * c_pad + c, zero for c >= C_in
+    (c_pad = C_in rounded up to 64: the K blocks of the implicit GEMM never straddle a tap)."""
+    c_out, c_in, k = weight.shape
+    assert k == 3
+    c_pad = (c_in + 63) // 64 * 64
+    w = torch.zeros((c_out, 3, c_pad), device=weight.device, dtype=torch.bfloat16)
+    w[:, :, :c_in] = weight.detach().permute(0, 2, 1).to(torch.bfloat16)
+    return w.reshape(c_out, 3 * c_pad).contiguous()
+
+
+def unpack_conv_weight_grad(dw: torch.Tensor, c_in: int) -> torch.Tensor:
+    """[C_out, 3 * c_pad] (tap, c) -> view shaped like conv.weight [C_out, C_in, 3]."""
+    c_out = dw.shape[0]
+    return dw.view(c_out, 3, -1)[:, :, :c_in].permute(0, 2, 1)
+
+
+def conv1d_k3(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride: int, gelu: bool,
+              out: torch.Tensor | None = None) -> torch.Tensor:
+    """Implicit-GEMM conv1d (kernel 3, padding 1): x bf16 [B, F, C_in] channels-last, weight from pack_conv_weight
+    -> bf16 [B, F / stride, C_out] (= gelu(conv + bias) when `gelu`, else the pre-activation)."""
+    _req(x, torch.bfloat16, "x")
     _req(weight, torch.bfloat16, "weight")
     _req(bias, torch.float32, "bias")
-    if x.dtype == torch.float32:
-        layout, (B, C, F) = 0, x.shape
-    else:
-        _req(x, torch.bfloat16, "x")
-        layout, (B, F, C) = 1, x.shape
-    assert x.is_contiguous() and weight.is_contiguous() and weight.shape[1] == 3 * C
-    c_out = weight.shape[0]
-    ld_ws = 3 * C
-    if ws is None:
-        ws = torch.empty((B * (F // stride), ld_ws), device=x.device, dtype=torch.bfloat16)
+    B, F, C = x.shape
+    assert x.is_contiguous() and weight.is_contiguous() and weight.shape[1] % 3 == 0
+    c_out, c_pad = weight.shape[0], weight.shape[1] // 3
     if out is None:
         out = torch.empty((B, F // stride, c_out), device=x.device, dtype=torch.bfloat16)
-    rc = _lib.load().cm3p_conv1d_k3_gelu_fwd(x.data_ptr(), layout, weight.data_ptr(), bias.data_ptr(), ws.data_ptr(),
-                                             ld_ws, out.data_ptr(), B, C, F, c_out, stride, _stream())
-    _lib.check(rc, "cm3p_conv1d_k3_gelu_fwd")
-    _count("conv")
+    rc = _lib.load().cm3p_conv1d_k3_fwd(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), B, C, c_pad, F,
+                                        c_out, stride, int(gelu), _stream())
+    _lib.check(rc, "cm3p_conv1d_k3_fwd")
+    _count("gemm")
     return out
+
+
+def conv1d_k3_wgrad(dz: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, stride: int) -> torch.Tensor:
+    """dw [C_out, 3 * c_pad] fp32 += conv weight gradient; dz bf16 [B, F / stride, C_out], x bf16 [B, F, C_in]."""
+    _req(dz, torch.bfloat16, "dz")
+    _req(x, torch.bfloat16, "x")
+    _req(dw, torch.float32, "dw")
+    B, F, C = x.shape
+    c_out = dz.shape[-1]
+    assert dz.is_contiguous() and x.is_contiguous() and dw.is_contiguous() and dw.shape[0] == c_out
+    assert dz.numel() == B * (F // stride) * c_out and dw.shape[1] % 3 == 0
+    sem = _tile_sem(x.device)
+    rc = _lib.load().cm3p_conv1d_k3_wgrad(dz.data_ptr(), x.data_ptr(), dw.data_ptr(), B, C, dw.shape[1] // 3, F, c_out,
+                                          stride, sem.data_ptr(), _SEM_COUNT, _stream())
+    _lib.check(rc, "cm3p_conv1d_k3_wgrad")
+    _count("gemm")
+    return dw
 
 
 def pool_project_normalize(hidden: torch.Tensor, cu_seqlens: torch.Tensor, mean_pool: bool,
@@ -438,22 +483,6 @@ def clip_loss_bwd(S: torch.Tensor, true_idx: torch.Tensor, row_lse: torch.Tensor
     _lib.check(rc, "cm3p_clip_loss_bwd")
     _count("rowwise")
     return dS[:, :Bb]
-
-
-def im2col_k3(x: torch.Tensor, stride: int, ws: torch.Tensor | None = None) -> torch.Tensor:
-    """GEMM rows of a k=3/pad=1 conv1d: x fp32 [B,C,F] (stride 1) or bf16 [B,F,C] (stride 2) -> [B*F/stride, 3C]."""
-    if x.dtype == torch.float32:
-        layout, (B, C, F) = 0, x.shape
-    else:
-        _req(x, torch.bfloat16, "x")
-        layout, (B, F, C) = 1, x.shape
-    assert x.is_contiguous()
-    if ws is None:
-        ws = torch.empty((B * (F // stride), 3 * C), device=x.device, dtype=torch.bfloat16)
-    rc = _lib.load().cm3p_im2col_k3(x.data_ptr(), layout, ws.data_ptr(), 3 * C, B, C, F, stride, _stream())
-    _lib.check(rc, "cm3p_im2col_k3")
-    _count("rowwise")
-    return ws
 
 
 def conv2_col2im_gelu_bwd(da2: torch.Tensor, z1: torch.Tensor) -> torch.Tensor:

@@ -257,17 +257,14 @@ def audio_forward(audio, input_features: torch.Tensor):
     cfg, pk = audio.config, audio.packed()
     B, _, Fr = input_features.shape
     C = cfg.hidden_size
-    feats = input_features.float().contiguous()
-    a1 = ops.im2col_k3(feats, 1)
-    z1 = ops.gemm(a1, pk["w1"], epilogue=ops.EPI_BIAS, aux=pk["b1"])
-    y1 = ops.gelu_fwd(z1).view(B, Fr, C)
-    a2 = ops.im2col_k3(y1, 2)
-    del y1
-    z2 = ops.gemm(a2, pk["w2"], epilogue=ops.EPI_BIAS, aux=pk["b2"])
+    xt = ops.transpose_cast(input_features.float().contiguous())      # [B, F, n_mels] bf16 channels-last
+    z1 = ops.conv1d_k3(xt, pk["w1"], pk["b1"], stride=1, gelu=False)  # pre-activations are kept for the backward
+    y1 = ops.gelu_fwd(z1)
+    z2 = ops.conv1d_k3(y1, pk["w2"], pk["b2"], stride=2, gelu=False)
     y2 = ops.gelu_fwd(z2)
     T2 = Fr // 2
-    dev = feats.device
-    x0 = ops.layernorm(y2, audio.encoder.packed()["emb_norm"], cfg.norm_eps)
+    dev = xt.device
+    x0 = ops.layernorm(y2.view(B * T2, C), audio.encoder.packed()["emb_norm"], cfg.norm_eps)
     cu = torch.arange(0, B * T2 + 1, T2, device=dev, dtype=torch.int32)
     pos = torch.remainder(torch.arange(B * T2, device=dev, dtype=torch.int32), T2).to(torch.int32)
     last, enc_saved = encoder_forward(audio.encoder, x0, cu, T2, pos)
@@ -275,7 +272,7 @@ def audio_forward(audio, input_features: torch.Tensor):
     zp = ops.gemm(grouped, pk["p1"])
     hp = ops.gelu_fwd(zp)
     audio_embeds = ops.gemm(hp, pk["p2"])
-    saved = dict(a1=a1, z1=z1, a2=a2, z2=z2, y2=y2, enc=enc_saved, last=last, zp=zp, hp=hp, B=B, Fr=Fr)
+    saved = dict(xt=xt, z1=z1, y1=y1, z2=z2, y2=y2, enc=enc_saved, last=last, zp=zp, hp=hp, B=B, Fr=Fr)
     return audio_embeds, last.view(B, T2, -1), saved
 
 
@@ -290,17 +287,22 @@ def audio_backward(audio, saved, d_audio_embeds: torch.Tensor, g: GradStore) -> 
     _wgrad(dzp, grouped, g(proj.linear_1.weight))
     dlast = _dgrad(dzp, pk["p1"]).view(-1, C)
     dx0 = encoder_backward(audio.encoder, saved["enc"], dlast, g)
-    dy2 = ops.layernorm_bwd(saved["y2"], dx0, audio.encoder.packed()["emb_norm"], cfg.norm_eps,
+    T2 = Fr // 2
+    dy2 = ops.layernorm_bwd(saved["y2"].view(B * T2, C), dx0, audio.encoder.packed()["emb_norm"], cfg.norm_eps,
                             dgamma=g(audio.encoder.embeddings.norm.weight))
-    dz2 = ops.gelu_bwd(saved["z2"], dy2)
+    dz2 = ops.gelu_bwd(saved["z2"].view(B * T2, C), dy2)
     ops.colsum_f32(dz2, g(audio.conv2.bias))
-    g_w2p = torch.zeros((C, 3 * C), device=dz2.device, dtype=F32)
-    _wgrad(dz2, saved["a2"], g_w2p)
-    g(audio.conv2.weight).add_(g_w2p.view(C, 3, C).permute(0, 2, 1))  # (out, tap, in) -> (out, in, tap)
+    # conv2 weight gradient: implicit GEMM over (window, frame) against the shifted conv1 output
+    g_w2p = torch.zeros_like(pk["w2"], dtype=F32)
+    ops.conv1d_k3_wgrad(dz2.view(B, T2, C), saved["y1"], g_w2p, stride=2)
+    g(audio.conv2.weight).add_(ops.unpack_conv_weight_grad(g_w2p, C))
+    # conv2 input gradient: dA2 = dz2 . W2 (all three taps), scattered back onto the frames + conv1's GELU backward
     da2 = _dgrad(dz2, pk["w2"])
-    dz1 = ops.conv2_col2im_gelu_bwd(da2, saved["z1"].view(B, Fr, C)).view(B * Fr, C)
+    dz1 = ops.conv2_col2im_gelu_bwd(da2, saved["z1"]).view(B * Fr, C)
     ops.colsum_f32(dz1, g(audio.conv1.bias))
-    _wgrad(dz1, saved["a1"], g(audio.conv1.weight).view(C, -1))
+    g_w1p = torch.zeros_like(pk["w1"], dtype=F32)
+    ops.conv1d_k3_wgrad(dz1.view(B, Fr, C), saved["xt"], g_w1p, stride=1)
+    g(audio.conv1.weight).add_(ops.unpack_conv_weight_grad(g_w1p, cfg.n_mels))
 
 
 # ------------------------------------------------------------------------------------------------

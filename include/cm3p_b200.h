@@ -128,14 +128,28 @@ int cm3p_embed_gather_ln(const int64_t* ids, const int32_t* src_index, const int
                          const void* audio_embeds, const float* gamma, void* y, float* stats, int64_t rows, int hidden,
                          int vocab, float eps, void* stream);
 
-/* gelu(conv1d(x, k=3, pad=1, stride)) written channels-last [B, F/stride, C_out] bf16.
- * Replaces cm3p/modeling_cm3p.py:501-504 (conv1 + gelu, conv2 + gelu, permute).
- *   x_layout 0: x fp32 [B,C_in,F] (log-mel), weight [C_out, C_in*3] bf16 = conv.weight.view(C_out,-1)
- *   x_layout 1: x bf16 [B,F,C_in] channels-last, weight [C_out, 3*C_in] bf16 = weight.permute(0,2,1)
- *   ws: workspace of B*(F/stride)*ld_ws bf16 for the GEMM rows; ld_ws >= 3*C_in, multiple of 8 */
-int cm3p_conv1d_k3_gelu_fwd(const void* x, int x_layout, const void* weight, const float* bias, void* ws,
-                            int64_t ld_ws, void* out, int batch, int c_in, int frames, int c_out, int stride,
-                            void* stream);
+/* (gelu of) conv1d(x, kernel 3, padding 1, stride 1 | 2) + bias as an IMPLICIT GEMM on the tensor cores: the
+ * im2col matrix is never formed.  For every 64-channel K block of a tap the producer fetches a {64 channels x 128
+ * frames} box of the channels-last input through a 4-D tensor map (channel, frame parity, frame / stride, window),
+ * shifted by the tap; the zero padding at the window edges is the tensor map's out-of-bounds fill, stride 2 is the
+ * parity dimension; the result is written channels-last [B, F/stride, C_out] (no permute pass).
+ * Replaces cm3p/modeling_cm3p.py:488-489, :501-504 (conv1 + gelu, conv2 + gelu, permute(0,2,1).contiguous()).
+ *   x: bf16 [batch, frames, c_in] channels-last (the log-mel input goes through cm3p_transpose_cast_bf16 once)
+ *   weight: bf16 [c_out, 3 * c_pad], column tap * c_pad + c = conv.weight[:, c, tap], zero for c >= c_in;
+ *           c_pad = c_in rounded up to a multiple of 64;  bias fp32 [c_out];  gelu != 0: exact-erf GELU fused
+ *   out: bf16 [batch, frames / stride, c_out] */
+int cm3p_conv1d_k3_fwd(const void* x, const void* weight, const float* bias, void* out, int batch, int c_in, int c_pad,
+                       int frames, int c_out, int stride, int gelu, void* stream);
+
+/* Weight gradient of the same convolution, again without an im2col matrix: dw [c_out, 3 * c_pad] fp32 +=
+ * sum over (window, frame) of dz[b, t, :]^T x[b, stride * t + tap - 1, :]  (K = frames, split across CTAs).
+ *   dz: bf16 [batch, frames / stride, c_out];  x as in the forward;  tile_sem as in cm3p_gemm_bf16 (may be NULL) */
+int cm3p_conv1d_k3_wgrad(const void* dz, const void* x, float* dw, int batch, int c_in, int c_pad, int frames, int c_out,
+                         int stride, int32_t* tile_sem, int64_t tile_sem_count, void* stream);
+
+/* [batch, channels, frames] fp32 (the processor's log-mel layout, cm3p/processing_cm3p.py:284-304) ->
+ * [batch, frames, channels] bf16. */
+int cm3p_transpose_cast_bf16(const float* x, void* out, int batch, int channels, int frames, void* stream);
 
 /* pooled = first token (mode 0) or masked mean (mode 1) of every sequence; e = pooled . W^T;
  * embeds = e / sqrt(sum e^2) (no epsilon).  Replaces cm3p/modeling_cm3p.py:624-642 / :382-396
@@ -152,11 +166,6 @@ int cm3p_pool_project_normalize(const void* hidden_states, const int32_t* cu_seq
  *   row_lse [Bm], col_lse [Bb] fp32 outputs (kept for backward); loss: 1 fp32 */
 int cm3p_clip_loss_fwd(const float* S, const int32_t* true_idx, float* row_lse, float* col_lse, float* loss, int Bm,
                        int V, int Bb, void* stream);
-
-/* im2col rows of a k=3, pad=1 conv1d (the A operand of cm3p_conv1d_k3_gelu_fwd's GEMM); the training
- * path keeps them as the activation operand of the conv weight gradients.  Layouts as above. */
-int cm3p_im2col_k3(const void* x, int x_layout, void* ws, int64_t ld_ws, int batch, int c_in, int frames, int stride,
-                   void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Backward entry points.  The reference has no backward code of its own: these are the gradients
@@ -212,7 +221,8 @@ int cm3p_clip_loss_bwd(const float* S, const int32_t* true_idx, const float* row
                        const float* grad_out, void* dS, int64_t ld_ds, float* dlogit_scale, int Bm, int V, int Bb,
                        void* stream);
 
-/* conv2 input gradient (col2im of dA2 [B*F/2, 3*C] onto [B,F,C]) fused with conv1's GELU backward:
+/* conv2 input gradient: dA2 [B*F/2, 3*C] = dz2 . W2 (a plain cm3p_gemm_bf16), scattered back onto [B,F,C] (col2im)
+ * and fused with conv1's GELU backward:
  * dz1 = col2im(dA2) * gelu'(z1).  Replaces autograd through cm3p/modeling_cm3p.py:501-502. */
 int cm3p_conv2_col2im_gelu_bwd(const void* da2, const void* z1, void* dz1, int batch, int frames, int channels,
                                void* stream);

@@ -372,21 +372,21 @@ def test_clip_loss_bwd(B, V):
     assert abs(float(dls) - float((want * S2).sum())) <= 2e-2 * float((want * S2).abs().sum())
 
 
-def test_conv_training_path():
-    """im2col + GEMM(bias) + gelu == conv1d+gelu, and the col2im / weight-gradient pieces against autograd."""
+@pytest.mark.parametrize("B,Fr,Co", [(2, 320, 64), (3, 1600, 512)])
+def test_conv_training_path(B, Fr, Co):
+    """Implicit-GEMM conv forward (bias, pre-activation kept) + gelu == conv1d + gelu, and the implicit weight
+    gradient / col2im input gradient against autograd."""
     ops = _ops()
-    B, C, Fr, Co = 2, 80, 320, 64
+    C = 80
     x = _rand((B, C, Fr), seed=1, dtype=torch.float32)
     w1, b1 = _rand((Co, C, 3), 0.1, seed=2), _rand((Co,), 0.1, seed=3, dtype=torch.float32)
-    w2, b2 = _rand((Co, Co, 3), 0.1, seed=4), _rand((Co,), 0.1, seed=5, dtype=torch.float32)
-    w1p = w1.reshape(Co, C * 3).contiguous()
-    w2p = w2.permute(0, 2, 1).reshape(Co, 3 * Co).contiguous()
-    a1 = ops.im2col_k3(x, 1)
-    z1 = ops.gemm(a1, w1p, epilogue=ops.EPI_BIAS, aux=b1)
-    y1 = ops.gelu_fwd(z1).view(B, Fr, Co)
-    a2 = ops.im2col_k3(y1, 2)
-    z2 = ops.gemm(a2, w2p, epilogue=ops.EPI_BIAS, aux=b2)
-    y2 = ops.gelu_fwd(z2)
+    w2, b2 = _rand((Co, Co, 3), 0.05, seed=4), _rand((Co,), 0.1, seed=5, dtype=torch.float32)
+    w1p, w2p = ops.pack_conv_weight(w1), ops.pack_conv_weight(w2)
+    xt = ops.transpose_cast(x)
+    z1 = ops.conv1d_k3(xt, w1p, b1, stride=1, gelu=False)
+    y1 = ops.gelu_fwd(z1)
+    z2 = ops.conv1d_k3(y1, w2p, b2, stride=2, gelu=False)
+    y2 = ops.gelu_fwd(z2).view(B * Fr // 2, Co)
     # autograd reference on the same bf16-rounded intermediates
     xr = x.bfloat16().float()
     w1r, b1r = w1.float().requires_grad_(True), b1.clone().requires_grad_(True)
@@ -397,22 +397,27 @@ def test_conv_training_path():
     dy2 = _rand((B * Fr // 2, Co), 1.0, seed=6)
     r2.backward(dy2.float())
     # ours
-    dz2 = ops.gelu_bwd(z2, dy2)
+    dz2 = ops.gelu_bwd(z2.view(B * Fr // 2, Co), dy2)
     db2 = torch.zeros((Co,), device=DEV)
     ops.colsum_f32(dz2, db2)
-    dw2p = torch.zeros((Co, 3 * Co), device=DEV)
-    ops.gemm(dz2, a2, trans_a=True, trans_b=True, epilogue=ops.EPI_SCALE_F32, accumulate=True, out=dw2p)
+    dw2p = torch.zeros((Co, w2p.shape[1]), device=DEV)
+    ops.conv1d_k3_wgrad(dz2.view(B, Fr // 2, Co), y1, dw2p, stride=2)
     da2 = ops.gemm(dz2, w2p, trans_b=True)
     dz1 = ops.conv2_col2im_gelu_bwd(da2, z1.view(B, Fr, Co))
     db1 = torch.zeros((Co,), device=DEV)
     ops.colsum_f32(dz1.view(B * Fr, Co), db1)
-    dw1p = torch.zeros((Co, 3 * C), device=DEV)
-    ops.gemm(dz1.view(B * Fr, Co), a1, trans_a=True, trans_b=True, epilogue=ops.EPI_SCALE_F32, accumulate=True, out=dw1p)
+    dw1p = torch.zeros((Co, w1p.shape[1]), device=DEV)
+    ops.conv1d_k3_wgrad(dz1.view(B, Fr, Co), xt, dw1p, stride=1)
     torch.cuda.synchronize()
     _relerr("conv db2", db2, b2r.grad, 2e-2)
-    _relerr("conv dw2", dw2p.view(Co, 3, Co).permute(0, 2, 1), w2r.grad, 2e-2)
+    _relerr("conv dw2", ops.unpack_conv_weight_grad(dw2p, Co), w2r.grad, 2e-2)
     _relerr("conv db1", db1, b1r.grad, 3e-2)
-    _relerr("conv dw1", dw1p.view(Co, C, 3), w1r.grad, 3e-2)
+    _relerr("conv dw1", ops.unpack_conv_weight_grad(dw1p, C), w1r.grad, 3e-2)
+    # the padded channel columns of the conv1 weight gradient (c >= C_in) stay exactly zero
+    assert float(dw1p.view(Co, 3, -1)[:, :, C:].abs().max()) == 0.0
+    # second call accumulates
+    ops.conv1d_k3_wgrad(dz1.view(B, Fr, Co), xt, dw1p, stride=1)
+    _relerr("conv dw1 x2", ops.unpack_conv_weight_grad(dw1p, C), 2 * w1r.grad, 3e-2)
 
 
 @pytest.mark.parametrize("V", [3968, 500, 2])

@@ -331,18 +331,26 @@ def test_embed_gather_ln():
     _report("embed_gather_ln", y, want, 2e-2, 1e-2)
 
 
-def test_conv1d_gelu_both_layers():
+@pytest.mark.parametrize("B,Fr,Co", [(3, 320, 64), (2, 1600, 512), (5, 200, 128)])
+def test_conv1d_gelu_both_layers(B, Fr, Co):
+    """Implicit-GEMM conv1d (no im2col matrix): shifted tensor-map boxes per tap, zero padding = out-of-bounds fill,
+    stride 2 through the frame-parity dimension, windows whose length is not a multiple of the 128-row tile."""
     ops = _ops()
-    B, C, Fr, Co = 3, 80, 320, 64
+    C = 80
     x = _rand((B, C, Fr), seed=1, dtype=torch.float32)
     w1, b1 = _rand((Co, C, 3), 0.1, seed=2), _rand((Co,), 0.1, seed=3, dtype=torch.float32)
-    w2, b2 = _rand((Co, Co, 3), 0.1, seed=4), _rand((Co,), 0.1, seed=5, dtype=torch.float32)
-    y1 = ops.conv1d_k3_gelu(x, w1.reshape(Co, C * 3).contiguous(), b1, stride=1)
+    w2, b2 = _rand((Co, Co, 3), 0.05, seed=4), _rand((Co,), 0.1, seed=5, dtype=torch.float32)
+    xt = ops.transpose_cast(x)
+    _report("transpose_cast", xt.reshape(B * Fr, C), x.bfloat16().permute(0, 2, 1).reshape(B * Fr, C), 0.0, 0.0)
+    y1 = ops.conv1d_k3(xt, ops.pack_conv_weight(w1), b1, stride=1, gelu=True)
     want1 = F.gelu(F.conv1d(x.bfloat16().float(), w1.float(), b1, padding=1)).permute(0, 2, 1)
     _report("conv1", y1.reshape(B * Fr, Co), want1.reshape(B * Fr, Co), 2e-2, 1e-2)
-    y2 = ops.conv1d_k3_gelu(y1, w2.permute(0, 2, 1).reshape(Co, 3 * Co).contiguous(), b2, stride=2)
+    y2 = ops.conv1d_k3(y1, ops.pack_conv_weight(w2), b2, stride=2, gelu=True)
     want2 = F.gelu(F.conv1d(y1.float().permute(0, 2, 1), w2.float(), b2, stride=2, padding=1)).permute(0, 2, 1)
     _report("conv2", y2.reshape(B * Fr // 2, Co), want2.reshape(B * Fr // 2, Co), 2e-2, 1e-2)
+    z2 = ops.conv1d_k3(y1, ops.pack_conv_weight(w2), b2, stride=2, gelu=False)   # pre-activation (training path)
+    want_z2 = F.conv1d(y1.float().permute(0, 2, 1), w2.float(), b2, stride=2, padding=1).permute(0, 2, 1)
+    _report("conv2 pre-activation", z2.reshape(B * Fr // 2, Co), want_z2.reshape(B * Fr // 2, Co), 3e-2, 1e-2)
 
 
 @pytest.mark.parametrize("mean_pool", [False, True])

@@ -46,7 +46,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--infer", action="store_true", help="probe the no-grad forward instead of the train step")
+    ap.add_argument("--opt", action="append", default=[], help="library option KEY=VALUE (cm3p_set_option), repeatable")
     args = ap.parse_args()
+    from cm3p_b200 import ops
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ops.set_option(int(k), int(v))
     dev = torch.device("cuda", 0)
     cfg = CM3PConfig(attn_implementation="flash_attention_2", **copy.deepcopy(base_config_dict()))
     model = CM3PModel(cfg)
