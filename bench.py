@@ -312,7 +312,8 @@ def _bench_workload(workload, args, dist, dev, world, rank, local_rank) -> dict 
         comm = {"all_reduce_ms": round(ar_ms, 3), "all_reduce_bytes": int(n_params * 4),
                 "all_reduce_busbw_gbs": round(2 * (world - 1) / world * n_params * 4 / (ar_ms * 1e-3) / 1e9, 1),
                 "step_ms_without_collectives": round(ms_nocomm, 3), "step_ms_with_collectives": round(ms_comm, 3),
-                "exposed_ms": round(exposed, 3),
+                "exposed_ms": round(exposed, 3), "grad_overlap": args.grad_overlap,
+                "nccl_max_ctas": args.nccl_max_ctas or None,
                 "overlap": round(min(1.0, max(0.0, 1.0 - exposed / ar_ms)), 3) if ar_ms > 0 else None,
                 "how": "all_reduce_ms = the whole fp32 gradient buffer reduced alone (CUDA events, max over ranks, "
                        "5 reps); exposed_ms = step time with minus without the collectives, 5 steps each, back to "
@@ -468,7 +469,14 @@ def run_ours(args) -> dict | None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        if args.nccl_max_ctas > 0:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = args.nccl_max_ctas
+            dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+        else:
+            dist.init_process_group("nccl", device_id=dev)
+    from cm3p_b200 import training as _training
+    _training.GradStore.OVERLAP = args.grad_overlap == "on"
     try:
         order = ["train", "infer"] if args.workload == "all" else [args.workload]
         results = {w: _bench_workload(w, args, dist, dev, world, rank, local_rank) for w in order}
@@ -614,6 +622,11 @@ def main():
                     help="train: all-gather embeddings and use the global loss (BASELINE.json configs[3]: "
                          "--train-batch 512 --variations 1 on 8 GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grad-overlap", choices=["on", "off"], default="on",
+                    help="train, N > 1: bucketed all-reduce during the backward pass (on) or one all-reduce after it (off)")
+    ap.add_argument("--nccl-max-ctas", type=int, default=0,
+                    help="cap the CTAs NCCL may use per collective (0 = NCCL's default); fewer CTAs leave more SMs to the "
+                         "persistent compute kernels the collective overlaps with")
     ap.add_argument("--opt", action="append", default=[],
                     help="library option KEY=VALUE (cm3p_set_option, include/cm3p_b200.h CM3P_OPT_*), for A/B runs")
     ap.add_argument("--quick", action="store_true",

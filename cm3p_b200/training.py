@@ -41,6 +41,7 @@ class GradStore:
     """
 
     BUCKET_BYTES = 64 << 20
+    OVERLAP = True  # False: one reduction of the whole buffer after the backward pass (A/B measurements)
 
     def __init__(self, params, order=None, dp=None, sum_reduce=False):
         self.params = list(params)
@@ -60,7 +61,8 @@ class GradStore:
         self._works = []
         self._hold = 0  # > 0: a section of the backward pass revisits parameters (chunked recompute): nothing is final
         # buckets over the laid-out order: (first position, end position, flat start, flat end)
-        self._pos = {id(p): k for k, p in enumerate(laid)} if (order is not None and self.dp is not None) else None
+        self._pos = ({id(p): k for k, p in enumerate(laid)}
+                     if (order is not None and self.dp is not None and self.OVERLAP) else None)
         self._buckets, self._next = [], 0
         if self._pos is not None:
             start_k, start_o = 0, 0

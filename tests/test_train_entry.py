@@ -101,3 +101,25 @@ def test_train_entry_runs_saves_and_resumes(tmp_path, model_cls, extra):
     res2 = train.main(common + ["training.max_steps=10"])
     assert [h["step"] for h in res2["log_history"]] == [10]
     assert os.path.isdir(os.path.join(out, "checkpoint-10"))
+
+
+@pytest.mark.gpu
+def test_train_entry_evaluates_with_compute_metrics(tmp_path):
+    """eval_strategy=steps: eval loss + the reference's compute_metrics (zero-shot variation accuracies per class,
+    masked-LM accuracy) on held-out synthetic batches with more metadata variations than in training."""
+    import train
+    out = str(tmp_path / "run")
+    res = train.main(["-cn", "synthetic_small", f"training.output_dir={out}", "training.max_steps=4",
+                      "training.logging_steps=2", "training.save_steps=0", "training.eval_strategy=steps",
+                      "training.eval_steps=2", "training.per_device_eval_batch_size=6",
+                      "dataset.test_metadata_variations=12", "dataset.labels=masked_lm",
+                      "model.has_decoder_head=true", "+model.loss_type=ForMaskedLM", "training.optim=adamw_torch"])
+    evals = [h for h in res["log_history"] if "eval_loss" in h]
+    assert [h["step"] for h in evals] == [2, 4]
+    for h in evals:
+        assert h["eval_loss"] == h["eval_loss"] and h["eval_loss"] > 0
+        for name in ("year", "status", "tags", "mapper", "masked_lm"):
+            assert f"eval_accuracy_{name}" in h
+            v = h[f"eval_accuracy_{name}"]
+            assert v is None or 0.0 <= v <= 1.0
+        assert "eval_top5_accuracy_tags" in h and "eval_top5_accuracy_masked_lm" in h

@@ -193,6 +193,42 @@ def main(argv=None) -> dict:
             for old in steps[:-keep]:
                 shutil.rmtree(os.path.join(output_dir, f"checkpoint-{old}"), ignore_errors=True)
 
+    # ---- evaluation (transformers.Trainer.evaluate with batch_eval_metrics + compute_metrics: train.py:38-160,
+    #      :366-371, :376-386): eval loss, zero-shot variation accuracies, masked-LM / classification accuracy
+    from cm3p_b200.metrics import EvalPrediction, compute_metrics
+    eval_every = int(tr.get("eval_steps", 0) or 0) if str(tr.get("eval_strategy", "no")) != "no" else 0
+    eval_batch = int(tr.get("per_device_eval_batch_size", per_dev))
+    eval_batches = int(ds.get("eval_batches", 2))
+    eval_ds = hydra_lite.Cfg(dict(hydra_lite.to_container(ds)))
+    eval_ds["train_metadata_variations"] = int(ds.get("test_metadata_variations", ds.get("train_metadata_variations", 1)))
+    eval_ds["fixed_batch"] = False
+    eval_data = SyntheticWindows(model_config, eval_ds, eval_batch, rank, seed + 7919, model_cls)
+
+    def evaluate(step: int) -> dict:
+        was_training = model.training
+        model.eval()
+        total = torch.zeros((), device=dev)
+        metrics = {}
+        with torch.no_grad():
+            for i in range(eval_batches):
+                batch = {k: v.to(dev, non_blocking=True) for k, v in eval_data.get(10 ** 6 + i, 0).items()}
+                out = model(**batch)
+                total += out.loss.detach().float()
+                preds = out.to_tuple() if hasattr(out, "logits_per_beatmap") else out.logits
+                labels = batch.get("labels")
+                if labels is not None and not isinstance(preds, tuple) and preds.dim() == 2 and labels.dim() == 2:
+                    labels = labels[labels != -100]  # sparse prediction returns only the labelled rows
+                metrics = compute_metrics(EvalPrediction(preds, labels, batch), i + 1 == eval_batches) or {}
+        if world > 1:
+            dist.all_reduce(total, op=dist.ReduceOp.AVG)
+        if was_training:
+            model.train()
+        rec = {"step": step, "eval_loss": float(total) / max(1, eval_batches)}
+        rec.update({f"eval_{k}": v for k, v in metrics.items()})
+        history.append(rec)
+        logger.info(json.dumps(rec))
+        return rec
+
     loss_acc = torch.zeros((), device=dev)
     for step in range(start_step, max_steps):
         lr = _lr_at(step, tr)
@@ -219,8 +255,12 @@ def main(argv=None) -> dict:
             logger.info(json.dumps(rec))
             loss_acc.zero_()
             t_log, seen = time.perf_counter(), 0
+        if eval_every and (step + 1) % eval_every == 0:
+            evaluate(step + 1)
         if save_every and (step + 1) % save_every == 0:
             save(step + 1)
+    if tr.get("do_eval", False) and not (eval_every and max_steps % eval_every == 0 and max_steps > start_step):
+        evaluate(max_steps)
     if tr.get("do_train", True) and max_steps > start_step:
         save(max_steps)
         if rank == 0:
