@@ -303,11 +303,27 @@ def _bench_workload(workload, args, dist, dev, world, rank, local_rank) -> dict 
             dist.all_reduce(flat, op=dist.ReduceOp.AVG)
         ar_ms = timed(lambda: dist.all_reduce(flat, op=dist.ReduceOp.AVG), 5)
         del flat
-        model._dp = None  # same per-rank work, no collective
-        step(resident)
-        ms_nocomm = timed(lambda: step(resident), min(steps, 5))
+        # step time with and without the collectives, INTERLEAVED step by step (the power-capped step drifts by a few
+        # per cent between runs, far more than the reduction costs): medians of per-step CUDA-event times
+        def one(with_dp):
+            model._dp = dp if with_dp else None
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step(resident)
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b)
+        one(False)
+        one(True)
+        t_with, t_without = [], []
+        for _ in range(max(6, min(steps, 12))):
+            t_without.append(one(False))
+            t_with.append(one(True))
         model._dp = dp
-        ms_comm = timed(lambda: step(resident), min(steps, 5))  # back to back with the no-collective run
+        med = torch.tensor([statistics.median(t_with), statistics.median(t_without)], device=dev, dtype=torch.float64)
+        dist.all_reduce(med, op=dist.ReduceOp.MAX)
+        ms_comm, ms_nocomm = float(med[0]), float(med[1])
         exposed = max(0.0, ms_comm - ms_nocomm)
         comm = {"all_reduce_ms": round(ar_ms, 3), "all_reduce_bytes": int(n_params * 4),
                 "all_reduce_busbw_gbs": round(2 * (world - 1) / world * n_params * 4 / (ar_ms * 1e-3) / 1e9, 1),
@@ -316,8 +332,8 @@ def _bench_workload(workload, args, dist, dev, world, rank, local_rank) -> dict 
                 "nccl_max_ctas": args.nccl_max_ctas or None,
                 "overlap": round(min(1.0, max(0.0, 1.0 - exposed / ar_ms)), 3) if ar_ms > 0 else None,
                 "how": "all_reduce_ms = the whole fp32 gradient buffer reduced alone (CUDA events, max over ranks, "
-                       "5 reps); exposed_ms = step time with minus without the collectives, 5 steps each, back to "
-                       "back; overlap = 1 - exposed / all_reduce"}
+                       "5 reps); exposed_ms = median step time with minus without the collectives, steps interleaved "
+                       "one by one (max over ranks of the medians); overlap = 1 - exposed / all_reduce"}
 
     # ---- optimizer step (Muon for the matrices, its internal AdamW for embeddings / vectors), reported separately
     opt_ms = None

@@ -52,6 +52,7 @@ struct AttnBwdArgs {
 };
 
 int attn_varlen_bwd(const AttnBwdArgs& args, cudaStream_t stream);
-int attn_varlen_bwd_v3(const AttnBwdArgs& args, cudaStream_t stream);  // 128x128 tiles, early S/dP issue (long sequences)
+int attn_varlen_bwd_v3(const AttnBwdArgs& args, cudaStream_t stream);
+int attn_varlen_bwd_window(const AttnBwdArgs& args, cudaStream_t stream);  // band walk: window <= 64, one kernel, 5 GEMMs  // 128x128 tiles, early S/dP issue (long sequences)
 
 }  // namespace cm3p

@@ -48,7 +48,8 @@ enum Option : int {
   kOptAttnForceTileKernels = 3,  // 1 = one-tile-per-CTA attention kernels for every sequence length
   kOptWgradDeterministic = 4,    // 1 = split-K partials through a workspace + ordered reduction (default), 0 = atomics
   kOptTmapCache = 5,             // 1 = cache encoded CUtensorMaps by (pointer, shape, pitch, box) (default)
-  kOptCount = 6,
+  kOptAttnWindowWalk = 6,        // 1 = fused band-walk backward for sliding-window layers (default), 0 = two-kernel v3
+  kOptCount = 7,
 };
 int get_option(int opt);
 int set_option(int opt, int value);

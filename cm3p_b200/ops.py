@@ -45,7 +45,7 @@ def _stream() -> int:
 
 # run-time knobs of the library (include/cm3p_b200.h CM3P_OPT_*)
 OPT_FWD_BLOCKS_PER_CTA, OPT_BWD_OUTER_PER_CTA, OPT_GEMM_CLUSTER = 0, 1, 2
-OPT_ATTN_FORCE_TILE_KERNELS, OPT_WGRAD_DETERMINISTIC, OPT_TMAP_CACHE = 3, 4, 5
+OPT_ATTN_FORCE_TILE_KERNELS, OPT_WGRAD_DETERMINISTIC, OPT_TMAP_CACHE, OPT_ATTN_WINDOW_WALK = 3, 4, 5, 6
 
 
 def set_option(option: int, value: int) -> None:

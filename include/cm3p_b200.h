@@ -59,6 +59,7 @@ int cm3p_num_sms(void); /* host query; 0 if no CUDA device */
 #define CM3P_OPT_ATTN_FORCE_TILE_KERNELS 3 /* 1 = one-tile-per-CTA attention kernels for every sequence length */
 #define CM3P_OPT_WGRAD_DETERMINISTIC 4     /* 1 = ordered split-K accumulation when turnstile counters are given (default) */
 #define CM3P_OPT_TMAP_CACHE 5              /* 1 = cache encoded CUtensorMaps by (pointer, shape, pitch, box) (default) */
+#define CM3P_OPT_ATTN_WINDOW_WALK 6         /* 1 = fused band-walk backward for sliding-window layers (default) */
 int cm3p_set_option(int option, int value);
 int cm3p_get_option(int option);
 

@@ -28,5 +28,8 @@ for _ in range(2):
 if "bwd" in sys.argv[1:]:
     dout = torch.randn(T, heads * 64, device="cuda").bfloat16()
     dqkv, delta = torch.empty_like(qkv), torch.empty_like(lse)
-    ops.attn_varlen_bwd(qkv, out, dout, lse, cu_t, L, heads, window, dqkv=dqkv, delta=delta)
+    pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens]).cuda()
+    tab = ops.rope_table(160000.0, 2048, "cuda")
+    ops.attn_varlen_bwd(qkv, out, dout, lse, cu_t, L, heads, window, positions=pos, rope_table=tab, dqkv=dqkv,
+                        delta=delta)
     torch.cuda.synchronize()

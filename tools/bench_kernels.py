@@ -163,6 +163,13 @@ def bench_geglu_bwd(T, I):
 
 
 if __name__ == "__main__":
+    for kv in [a[6:] for a in sys.argv[1:] if a.startswith("--opt=")]:   # library option KEY=VALUE (A/B runs)
+        ops.set_option(int(kv.split("=")[0]), int(kv.split("=")[1]))
+    if "winbwd" in sys.argv[1:]:
+        B = int(os.environ.get("CM3P_BENCH_B", "256"))
+        bench_attn_bwd(B, 2000, 12, 64)
+        bench_attn_bwd(B, 800, 8, 64)
+        sys.exit(0)
     if "gemmbwd" in sys.argv[1:]:
         T = 343608
         bench_gemm_bwd(T, 2304, 768, "_wqkv")
