@@ -68,7 +68,7 @@ void DeviceOnce::mark() {
   __atomic_fetch_or(&mask[dev >> 6], 1ull << (dev & 63), __ATOMIC_RELEASE);
 }
 
-static std::atomic<int> g_options[kOptCount] = {{0}, {0}, {2}, {0}, {1}, {1}, {1}};
+static std::atomic<int> g_options[kOptCount] = {{0}, {0}, {2}, {0}, {0}, {1}, {1}};
 
 int get_option(int opt) { return (opt >= 0 && opt < kOptCount) ? g_options[opt].load(std::memory_order_relaxed) : 0; }
 int set_option(int opt, int value) {

@@ -46,7 +46,8 @@ enum Option : int {
   kOptBwdOuterPerCta = 1,    // attention backward: outer tiles streamed per CTA (0 = heuristic)
   kOptGemmCluster = 2,       // 1 = no clusters, 2 = CTA pairs sharing B tiles by TMA multicast (default)
   kOptAttnForceTileKernels = 3,  // 1 = one-tile-per-CTA attention kernels for every sequence length
-  kOptWgradDeterministic = 4,    // 1 = split-K partials through a workspace + ordered reduction (default), 0 = atomics
+  kOptWgradDeterministic = 4,    // 1 = split-K partial sums added in split order through per-tile turnstiles (bit-
+                                 // reproducible weight gradients, ~+70 % on those GEMMs), 0 = fp32 atomics (default)
   kOptTmapCache = 5,             // 1 = cache encoded CUtensorMaps by (pointer, shape, pitch, box) (default)
   kOptAttnWindowWalk = 6,        // 1 = fused band-walk backward for sliding-window layers (default), 0 = two-kernel v3
   kOptCount = 7,

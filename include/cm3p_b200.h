@@ -57,7 +57,8 @@ int cm3p_num_sms(void); /* host query; 0 if no CUDA device */
 #define CM3P_OPT_BWD_OUTER_PER_CTA 1       /* attention backward: outer tiles streamed per CTA; 0 = heuristic */
 #define CM3P_OPT_GEMM_CLUSTER 2            /* 2 = CTA pairs share B tiles through TMA multicast (default), 1 = off */
 #define CM3P_OPT_ATTN_FORCE_TILE_KERNELS 3 /* 1 = one-tile-per-CTA attention kernels for every sequence length */
-#define CM3P_OPT_WGRAD_DETERMINISTIC 4     /* 1 = ordered split-K accumulation when turnstile counters are given (default) */
+#define CM3P_OPT_WGRAD_DETERMINISTIC 4     /* 1 = ordered split-K accumulation (bit-reproducible weight gradients; the
+                                              split-K GEMMs get ~1.7x slower), 0 = fp32 atomics (default) */
 #define CM3P_OPT_TMAP_CACHE 5              /* 1 = cache encoded CUtensorMaps by (pointer, shape, pitch, box) (default) */
 #define CM3P_OPT_ATTN_WINDOW_WALK 6         /* 1 = fused band-walk backward for sliding-window layers (default) */
 int cm3p_set_option(int option, int value);

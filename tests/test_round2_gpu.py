@@ -156,15 +156,20 @@ def test_metadata_chunked_recompute_matches_single_pass(monkeypatch):
 
 
 def test_train_step_is_bit_reproducible():
-    """Same weights, same batch, two independent runs: identical loss and identical gradients, bit for bit
-    (ordered split-K weight gradients, no-atomics attention backward).  The token-embedding gradient is a
+    """Same weights, same batch, two independent runs with the deterministic option on: identical loss and identical
+    gradients, bit for bit (ordered split-K weight gradients, no-atomics attention backward).  The token-embedding gradient is a
     scatter-add with fp32 atomics and is only required to agree to rounding."""
+    from cm3p_b200 import ops
     case = CASES["small_b4_l400_v3_grads"]
     cfg = CM3PConfig(**copy.deepcopy(case["cfg"]))
     sd = synthetic_state_dict(cfg, seed=case["wseed"], gain=case["gain"])
     batch = synthetic_batch(cfg, **case["batch"])
-    loss_a, ga = _train_grads(cfg, sd, batch)
-    loss_b, gb = _train_grads(cfg, sd, batch)
+    ops.set_option(ops.OPT_WGRAD_DETERMINISTIC, 1)  # `training.deterministic=true` in train.py
+    try:
+        loss_a, ga = _train_grads(cfg, sd, batch)
+        loss_b, gb = _train_grads(cfg, sd, batch)
+    finally:
+        ops.set_option(ops.OPT_WGRAD_DETERMINISTIC, 0)
     assert loss_a == loss_b
     loose = ("tok_embeddings.weight", "norm.weight", "bias", "logit_scale")
     for k in ga:

@@ -63,7 +63,7 @@ class SyntheticWindows:
         if ds.get("fixed_batch", False):  # overfit-one-batch mode (smoke tests)
             step = micro = 0
         b = synthetic_batch(self.config, batch=self.batch, seq_len=int(ds.get("seq_len", 2000)), variations=max(V, 1),
-                            seed=self.seed + 1000003 * step + 101 * micro + 7 * self.rank,
+                            seed=(self.seed + 1000003 * step + 101 * micro + 7 * self.rank) % (2 ** 32 - 1),
                             min_len=ds.get("min_len"), with_labels=(ds.get("labels") == "masked_lm"))
         if self.model_cls == "CM3PForMaskedLM":
             return {k: b[k] for k in ("input_ids", "attention_mask", "input_features", "labels")}
@@ -123,6 +123,10 @@ def main(argv=None) -> dict:
 
     seed = int(tr.get("seed", 42))
     torch.manual_seed(seed)
+    if tr.get("deterministic", False):
+        # bit-reproducible weight gradients (ordered split-K accumulation instead of fp32 atomics); slower
+        from cm3p_b200 import ops as _ops
+        _ops.set_option(_ops.OPT_WGRAD_DETERMINISTIC, 1)
 
     # ---- model (train.py:274-321)
     from cm3p_b200.modeling_cm3p import CM3PForBeatmapClassification, CM3PForMaskedLM, CM3PModel
@@ -211,7 +215,7 @@ def main(argv=None) -> dict:
         metrics = {}
         with torch.no_grad():
             for i in range(eval_batches):
-                batch = {k: v.to(dev, non_blocking=True) for k, v in eval_data.get(10 ** 6 + i, 0).items()}
+                batch = {k: v.to(dev, non_blocking=True) for k, v in eval_data.get(4000 + i, 0).items()}
                 out = model(**batch)
                 total += out.loss.detach().float()
                 preds = out.to_tuple() if hasattr(out, "logits_per_beatmap") else out.logits
