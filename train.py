@@ -218,7 +218,12 @@ def main(argv=None) -> dict:
                 batch = {k: v.to(dev, non_blocking=True) for k, v in eval_data.get(4000 + i, 0).items()}
                 out = model(**batch)
                 total += out.loss.detach().float()
-                preds = out.to_tuple() if hasattr(out, "logits_per_beatmap") else out.logits
+                if hasattr(out, "logits_per_beatmap"):
+                    # what transformers.Trainer.prediction_step hands to compute_metrics: every output but the loss,
+                    # in CM3POutput's field order (predictions[0] = logits_per_beatmap, [4] = logits; train.py:77,101)
+                    preds = tuple(v for k, v in out.items() if k != "loss")
+                else:
+                    preds = out.logits
                 labels = batch.get("labels")
                 if labels is not None and not isinstance(preds, tuple) and preds.dim() == 2 and labels.dim() == 2:
                     labels = labels[labels != -100]  # sparse prediction returns only the labelled rows
