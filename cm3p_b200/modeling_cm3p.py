@@ -449,12 +449,13 @@ class CM3PBeatmapTransformer(nn.Module):
     def set_input_embeddings(self, value):
         self.encoder.set_input_embeddings(value)
 
-    def encode(self, input_ids, input_features, attention_mask):
+    def encode(self, input_ids, input_features, attention_mask, up=None):
         """-> (last_hidden unpadded [T,H] bf16, _Unpadded, audio output | None)."""
         _require_cuda(input_ids, "input_ids")
         B, L = input_ids.shape
         dev = input_ids.device
-        up = _unpad(attention_mask, B, L, dev)
+        if up is None:
+            up = _unpad(attention_mask, B, L, dev)
         ids_flat = input_ids.reshape(-1).contiguous()
         audio_out, audio_embeds, slot = None, None, None
         if input_features is not None:

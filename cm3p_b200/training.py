@@ -310,11 +310,12 @@ def audio_backward(audio, saved, d_audio_embeds: torch.Tensor, g: GradStore) -> 
 # ------------------------------------------------------------------------------------------------
 # towers
 
-def beatmap_forward(tower, input_ids, input_features, attention_mask):
+def beatmap_forward(tower, input_ids, input_features, attention_mask, up=None):
     from .modeling_cm3p import _unpad
     B, L = input_ids.shape
     dev = input_ids.device
-    up = _unpad(attention_mask, B, L, dev)
+    if up is None:
+        up = _unpad(attention_mask, B, L, dev)
     ids_flat = input_ids.reshape(-1).contiguous()
     audio_embeds = slot = audio_last = audio_saved = None
     if input_features is not None:
@@ -331,7 +332,69 @@ def beatmap_forward(tower, input_ids, input_features, attention_mask):
     return last, up, audio_last, saved
 
 
+# Saved activations of the beatmap tower (+ audio encoder) above which the train step switches to recompute: the
+# forward pass runs without keeping anything (inference kernels), the loss and the gradient of the embeddings are
+# formed on the whole batch, and the backward pass re-runs the forward with saving, window chunk by window chunk
+# (GradCache-style; exact gradients, one extra forward).  BASELINE.json configs[3] (512 windows per GPU with global
+# negatives) needs ~290 GB of saved activations otherwise.  None = 84 % of the device memory.
+BEATMAP_SAVE_BUDGET = None
+
+
+def _beatmap_save_budget(dev) -> int:
+    if BEATMAP_SAVE_BUDGET is not None:
+        return int(BEATMAP_SAVE_BUDGET)
+    return int(0.84 * torch.cuda.get_device_properties(dev).total_memory)
+
+
+def _beatmap_saved_bytes(tower, tokens: int, windows: int, frames: int) -> int:
+    est = tokens * _encoder_saved_bytes_per_token(tower.config)
+    ac = tower.audio_encoder.config
+    return est + windows * (frames // 2) * (_encoder_saved_bytes_per_token(ac) + 10 * ac.hidden_size)
+
+
+def beatmap_forward_auto(tower, input_ids, input_features, attention_mask):
+    """beatmap_forward, or — when the saved activations would not fit — a forward pass that keeps nothing and leaves
+    the saving to the chunked backward.  -> (last, up, audio_last, saved)."""
+    from .modeling_cm3p import _unpad
+    B, L = input_ids.shape
+    frames = input_features.shape[-1] if input_features is not None else 0
+    up = _unpad(attention_mask, B, L, input_ids.device)
+    if _beatmap_saved_bytes(tower, up.total, B if input_features is not None else 0, frames) <= _beatmap_save_budget(
+            input_ids.device):
+        return beatmap_forward(tower, input_ids, input_features, attention_mask, up=up)
+    last, up, audio_out = tower.encode(input_ids, input_features, attention_mask, up=up)
+    audio_last = None if audio_out is None else audio_out.last_hidden_state
+    saved = dict(chunked=True, up=up, input_ids=input_ids, input_features=input_features,
+                 attention_mask=attention_mask, frames=frames)
+    return last, up, audio_last, saved
+
+
 def beatmap_backward(tower, saved, dlast, g: GradStore) -> None:
+    if saved.get("chunked"):
+        # recompute: forward with saving + backward for as many windows at a time as fit the budget; the weight
+        # gradients of all chunks accumulate into the same buffers, so no gradient bucket may leave before the end
+        import numpy as np
+        up = saved["up"]
+        ids, feats, mask = saved["input_ids"], saved["input_features"], saved["attention_mask"]
+        B = ids.shape[0]
+        cum = np.concatenate(([0], np.cumsum(np.asarray(up.lens_cpu, dtype=np.int64))))
+        budget = _beatmap_save_budget(ids.device)
+        g.hold()
+        try:
+            b0 = 0
+            while b0 < B:
+                b1 = b0 + 1
+                while b1 < B and _beatmap_saved_bytes(tower, int(cum[b1 + 1] - cum[b0]), b1 + 1 - b0,
+                                                      saved["frames"]) <= budget:
+                    b1 += 1
+                _, _, _, sv_c = beatmap_forward(tower, ids[b0:b1], None if feats is None else feats[b0:b1],
+                                                None if mask is None else mask[b0:b1])
+                beatmap_backward(tower, sv_c, dlast[int(cum[b0]):int(cum[b1])], g)
+                del sv_c
+                b0 = b1
+        finally:
+            g.release()
+        return
     enc, up = tower.encoder, saved["up"]
     pk = enc.packed()
     dx0 = encoder_backward(enc, saved["enc"], dlast, g)
@@ -598,8 +661,8 @@ def forward_with_grad(model, *, input_ids=None, input_features=None, metadata_id
     st = _StepState(model, params, _contrastive_backward)
     sv = st.saved
 
-    last_b, up_b, audio_last, sv["beat"] = beatmap_forward(model.beatmap_model, input_ids, input_features,
-                                                           attention_mask)
+    last_b, up_b, audio_last, sv["beat"] = beatmap_forward_auto(model.beatmap_model, input_ids, input_features,
+                                                                attention_mask)
     sv["w_bp"] = _pack_linear(model.beatmap_projection, model._wcache, "bp")
     be32, be16, sv["bhead"] = head_forward(last_b, up_b.cu_seqlens, not cfg.beatmap_config.cls_embed, sv["w_bp"])
     last_m, up_m, sv["meta"] = metadata_forward(model.metadata_model, metadata_ids, metadata_attention_mask)
