@@ -58,6 +58,13 @@ SIGNATURES = {
     "cm3p_logmel_frames": (_I, [_P, _P, _P, _P, _I, _L, _I, _I, _I, _I, _P]),
     "cm3p_logmel_power_mel": (_I, [_P, _L, _P, _P, _P, _I, _I, _I, _I, _P]),
     "cm3p_logmel_finalize": (_I, [_P, _P, _I, _L, _P]),
+    "cm3p_normalize_vectors": (_I, [_P, _P, _L, _I, _P]),
+    "cm3p_knn_workspace_bytes": (_L, [_L, _I]),
+    "cm3p_knn_cosine": (_I, [_P, _L, _I, _L, _I, _P, _P, _P, _L, _P]),
+    "cm3p_pca2_workspace_floats": (_L, [_L, _I]),
+    "cm3p_pca2": (_I, [_P, _L, _I, _P, _I, _P, _P, _P, _P, _L, _P]),
+    "cm3p_kmeans_workspace_bytes": (_L, [_L, _I, _I]),
+    "cm3p_kmeans": (_I, [_P, _L, _I, _I, _L, _I, _P, _P, _P, _P, _L, _P]),
     "cm3p_muon_momentum": (_I, [_P, _P, _P, _L, _F, _I, _P, _P]),
     "cm3p_bf16_normalize": (_I, [_P, _L, _P, _F, _P]),
     "cm3p_bf16_axpy": (_I, [_P, _L, _F, _P, _L, _P, _L, _L, _L, _P]),

@@ -4,6 +4,7 @@
 
 #include "attn.h"
 #include "common.h"
+#include "embed_tools.h"
 #include "gemm.h"
 #include "logmel.h"
 #include "optim.h"
@@ -309,6 +310,33 @@ int cm3p_adamw_step(float* param, const float* grad, float* moment1, float* mome
                     float beta2, float eps, float decay, float step_size, void* stream) {
   CM3P_ARCH_GUARD();
   return adamw_step(param, grad, moment1, moment2, n, beta1, beta2, eps, decay, step_size, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------------ embedding-table analysis
+int cm3p_normalize_vectors(const float* x, float* out, int64_t n, int d, void* stream) {
+  CM3P_ARCH_GUARD();
+  return embed_normalize(x, out, n, d, as_stream(stream));
+}
+int64_t cm3p_pca2_workspace_floats(int64_t n, int d) { return embed_pca_workspace_floats(n, d); }
+int cm3p_pca2(const float* x, int64_t n, int d, const float* init, int iterations, float* mean, float* components,
+              float* proj, float* ws, int64_t ws_floats, void* stream) {
+  CM3P_ARCH_GUARD();
+  CM3P_REQUIRE(ws_floats >= embed_pca_workspace_floats(n, d), kBadShape, "pca2: workspace too small");
+  return embed_pca2(x, n, d, init, iterations, mean, components, proj, ws, as_stream(stream));
+}
+int64_t cm3p_knn_workspace_bytes(int64_t n, int k) { return embed_knn_workspace_bytes(n, k); }
+int cm3p_knn_cosine(const float* xn, int64_t n, int d, int64_t query, int k, int64_t* out_idx, float* out_dist,
+                    void* ws, int64_t ws_bytes, void* stream) {
+  CM3P_ARCH_GUARD();
+  CM3P_REQUIRE(ws_bytes >= embed_knn_workspace_bytes(n, k), kBadShape, "knn: workspace too small");
+  return embed_knn(xn, n, d, query, k, out_idx, out_dist, ws, as_stream(stream));
+}
+int64_t cm3p_kmeans_workspace_bytes(int64_t n, int d, int k) { return embed_kmeans_workspace_bytes(n, d, k); }
+int cm3p_kmeans(const float* x, int64_t n, int d, int k, int64_t first_index, int iterations, float* centroids,
+                int8_t* labels, int32_t* changed_per_iter, void* ws, int64_t ws_bytes, void* stream) {
+  CM3P_ARCH_GUARD();
+  CM3P_REQUIRE(ws_bytes >= embed_kmeans_workspace_bytes(n, d, k), kBadShape, "kmeans: workspace too small");
+  return embed_kmeans(x, n, d, k, first_index, iterations, centroids, labels, changed_per_iter, ws, as_stream(stream));
 }
 
 }  // extern "C"

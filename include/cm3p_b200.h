@@ -268,6 +268,33 @@ int cm3p_logmel_power_mel(const float* spec, int64_t ld_spec, const float* mel_f
 int cm3p_logmel_finalize(float* out, const float* clip_max, int batch, int64_t per_clip, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Analysis of the embedding table [n, d] fp32 (row-major): what the reference's browser visualizer computes in its
+ * Rust -> WASM core over the parquet written by extract_beatmap_embeddings.py (visualizer/wasm/src/lib.rs).  All
+ * HBM-bound streaming kernels with fixed-order reductions (bit-reproducible); ties go to the lower index.
+ *   cm3p_normalize_vectors : out[i] = x[i] / |x[i]|, zero rows stay zero                       (lib.rs:371-432)
+ *   cm3p_knn_cosine        : the k rows nearest to row `query` of a NORMALISED table by 1 - <x_i, x_q>, the query
+ *                            excluded, ascending; k <= min(n - 1, 1024) and ceil(n / 4096) * k <= 4096  (lib.rs:448-488)
+ *   cm3p_pca2              : mean[d]; components[2][d] by `iterations` (reference: 8) power iterations of X_c^T X_c
+ *                            from the start vectors `init[2][d]` (the reference draws them from Math.random / an LCG),
+ *                            second one orthogonalised against the first at the end; proj[n][2]       (lib.rs:82-237)
+ *   cm3p_kmeans            : farthest-point seeding from row `first_index` (reference: LCG(seed) %% n), `iterations`
+ *                            (reference: up to 10) Lloyd steps, first-minimum assignment, empty clusters keep their
+ *                            centroid; labels int8 [n], centroids [k][d], changed_per_iter[iterations] = labels that
+ *                            changed in each step (a converged run stops changing: same labels as the reference's early
+ *                            stop); k <= 127                                                          (lib.rs:242-365)
+ * Workspaces are caller-owned; the *_workspace_* queries give their sizes. */
+int cm3p_normalize_vectors(const float* x, float* out, int64_t n, int d, void* stream);
+int64_t cm3p_knn_workspace_bytes(int64_t n, int k);
+int cm3p_knn_cosine(const float* xn, int64_t n, int d, int64_t query, int k, int64_t* out_idx, float* out_dist,
+                    void* ws, int64_t ws_bytes, void* stream);
+int64_t cm3p_pca2_workspace_floats(int64_t n, int d);
+int cm3p_pca2(const float* x, int64_t n, int d, const float* init, int iterations, float* mean, float* components,
+              float* proj, float* ws, int64_t ws_floats, void* stream);
+int64_t cm3p_kmeans_workspace_bytes(int64_t n, int d, int k);
+int cm3p_kmeans(const float* x, int64_t n, int d, int k, int64_t first_index, int iterations, float* centroids,
+                int8_t* labels, int32_t* changed_per_iter, void* ws, int64_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Optimizer step of the reference's Muon (utils/muon_utils.py).  The three GEMMs of every Newton-Schulz
  * iteration (:50-53) are cm3p_gemm_bf16 calls; these are the element-wise pieces, with the reference's
  * bf16 roundings.
