@@ -108,11 +108,7 @@ int logmel_frames(const float* wave, const float* window, void* hi, void* lo, in
 int logmel_power_mel(const float* spec, int64_t ld_spec, const float* filt, float* out, float* clip_max, int batch,
                      int frames, int bins, int mels, cudaStream_t s) {
   const size_t smem = (static_cast<size_t>(bins) * mels + 32 * (bins + 1)) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    CM3P_CUDA_TRY(cudaFuncSetAttribute(power_mel_log_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    configured = true;
-  }
+  CM3P_ENSURE_DYN_SMEM(power_mel_log_kernel, 160 * 1024);
   CM3P_REQUIRE(smem <= 160 * 1024, kBadShape, "logmel: filter bank too large for shared memory");
   dim3 grid((frames + 31) / 32, batch);
   power_mel_log_kernel<<<grid, 256, smem, s>>>(spec, ld_spec, filt, out, clip_max, frames, bins, mels);
