@@ -63,11 +63,19 @@ struct WinParams {
   int ctas_per_seq;
 };
 
-// One (query tile, key tile) pair of the walk and what happens to the accumulators around it.
+// One (query tile, key tile) pair of the walk and what happens to the accumulators around it (flags packed in one
+// register: a struct of bools ended up in local memory, and with 1 CTA x 640 threads per SM the local-memory lines
+// do not survive in the small L1 next to 227 KB of shared memory: every reload was an L2 round trip).
 struct Part {
   int q, k;
-  bool need_q, q_first, q_last;     // dQ_q: computed here / first pair of its accumulation / complete after this pair
-  bool need_kv, kv_first, kv_last;  // dK_k, dV_k likewise
+  uint32_t f;
+  // dQ_q: computed here / first pair of its accumulation / complete after this pair; dK_k, dV_k likewise
+  __device__ __forceinline__ bool need_q() const { return f & 1u; }
+  __device__ __forceinline__ bool q_first() const { return f & 2u; }
+  __device__ __forceinline__ bool q_last() const { return f & 4u; }
+  __device__ __forceinline__ bool need_kv() const { return f & 8u; }
+  __device__ __forceinline__ bool kv_first() const { return f & 16u; }
+  __device__ __forceinline__ bool kv_last() const { return f & 32u; }
 };
 
 struct Walk {
@@ -84,18 +92,18 @@ struct Walk {
     p.q = step;
     p.k = step + phase;
     const bool halo = step < i0;
-    p.need_q = !halo;
-    p.q_first = phase == 0;
-    p.q_last = phase == 1 || step + 1 >= n_k;
+    bool need_kv, kv_first, kv_last;
     if (phase == 0) {
-      p.need_kv = true;
-      p.kv_first = step == 0;  // key tile 0 has no pair above it
-      p.kv_last = true;
+      need_kv = true;
+      kv_first = step == 0;  // key tile 0 has no pair above it
+      kv_last = true;
     } else {
-      p.need_kv = halo || step + 1 < i1 || i1 == n_q;  // does this CTA own key tile step + 1 ?
-      p.kv_first = true;
-      p.kv_last = step + 1 >= n_q;  // the key tile below the last query tile has no second pair
+      need_kv = halo || step + 1 < i1 || i1 == n_q;  // does this CTA own key tile step + 1 ?
+      kv_first = true;
+      kv_last = step + 1 >= n_q;  // the key tile below the last query tile has no second pair
     }
+    p.f = (!halo ? 1u : 0u) | (phase == 0 ? 2u : 0u) | ((phase == 1 || step + 1 >= n_k) ? 4u : 0u) |
+          (need_kv ? 8u : 0u) | (kv_first ? 16u : 0u) | (kv_last ? 32u : 0u);
     return p;
   }
   __device__ __forceinline__ void advance() {
@@ -107,6 +115,45 @@ struct Walk {
     }
   }
 };
+
+// One 32-query chunk of a pair for one key row (= TMEM lane): P^T = exp2(S^T c - lse_q), dZ^T = P^T o (dP^T / 8 -
+// delta_q / 8), both packed to bf16.  `taddr` = this lane's row at the chunk's first column (S^T; dP^T sits TM_DPT
+// columns further), `vec` = lse | delta / 8 of the chunk's queries in shared memory.  MASK: columns outside [a, b)
+// are zeroed (chunks cut by the band edge or the end of the sequence); interior chunks skip the compares.
+template <bool MASK>
+__device__ __forceinline__ void chunk_math(uint32_t taddr, const float* vec, float c, float scale, int a, int b,
+                                           uint32_t (&pp)[16], uint32_t (&pz)[16]) {
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {  // 8 columns at a time: 16 live score registers next to the 32 packed results
+    uint32_t rs[8], rp[8];
+    ptx::tmem_ld_32x32b_x8(taddr + TM_ST + h * 8, rs);
+    ptx::tmem_ld_32x32b_x8(taddr + TM_DPT + h * 8, rp);
+    ptx::tmem_ld_wait();
+    const float4* lse4 = reinterpret_cast<const float4*>(vec + h * 8);
+    const float4* del4 = reinterpret_cast<const float4*>(vec + BT + h * 8);
+#pragma unroll
+    for (int i4 = 0; i4 < 8; i4 += 4) {
+      const float4 l4 = lse4[i4 >> 2];
+      const float4 d4 = del4[i4 >> 2];
+      const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
+      const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
+      float pv[4], zv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = h * 8 + i4 + e;
+        const float ex = ptx::ex2_approx(__uint_as_float(rs[i4 + e]) * c - ls[e]);
+        const float dz = ex * (__uint_as_float(rp[i4 + e]) * scale - dl[e]);
+        const bool on = !MASK || (j >= a && j < b);
+        pv[e] = on ? ex : 0.f;
+        zv[e] = on ? dz : 0.f;
+      }
+      pp[h * 4 + (i4 >> 1)] = ptx::pack_bf16x2(pv[0], pv[1]);
+      pp[h * 4 + (i4 >> 1) + 1] = ptx::pack_bf16x2(pv[2], pv[3]);
+      pz[h * 4 + (i4 >> 1)] = ptx::pack_bf16x2(zv[0], zv[1]);
+      pz[h * 4 + (i4 >> 1) + 1] = ptx::pack_bf16x2(zv[2], zv[3]);
+    }
+  }
+}
 
 __global__ void __launch_bounds__(THREADS, 1)
 attn_bwd_win_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
@@ -179,7 +226,7 @@ attn_bwd_win_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
       const Part pt = w.get();
       if (pt.q != prev_q) {
         const int b = qn & 1;
-        ptx::mbar_wait(&q_empty[b], ((qn >> 1) & 1) ^ 1);
+        ptx::mbar_wait_trap(&q_empty[b], ((qn >> 1) & 1) ^ 1);
         const int row0 = seq_start + pt.q * BT;
         if (lane == 0) {
           ptx::mbar_arrive_expect_tx(&q_full[b], 2 * TILE);
@@ -191,8 +238,8 @@ attn_bwd_win_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
         for (int h = 0; h < BT; h += 32) {
           const int c = h + lane;
           const bool ok = pt.q * BT + c < len;
-          vec[c] = ok ? lse_h[row0 + c] : 0.f;
-          vec[BT + c] = ok ? delta_h[row0 + c] * p.scale : 0.f;
+          vec[c] = ok ? __ldcg(lse_h + row0 + c) : 0.f;
+          vec[BT + c] = ok ? __ldcg(delta_h + row0 + c) * p.scale : 0.f;
         }
         ptx::mbar_arrive(&q_full[b]);
         prev_q = pt.q;
@@ -200,7 +247,7 @@ attn_bwd_win_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
       }
       if (pt.k != prev_k) {
         const int b = kn & 1;
-        ptx::mbar_wait(&kv_empty[b], ((kn >> 1) & 1) ^ 1);
+        ptx::mbar_wait_trap(&kv_empty[b], ((kn >> 1) & 1) ^ 1);
         if (lane == 0) {
           const int row0 = seq_start + pt.k * BT - KOFF;  // may be negative for the first tile: zero-filled / masked
           ptx::mbar_arrive_expect_tx(&kv_full[b], 2 * TILE);
@@ -213,7 +260,11 @@ attn_bwd_win_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
     }
   } else if (warp == EW_WARPS + 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp runs the loop (warp-uniform control flow keeps the descriptor arithmetic in the uniform datapath:
+    // a single diverged lane paid ~120 clk per MMA, 2850 clk per pair for the accumulating GEMMs alone); one elected
+    // lane issues the MMAs and the commits.
+    {
+      const bool leader = ptx::elect_one();
       const uint32_t idesc_s = ptx::umma_idesc_bf16(BT, BT, 0, 0);
       const uint32_t idesc_acc = ptx::umma_idesc_bf16(BT, D, 0, 1);  // A K-major (or TMEM), B MN-major
       const uint32_t idesc_dq = ptx::umma_idesc_bf16(BT, D, 1, 1);   // A = dZ read MN-major from the dZ^T tile
@@ -225,12 +276,12 @@ attn_bwd_win_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
       int qb_cur = 0, kb_cur = 0;
       auto issue_scores = [&](const Part& pt) {
         if (pt.q != prev_q) {
-          ptx::mbar_wait(&q_full[qn & 1], (qn >> 1) & 1);
+          ptx::mbar_wait_trap(&q_full[qn & 1], (qn >> 1) & 1);
           prev_q = pt.q;
           ++qn;
         }
         if (pt.k != prev_k) {
-          ptx::mbar_wait(&kv_full[kn & 1], (kn >> 1) & 1);
+          ptx::mbar_wait_trap(&kv_full[kn & 1], (kn >> 1) & 1);
           prev_k = pt.k;
           ++kn;
         }
@@ -241,13 +292,13 @@ attn_bwd_win_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
         ptx::tc_fence_after();
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
-          ptx::umma_bf16(tmem_base + TM_ST, ptx::umma_smem_desc_sw128(k_addr + k * 32, 16, 1024),
+          if (leader) ptx::umma_bf16(tmem_base + TM_ST, ptx::umma_smem_desc_sw128(k_addr + k * 32, 16, 1024),
                          ptx::umma_smem_desc_sw128(q_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
-          ptx::umma_bf16(tmem_base + TM_DPT, ptx::umma_smem_desc_sw128(v_addr + k * 32, 16, 1024),
+          if (leader) ptx::umma_bf16(tmem_base + TM_DPT, ptx::umma_smem_desc_sw128(v_addr + k * 32, 16, 1024),
                          ptx::umma_smem_desc_sw128(do_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
-        ptx::umma_commit(s_full);
+        if (leader) ptx::umma_commit(s_full);
       };
       int pi = 0;
 #ifdef CM3P_ATTN_PROF
@@ -261,7 +312,7 @@ attn_bwd_win_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
         const Part pt = w.get();
         const int qb = qb_cur, kb = kb_cur;  // operand buffers of pair pi
         PFI(pf_acc);
-        ptx::mbar_wait(pz_full, pi & 1);  // P^T / dZ^T of this pair written, S^T / dP^T drained, previous epilogue read
+        ptx::mbar_wait_trap(pz_full, pi & 1);  // P^T / dZ^T of this pair written, S^T / dP^T drained, previous epilogue read
         PFI(pf_wait);
         ptx::tc_fence_after();
         w.advance();
@@ -271,157 +322,237 @@ attn_bwd_win_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
         PFI(pf_sc);
         const uint32_t q_addr = ptx::smem_u32(smem_q + qb * TILE), do_addr = ptx::smem_u32(smem_do + qb * TILE);
         const uint32_t k_addr = ptx::smem_u32(smem_k + kb * TILE);
-        if (pt.need_kv) {
+        if (pt.need_kv()) {
           const uint32_t do_lo = ptx::umma_desc_lo(do_addr, 8192);
 #pragma unroll
           for (int k = 0; k < BT / 16; ++k)  // dV (+)= P^T dO: 16 queries per step = 8 TMEM columns of P^T
-            ptx::umma_bf16_ts(tmem_base + TM_DV, tmem_base + TM_PT + k * 8, do_lo + ((k * 2048) >> 4), HI, idesc_acc,
-                              (k != 0 || !pt.kv_first) ? 1u : 0u);
+            if (leader) ptx::umma_bf16_ts(tmem_base + TM_DV, tmem_base + TM_PT + k * 8, do_lo + ((k * 2048) >> 4), HI, idesc_acc,
+                              (k != 0 || !pt.kv_first()) ? 1u : 0u);
 #pragma unroll
           for (int k = 0; k < BT / 16; ++k)  // dK (+)= dZ^T Q
-            ptx::umma_bf16(tmem_base + TM_DK,
+            if (leader) ptx::umma_bf16(tmem_base + TM_DK,
                            ptx::umma_smem_desc_sw128(dzt_addr + (k >> 2) * (BT * 128) + (k & 3) * 32, 16, 1024),
                            ptx::umma_smem_desc_sw128(q_addr + k * 2048, 8192, 1024), idesc_acc,
-                           (k != 0 || !pt.kv_first) ? 1u : 0u);
+                           (k != 0 || !pt.kv_first()) ? 1u : 0u);
         }
-        if (pt.need_q) {
+        if (pt.need_q()) {
 #pragma unroll
           for (int k = 0; k < BT / 16; ++k)  // dQ (+)= dZ K: 16 keys per step = 16 rows of the dZ^T tile
-            ptx::umma_bf16(tmem_base + TM_DQ, ptx::umma_smem_desc_sw128(dzt_addr + k * 2048, BT * 128, 1024),
+            if (leader) ptx::umma_bf16(tmem_base + TM_DQ, ptx::umma_smem_desc_sw128(dzt_addr + k * 2048, BT * 128, 1024),
                            ptx::umma_smem_desc_sw128(k_addr + k * 2048, 8192, 1024), idesc_dq,
-                           (k != 0 || !pt.q_first) ? 1u : 0u);
+                           (k != 0 || !pt.q_first()) ? 1u : 0u);
         }
-        ptx::umma_commit(acc_done);
-        // operand buffers go back to the producer after their last pair
-        if (!more || np.q != pt.q) ptx::umma_commit(&q_empty[qb]);
-        if (!more || np.k != pt.k) ptx::umma_commit(&kv_empty[kb]);
+        if (leader) {
+          ptx::umma_commit(acc_done);
+          // operand buffers go back to the producer after their last pair
+          if (!more || np.q != pt.q) ptx::umma_commit(&q_empty[qb]);
+          if (!more || np.k != pt.k) ptx::umma_commit(&kv_empty[kb]);
+        }
+        __syncwarp();
       }
 #ifdef CM3P_ATTN_PROF
       PFI(pf_acc);
-      if (blockIdx.x == 0 && blockIdx.y == 0)
+      if (lane == 0 && blockIdx.x == 0 && blockIdx.y == 0)
         printf("win bwd issuer: pairs=%d total=%lld wait_pz=%lld scores(incl operand wait)=%lld acc_issue=%lld\n", pi,
                clock64() - pf_t0, pf_wait, pf_sc, pf_acc);
 #endif
     }
-  } else {
+  } else if (warp < EW_WARPS) {
     // ------------------------------------------------------------------ element-wise warps + epilogues
+    // 8 warps: TMEM lane quadrant (warp & 3) x 64-query column half (warp >> 2), two 32-column chunks each; chunks
+    // outside the band are skipped, chunks entirely inside it skip the mask.  (16 one-chunk warps were tried: at 96
+    // registers per thread the loop state spilled, and with 1 CTA x 640 threads per SM the local-memory lines do not
+    // survive in the small L1 next to 227 KB of shared memory - every reload was an L2 round trip.)
     const int quad = warp & 3, half = warp >> 2;
     const int t = quad * 32 + lane;  // TMEM lane: key row of the key tile, query row of the dQ accumulator
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const float c = p.scale_log2;
     const bool rope = p.rope_table != nullptr && p.positions != nullptr;
-    // Epilogue of pair p (dK / dV of a finished key tile, dQ of a finished query tile) runs one pair late, in the
-    // shadow of the accumulating MMAs: its rotation factors travel global -> shared memory with cp.async right after
-    // the element-wise work of pair p (two dependent global loads per row otherwise sit in the serial chain of every
-    // pair), and its TMEM reads sit between the two chunks of pair p+1.
-    uint8_t* cs_row = smem_cs + (half * BT + t) * 256;  // this thread's row of rotation factors
-    bool cs_loaded = false;
+    // Epilogue of pair p (dK / dV of a finished key tile, dQ of a finished query tile) in "units" of 2 x 16 accumulator
+    // columns for the warp's 32 rows:
+    //   key tile finished:   half-0 warps write dK (unit s = columns {16s.., 32+16s..}, s = 0, 1: a rotation pair stays
+    //                        in one thread), half-1 warps dV (unit s = columns [32s, 32s + 32))
+    //   query tile finished: both halves write dQ, unit {16h.., 32+16h..} with h = half
+    // The TMEM reads happen before this pair's pz_full arrive (the accumulating MMAs of the pair may then touch the
+    // accumulators), the arithmetic and the global stores after it, under the score MMAs of the next pair.
+    // Global traffic is issued by rows, not by lanes: with one table row / one gradient row per lane every load and
+    // store instruction touched 32 different 128-byte lines, and the L1 tag stage set the pace of the whole pair
+    // (measured: ~4000 of 11000 clk per pair).  Here 8 lanes fetch one 128-byte half row of rotation factors (4 rows
+    // per cp.async instruction) into the warp's shared-memory slot one pair ahead; after the rotation each lane parks
+    // its 64 output bytes in the same (now dead) row and the warp writes them out as 4 lanes per row, 8 rows per
+    // store instruction.
+    uint8_t* cs_warp = smem_cs + warp * 8192;  // [2 slots][32 rows][128 B], 16-byte unit u of row r at u ^ (r & 7)
+    uint32_t cs_mask = 0;          // slots holding prefetched factors (warp-uniform)
     Part pend;                     // the pair whose epilogue is pending
     bool have_pend = false;
-    int pend_kk = 0;
-    // row whose gradient this warp rotates in the epilogue of pair pt (-1: none): half 0 warps write dK of a finished
-    // key tile, half 1 warps dQ of a finished query tile (and the un-rotated dV)
-    auto rotation_row = [&](const Part& pt, int kk) -> int64_t {
+    auto kv_unit = [&](const Part& pt) { return pt.need_kv() && pt.kv_last(); };
+    auto q_unit = [&](const Part& pt) { return pt.need_q() && pt.q_last(); };
+    // sequence position of row 0 of this warp's 32 rows in the unit it writes after pair pt (warp-uniform)
+    auto unit_row0 = [&](const Part& pt, bool want_q) { return (want_q ? pt.q * BT : pt.k * BT - KOFF) + quad * 32; };
+    struct Unit {
+      uint32_t acc;   // TMEM column base of the accumulator
+      int x1, x2;     // first column of the two 16-column runs
+      bool rotate;    // the runs are the two halves of rotation pairs (dK, dQ); dV is stored as is
+      int row0;       // sequence position of the warp's first row
+      int col0;       // column of the head's first element in the dqkv row (q | k | v block)
+      int slot;       // shared-memory slot (rotation factors in, staged rows out)
+      int hsel;       // which 16 frequencies the unit rotates
+    };
+    auto make_unit = [&](const Part& pt, bool want_q, int s) -> Unit {
+      Unit u;
+      u.row0 = unit_row0(pt, want_q);
+      u.slot = s;
+      if (want_q) {          // dQ
+        u.hsel = half; u.acc = TM_DQ; u.x1 = half * 16; u.x2 = 32 + half * 16; u.rotate = rope; u.col0 = head * D;
+      } else if (half == 0) {  // dK
+        u.hsel = s; u.acc = TM_DK; u.x1 = s * 16; u.x2 = 32 + s * 16; u.rotate = rope; u.col0 = p.hidden + head * D;
+      } else {                 // dV
+        u.hsel = s; u.acc = TM_DV; u.x1 = s * 32; u.x2 = s * 32 + 16; u.rotate = false; u.col0 = 2 * p.hidden + head * D;
+      }
+      return u;
+    };
+    // position id of this lane's row in the unit(s) this warp rotates after pair pt (-1: none); issued at the top of
+    // the pair so that the load completes under the score wait
+    auto rotation_pos = [&](const Part& pt) -> int {
       if (!rope) return -1;
-      if (half == 0) {
-        if (pt.need_kv && pt.kv_last && kk >= 0 && kk < len) return static_cast<int64_t>(seq_start) + kk;
-      } else {
-        if (pt.need_q && pt.q_last && pt.q * BT + t < len) return static_cast<int64_t>(seq_start) + pt.q * BT + t;
-      }
-      return -1;
+      const bool want_q = !kv_unit(pt);  // (a pair that finishes both: dQ's factors are fetched in the cold path)
+      if (want_q ? !q_unit(pt) : (half != 0)) return -1;
+      const int r_mine = unit_row0(pt, want_q) + lane;
+      return (r_mine >= 0 && r_mine < len) ? __ldg(p.positions + seq_start + r_mine) : -1;
     };
-    auto prefetch_rotation = [&](int pos) {  // pos = positions[rotation_row], fetched a pair earlier; -1: nothing to do
-      cs_loaded = false;
-      if (pos >= 0) {
-        const uint8_t* tab = reinterpret_cast<const uint8_t*>(p.rope_table + static_cast<int64_t>(pos) * 32);
+    // rotation factors of those rows -> shared memory (asynchronously, L1 bypassed)
+    auto prefetch_rotation = [&](const Part& pt, int pos) {
+      __syncwarp();  // the slots are also the staging buffers of the previous units' stores
+      cs_mask = 0;
+      if (!__any_sync(0xffffffffu, pos >= 0)) return;
+      const bool want_q = !kv_unit(pt);
+      const int slots = want_q ? 1 : 2;
+      for (int s = 0; s < slots; ++s) {
+        const int hs = want_q ? half : s;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) ptx::cp_async_16(cs_row + ((k ^ (t & 15)) << 4), tab + k * 16);
-        cs_loaded = true;
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + (lane >> 3), u = lane & 7;
+          const int pr = __shfl_sync(0xffffffffu, pos, r);
+          if (pr >= 0)
+            ptx::cp_async_16_cg(cs_warp + s * 4096 + r * 128 + ((u ^ (r & 7)) << 4),
+                                reinterpret_cast<const uint8_t*>(p.rope_table + static_cast<int64_t>(pr) * 32) + hs * 128 + u * 16);
+        }
+        cs_mask |= 1u << s;
       }
     };
-#ifdef CM3P_ATTN_PROF
-    long long pq_ld = 0, pq_rot = 0, pq_stg = 0, pq_tl = 0, pq_math = 0, pq_a, pq_b;
-#define PFQ0() pq_a = clock64()
-#define PFQ(acc) do { pq_b = clock64(); acc += pq_b - pq_a; pq_a = pq_b; } while (0)
-#else
-#define PFQ0()
-#define PFQ(acc)
-#endif
-    auto rotate_store = [&](uint32_t taddr, __nv_bfloat16* dst, bool valid, bool use_cs) {
-      uint32_t r1[32], r2[32];
-      PFQ0();
-      ptx::tmem_ld_32x32b_x32(taddr, r1);
-      ptx::tmem_ld_32x32b_x32(taddr + 32, r2);
-      ptx::tmem_ld_wait();
-      PFQ(pq_ld);
-      if (!valid) return;
-      uint32_t o1[16], o2[16];
-      if (use_cs) {
-        if (cs_loaded) ptx::cp_async_wait_all();  // this lane's own copies: no cross-thread visibility needed
+    auto unit_load = [&](const Unit& u, uint32_t (&r1)[16], uint32_t (&r2)[16]) {  // warp-collective
+      ptx::tmem_ld_32x32b_x16(tmem_base + u.acc + lane_off + u.x1, r1);
+      ptx::tmem_ld_32x32b_x16(tmem_base + u.acc + lane_off + u.x2, r2);
+    };
+    // accumulator registers -> (inverse rotation) -> 16 packed bf16 pairs: o[0..7] = first run, o[8..15] = second run
+    auto unit_rotate = [&](const Unit& u, const uint32_t (&r1)[16], const uint32_t (&r2)[16], uint32_t (&o)[16]) {
+      const uint8_t* my_row = cs_warp + u.slot * 4096 + lane * 128;
+      const int rr = u.row0 + lane;
+      if (u.rotate && rr >= 0 && rr < len) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {  // dx1 = dy1 c + dy2 s, dx2 = dy2 c - dy1 s  (inverse of the forward rotation)
-          const float4 f = *reinterpret_cast<const float4*>(cs_row + ((k ^ (t & 15)) << 4));
+        for (int k = 0; k < 8; ++k) {  // dx1 = dy1 c + dy2 s, dx2 = dy2 c - dy1 s  (inverse of the forward rotation)
+          const float4 f = *reinterpret_cast<const float4*>(my_row + ((k ^ (lane & 7)) << 4));
           const float a0 = __uint_as_float(r1[2 * k]), b0 = __uint_as_float(r2[2 * k]);
           const float a1 = __uint_as_float(r1[2 * k + 1]), b1 = __uint_as_float(r2[2 * k + 1]);
-          o1[k] = ptx::pack_bf16x2(a0 * f.x + b0 * f.y, a1 * f.z + b1 * f.w);
-          o2[k] = ptx::pack_bf16x2(b0 * f.x - a0 * f.y, b1 * f.z - a1 * f.w);
+          o[k] = ptx::pack_bf16x2(a0 * f.x + b0 * f.y, a1 * f.z + b1 * f.w);
+          o[8 + k] = ptx::pack_bf16x2(b0 * f.x - a0 * f.y, b1 * f.z - a1 * f.w);
         }
       } else {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          o1[k] = ptx::pack_bf16x2(__uint_as_float(r1[2 * k]), __uint_as_float(r1[2 * k + 1]));
-          o2[k] = ptx::pack_bf16x2(__uint_as_float(r2[2 * k]), __uint_as_float(r2[2 * k + 1]));
+        for (int k = 0; k < 8; ++k) {  // dV; rows outside the sequence are never written out
+          o[k] = ptx::pack_bf16x2(__uint_as_float(r1[2 * k]), __uint_as_float(r1[2 * k + 1]));
+          o[8 + k] = ptx::pack_bf16x2(__uint_as_float(r2[2 * k]), __uint_as_float(r2[2 * k + 1]));
         }
       }
-      PFQ(pq_rot);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        *reinterpret_cast<uint4*>(dst + i * 8) = make_uint4(o1[4 * i], o1[4 * i + 1], o1[4 * i + 2], o1[4 * i + 3]);
-        *reinterpret_cast<uint4*>(dst + 32 + i * 8) = make_uint4(o2[4 * i], o2[4 * i + 1], o2[4 * i + 2], o2[4 * i + 3]);
-      }
-      PFQ(pq_stg);
     };
-    auto epilogue = [&](const Part& pt, int kk) {  // accumulators of pair pt are final (acc_done waited by the caller)
-      if (pt.need_kv && pt.kv_last) {
-        const bool key_valid = kk >= 0 && kk < len;
-        const int64_t row = static_cast<int64_t>(seq_start) + kk;
-        __nv_bfloat16* base = p.dqkv + row * 3 * p.hidden + head * D;
-        if (half == 0) rotate_store(tmem_base + TM_DK + lane_off, base + p.hidden, key_valid, rope);
-        else rotate_store(tmem_base + TM_DV + lane_off, base + 2 * p.hidden, key_valid, false);
+    // packed rows -> the warp's shared-memory slot (the factors are dead by now) -> global, 8 rows per instruction
+    auto unit_write = [&](const Unit& u, const uint32_t (&o)[16]) {  // warp-collective
+      uint8_t* slot = cs_warp + u.slot * 4096;
+      uint8_t* my_row = slot + lane * 128;
+      __syncwarp();  // every lane has read its factors
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(my_row + ((j ^ (lane & 7)) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {  // 4 lanes (two 32-byte sectors) per row
+        const int r = 8 * i + (lane >> 2), j = lane & 3;
+        const int pos = u.row0 + r;
+        if (pos >= 0 && pos < len) {
+          const uint4 v = *reinterpret_cast<const uint4*>(slot + r * 128 + ((j ^ (r & 7)) << 4));
+          __nv_bfloat16* dst = p.dqkv + (static_cast<int64_t>(seq_start) + pos) * 3 * p.hidden + u.col0 +
+                               (j < 2 ? u.x1 + 8 * j : u.x2 + 8 * (j - 2));
+          *reinterpret_cast<uint4*>(dst) = v;
+        }
       }
-      if (pt.need_q && pt.q_last && half == 1) {
-        const int qq = pt.q * BT + t;
-        const bool q_valid = qq < len;
-        const int64_t row = static_cast<int64_t>(seq_start) + qq;
-        rotate_store(tmem_base + TM_DQ + lane_off, p.dqkv + row * 3 * p.hidden + head * D, q_valid, rope);
+    };
+    // factors fetched by prefetch_rotation have landed and are visible to the whole warp
+    auto rotation_ready = [&]() {
+      if (cs_mask != 0) {
+        ptx::cp_async_wait_all();
+        __syncwarp();
+      }
+    };
+    // All units of pair pt, start to finish, one after the other (cold path, one copy of the code: the last pair of
+    // the walk, and a pair that finishes both its tiles - dQ's factors were not prefetched then, the slots held dK's)
+    auto units_cold = [&](const Part& pt) {
+      const bool kvu = kv_unit(pt), qu = q_unit(pt);
+      rotation_ready();
+#pragma unroll 1
+      for (int i = 0; i < 3; ++i) {
+        const bool want_q = i == 2;
+        if (want_q ? !qu : !kvu) continue;
+        if (want_q && kvu && rope) {
+          __syncwarp();
+          const int r_mine = unit_row0(pt, true) + lane;
+          const int pos = (r_mine >= 0 && r_mine < len) ? __ldg(p.positions + seq_start + r_mine) : -1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int r = 4 * j + (lane >> 3), u = lane & 7;
+            const int pr = __shfl_sync(0xffffffffu, pos, r);
+            if (pr >= 0)
+              ptx::cp_async_16_cg(cs_warp + r * 128 + ((u ^ (r & 7)) << 4),
+                               reinterpret_cast<const uint8_t*>(p.rope_table + static_cast<int64_t>(pr) * 32) + half * 128 + u * 16);
+          }
+          ptx::cp_async_wait_all();
+          __syncwarp();
+        }
+        uint32_t r1[16], r2[16], o[16];
+        const Unit u = make_unit(pt, want_q, want_q ? 0 : i);
+        unit_load(u, r1, r2);
+        ptx::tmem_ld_wait();
+        unit_rotate(u, r1, r2, o);
+        unit_write(u, o);
+        __syncwarp();
       }
     };
 
     int prev_q = -1, qn = 0, pi = 0;
 #ifdef CM3P_ATTN_PROF
-    long long pe_s = 0, pe_c = 0, pe_acc = 0, pe_epi = 0, pe_st = 0, pe_t0 = clock64(), pe_a = pe_t0, pe_b;
+    long long pe_q = 0, pe_s = 0, pe_c = 0, pe_acc = 0, pe_st = 0, pe_post = 0, pe_t0 = clock64(), pe_a = pe_t0, pe_b;
+    long long pe_c1 = 0, pe_ul = 0, pe_ar = 0, pe_rr = 0, pe_us = 0, pe_pf = 0;
 #define PFE(acc) do { pe_b = clock64(); acc += pe_b - pe_a; pe_a = pe_b; } while (0)
 #else
 #define PFE(acc)
 #endif
     for (; !w.done(); w.advance(), ++pi) {
       const Part pt = w.get();
+      PFE(pe_post);
       if (pt.q != prev_q) {
-        ptx::mbar_wait(&q_full[qn & 1], (qn >> 1) & 1);  // lse / delta of the query tile are staged
+        ptx::mbar_wait_trap(&q_full[qn & 1], (qn >> 1) & 1);  // lse / delta of the query tile are staged
         prev_q = pt.q;
         ++qn;
       }
       const float* vec = smem_vec + ((qn - 1) & 1) * 2 * BT;
       const int kk = pt.k * BT - KOFF + t;  // position of this lane's key in the sequence
       const bool key_valid = kk >= 0 && kk < len;
-      // position id of the row this warp rotates after this pair: the load completes under the score wait below
-      const int64_t rot_row = rotation_row(pt, kk);
-      const int rot_pos = rot_row >= 0 ? __ldg(p.positions + rot_row) : -1;
-      PFE(pe_st);
-      ptx::mbar_wait(s_full, pi & 1);
+      const int rot_pos = rotation_pos(pt);
+      PFE(pe_q);
+      ptx::mbar_wait_trap(s_full, pi & 1);
       PFE(pe_s);
       ptx::tc_fence_after();
-#pragma unroll 1
+      uint8_t* dz_tile = smem_dzt + half * (BT * 128);
+#pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
         const int c0 = half * 64 + ch * 32;  // first query column of the chunk inside the tile
         const int q0 = pt.q * BT + c0;       // its position in the sequence
@@ -429,78 +560,85 @@ attn_bwd_win_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
         int a = max(0, kk - p.window - q0);
         int b = min(min(32, len - q0), kk + p.window + 1 - q0);
         if (!key_valid) b = a;
-        const bool skip = __all_sync(0xffffffffu, a >= b);  // chunk outside the band for the whole warp
-        uint8_t* dz_tile = smem_dzt + half * (BT * 128);
+        const bool skip = __all_sync(0xffffffffu, a >= b);               // chunk outside the band for the whole warp
+        const bool inside = __all_sync(0xffffffffu, a <= 0 && b >= 32);  // chunk entirely inside it: no mask
         uint32_t pp[16], pz[16];
         if (skip) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) pp[i] = 0u;
+        } else if (inside) {
+          chunk_math<false>(tmem_base + lane_off + c0, vec + c0, c, p.scale, a, b, pp, pz);
         } else {
-          uint32_t rs[32], rp[32];
-          PFQ0();
-          ptx::tmem_ld_32x32b_x32(tmem_base + TM_ST + lane_off + c0, rs);
-          ptx::tmem_ld_32x32b_x32(tmem_base + TM_DPT + lane_off + c0, rp);
-          ptx::tmem_ld_wait();
-          PFQ(pq_tl);
-          const float4* lse4 = reinterpret_cast<const float4*>(vec + c0);
-          const float4* del4 = reinterpret_cast<const float4*>(vec + BT + c0);
-#pragma unroll
-          for (int i4 = 0; i4 < 32; i4 += 4) {
-            const float4 l4 = lse4[i4 >> 2];
-            const float4 d4 = del4[i4 >> 2];
-            const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
-            const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
-            float pv[4], zv[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = i4 + e;
-              const bool on = j >= a && j < b;
-              const float ex = ptx::ex2_approx(__uint_as_float(rs[j]) * c - ls[e]);
-              pv[e] = on ? ex : 0.f;
-              zv[e] = on ? ex * (__uint_as_float(rp[j]) * p.scale - dl[e]) : 0.f;
-            }
-            pp[i4 >> 1] = ptx::pack_bf16x2(pv[0], pv[1]);
-            pp[(i4 >> 1) + 1] = ptx::pack_bf16x2(pv[2], pv[3]);
-            pz[i4 >> 1] = ptx::pack_bf16x2(zv[0], zv[1]);
-            pz[(i4 >> 1) + 1] = ptx::pack_bf16x2(zv[2], zv[3]);
-          }
-          PFQ(pq_math);
+          chunk_math<true>(tmem_base + lane_off + c0, vec + c0, c, p.scale, a, b, pp, pz);
         }
-        PFE(pe_c);
-        if (ch == 0 && pi > 0) {
-          // P^T / dZ^T still belong to the accumulating MMAs of the previous pair until they have retired; its
-          // accumulators are final then: read them out before this pair's MMAs can touch them
-          ptx::mbar_wait(acc_done, (pi - 1) & 1);
+        if (ch == 0) {
+          PFE(pe_c);
+          if (pi > 0) {
+            // P^T / dZ^T still belong to the accumulating MMAs of the previous pair until they have retired; its
+            // accumulators are final then
+            ptx::mbar_wait_trap(acc_done, (pi - 1) & 1);
+            ptx::tc_fence_after();
+          }
           PFE(pe_acc);
-          ptx::tc_fence_after();
-          if (have_pend) epilogue(pend, pend_kk);
-          PFE(pe_epi);
         }
         ptx::tmem_st_32x32b_x16(tmem_base + TM_PT + lane_off + half * 32 + ch * 16, pp);
         if (skip) store_zero_units(dz_tile, t, ch * 4);
         else store_row_units(dz_tile, t, ch * 4, pz);
       }
+      PFE(pe_c1);
+      // the previous pair's finished accumulators: into registers before this pair's MMAs may touch them
+      uint32_t o[2][16];
+      int n_units = 0;
+      bool unit_q = false;
+      if (have_pend) {
+        const bool kvu = kv_unit(pend), qu = q_unit(pend);
+        if (kvu && qu) {  // a pair that finished both its tiles (the last pair of a sequence)
+          units_cold(pend);
+        } else if (kvu || qu) {
+          unit_q = qu;
+          n_units = qu ? 1 : 2;
+          rotation_ready();
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            if (s2 < n_units) {
+              uint32_t r1[16], r2[16];
+              const Unit u = make_unit(pend, unit_q, s2);
+              unit_load(u, r1, r2);
+              ptx::tmem_ld_wait();
+              unit_rotate(u, r1, r2, o[s2]);
+            }
+          }
+        }
+      }
+      PFE(pe_ul);
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(pz_full);
-      have_pend = (pt.need_kv && pt.kv_last) || (pt.need_q && pt.q_last);
+      PFE(pe_ar);
+      if (n_units > 0) {
+        unit_write(make_unit(pend, unit_q, 0), o[0]);
+        if (n_units == 2) unit_write(make_unit(pend, unit_q, 1), o[1]);
+        PFE(pe_us);
+      }
+      have_pend = kv_unit(pt) || q_unit(pt);
       pend = pt;
-      pend_kk = kk;
-      prefetch_rotation(rot_pos);
+      prefetch_rotation(pt, rot_pos);
+      PFE(pe_pf);
     }
-    // the last pair
-    ptx::mbar_wait(acc_done, (pi - 1) & 1);
-    ptx::tc_fence_after();
-    if (have_pend) epilogue(pend, pend_kk);
-    ptx::tc_fence_before();
 #ifdef CM3P_ATTN_PROF
-    PFE(pe_st);
+    PFE(pe_post);
     if (lane == 0 && blockIdx.x == 0 && blockIdx.y == 0)
-      printf("win bwd warp %d: pairs=%d total=%lld wait_s=%lld chunk_compute=%lld (tmem_ld %lld math %lld) wait_acc=%lld "
-             "epilogue=%lld (tmem_ld %lld rotate %lld stg %lld) store+arrive+prefetch=%lld\n", warp, pi,
-             clock64() - pe_t0, pe_s, pe_c, pq_tl, pq_math, pe_acc, pe_epi, pq_ld, pq_rot, pq_stg, pe_st);
+      printf("win bwd warp %d: pairs=%d total=%lld wait_q+setup=%lld wait_s=%lld chunk0=%lld wait_acc=%lld "
+             "st0+chunk1+st1=%lld unit_load=%lld fences+arrive=%lld rotation_ready=%lld unit_store=%lld prefetch=%lld "
+             "walk=%lld\n", warp, pi, clock64() - pe_t0, pe_q, pe_s, pe_c, pe_acc, pe_c1, pe_ul, pe_ar, pe_rr, pe_us, pe_pf,
+             pe_post);
 #endif
+    // the last pair
+    ptx::mbar_wait_trap(acc_done, (pi - 1) & 1);
+    ptx::tc_fence_after();
+    if (have_pend) units_cold(pend);
+    ptx::tc_fence_before();
   }
 
   ptx::tc_fence_before();

@@ -88,6 +88,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same bounded spin without the printf: a call site (vprintf) in an inlined wait costs the surrounding loop caller-saved
+// registers / spill slots; kernels whose hot loops are register-tight use this one (a protocol bug still traps).
+__device__ __forceinline__ void mbar_wait_trap(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > CM3P_MBAR_TIMEOUT_CYCLES) __trap();
+  }
+}
+
 // generic-proxy writes (st.shared) -> visible to the async proxy (TMA / UMMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -97,6 +107,10 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 // 16 bytes global -> shared without passing through registers; completion per thread with wait_all.
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+// the same copy bypassing L1 (streamed once: keeps the few L1 lines next to a 227 KB shared-memory carve-out free)
+__device__ __forceinline__ void cp_async_16_cg(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 

@@ -1,0 +1,2 @@
+mkdir -p gpurun_out
+CM3P_LIB_PATH=variants/libprof.so timeout 120 python tools/attn_one.py 64 bwd > gpurun_out/r2q_prof.log 2>&1; echo "rc=$?"; grep "win bwd" gpurun_out/r2q_prof.log | tail -24 | cut -c1-330
