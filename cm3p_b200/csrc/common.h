@@ -44,7 +44,7 @@ struct DeviceOnce {
 enum Option : int {
   kOptFwdBlocksPerCta = 0,   // attention forward: 256-query blocks streamed per CTA (0 = heuristic)
   kOptBwdOuterPerCta = 1,    // attention backward: outer tiles streamed per CTA (0 = heuristic)
-  kOptGemmCluster = 2,       // 1 = no clusters, 2 = CTA pairs sharing B tiles by TMA multicast (default)
+  kOptGemmCluster = 2,       // 1 = no clusters, 2 = CTA pairs with one cta_group::2 MMA (default), 3 = pairs with B multicast
   kOptAttnForceTileKernels = 3,  // 1 = one-tile-per-CTA attention kernels for every sequence length
   kOptWgradDeterministic = 4,    // 1 = split-K partial sums added in split order through per-tile turnstiles (bit-
                                  // reproducible weight gradients, ~+70 % on those GEMMs), 0 = fp32 atomics (default)

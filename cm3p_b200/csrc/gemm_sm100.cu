@@ -1,15 +1,23 @@
-// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma
-// (cta_group::1, M=128, N=256, K=16) -> fp32 accumulators in TMEM (2 stages x 256 columns, so the
-// epilogue of tile i overlaps the MMAs of tile i+1) -> fused epilogue.  bf16 outputs are staged per
-// 128x64 slab in 128B-swizzled shared memory and written with TMA stores (the residual slab is
-// TMA-loaded into the same buffer one slab ahead), so the LSU never sees row-strided global
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma -> fp32
+// accumulators in TMEM (2 stages x 256 columns, so the epilogue of tile i overlaps the MMAs of tile i+1) -> fused
+// epilogue.  bf16 outputs are staged per 128x64 slab in 128B-swizzled shared memory and written with TMA stores
+// (the residual slab is TMA-loaded into the same buffer one slab ahead), so the LSU never sees row-strided global
 // accesses; fp32 / unaligned outputs use the direct register->global path.
 //
 //   C[M,N] = epilogue( A[M,K] . B[N,K]^T )
 //
+// Default form (MMA2): CTA pairs (2-CTA clusters, the two SMs of a TPC) on adjacent M tiles run ONE
+// tcgen05.mma.cta_group::2 of M = 256, N = 256, K = 16 per step: each CTA holds its 128 rows of A, HALF of the B tile
+// and its 128 accumulator rows; the rank-0 CTA issues, both CTAs' TMA loads report to its barrier, its commits free
+// the stage / publish the accumulator in both CTAs.  Per CTA and k-block 32 KB instead of 48 KB enter shared memory
+// and 8 KB instead of 12 KB are read per MMA step, and the same 192 KB hold 6 stages instead of 4 (measured against
+// the previous form - pairs sharing B by TMA multicast, each CTA its own M = 128 MMA: +4 .. +15 % on the train-step
+// shapes, profiles/r2_kernel_microbench_mma2.jsonl).  Single CTAs (cluster 1) and the implicit-GEMM convolutions use
+// cta_group::1, M = 128.
+//
 // Replaces every nn.Linear on the hot path (reference: ModernBERT Wqkv/Wo/Wi/Wo, the audio projector
 // modeling_cm3p.py:470-481, the projections :959/:971, the logits matmul :976-977, the MLM head
-// :1229-1238) and, through im2col rows, the two Conv1d of the audio front-end (:488-489).
+// :1229-1238) and, as an implicit GEMM, the two Conv1d of the audio front-end (:488-489).
 //
 // Warp roles (256 threads, 1 CTA / SM):
 //   warp 0 lane 0 : TMA producer            warp 1 lane 0 : MMA issuer
@@ -31,10 +39,16 @@ constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+// CTA-pair MMA (cta_group::2, M = 256 over two CTAs): a CTA holds only its half of every B tile, so the same 192 KB
+// give 6 stages of (16 KB A + 16 KB B-half)
+constexpr int STAGES_2CTA = 6;
+constexpr int MAX_STAGES = 6;
+static_assert(STAGES_2CTA * (A_STAGE_BYTES + B_STAGE_BYTES / 2) == STAGES * STAGE_BYTES, "same operand ring size");
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
 constexpr int SLAB_BYTES = BM * 128;  // 128 rows x 64 bf16
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+static_assert((2 * MAX_STAGES + 2 * ACC_STAGES + 2) * 8 + 4 <= 256, "barrier block");
 constexpr int THREADS = 256;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
@@ -56,6 +70,7 @@ struct Params {
   int splits;        // split-K factor (>1 only with the atomic F32 epilogue: weight gradients, K = tokens)
   int kb_per_split;  // k-blocks per split
   int cluster;       // 1, or 2: CTA pairs on adjacent M tiles share every B tile through TMA multicast
+  int mma2;          // cluster == 2 only: ONE tcgen05.mma.cta_group::2 of M = 256 per pair instead (each CTA loads half of B)
   float* stats_out;        // RESIDUAL: [ceil(N/256)][M] (sum, sum^2) partials of the written rows, one per N tile, or null
   const float* row_stats;  // ROPE / GEGLU(_SAVE): [ceil(K/256)][M] partials of the A rows -> LayerNorm folded in, or null
   const float* col_corr;   // [N] column sums of B (= W . diag(gamma))
@@ -526,7 +541,7 @@ __device__ __forceinline__ void epilogue_tile_staged(const Params& p, const CUte
   }
 }
 
-template <int EPI, bool STAGED>
+template <int EPI, bool STAGED, bool MMA2>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                        const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_c2,
@@ -534,16 +549,20 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                        const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // MMA2 is a template parameter: a kernel that contains cta_group::2 instructions can only be launched as CTA pairs
+  constexpr bool mma2 = MMA2;
+  constexpr int nstages = mma2 ? STAGES_2CTA : STAGES;
+  constexpr int b_stage_bytes = mma2 ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint8_t* smem_b = smem + nstages * A_STAGE_BYTES;
   uint8_t* slabs = smem + STAGES * STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(slabs + 2 * SLAB_BYTES);
   uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* tmem_full = bars + 2 * STAGES;
-  uint64_t* tmem_empty = bars + 2 * STAGES + ACC_STAGES;
-  uint64_t* res_full = bars + 2 * STAGES + 2 * ACC_STAGES;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES + 2);
+  uint64_t* empty = bars + MAX_STAGES;
+  uint64_t* tmem_full = bars + 2 * MAX_STAGES;
+  uint64_t* tmem_empty = bars + 2 * MAX_STAGES + ACC_STAGES;
+  uint64_t* res_full = bars + 2 * MAX_STAGES + 2 * ACC_STAGES;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * ACC_STAGES + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -556,20 +575,26 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
   // stage may only be refilled once BOTH tensor pipes have drained it (empty barriers count 2 arrivals)
   const uint32_t crank = p.cluster > 1 ? ptx::cluster_ctarank() : 0u;
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < nstages; ++s) {
       ptx::mbar_init(&full[s], 1);
-      ptx::mbar_init(&empty[s], p.cluster);
+      ptx::mbar_init(&empty[s], mma2 ? 1 : p.cluster);  // pair MMA: one commit (the leader's) frees the stage in both CTAs
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
-      ptx::mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+      // one arrive per epilogue warp; pair MMA: the leader's issuer waits for the epilogue warps of BOTH CTAs
+      ptx::mbar_init(&tmem_empty[s], mma2 ? 8 : 4);
       ptx::mbar_init(&res_full[s], 1);
     }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
-    ptx::tmem_relinquish();
+    if constexpr (mma2) {
+      ptx::tmem_alloc_2cta(tmem_slot, TMEM_COLS);
+      ptx::tmem_relinquish_2cta();
+    } else {
+      ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   if (p.cluster > 1) ptx::cluster_sync_all();  // barrier inits visible to the peer before any remote arrive
@@ -609,9 +634,30 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       }
       for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&empty[s], ph ^ 1);
-        ptx::mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
         uint8_t* sa = smem_a + s * A_STAGE_BYTES;
-        uint8_t* sb = smem_b + s * B_STAGE_BYTES;
+        uint8_t* sb = smem_b + s * b_stage_bytes;
+        if constexpr (mma2) {
+          // this CTA's 128 rows of A and its half of the B tile; the bytes of both CTAs are counted by the leader's barrier
+          if (crank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * (A_STAGE_BYTES + B_STAGE_BYTES / 2));
+          if (!p.trans_a) {
+            ptx::tma_load_2d_2cta(sa, &tma_a, &full[s], kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              ptx::tma_load_2d_2cta(sa + i * (BK * 128), &tma_a, &full[s], a_m + i * 64, kb * BK + a_koff);
+          }
+          if (!p.trans_b) {
+            ptx::tma_load_2d_2cta(sb, &tma_bh, &full[s], kb * BK, n0 + b_noff + static_cast<int32_t>(crank) * (BN / 2));
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 128; ++i)
+              ptx::tma_load_2d_2cta(sb + i * (BK * 128), &tma_b, &full[s],
+                                    n0 + (static_cast<int>(crank) * (BN / 128) + i) * 64, kb * BK + b_koff);
+          }
+          if (++s == nstages) { s = 0; ph ^= 1; }
+          continue;
+        }
+        ptx::mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
         if (p.conv_mode == 1) {
           // A rows = output frames t0 .. t0+127 of window b; K block = 64 input channels of one tap
           const int tile_idx = m0 / BM, b = tile_idx / p.conv_per_win, t0 = (tile_idx % p.conv_per_win) * BM;
@@ -663,15 +709,16 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
             }
           }
         }
-        if (++s == STAGES) { s = 0; ph ^= 1; }
+        if (++s == nstages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     // The whole warp runs the loop (warp-uniform control flow keeps the descriptor arithmetic in the uniform
     // datapath); one elected lane issues the MMAs and commits.
-    const bool leader = ptx::elect_one();
-    const uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, p.trans_a ? 1u : 0u, p.trans_b ? 1u : 0u);
+    // Pair MMA: only the rank-0 CTA issues (M = 256: its own 128 rows and the peer's); its commits arrive in both CTAs.
+    const bool leader = ptx::elect_one() && !(mma2 && crank != 0);
+    const uint32_t idesc = ptx::umma_idesc_bf16(mma2 ? 2 * BM : BM, BN, p.trans_a ? 1u : 0u, p.trans_b ? 1u : 0u);
     // K-major: 8-row groups 1024 B apart; one UMMA_K (16 elem) step = +32 B inside the swizzle row.
     // MN-major: 8-k groups 1024 B apart (SBO), 64-wide MN chunks BK*128 B apart (LBO); UMMA_K step = +2048 B.
     const uint32_t a_lbo = p.trans_a ? BK * 128 : 16, b_lbo = p.trans_b ? BK * 128 : 16;
@@ -680,7 +727,8 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     uint32_t ph = 0;
     int as = 0;
     uint32_t aph = 0;
-    for (int64_t t = unit0; t < num_tiles; t += unit_step) {
+    const bool issues = !(mma2 && crank != 0);  // the peer CTA of a pair MMA has nothing to issue
+    for (int64_t t = unit0; issues && t < num_tiles; t += unit_step) {
       ptx::mbar_wait(&tmem_empty[as], aph ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
@@ -690,20 +738,28 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         ptx::mbar_wait(&full[s], ph);
         ptx::tc_fence_after();
         const uint32_t a_addr = ptx::smem_u32(smem_a + s * A_STAGE_BYTES);
-        const uint32_t b_addr = ptx::smem_u32(smem_b + s * B_STAGE_BYTES);
+        const uint32_t b_addr = ptx::smem_u32(smem_b + s * b_stage_bytes);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           const uint64_t da = ptx::umma_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
           const uint64_t db = ptx::umma_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
-          if (leader) ptx::umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          if (leader) {
+            if constexpr (mma2) ptx::umma_bf16_2cta(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else ptx::umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
         }
         // frees the smem stage once these MMAs have read it (in both CTAs of a pair: either may refill it)
         if (leader) {
-          if (p.cluster > 1) ptx::umma_commit_multicast(&empty[s], 0x3);
-          else ptx::umma_commit(&empty[s]);
-          if (kb == kb1 - 1) ptx::umma_commit(&tmem_full[as]);
+          if constexpr (mma2) {
+            ptx::umma_commit_2cta(&empty[s], 0x3);
+            if (kb == kb1 - 1) ptx::umma_commit_2cta(&tmem_full[as], 0x3);
+          } else {
+            if (p.cluster > 1) ptx::umma_commit_multicast(&empty[s], 0x3);
+            else ptx::umma_commit(&empty[s]);
+            if (kb == kb1 - 1) ptx::umma_commit(&tmem_full[as]);
+          }
         }
-        if (++s == STAGES) { s = 0; ph ^= 1; }
+        if (++s == nstages) { s = 0; ph ^= 1; }
       }
       if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
     }
@@ -760,7 +816,10 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
+      if (lane == 0) {
+        if constexpr (mma2) ptx::mbar_arrive_leader(&tmem_empty[as]);
+        else ptx::mbar_arrive(&tmem_empty[as]);
+      }
       if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
     }
     if constexpr (STAGED) {
@@ -773,14 +832,15 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
   else __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (mma2) ptx::tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+    else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-template <int EPI, bool STAGED>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2,
+template <int EPI, bool STAGED, bool MMA2>
+int launch_kernel(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2,
            const CUtensorMap& taux, const CUtensorMap& tbh, const Params& p, cudaStream_t stream) {
-  CM3P_ENSURE_DYN_SMEM((gemm_bf16_sm100_kernel<EPI, STAGED>), SMEM_BYTES);
+  CM3P_ENSURE_DYN_SMEM((gemm_bf16_sm100_kernel<EPI, STAGED, MMA2>), SMEM_BYTES);
   const int64_t tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
   const int64_t units = ((tiles_m + p.cluster - 1) / p.cluster) * tiles_n * p.splits;
   const int64_t max_clusters = num_sms() / p.cluster;
@@ -797,8 +857,15 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CM3P_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_bf16_sm100_kernel<EPI, STAGED>, ta, tb, tc, tc2, taux, tbh, p));
+  CM3P_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_bf16_sm100_kernel<EPI, STAGED, MMA2>, ta, tb, tc, tc2, taux, tbh, p));
   return kOk;
+}
+
+template <int EPI, bool STAGED>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2,
+           const CUtensorMap& taux, const CUtensorMap& tbh, const Params& p, cudaStream_t stream) {
+  return p.mma2 ? launch_kernel<EPI, STAGED, true>(ta, tb, tc, tc2, taux, tbh, p, stream)
+                : launch_kernel<EPI, STAGED, false>(ta, tb, tc, tc2, taux, tbh, p, stream);
 }
 
 template <int EPI>
@@ -996,6 +1063,8 @@ int gemm_bf16(const GemmArgs& g_in, cudaStream_t stream) {
   const int cluster_mode = get_option(kOptGemmCluster) == 1 ? 1 : 2;
   const int64_t tiles_m_total = (g.M + BM - 1) / BM;
   p.cluster = (cluster_mode == 2 && tiles_m_total >= 2 && g.N > BN / 2 && g.conv_mode != 2) ? 2 : 1;
+  // pair MMA for plain / grouped / split-K GEMMs (the implicit-GEMM convolutions keep the multicast form)
+  p.mma2 = (p.cluster == 2 && g.conv_mode == 0 && get_option(kOptGemmCluster) != 3) ? 1 : 0;
   CUtensorMap tbh = tb;
   if (p.cluster == 2 && !g.trans_b) {
     rc = encode_tmap_2d_bf16(&tbh, g.b, g.K, g.N * groups, g.ldb * 2, BK, BN / 2);

@@ -55,7 +55,8 @@ int cm3p_num_sms(void); /* host query; 0 if no CUDA device */
  * and the benchmarks use the others for A/B measurements.  Nothing is read from the environment. */
 #define CM3P_OPT_FWD_BLOCKS_PER_CTA 0      /* attention forward: 256-query blocks streamed per CTA; 0 = heuristic */
 #define CM3P_OPT_BWD_OUTER_PER_CTA 1       /* attention backward: outer tiles streamed per CTA; 0 = heuristic */
-#define CM3P_OPT_GEMM_CLUSTER 2            /* 2 = CTA pairs share B tiles through TMA multicast (default), 1 = off */
+#define CM3P_OPT_GEMM_CLUSTER 2            /* 2 = CTA pairs run one tcgen05.mma.cta_group::2 of M = 256 (default), 3 = CTA pairs
+                                              share B tiles through TMA multicast (each its own MMA), 1 = single CTAs */
 #define CM3P_OPT_ATTN_FORCE_TILE_KERNELS 3 /* 1 = one-tile-per-CTA attention kernels for every sequence length */
 #define CM3P_OPT_WGRAD_DETERMINISTIC 4     /* 1 = ordered split-K accumulation (bit-reproducible weight gradients; the
                                               split-K GEMMs get ~1.7x slower), 0 = fp32 atomics (default) */

@@ -11,6 +11,10 @@ def main(path, disasm=None, top=40):
     hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     hdr = rows[hdr_i]
     body = rows[hdr_i + 1:]
+    for j, r in enumerate(body):  # several launches of the kernel in the report: keep the first
+        if not r or r[0] in ("Kernel Name", "Address") or len(r) < len(hdr):
+            body = body[:j]
+            break
     col = {h: i for i, h in enumerate(hdr)}
     stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     lines = {}
