@@ -54,8 +54,8 @@ MLM_SEQ_LEN, MLM_BATCH = 8192, 8
 # dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch (average over the GEMM launches of one step), from
 # the ncu launch lists committed under profiles/ (it cannot be measured from inside this script)
 GEMM_TRAFFIC = {
-    "infer": (264.2e6, "profiles/r2_infer_launch_summary.txt (ncu, batch 64)"),
-    "train": (1245.9e6, "profiles/r2_train256_launch_summary.txt (ncu, batch 256, V=8)"),
+    "infer": (263.1e6, "profiles/r2_infer_launch_summary_v2.txt (ncu, batch 64)"),
+    "train": (1302.4e6, "profiles/r2_train256_launch_summary_v2.txt (ncu, batch 256, V=8)"),
 }
 
 
@@ -446,8 +446,8 @@ def _bench_workload(workload, args, dist, dev, world, rank, local_rank) -> dict 
                      "algorithmic_bytes_per_launch": round(gemm_bytes / max(1, len(gemm_events))),
                      "launches_per_step": len(gemm_events), "share_of_step": round(gemm_ms / ms_step, 3),
                      "peak_source": peaks["source"]},
-        "roofline_attention": {"kernel": "attn_fwd_v2 / attn_bwd_dq + attn_bwd_dkv (varlen, D=64); packed short-sequence "
-                                         "kernels for the metadata tower", "bound": "tensor",
+        "roofline_attention": {"kernel": "attn_fwd_v2 / attn_bwd_dq + attn_bwd_dkv (global layers) / attn_bwd_win band walk "
+                                         "(window layers), varlen, D=64; packed short-sequence kernels for the metadata tower", "bound": "tensor",
                                "achieved": round(attn_flops / (attn_ms * 1e-3) / 1e12, 1) if attn_ms > 0 else 0.0,
                                "peak": peaks["tflops"], "unit": "TFLOP/s",
                                "frac": round(attn_flops / (attn_ms * 1e-3) / 1e12 / peaks["tflops"], 4) if attn_ms > 0 else 0.0,

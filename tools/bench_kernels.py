@@ -32,8 +32,10 @@ def bench_gemm(M, N, K, epi=0, name=""):
     n_out = N
     if epi == ops.EPI_RESIDUAL:
         kw["aux"] = torch.randn(M, N, device=DEV).bfloat16()
-    if epi == ops.EPI_GEGLU:
+    if epi in (ops.EPI_GEGLU, ops.EPI_GEGLU_SAVE):
         n_out = N // 2
+    if epi == ops.EPI_GEGLU_SAVE:
+        kw["c2"] = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
     if epi == ops.EPI_ROPE:
         kw["positions"] = (torch.arange(M, device=DEV, dtype=torch.int32) % 2000)
         kw["rope_table"] = ops.rope_table(160000.0, 2048, DEV)
@@ -206,6 +208,7 @@ if __name__ == "__main__":
     T = 64 * 1300
     for (N, K, epi, name) in [(2304, 768, ops.EPI_ROPE, "_wqkv_rope"), (2304, 768, 0, "_wqkv_plain"),
                               (768, 768, ops.EPI_RESIDUAL, "_wo_res"), (2304, 768, ops.EPI_GEGLU, "_wi_geglu"),
+                              (2304, 768, ops.EPI_GEGLU_SAVE, "_wi_geglu_save"),
                               (768, 1152, ops.EPI_RESIDUAL, "_wo2_res")]:
         bench_gemm(T, N, K, epi, name)
     bench_gemm(8192, 8192, 8192, 0, "_square")

@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_kernels_bwd_gpu.py -m gpu -q -x -k "gemm or conv or linear or wgrad or split" > gpurun_out/r2af_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2af_pytest.log | cut -c1-300
+timeout 300 python tools/bench_kernels.py 2>&1 | grep gemm | cut -c1-140
