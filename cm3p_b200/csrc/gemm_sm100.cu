@@ -39,16 +39,21 @@ constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-// CTA-pair MMA (cta_group::2, M = 256 over two CTAs): a CTA holds only its half of every B tile, so the same 192 KB
-// give 6 stages of (16 KB A + 16 KB B-half)
-constexpr int STAGES_2CTA = 6;
+// CTA-pair MMA (cta_group::2, M = 256 over two CTAs): a CTA holds only its half of every B tile, so the same 192 KB would
+// give 6 stages of (16 KB A + 16 KB B-half); 5 measure the same (profiles/r2_kernel_microbench_mma2.jsonl), and the
+// 32 KB they leave hold two more output slabs: with two, every slab of the residual epilogue waited for the previous
+// slab's TMA store to drain before it could prefetch the next residual into that buffer
+constexpr int STAGES_2CTA = 5;
 constexpr int MAX_STAGES = 6;
-static_assert(STAGES_2CTA * (A_STAGE_BYTES + B_STAGE_BYTES / 2) == STAGES * STAGE_BYTES, "same operand ring size");
+constexpr int SLAB_BUFS = 2, SLAB_BUFS_2CTA = 4;
+constexpr int MAX_SLAB_BUFS = 4;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
 constexpr int SLAB_BYTES = BM * 128;  // 128 rows x 64 bf16
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-static_assert((2 * MAX_STAGES + 2 * ACC_STAGES + 2) * 8 + 4 <= 256, "barrier block");
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SLAB_BUFS * SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+static_assert(STAGES_2CTA * (A_STAGE_BYTES + B_STAGE_BYTES / 2) + SLAB_BUFS_2CTA * SLAB_BYTES ==
+                  STAGES * STAGE_BYTES + SLAB_BUFS * SLAB_BYTES, "both forms use the same shared-memory footprint");
+static_assert((2 * MAX_STAGES + 2 * ACC_STAGES + MAX_SLAB_BUFS) * 8 + 4 <= 256, "barrier block");
 constexpr int THREADS = 256;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
@@ -314,7 +319,8 @@ __device__ __forceinline__ void st_release_gpu(int32_t* p, int32_t v) {
 // sum is written back in place.  Two slab buffers alternate; `leader` = first epilogue thread.
 struct EpiState {
   int g = 0;                  // processed-slab counter (selects the buffer)
-  uint32_t res_parity[2] = {0, 0};
+  uint32_t res_parity = 0;    // bit b = parity of the next residual load into buffer b
+  int pair = 0;               // GeGLU+save: product slabs stored so far (selects the product buffer)
 };
 
 template <int EPI>
@@ -333,7 +339,7 @@ __device__ __forceinline__ uint4 pack8f(const float* v) {
                     ptx::pack_bf16x2(v[6], v[7]));
 }
 
-template <int EPI>
+template <int EPI, int NBUF>
 __device__ __forceinline__ void epilogue_tile_staged(const Params& p, const CUtensorMap* tma_c,
                                                      const CUtensorMap* tma_c2, const CUtensorMap* tma_aux,
                                                      uint8_t* slabs, uint64_t* res_full, EpiState& st,
@@ -397,24 +403,34 @@ __device__ __forceinline__ void epilogue_tile_staged(const Params& p, const CUte
   for (int sl = 0; sl < NSLAB; ++sl) {
     const int64_t col = n0 + sl * ACC;  // first accumulator column of the slab
     if (col >= p.N) break;              // CTA-uniform
-    const int buf = st.g & 1;
+    // NBUF slab buffers in rotation: slab g is assembled in buffer g % NBUF, whose previous TMA store (slab g - NBUF)
+    // must have left shared memory: at most NBUF - 1 younger stores may still be reading.  The residual of slab g + 1
+    // is prefetched one slab ahead into ITS buffer, last stored by slab g + 1 - NBUF: at most NBUF - 2 pending.
+    // GeGLU+save with 4 buffers: buffers 0, 1 rotate for the raw slabs; buffers 2, 3 collect the PRODUCT of two
+    // consecutive raw slabs (2 x 32 columns = one 128-byte row per token) and go out with one TMA store in the bulk
+    // group of the second slab, so a bulk group still is "one slab" for the wait counts.  (Writing the product with
+    // one 64-byte row segment per lane cost 32 L1 lines per store instruction.)
+    constexpr bool PSTAGE = (EPI == EPI_GEGLU_SAVE) && NBUF == 4;
+    constexpr int RBUF = PSTAGE ? 2 : NBUF;  // buffers in rotation for the staged slab itself
+    const int buf = st.g % RBUF, nbuf = (st.g + 1) % RBUF;
     uint8_t* slab = slabs + buf * SLAB_BYTES;
+    uint8_t* pslab = slabs + (2 + ((st.pair + (sl >> 1)) & 1)) * SLAB_BYTES;  // PSTAGE only
     const int64_t out_col = (EPI == EPI_GEGLU) ? (col >> 1) : col;
 
     // ---- free the buffer(s); prefetch the next residual slab
     if (leader) {
       if constexpr (EPI == EPI_RESIDUAL) {
-        ptx::tma_store_wait_read<0>();
+        ptx::tma_store_wait_read<RBUF - 2>();
         int64_t ncol = col + ACC, nm0 = m0;
         bool have = (sl + 1 < NSLAB) && (ncol < p.N);
         if (!have && has_next_tile) { have = true; ncol = next_n0; nm0 = next_m0; }
         if (have) {
-          ptx::mbar_arrive_expect_tx(&res_full[buf ^ 1], SLAB_BYTES);
-          ptx::tma_load_2d(slabs + (buf ^ 1) * SLAB_BYTES, tma_aux, &res_full[buf ^ 1], static_cast<int32_t>(ncol),
+          ptx::mbar_arrive_expect_tx(&res_full[nbuf], SLAB_BYTES);
+          ptx::tma_load_2d(slabs + nbuf * SLAB_BYTES, tma_aux, &res_full[nbuf], static_cast<int32_t>(ncol),
                            static_cast<int32_t>(nm0));
         }
       } else {
-        ptx::tma_store_wait_read<1>();
+        ptx::tma_store_wait_read<RBUF - 1>();
       }
     }
     ptx::named_bar_sync(1, 128);
@@ -461,8 +477,8 @@ __device__ __forceinline__ void epilogue_tile_staged(const Params& p, const CUte
         if (ln) ln_fix(v, col);
       }
       if constexpr (EPI == EPI_RESIDUAL) {
-        ptx::mbar_wait(&res_full[buf], st.res_parity[buf]);
-        st.res_parity[buf] ^= 1;
+        ptx::mbar_wait(&res_full[buf], (st.res_parity >> buf) & 1u);
+        st.res_parity ^= 1u << buf;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const uint4 u = slab_read_row(slab, r, c);
@@ -503,15 +519,19 @@ __device__ __forceinline__ void epilogue_tile_staged(const Params& p, const CUte
           }
         }
       } else if constexpr (EPI == EPI_GEGLU_SAVE) {
-        // product written directly (1/3 of the bytes); the raw slab goes through the staged path
-        if (row < p.M) {
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + (col >> 1);
-          float o[32];
+        float o[32];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            o[i] = ptx::gelu_erf(v[i]) * v[16 + i];
-            o[16 + i] = ptx::gelu_erf(v[32 + i]) * v[48 + i];
-          }
+        for (int i = 0; i < 16; ++i) {
+          o[i] = ptx::gelu_erf(v[i]) * v[16 + i];
+          o[16 + i] = ptx::gelu_erf(v[32 + i]) * v[48 + i];
+        }
+        if constexpr (PSTAGE) {
+          // half of a product row: 16-byte units 0..3 (even slab of the pair) or 4..7 (odd slab)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) slab_write_row(pslab, r, (sl & 1) * 4 + c, pack8f(o + c * 8));
+        } else if (row < p.M) {
+          // product written directly (1/3 of the bytes); the raw slab goes through the staged path
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + (col >> 1);
 #pragma unroll
           for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(dst + c * 8) = pack8f(o + c * 8);
         }
@@ -530,10 +550,21 @@ __device__ __forceinline__ void epilogue_tile_staged(const Params& p, const CUte
       } else {
         ptx::tma_store_2d((EPI == EPI_GEGLU_SAVE) ? tma_c2 : tma_c, slab, static_cast<int32_t>(out_col),
                           static_cast<int32_t>(m0));
+        if constexpr (PSTAGE) {
+          // the pair's product slab is complete after its odd slab (or at the end of the tile / of N: the unwritten
+          // half then lies beyond column N / 2 and is clipped by the tensor map)
+          const bool last = (sl + 1 == NSLAB) || (col + ACC >= p.N);
+          if ((sl & 1) || last)
+            ptx::tma_store_2d(tma_c, pslab, static_cast<int32_t>((col - (sl & 1) * ACC) >> 1), static_cast<int32_t>(m0));
+        }
       }
       ptx::tma_store_commit();
     }
     ++st.g;
+  }
+  if constexpr (EPI == EPI_GEGLU_SAVE) {
+    const int64_t cols = (p.N - n0 < BN) ? p.N - n0 : BN;
+    st.pair += static_cast<int>((cols + 2 * ACC - 1) / (2 * ACC));  // product slabs of this tile
   }
   if constexpr (EPI == EPI_RESIDUAL) {
     if (p.stats_out && row < p.M)  // this tile's partial: slot [n0 / BN][row]
@@ -555,14 +586,15 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
   constexpr int b_stage_bytes = mma2 ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + nstages * A_STAGE_BYTES;
-  uint8_t* slabs = smem + STAGES * STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(slabs + 2 * SLAB_BYTES);
+  constexpr int nslab_bufs = mma2 ? SLAB_BUFS_2CTA : SLAB_BUFS;
+  uint8_t* slabs = smem + nstages * (A_STAGE_BYTES + b_stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slabs + nslab_bufs * SLAB_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + MAX_STAGES;
   uint64_t* tmem_full = bars + 2 * MAX_STAGES;
   uint64_t* tmem_empty = bars + 2 * MAX_STAGES + ACC_STAGES;
-  uint64_t* res_full = bars + 2 * MAX_STAGES + 2 * ACC_STAGES;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * ACC_STAGES + 2);
+  uint64_t* res_full = bars + 2 * MAX_STAGES + 2 * ACC_STAGES;  // [nslab_bufs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * ACC_STAGES + MAX_SLAB_BUFS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -583,8 +615,8 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       ptx::mbar_init(&tmem_full[s], 1);
       // one arrive per epilogue warp; pair MMA: the leader's issuer waits for the epilogue warps of BOTH CTAs
       ptx::mbar_init(&tmem_empty[s], mma2 ? 8 : 4);
-      ptx::mbar_init(&res_full[s], 1);
     }
+    for (int s = 0; s < nslab_bufs; ++s) ptx::mbar_init(&res_full[s], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -784,7 +816,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       ptx::tc_fence_after();
       if constexpr (STAGED) {
         const int64_t tn = t + unit_step;
-        epilogue_tile_staged<EPI>(p, &tma_c, &tma_c2, &tma_aux, slabs, res_full, st, tmem_base + as * BN, quad, m0,
+        epilogue_tile_staged<EPI, nslab_bufs>(p, &tma_c, &tma_c2, &tma_aux, slabs, res_full, st, tmem_base + as * BN, quad, m0,
                                   n0, tile_m0(tn), tile_n0(tn), tn < num_tiles);
       } else {
         if constexpr (EPI == EPI_SCALE_F32) {
@@ -983,6 +1015,7 @@ int gemm_bf16(const GemmArgs& g_in, cudaStream_t stream) {
     const int64_t n_out = (g.epilogue == EPI_GEGLU) ? g.N / 2 : g.N;
     if (g.epilogue == EPI_GEGLU_SAVE) {
       rc = encode_tmap_2d_bf16(&tc2, g.c2, g.N, g.M, g.ldc2 * 2, 64, BM);
+      if (rc == kOk) rc = encode_tmap_2d_bf16(&tc, g.c, g.N / 2, g.M, g.ldc * 2, 64, BM);  // product, via staging
     } else if (g.conv_mode == 1) {
       rc = encode_tmap_3d_bf16(&tc, g.c, g.N, conv_rows, g.conv_batch, static_cast<uint64_t>(g.N) * 2,
                                static_cast<uint64_t>(conv_rows) * g.N * 2, 64, BM, 1);
