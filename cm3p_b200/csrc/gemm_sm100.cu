@@ -344,7 +344,8 @@ __device__ __forceinline__ void epilogue_tile_staged(const Params& p, const CUte
                                                      const CUtensorMap* tma_c2, const CUtensorMap* tma_aux,
                                                      uint8_t* slabs, uint64_t* res_full, EpiState& st,
                                                      uint32_t tmem_acc, int quad, int64_t m0, int64_t n0,
-                                                     int64_t next_m0, int64_t next_n0, bool has_next_tile) {
+                                                     int64_t next_m0, int64_t next_n0, bool has_next_tile,
+                                                     const float2 (&cs)[32]) {
   constexpr int ACC = slab_acc_cols<EPI>();
   constexpr int NSLAB = BN / ACC;
   const int lane = ptx::lane_id();
@@ -384,20 +385,6 @@ __device__ __forceinline__ void epilogue_tile_staged(const Params& p, const CUte
     }
   };
   float st_sum = 0.f, st_sq = 0.f;  // RESIDUAL: statistics of the rows written by this thread
-
-  float2 cs[32];
-  if constexpr (EPI == EPI_ROPE) {
-    if (n0 < p.rope_cols) {
-      const int pos = (row < p.M) ? p.positions[row] : 0;
-      const float4* tab = reinterpret_cast<const float4*>(p.rope_table + static_cast<int64_t>(pos) * 32);
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const float4 f = __ldg(tab + k);
-        cs[2 * k] = make_float2(f.x, f.y);
-        cs[2 * k + 1] = make_float2(f.z, f.w);
-      }
-    }
-  }
 
 #pragma unroll 1
   for (int sl = 0; sl < NSLAB; ++sl) {
@@ -812,12 +799,29 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     for (int64_t t = unit0; t < num_tiles; t += unit_step) {
       const int64_t m0 = tile_m0(t);
       const int64_t n0 = tile_n0(t);
+      [[maybe_unused]] float2 cs[32];
+      if constexpr (STAGED && EPI == EPI_ROPE) {
+        // (cos, sin) of this row's position for the tile's heads: two dependent global loads (position -> table row),
+        // issued BEFORE the wait for the accumulator so that they travel under the tile's MMAs, not in front of the
+        // epilogue
+        if (n0 < p.rope_cols) {
+          const int64_t row = m0 + quad * 32 + lane;
+          const int pos = (row < p.M) ? p.positions[row] : 0;
+          const float4* tab = reinterpret_cast<const float4*>(p.rope_table + static_cast<int64_t>(pos) * 32);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float4 f = __ldg(tab + k);
+            cs[2 * k] = make_float2(f.x, f.y);
+            cs[2 * k + 1] = make_float2(f.z, f.w);
+          }
+        }
+      }
       ptx::mbar_wait(&tmem_full[as], aph);
       ptx::tc_fence_after();
       if constexpr (STAGED) {
         const int64_t tn = t + unit_step;
         epilogue_tile_staged<EPI, nslab_bufs>(p, &tma_c, &tma_c2, &tma_aux, slabs, res_full, st, tmem_base + as * BN, quad, m0,
-                                  n0, tile_m0(tn), tile_n0(tn), tn < num_tiles);
+                                  n0, tile_m0(tn), tile_n0(tn), tn < num_tiles, cs);
       } else {
         if constexpr (EPI == EPI_SCALE_F32) {
           if (p.accumulate == 2) {
