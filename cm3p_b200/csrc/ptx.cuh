@@ -305,8 +305,9 @@ __device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorM
 }
 // one arrival on the leader's barrier at the offset of `bar` (from either CTA of the pair)
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(smem_u32(bar) & kLeaderCtaMask)
-               : "memory");
+  // default semantics (.release.cta): what is handed over is TMEM, ordered by tcgen05.wait::ld + fence::before_thread_sync
+  // before this arrive; `.release.cluster` compiled to MEMBAR.ALL + ERRBAR (4 % of the residual GEMM's stall samples)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(smem_u32(bar) & kLeaderCtaMask) : "memory");
 }
 
 // mbarrier arrives once every previously issued tcgen05.mma of this thread has completed.
