@@ -90,6 +90,37 @@ def test_gemm_geglu(I, H):
     _report("gemm_geglu_save.raw", ops.deinterleave_wi(raw.t().contiguous()).t(), acc, 2e-2, 1e-2)
 
 
+def test_gemm_cluster_forms_agree():
+    """The three GEMM forms (single CTAs, CTA pairs with B multicast, CTA pairs with one cta_group::2 MMA = default)
+    accumulate in the same order: bitwise-equal outputs, staged and direct epilogues, odd numbers of M tiles."""
+    ops = _ops()
+    M, H, I = 128 * 5 + 40, 768, 1152
+    a, w = _rand((M, H), seed=11), _rand((2 * I, H), 0.05, seed=12)
+    res = _rand((M, 2 * I), seed=13)
+    wi_il = ops.interleave_wi(w).contiguous()
+    dy = _rand((M, 256), 0.5, seed=14)
+    outs = {}
+    try:
+        for mode in (2, 3, 1):
+            ops.set_option(ops.OPT_GEMM_CLUSTER, mode)
+            raw = torch.empty((M, 2 * I), device=DEV, dtype=torch.bfloat16)
+            dw = torch.zeros((256, H), device=DEV)
+            ops.set_option(ops.OPT_WGRAD_DETERMINISTIC, 1)
+            ops.gemm(dy, a, trans_a=True, trans_b=True, epilogue=ops.EPI_SCALE_F32, accumulate=True, out=dw)
+            ops.set_option(ops.OPT_WGRAD_DETERMINISTIC, 0)
+            outs[mode] = (ops.gemm(a, w), ops.gemm(a, w, epilogue=ops.EPI_RESIDUAL, aux=res),
+                          ops.gemm(a, wi_il, epilogue=ops.EPI_GEGLU_SAVE, c2=raw), raw, dw,
+                          ops.gemm(res, w, trans_b=True))
+    finally:
+        ops.set_option(ops.OPT_GEMM_CLUSTER, 2)
+        ops.set_option(ops.OPT_WGRAD_DETERMINISTIC, 0)
+    torch.cuda.synchronize()
+    for mode in (3, 1):
+        for k, (x, y) in enumerate(zip(outs[2], outs[mode])):
+            assert torch.equal(x, y), f"form {mode} differs from the pair-MMA form in output {k}"
+    _report("gemm_pair_form", outs[2][0], a.float() @ w.float().t(), 2e-2, 1e-2)
+
+
 def test_gemm_rope():
     ops = _ops()
     heads, T = 3, 500
