@@ -79,6 +79,9 @@ def _ptr(t) -> int | None:
 def _req(t: torch.Tensor, dtype, name: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor (cm3p_b200 has no CPU path)")
+    if t.device.index != torch.cuda.current_device():
+        # launches go to the CURRENT device's stream: run under `torch.cuda.device(t.device)` for other GPUs
+        raise RuntimeError(f"{name} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}")
     if t.dtype != dtype:
         raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
 

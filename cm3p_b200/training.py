@@ -42,6 +42,7 @@ class GradStore:
 
     BUCKET_BYTES = 64 << 20
     OVERLAP = True  # False: one reduction of the whole buffer after the backward pass (A/B measurements)
+    TAIL_EVENTS = None  # a list: finish() appends (start, end) CUDA events around its wait for the collectives (bench.py)
 
     def __init__(self, params, order=None, dp=None, sum_reduce=False):
         self.params = list(params)
@@ -99,6 +100,10 @@ class GradStore:
         """Reduce whatever has not been sent yet and make the compute stream wait for all reductions."""
         if self.dp is None:
             return
+        tail = GradStore.TAIL_EVENTS
+        if tail is not None:  # how long the compute stream stalls for collectives the backward pass could not hide
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
         if self._pos is None:
             self._works.append(dp_utils.reduce_gradients_async(self.flat, self.dp, self.sum_reduce))
         else:
@@ -108,6 +113,10 @@ class GradStore:
         for w in self._works:
             w.wait()
         self._works = []
+        if tail is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            tail.append((e0, e1))
 
     def order(self) -> list[int]:
         """Parameter indices in first-touch order, untouched (frozen / unused) parameters last."""
