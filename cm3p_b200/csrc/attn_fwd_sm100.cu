@@ -121,7 +121,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params 
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j & 1;
         const uint32_t ph = (j >> 1) & 1;
-        ptx::mbar_wait(&kv_empty[s], ph ^ 1);
+        ptx::mbar_wait_trap(&kv_empty[s], ph ^ 1);
         ptx::mbar_arrive_expect_tx(&kv_full[s], 2 * KV_TILE_BYTES);
         const int row = seq_start + (tile_lo + j) * BKV;
         ptx::tma_load_2d(smem_k + s * KV_TILE_BYTES, &tma_qkv, &kv_full[s], col_k, row);
@@ -137,7 +137,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params 
       const uint32_t p_addr = ptx::smem_u32(smem_p);
       auto issue_s = [&](int j) {
         const int s = j & 1;
-        ptx::mbar_wait(&kv_full[s], (j >> 1) & 1);
+        ptx::mbar_wait_trap(&kv_full[s], (j >> 1) & 1);
         ptx::tc_fence_after();
         const uint32_t k_addr = ptx::smem_u32(smem_k + s * KV_TILE_BYTES);
 #pragma unroll
@@ -146,10 +146,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params 
                          ptx::umma_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
         ptx::umma_commit(s_full);
       };
-      ptx::mbar_wait(q_full, 0);
+      ptx::mbar_wait_trap(q_full, 0);
       issue_s(0);
       for (int j = 0; j < n_tiles; ++j) {
-        ptx::mbar_wait(p_full, j & 1);  // P_j in smem, S_j and O_{j-1} consumed
+        ptx::mbar_wait_trap(p_full, j & 1);  // P_j in smem, S_j and O_{j-1} consumed
         ptx::tc_fence_after();
         if (j + 1 < n_tiles) issue_s(j + 1);
         const int s = j & 1;
@@ -176,7 +176,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params 
 
     for (int j = 0; j < n_tiles; ++j) {
       const int kv0 = (tile_lo + j) * BKV;
-      ptx::mbar_wait(s_full, j & 1);
+      ptx::mbar_wait_trap(s_full, j & 1);
       ptx::tc_fence_after();
       // allowed kv range for this row inside the tile: [a, b)
       int a = 0, b = min(BKV, len - kv0);
@@ -203,7 +203,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params 
       const float alpha = ptx::ex2_approx((m_prev - m_use) * c);  // 0 when m_prev = -inf
       // fold O_{j-1} (relative to m_prev) and rescale to m_new
       if (j > 0) {
-        ptx::mbar_wait(o_full, (j - 1) & 1);
+        ptx::mbar_wait_trap(o_full, (j - 1) & 1);
         ptx::tc_fence_after();
 #pragma unroll
         for (int h = 0; h < D; h += 32) {
@@ -249,7 +249,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params 
       ptx::mbar_arrive(p_full);
     }
     // last P.V
-    ptx::mbar_wait(o_full, (n_tiles - 1) & 1);
+    ptx::mbar_wait_trap(o_full, (n_tiles - 1) & 1);
     ptx::tc_fence_after();
 #pragma unroll
     for (int h = 0; h < D; h += 32) {
@@ -417,14 +417,14 @@ attn_fwd_packed_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Packed
       const uint32_t idesc_o = ptx::umma_idesc_bf16(BQ, D, 0, 1);  // V is MN-major
       const uint32_t q_addr = ptx::smem_u32(smem_q), k_addr = ptx::smem_u32(smem_k);
       const uint32_t v_addr = ptx::smem_u32(smem_v), p_addr = ptx::smem_u32(smem_p);
-      ptx::mbar_wait(ld_full, 0);
+      ptx::mbar_wait_trap(ld_full, 0);
       ptx::tc_fence_after();
 #pragma unroll
       for (int k = 0; k < D / 16; ++k)
         ptx::umma_bf16(tmem_base + TMEM_S, ptx::umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
                        ptx::umma_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
       ptx::umma_commit(s_full);
-      ptx::mbar_wait(p_full, 0);
+      ptx::mbar_wait_trap(p_full, 0);
       ptx::tc_fence_after();
       for (int k = 0; k < ksteps; ++k)
         ptx::umma_bf16(tmem_base + TMEM_O,
@@ -442,7 +442,7 @@ attn_fwd_packed_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Packed
     // columns any row of this warp may attend to: chunks outside are skipped (zeros, no TMEM read, no exp)
     const int wa = __reduce_min_sync(0xffffffffu, valid ? lo : BKV);
     const int wb = __reduce_max_sync(0xffffffffu, valid ? hi : 0);
-    ptx::mbar_wait(s_full, 0);
+    ptx::mbar_wait_trap(s_full, 0);
     ptx::tc_fence_after();
     float mx = -INFINITY;
 #pragma unroll 1
@@ -489,7 +489,7 @@ attn_fwd_packed_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Packed
     ptx::tc_fence_before();
     ptx::fence_proxy_async_smem();
     ptx::mbar_arrive(p_full);
-    ptx::mbar_wait(o_full, 0);
+    ptx::mbar_wait_trap(o_full, 0);
     ptx::tc_fence_after();
     uint32_t o[64];
     {
@@ -657,14 +657,14 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
       for (int bi = 0; bi < n_b; ++bi) {
         const int q0 = (b_begin + bi) * 2 * BQ;
         const int qb = bi & 1;
-        ptx::mbar_wait(&q_empty[qb], ((bi >> 1) & 1) ^ 1);
+        ptx::mbar_wait_trap(&q_empty[qb], ((bi >> 1) & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(&q_full[qb], 2 * Q_BYTES);
         ptx::tma_load_2d(smem_q + qb * 2 * Q_BYTES, &tma_qkv, &q_full[qb], col_q, seq_start + q0);
         ptx::tma_load_2d(smem_q + qb * 2 * Q_BYTES + Q_BYTES, &tma_qkv, &q_full[qb], col_q, seq_start + q0 + BQ);
         const BlockRange br = block_range(q0, len, p.window);
         for (int u = 0; u < br.U; ++u, ++ring) {
           const int s = ring % KV_STAGES2;
-          ptx::mbar_wait(&kv_empty[s], ((ring / KV_STAGES2) & 1) ^ 1);
+          ptx::mbar_wait_trap(&kv_empty[s], ((ring / KV_STAGES2) & 1) ^ 1);
           ptx::mbar_arrive_expect_tx(&kv_full[s], 2 * KV_TILE_BYTES);
           const int row = seq_start + br.kv_base + u * BKV;
           ptx::tma_load_2d(smem_k + s * KV_TILE_BYTES, &tma_qkv, &kv_full[s], col_k, row);
@@ -700,7 +700,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
         auto issue_s = [&](int t) {
           const int r = ring_base + t;
           const int s = r % KV_STAGES2;
-          ptx::mbar_wait(&kv_full[s], (r / KV_STAGES2) & 1);
+          ptx::mbar_wait_trap(&kv_full[s], (r / KV_STAGES2) & 1);
           ptx::tc_fence_after();
           const uint32_t k_addr = ptx::smem_u32(smem_k + s * KV_TILE_BYTES);
 #pragma unroll
@@ -715,17 +715,17 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
         };
         auto ack = [&](int u) {  // tile outside this Q tile's range: hand the stage back once it has landed
           const int r = ring_base + u;
-          ptx::mbar_wait(&kv_full[r % KV_STAGES2], (r / KV_STAGES2) & 1);
+          ptx::mbar_wait_trap(&kv_full[r % KV_STAGES2], (r / KV_STAGES2) & 1);
           if (leader) ptx::umma_commit(&kv_empty[r % KV_STAGES2]);
         };
-        ptx::mbar_wait(&q_full[qb], (bi >> 1) & 1);
+        ptx::mbar_wait_trap(&q_full[qb], (bi >> 1) & 1);
         for (int u = 0; u < lo_x; ++u) ack(u);
         if (hi_x > lo_x) {
           // the S buffer was drained when the group loaded the last tile of the previous block (s_free of tile
           // it-1 has completed long ago)
           issue_s(lo_x);
           // O_x of the previous block must have been copied out before the first PV overwrites it
-          if (blk > 0) ptx::mbar_wait(&o_free[x], (blk - 1) & 1);
+          if (blk > 0) ptx::mbar_wait_trap(&o_free[x], (blk - 1) & 1);
           ptx::tc_fence_after();
         } else if (leader) {
           ptx::umma_commit(&q_empty[qb]);
@@ -734,14 +734,14 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
         for (int t = lo_x; t < hi_x; ++t, ++it) {
           const int j = t - lo_x;
           if (t + 1 < hi_x) {
-            ptx::mbar_wait(&s_free[x], it & 1);
+            ptx::mbar_wait_trap(&s_free[x], it & 1);
             issue_s(t + 1);
           }
           // V tile as the MN-major B operand (LBO = 8192: distance of 64-element MN chunks, unused)
           const uint32_t v_lo = ptx::umma_desc_lo(ptx::smem_u32(smem_v + ((ring_base + t) % KV_STAGES2) * KV_TILE_BYTES), 8192);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            ptx::mbar_wait(&p_full[2 * x + h], it & 1);  // this half of P_x(t) is in TMEM (O_x rescaled if needed)
+            ptx::mbar_wait_trap(&p_full[2 * x + h], it & 1);  // this half of P_x(t) is in TMEM (O_x rescaled if needed)
             ptx::tc_fence_after();
 #pragma unroll
             for (int k = 0; k < 4; ++k)  // 16-key steps: 8 TMEM columns of P (A operand), 16 rows of V
@@ -802,7 +802,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
       for (int jj = 0; jj < n_iter; ++jj, ++it) {
         const int kv0 = br.kv_base + (lo_x + jj) * BKV;
         PF_B(pf_epi);
-        ptx::mbar_wait(&s_full[x], it & 1);
+        ptx::mbar_wait_trap(&s_full[x], it & 1);
         PF_B(pf_s);
         ptx::tc_fence_after();
         uint32_t sr[2][32];
@@ -878,8 +878,8 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
           const bool grow = (m_new - m_run) * c > RESCALE_LOG2;  // also true for -inf -> finite
           if (__any_sync(0xffffffffu, grow)) {  // same vote in both warps of the pair: same rows, same maxima
             // both halves of PV(jj-1) must have retired before O is rescaled
-            ptx::mbar_wait(&pv_done[2 * x], (it - 1) & 1);
-            ptx::mbar_wait(&pv_done[2 * x + 1], (it - 1) & 1);
+            ptx::mbar_wait_trap(&pv_done[2 * x], (it - 1) & 1);
+            ptx::mbar_wait_trap(&pv_done[2 * x + 1], (it - 1) & 1);
             ptx::tc_fence_after();
             const float alpha = grow ? ptx::ex2_approx((m_run - m_new) * c) : 1.f;
 #pragma unroll 1
@@ -906,7 +906,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
         float2 rs[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};  // independent partial row sums (ILP)
         // this half of P_x in TMEM is still being read by the PV of the previous tile until pv_done fires; that
         // MMA was issued a whole exp phase ago, so this wait is normally already satisfied
-        if (it > 0) ptx::mbar_wait(&pv_done[2 * x + hc], (it - 1) & 1);
+        if (it > 0) ptx::mbar_wait_trap(&pv_done[2 * x + hc], (it - 1) & 1);
         ptx::tc_fence_after();
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -940,7 +940,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Params p) 
         ptx::named_bar_sync(pair_bar, 64);
         l += peer_x[2 * XS];
         ptx::named_bar_sync(pair_bar, 64);  // both sums are read before the next block's are written
-        ptx::mbar_wait(&o_full[x], blk & 1);
+        ptx::mbar_wait_trap(&o_full[x], blk & 1);
         ptx::tc_fence_after();
         uint32_t rr[32];
         ptx::tmem_ld_32x32b_x32(t_o, rr);
