@@ -44,7 +44,7 @@ constexpr int TILE_BYTES = 128 * D * 2;  // 16 KB: one 128-row operand tile, or 
 constexpr int NS = 3;                    // ring stages of the streamed operands
 constexpr int THREADS = 640;  // 16 element-wise warps, producer, issuer, 2 idle (warpgroup granularity)
 constexpr int EW_WARPS = 16;
-constexpr int REG_EW = 104, REG_AUX = 64;  // (112 / 64 = all 65536 registers removes the dKV loop's two spilled values but never starts: setmaxnreg.inc needs headroom)
+constexpr int REG_EW = 104, REG_AUX = 64;  // known: at 104 the dKV loop keeps t_s and the tile counter in local memory (two reloads per inner tile); 112 / 64 = all 65536 registers removes them but never starts (setmaxnreg.inc needs headroom)  // (112 / 64 = all 65536 registers removes the dKV loop's two spilled values but never starts: setmaxnreg.inc needs headroom)
 
 struct BwdParams {
   const int32_t* cu_seqlens;
