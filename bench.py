@@ -54,8 +54,8 @@ MLM_SEQ_LEN, MLM_BATCH = 8192, 8
 # dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch (average over the GEMM launches of one step), from
 # the ncu launch lists committed under profiles/ (it cannot be measured from inside this script)
 GEMM_TRAFFIC = {
-    "infer": (264.0e6, "profiles/r2_infer_launch_summary_v3.txt (ncu, batch 64)"),
-    "train": (1276.4e6, "profiles/r2_train256_launch_summary_v3.txt (ncu, batch 256, V=8)"),
+    "infer": (271.4e6, "profiles/r2_infer_launch_summary_v4.txt (ncu, batch 64)"),
+    "train": (1334.4e6, "profiles/r2_train256_launch_summary_v4.txt (ncu, batch 256, V=8)"),
 }
 
 
