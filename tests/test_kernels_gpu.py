@@ -43,7 +43,8 @@ def _report(name, got, want, atol, rtol):
 
 # ------------------------------------------------------------------------------------------ GEMM
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 384, 128), (1000, 768, 768), (4096, 2304, 768),
-                                   (77, 64, 240), (515, 1536, 512), (100, 7, 64), (9, 3, 512)])
+                                   (77, 64, 240), (515, 1536, 512), (100, 7, 64), (9, 3, 512),
+                                   (700, 300, 200), (257, 136, 72)])  # pair-MMA form with M / N / K tails
 def test_gemm_store(M, N, K):
     ops = _ops()
     a, b = _rand((M, K), seed=1), _rand((N, K), 0.05, seed=2)
